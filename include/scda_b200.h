@@ -1,0 +1,153 @@
+/*
+ * scda_b200.h — C ABI of libscda_b200.so, the sm_100a operator library behind
+ * the SCDA Faster R-CNN hot path.
+ *
+ * Boundary rules (all entry points):
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless
+ *     the parameter name ends in _host;
+ *   - the caller allocates every output (and the workspace, sized by the
+ *     matching *_workspace_bytes query); nothing is allocated or freed inside;
+ *   - work is enqueued on the cudaStream_t passed in and the call returns
+ *     without synchronising; no global state, re-entrant;
+ *   - return value: 1 = launched, 0 = rejected arguments, negative =
+ *     -(cudaError_t) of the failed launch.  Never exit()s (the reference
+ *     launchers do: extensions/_roi_pooling/src/roi_pooling_kernel.cu:117-122).
+ *
+ * Section A keeps the names and parameter lists of the reference's own
+ * launcher layer (sic "Laucher"), one level below its TH/THC cffi glue which
+ * no longer exists in torch >= 1.0, so the unmodified reference objects
+ * (oracle/_ref/libscda_ref.so) and this library are interchangeable under one
+ * binding.  Section B adds the fused / on-device forms the B200 path uses.
+ * All file:line citations are relative to the reference tree.
+ */
+#ifndef SCDA_B200_H_
+#define SCDA_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#ifndef __DRIVER_TYPES_H__
+typedef struct CUstream_st *cudaStream_t;
+#endif
+
+/* ===================================================================== */
+/* A. Reference launcher layer, same symbols                               */
+/* ===================================================================== */
+
+/* replaces extensions/_roi_pooling/src/roi_pooling_kernel.h:8-12
+ * (behind roi_pooling_forward_cuda, src/roi_pooling_cuda.c:7-38).
+ * bottom_data NCHW fp32; bottom_rois [num_rois,5] = (batch, x1, y1, x2, y2)
+ * in image coordinates; top_data [num_rois,C,PH,PW]; argmax_data same shape,
+ * flat offset into bottom_data of the max (-1 for an empty bin), may be NULL. */
+int ROIPoolForwardLaucher(const float *bottom_data, const float spatial_scale, const int num_rois,
+                          const int height, const int width, const int channels,
+                          const int pooled_height, const int pooled_width,
+                          const float *bottom_rois, float *top_data, int *argmax_data,
+                          cudaStream_t stream);
+
+/* replaces roi_pooling_kernel.h:15-18 (behind roi_pooling_backward_cuda,
+ * src/roi_pooling_cuda.c:41-88).  bottom_diff [batch,C,H,W] is overwritten. */
+int ROIPoolBackwardLaucher(const float *top_diff, const float spatial_scale, const int batch_size,
+                           const int num_rois, const int height, const int width,
+                           const int channels, const int pooled_height, const int pooled_width,
+                           const float *bottom_rois, float *bottom_diff, const int *argmax_data,
+                           cudaStream_t stream);
+
+/* replaces extensions/_roi_align/src/roi_align_kernel.h:13-17
+ * (behind roi_align_forward_cuda, src/roi_align_cuda.c:7-38). */
+int ROIAlignForwardLaucher(const float *bottom_data, const float spatial_scale, const int num_rois,
+                           const int height, const int width, const int channels,
+                           const int aligned_height, const int aligned_width,
+                           const float *bottom_rois, float *top_data, cudaStream_t stream);
+
+/* replaces roi_align_kernel.h:24-27 (behind roi_align_backward_cuda,
+ * src/roi_align_cuda.c:40-76).  Accumulates INTO bottom_diff, which the
+ * caller zeroes (functions/roi_align.py:40-41), like the reference. */
+int ROIAlignBackwardLaucher(const float *top_diff, const float spatial_scale, const int batch_size,
+                            const int num_rois, const int height, const int width,
+                            const int channels, const int aligned_height, const int aligned_width,
+                            const float *bottom_rois, float *bottom_diff, cudaStream_t stream);
+
+/* replaces extensions/_nms/src/cuda/nms_kernel.h:11-12: the N x ceil(N/64)
+ * suppression bitmask on the legacy default stream (the reference passes no
+ * stream, nms_kernel.cu:79).  Lower-triangle words are written as 0. */
+void _nms(int boxes_num, float *boxes_dev, unsigned long long *mask_dev, float nms_overlap_thresh);
+
+/* replaces extensions/_bbox_helper/src/cuda/iou_overlap_kernel.h:8-14
+ * (behind gpu_iou_overlaps, src/bbox_helper_cuda.c:16-47). */
+int IOUOverlap(const float *bboxes1_data, const float *bboxes2_data, const int size_bbox,
+               const int num_bbox1, const int num_bbox2, float *top_data, cudaStream_t stream);
+
+/* replace extensions/_focal_loss/src/cuda/focal_loss_sigmoid_kernel.h:8-18
+ * (behind focal_loss_sigmoid_{forward,backward}_cuda,
+ * src/focal_loss_cuda.c:10-53).  N = rows * num_classes. */
+int SigmoidFocalLossForwardLaucher(const int N, const float *logits, const int *targets,
+                                   const float weight_pos, const float gamma, const float alpha,
+                                   const int num_classes, float *losses, cudaStream_t stream);
+int SigmoidFocalLossBackwardLaucher(const int N, const float *logits, const int *targets,
+                                    float *dX_data, const float weight_pos, const float gamma,
+                                    const float alpha, const int num_classes, cudaStream_t stream);
+
+/* replace focal_loss_softmax_kernel.h:8-19 (behind
+ * focal_loss_softmax_{forward,backward}_cuda, src/focal_loss_cuda.c:55-108). */
+int SoftmaxFocalLossForwardLaucher(const int N, const float *logits, const int *targets,
+                                   const float weight_pos, const float gamma, const float alpha,
+                                   const int num_classes, float *losses, float *priors,
+                                   cudaStream_t stream);
+int SoftmaxFocalLossBackwardLaucher(const int N, const float *logits, const int *targets,
+                                    float *dX_data, const float weight_pos, const float gamma,
+                                    const float alpha, const int num_classes, const float *priors,
+                                    float *buff, cudaStream_t stream);
+
+/* ===================================================================== */
+/* B. B200 path                                                            */
+/* ===================================================================== */
+
+int scda_abi_version(void);
+
+/* --- NMS, wholly on device -------------------------------------------- */
+/* replaces gpu_nms (extensions/_nms/src/nms_cuda.c:17-67): bitmask kernel +
+ * D2H of the mask + sequential host scan become bitmask kernel (upper
+ * triangle only) + single-CTA device scan; the mask never leaves HBM/L2.
+ * boxes [n,5] = (x1,y1,x2,y2,score) sorted by descending score; keep_out
+ * int64[n] receives ascending kept indices, num_out int64[1] their count.
+ * max_keep > 0 stops the scan after that many survivors (what the callers'
+ * keep[:post_nms_top_n] slicing discards, functions/rpn_proposal.py:65-66);
+ * 0 = scan everything.  workspace >= scda_nms_workspace_bytes(n). */
+size_t scda_nms_workspace_bytes(int n);
+int scda_nms(int n, const float *boxes, float thresh, int max_keep, int64_t *keep_out,
+             int64_t *num_out, void *workspace, size_t workspace_bytes, cudaStream_t stream);
+/* the bitmask alone, on a stream (the _nms symbol above is the stream-less form) */
+int scda_nms_mask(int n, const float *boxes, unsigned long long *mask, float thresh,
+                  cudaStream_t stream);
+
+/* --- IoU, cython_bbox convention -------------------------------------- */
+/* replaces cython_bbox.bbox_overlaps (extensions/_cython_bbox/cython_bbox.pyx:32-73,
+ * reached through utils/bbox_helper.py:8-9): boxes [n,4], query [k,4] -> out [n,k];
+ * no +1, zero unless both overlaps > 0, no clamp.  Bit-exact with the host code. */
+int scda_bbox_overlaps(int n, const float *boxes, int k, const float *query, float *out,
+                       cudaStream_t stream);
+
+/* --- focal losses with the reduction fused ---------------------------- */
+/* SigmoidFocalLossFunction.forward = kernel + losses.sum() in Python
+ * (extensions/_focal_loss/focal_loss.py:31-46): one pass, loss_sum[0] is
+ * overwritten with the total.  losses may be NULL (skip the M x K write). */
+int scda_sigmoid_focal_loss_sum(const int N, const float *logits, const int *targets,
+                                const float weight_pos, const float gamma, const float alpha,
+                                const int num_classes, float *losses, float *loss_sum,
+                                cudaStream_t stream);
+/* SoftmaxFocalLossFunction.forward (focal_loss.py:103-118), same fusion;
+ * priors [N] is still written (backward needs it), losses may be NULL. */
+int scda_softmax_focal_loss_sum(const int N, const float *logits, const int *targets,
+                                const float weight_pos, const float gamma, const float alpha,
+                                const int num_classes, float *losses, float *priors,
+                                float *loss_sum, cudaStream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SCDA_B200_H_ */

@@ -1,0 +1,90 @@
+"""ctypes binding of libscda_b200.so (the C ABI declared in include/scda_b200.h).
+
+There is no fallback of any kind: if the shared object is missing or a symbol
+is absent, importing the operators raises.  Tensors cross the boundary as raw
+device pointers (`tensor.data_ptr()`), sizes and the current CUDA stream.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libscda_b200.so")
+
+_p = C.c_void_p
+_i = C.c_int
+_f = C.c_float
+_z = C.c_size_t
+
+# name -> (restype, argtypes); mirrors include/scda_b200.h one to one
+SIGNATURES = {
+    "ROIPoolForwardLaucher": (_i, [_p, _f, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p]),
+    "ROIPoolBackwardLaucher": (_i, [_p, _f, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p]),
+    "ROIAlignForwardLaucher": (_i, [_p, _f, _i, _i, _i, _i, _i, _i, _p, _p, _p]),
+    "ROIAlignBackwardLaucher": (_i, [_p, _f, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p]),
+    "_nms": (None, [_i, _p, _p, _f]),
+    "IOUOverlap": (_i, [_p, _p, _i, _i, _i, _p, _p]),
+    "SigmoidFocalLossForwardLaucher": (_i, [_i, _p, _p, _f, _f, _f, _i, _p, _p]),
+    "SigmoidFocalLossBackwardLaucher": (_i, [_i, _p, _p, _p, _f, _f, _f, _i, _p]),
+    "SoftmaxFocalLossForwardLaucher": (_i, [_i, _p, _p, _f, _f, _f, _i, _p, _p, _p]),
+    "SoftmaxFocalLossBackwardLaucher": (_i, [_i, _p, _p, _p, _f, _f, _f, _i, _p, _p, _p]),
+    "scda_abi_version": (_i, []),
+    "scda_nms_workspace_bytes": (_z, [_i]),
+    "scda_nms": (_i, [_i, _p, _f, _i, _p, _p, _p, _z, _p]),
+    "scda_nms_mask": (_i, [_i, _p, _p, _f, _p]),
+    "scda_bbox_overlaps": (_i, [_i, _p, _i, _p, _p, _p]),
+    "scda_sigmoid_focal_loss_sum": (_i, [_i, _p, _p, _f, _f, _f, _i, _p, _p, _p]),
+    "scda_softmax_focal_loss_sum": (_i, [_i, _p, _p, _f, _f, _f, _i, _p, _p, _p, _p]),
+}
+
+_LIB = None
+
+
+class ScdaLibraryError(RuntimeError):
+    pass
+
+
+def load(path: str | None = None) -> C.CDLL:
+    """dlopen the library and attach prototypes.  Raises if it is not built."""
+    global _LIB
+    if _LIB is not None and path is None:
+        return _LIB
+    p = path or LIB_PATH
+    if not os.path.exists(p):
+        raise ScdaLibraryError(
+            "%s not found: build it with `python -m scda_b200.build` (nvcc, sm_100a). "
+            "There is no CPU or PyTorch fallback for these operators." % p)
+    lib = C.CDLL(p)
+    for name, (res, args) in SIGNATURES.items():
+        try:
+            fn = getattr(lib, name)
+        except AttributeError as e:
+            raise ScdaLibraryError("symbol %s missing from %s" % (name, p)) from e
+        fn.restype = res
+        fn.argtypes = args
+    if path is None:
+        _LIB = lib
+    return lib
+
+
+def check(status: int, what: str) -> None:
+    """Status convention of include/scda_b200.h: 1 ok, 0 bad arguments, <0 = -cudaError_t."""
+    if status == 1:
+        return
+    if status == 0:
+        raise ValueError("%s: arguments rejected by libscda_b200" % what)
+    raise ScdaLibraryError("%s: CUDA error %d" % (what, -status))
+
+
+def stream_ptr(device=None) -> int:
+    import torch
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def require_cuda(*tensors) -> None:
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise ScdaLibraryError(
+                "scda_b200 operators run on CUDA tensors only (got a %s tensor); "
+                "there is no CPU path" % t.device.type)
