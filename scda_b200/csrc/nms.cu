@@ -9,12 +9,13 @@
 //      64-row block x 4 column blocks; column boxes are staged in shared
 //      memory with their +1 widths/heights precomputed; each thread builds its
 //      64-bit word in registers.
-//   2. nms_scan_kernel: one CTA walks the 64-box blocks in order.  Within a
-//      block one thread resolves the survivors from the diagonal words with
-//      ffs jumps (work ~ survivors, not 64); then all threads OR the survivors'
-//      mask rows into the shared `remv` words of the later blocks, each thread
-//      owning its columns.  Indices and the count are written to device
-//      memory; nothing crosses PCIe.
+//      For the scan the words are stored column-block-major (mask[b][i]) so that
+//      step 2 reads them with coalesced loads.
+//   2. nms_scan_kernel: one CTA walks the 64-box blocks in order: a coalesced
+//      pull of the words of already-kept boxes gives the block's removed set, a
+//      warp-parallel fixpoint settles the 64 boxes (see the kernel), and the kept
+//      bits are expanded to ascending indices at the end.  Indices and the count
+//      are written to device memory; nothing crosses PCIe.
 //
 // Bit-exactness: survivors depend on `IoU > thresh` comparisons, so the IoU
 // must round exactly as the reference kernel's does.  nvcc contracts the
@@ -46,9 +47,12 @@ __device__ __forceinline__ bool suppresses(float ax1, float ay1, float ax2, floa
 }
 
 // grid = (ceil(cb / kColsPerCta), cb): blockIdx.y = row block, blockIdx.x = group
-// of column blocks.  kFull: also write (zero) words below the diagonal so the
-// output is a complete N x cb matrix as the reference's callers expect.
-template <bool kFull>
+// of column blocks.
+//   kRowMajor = true : mask[i * cb + colb], every word written (zero below the
+//                      diagonal) — the reference's N x cb layout, for _nms callers.
+//   kRowMajor = false: mask[colb * n + i], diagonal and above only — the layout the
+//                      device scan pulls from with coalesced loads.
+template <bool kRowMajor>
 __global__ void __launch_bounds__(kMaskThreads)
 nms_mask_kernel(int n, float thresh, const float *__restrict__ boxes,
                 unsigned long long *__restrict__ mask, int cb)
@@ -58,7 +62,7 @@ nms_mask_kernel(int n, float thresh, const float *__restrict__ boxes,
     const int sub = threadIdx.x / kTile, lane = threadIdx.x % kTile;
     const int colb = blockIdx.x * kColsPerCta + sub;
     // whole CTA below the diagonal: nothing to compute
-    if (!kFull && (blockIdx.x + 1) * kColsPerCta - 1 < rb) return;
+    if (!kRowMajor && (blockIdx.x + 1) * kColsPerCta - 1 < rb) return;
 
     const bool active = colb < cb && colb >= rb;
     if (active) {
@@ -87,81 +91,143 @@ nms_mask_kernel(int n, float thresh, const float *__restrict__ boxes,
 #pragma unroll 4
         for (int j = start; j < cols; ++j)
             if (suppresses(ax1, ay1, ax2, ay2, Sa, s_col[sub][j], thresh)) word |= 1ull << j;
-    } else if (!kFull) {
+    } else if (!kRowMajor) {
         return;
     }
-    mask[(long long)i * cb + colb] = word;
+    if (kRowMajor)
+        mask[(long long)i * cb + colb] = word;
+    else
+        mask[(long long)colb * n + i] = word;
 }
 
 constexpr int kScanThreads = 1024;
 
+__device__ __forceinline__ unsigned long long warp_or64(unsigned long long v)
+{
+    const unsigned lo = __reduce_or_sync(0xffffffffu, (unsigned)v);
+    const unsigned hi = __reduce_or_sync(0xffffffffu, (unsigned)(v >> 32));
+    return ((unsigned long long)hi << 32) | lo;
+}
+
+// Single CTA.  For block b (boxes 64b .. 64b+63):
+//   pull   : removed = OR over kept boxes i < 64b of mask[b][i]   (all threads,
+//            coalesced predicated loads, warp redux + one shared round)
+//   resolve: warp 0 settles the 64 boxes of the block with a parallel fixpoint on
+//            the diagonal words — a box with no earlier undecided overlapper is
+//            kept, what the newly kept suppress is removed — 4 redux per round,
+//            rounds = longest suppression chain inside the block.
+//   The kept bits live in shared memory; indices are expanded at the end
+//   (ordered compaction by popcount prefix), truncated to max_keep.
 __global__ void __launch_bounds__(kScanThreads)
 nms_scan_kernel(const unsigned long long *__restrict__ mask, int n, int cb, int max_keep,
                 long long *__restrict__ keep_out, long long *__restrict__ num_out)
 {
-    extern __shared__ unsigned long long s_remv[];  // cb words
-    __shared__ unsigned long long s_diag[kTile];
-    __shared__ int s_kept[kTile];
-    __shared__ int s_nkept, s_total, s_done;
+    extern __shared__ unsigned long long s_kept[];  // cb words
+    __shared__ unsigned long long s_red[kScanThreads / 32];
+    __shared__ int s_prefix[kScanThreads / 32];
+    __shared__ int s_total, s_last;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-    for (int j = threadIdx.x; j < cb; j += kScanThreads) s_remv[j] = 0;
-    if (threadIdx.x == 0) { s_total = 0; s_done = 0; }
+    if (tid == 0) { s_total = 0; s_last = cb; }
     __syncthreads();
 
-    for (int blk = 0; blk < cb; ++blk) {
-        if (threadIdx.x < kTile) {
-            const int i = blk * kTile + threadIdx.x;
-            s_diag[threadIdx.x] = i < n ? __ldg(mask + (long long)i * cb + blk) : 0ull;
+    for (int b = 0; b < cb; ++b) {
+        const unsigned long long *__restrict__ col = mask + (long long)b * n;
+        const int before = b * kTile;
+        const int rows = min(n - before, kTile);
+        // diagonal words of this block: independent of the pull, issue them first
+        unsigned long long d0 = 0, d1 = 0;
+        if (warp == 0) {
+            if (lane < rows) d0 = __ldg(col + before + lane);
+            if (lane + 32 < rows) d1 = __ldg(col + before + lane + 32);
         }
+        unsigned long long acc = 0;
+        for (int i0 = tid; i0 < before; i0 += kScanThreads * 4) {
+            unsigned long long v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + u * kScanThreads;
+                v[u] = 0;
+                if (i < before && ((s_kept[i >> 6] >> (i & 63)) & 1ull)) v[u] = __ldg(col + i);
+            }
+            acc |= v[0] | v[1] | v[2] | v[3];
+        }
+        acc = warp_or64(acc);
+        if (lane == 0) s_red[warp] = acc;
         __syncthreads();
-        if (threadIdx.x == 0) {
-            const int rows = min(n - blk * kTile, kTile);
+        if (warp == 0) {
+            const unsigned long long removed = warp_or64(s_red[lane]);
             const unsigned long long valid = rows == 64 ? ~0ull : ((1ull << rows) - 1);
-            unsigned long long removed = s_remv[blk];
-            unsigned long long avail = ~removed & valid;
-            int k = 0, total = s_total;
-            while (avail) {
-                const int b = __ffsll((long long)avail) - 1;
-                s_kept[k++] = b;
-                keep_out[total++] = (long long)blk * kTile + b;
-                if (max_keep > 0 && total >= max_keep) { s_done = 1; break; }
-                removed |= s_diag[b] | (1ull << b);
-                avail &= ~removed;
+            unsigned long long und = ~removed & valid, kept = 0;
+            while (und) {
+                const unsigned long long mine =
+                    (((und >> lane) & 1ull) ? d0 : 0ull) | (((und >> (lane + 32)) & 1ull) ? d1 : 0ull);
+                const unsigned long long contested = warp_or64(mine);
+                const unsigned long long now = und & ~contested;   // never empty: lowest bit of und
+                kept |= now;
+                const unsigned long long hit =
+                    (((now >> lane) & 1ull) ? d0 : 0ull) | (((now >> (lane + 32)) & 1ull) ? d1 : 0ull);
+                und &= ~now & ~warp_or64(hit);
             }
-            s_nkept = k;
-            s_total = total;
+            if (lane == 0) {
+                s_kept[b] = kept;
+                const int total = s_total + __popcll(kept);
+                s_total = total;
+                if (max_keep > 0 && total >= max_keep) s_last = b + 1;
+            }
         }
         __syncthreads();
-        if (s_done) break;
-        const int k = s_nkept;
-        if (k > 0) {
-            for (int j = blk + 1 + threadIdx.x; j < cb; j += kScanThreads) {
-                unsigned long long acc = 0;
-                int t = 0;
-                for (; t + 4 <= k; t += 4) {
-                    const unsigned long long a0 = __ldg(mask + (long long)(blk * kTile + s_kept[t]) * cb + j);
-                    const unsigned long long a1 = __ldg(mask + (long long)(blk * kTile + s_kept[t + 1]) * cb + j);
-                    const unsigned long long a2 = __ldg(mask + (long long)(blk * kTile + s_kept[t + 2]) * cb + j);
-                    const unsigned long long a3 = __ldg(mask + (long long)(blk * kTile + s_kept[t + 3]) * cb + j);
-                    acc |= a0 | a1 | a2 | a3;
-                }
-                for (; t < k; ++t) acc |= __ldg(mask + (long long)(blk * kTile + s_kept[t]) * cb + j);
-                s_remv[j] |= acc;
-            }
-        }
-        // the next iteration's first __syncthreads orders these writes before
-        // thread 0 reads s_remv[blk + 1]
+        if (s_last <= b + 1) break;
     }
+
+    // ordered expansion of the kept bits into indices
+    const int nb = min(s_last, cb);
     __syncthreads();
-    if (threadIdx.x == 0) *num_out = s_total;
+    int base = 0;   // running count of survivors before the current chunk of words
+    for (int w0 = 0; w0 < nb; w0 += kScanThreads) {
+        const int w = w0 + tid;
+        const unsigned long long word = w < nb ? s_kept[w] : 0ull;
+        const int cnt = __popcll(word);
+        int incl = cnt;   // inclusive scan inside the warp
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) s_prefix[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            const int v = s_prefix[lane];
+            int inc2 = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, inc2, o);
+                if (lane >= o) inc2 += t;
+            }
+            s_prefix[lane] = inc2 - v;                 // exclusive warp offsets
+            if (lane == 31) s_red[0] = (unsigned long long)inc2;  // chunk total
+        }
+        __syncthreads();
+        int pos = base + s_prefix[warp] + incl - cnt;
+        unsigned long long bits = word;
+        while (bits) {
+            const int bit = __ffsll((long long)bits) - 1;
+            bits &= bits - 1;
+            if (max_keep <= 0 || pos < max_keep) keep_out[pos] = (long long)w * kTile + bit;
+            ++pos;
+        }
+        base += (int)s_red[0];
+        __syncthreads();
+    }
+    if (tid == 0) *num_out = (max_keep > 0 && base > max_keep) ? max_keep : base;
 }
 
-int launch_mask(int n, const float *boxes, unsigned long long *mask, float thresh, bool full,
+int launch_mask(int n, const float *boxes, unsigned long long *mask, float thresh, bool row_major,
                 cudaStream_t stream)
 {
     const int cb = ceil_div(n, kTile);
     dim3 grid(ceil_div(cb, kColsPerCta), cb);
-    if (full)
+    if (row_major)
         nms_mask_kernel<true><<<grid, kMaskThreads, 0, stream>>>(n, thresh, boxes, mask, cb);
     else
         nms_mask_kernel<false><<<grid, kMaskThreads, 0, stream>>>(n, thresh, boxes, mask, cb);

@@ -9,9 +9,10 @@
 // + 51.4 MB argmax written -> HBM-write bound.  Design:
 //   forward : one CTA per (RoI, 64-channel chunk); the RoI's integer bin edges
 //             are derived once per CTA into shared memory instead of once per
-//             output element; each thread produces 4 consecutive outputs and
-//             issues one 128-bit streaming store for values and one for argmax
-//             (the chunk base is 16 B aligned whenever C % 4 == 0).
+//             output element.  Main form (pooled_height <= 8): separable max,
+//             one warp per (RoI, channel[s]) — see roi_pool_fwd_warp_kernel.
+//             Generic form: each thread produces 4 consecutive outputs and
+//             issues one 128-bit streaming store for values and one for argmax.
 //   backward: the reference gathers — every input element loops over all RoIs
 //             (O(B*C*H*W*R)).  Here the 51 MB gradient and argmax streams are
 //             read exactly once with 128-bit loads and scattered with
@@ -115,6 +116,137 @@ roi_pool_fwd_kernel(const float *__restrict__ feat, float scale, int H, int W, i
     }
 }
 
+// ---------------------------------------------------------------------------
+// Forward, warp-cooperative form (used when pooled_height <= 8).
+//
+// Max over a bin window is separable.  A warp owns (RoI, channel[s]):
+//   phase A: lanes lie along the RoI's clipped column range; each lane reduces
+//            its column over the h-range of every row-bin -> T[ph][w] (value and
+//            the first row that attains it).  Loads are coalesced row segments
+//            and every lane runs the same trip counts (edges come from shared
+//            memory), so there is no divergence.  Narrow RoIs pack 32/Lc
+//            channels into one warp so lanes stay busy.
+//   phase B: lanes take (channel, ph, pw) outputs and reduce T[ph][ws..we) from
+//            shared memory, keeping the lexicographically first (h, w) among
+//            equal maxima — the element the reference's row-major strict-'>'
+//            scan selects (post-ReLU maps are full of exact ties at 0).
+//   Stores are consecutive addresses across the warp.
+constexpr int kPoolWarps = kPoolThreads / 32;
+
+template <int kPH>
+__global__ void __launch_bounds__(kPoolThreads)
+roi_pool_fwd_warp_kernel(const float *__restrict__ feat, float scale, int H, int W, int C, int PW,
+                         const float *__restrict__ rois, float *__restrict__ out,
+                         int *__restrict__ argmax, int rowlen, int edge_words)
+{
+    extern __shared__ int s_raw[];
+    int *hs = s_raw, *he = hs + kPH, *ws = he + kPH, *we = ws + PW;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float *Tv = reinterpret_cast<float *>(s_raw + edge_words) + warp * (2 * kPH * rowlen);
+    int *Th = reinterpret_cast<int *>(Tv + kPH * rowlen);
+
+    const int n = blockIdx.x;
+    const int c0 = blockIdx.y * kPoolChunkC;
+    const PoolRoi q = load_pool_roi(rois + 5 * n, scale, kPH, PW);
+    for (int i = threadIdx.x; i < kPH + PW; i += kPoolThreads) {
+        if (i < kPH) {
+            hs[i] = clamp_edge((int)floorf(__fmul_rn((float)i, q.bin_h)) + q.y0, H);
+            he[i] = clamp_edge((int)ceilf(__fmul_rn((float)(i + 1), q.bin_h)) + q.y0, H);
+        } else {
+            int j = i - kPH;
+            ws[j] = clamp_edge((int)floorf(__fmul_rn((float)j, q.bin_w)) + q.x0, W);
+            we[j] = clamp_edge((int)ceilf(__fmul_rn((float)(j + 1), q.bin_w)) + q.x0, W);
+        }
+    }
+    __syncthreads();
+
+    const int w_lo = ws[0];
+    const int rw = we[PW - 1] - w_lo;  // clipped column extent (<= W); <= 0: every bin empty
+    int Lc = 32;
+    if (rw <= 16) Lc = 16;
+    if (rw <= 8) Lc = 8;
+    if (rw <= 4) Lc = 4;
+    if (rw <= 2) Lc = 2;
+    if (rw <= 1) Lc = 1;
+    const int cpw = 32 / Lc;
+    const int sub = lane / Lc, wl = lane - sub * Lc;
+    const int nchunk = Lc == 32 ? (rw + 31) / 32 : (rw > 0 ? 1 : 0);
+    const int bins = kPH * PW;
+    const int cn = min(kPoolChunkC, C - c0);
+    const int HW = H * W;
+    const long long obase = ((long long)n * C + c0) * bins;
+    const int plane0 = (q.batch * C + c0) * HW;
+
+    for (int cb = warp * cpw; cb < cn; cb += kPoolWarps * cpw) {
+        // ---- phase A
+        const bool cvalid = cb + sub < cn;
+        for (int ch = 0; ch < nchunk; ++ch) {
+            const int wcol = ch * 32 + wl;
+            const bool valid = cvalid && wcol < rw;
+            const float *__restrict__ p = feat + plane0 + (cb + sub) * HW + w_lo + wcol;
+#pragma unroll
+            for (int ph = 0; ph < kPH; ++ph) {
+                const int h0 = hs[ph], h1 = he[ph];
+                float best = -FLT_MAX;
+                int bh = -1;
+                if (valid) {
+                    for (int h = h0; h < h1; ++h) {
+                        const float v = __ldg(p + h * W);
+                        if (v > best) { best = v; bh = h; }
+                    }
+                }
+                if (Lc < 32 || wcol < rw) {  // the last 32-column chunk may overhang the row
+                    const int ti = ph * rowlen + sub * Lc + wcol;
+                    Tv[ti] = best;
+                    Th[ti] = bh;
+                }
+            }
+        }
+        __syncwarp();
+        // ---- phase B
+        const int ntask = min(cpw, cn - cb) * bins;
+        for (int t = lane; t < ntask; t += 32) {
+            const int s = t / bins, b = t - s * bins;
+            const int ph = b / PW, pw = b - ph * PW;
+            const int w0 = ws[pw], w1 = we[pw];
+            const bool empty = he[ph] <= hs[ph] || w1 <= w0;
+            float best = empty ? 0.f : -FLT_MAX;
+            int bh = 0x7fffffff, bw = -1;
+            if (!empty) {
+                const int row = ph * rowlen + s * Lc - w_lo;
+                for (int w = w0; w < w1; ++w) {
+                    const float v = Tv[row + w];
+                    const int h = Th[row + w];
+                    if (h >= 0 && (v > best || (v == best && h < bh))) { best = v; bh = h; bw = w; }
+                }
+            }
+            const long long o = obase + (long long)(cb + s) * bins + b;
+            out[o] = best;
+            if (argmax) argmax[o] = bw >= 0 ? plane0 + (cb + s) * HW + bh * W + bw : -1;
+        }
+        __syncwarp();
+    }
+}
+
+template <int kPH>
+int launch_pool_fwd_warp(const float *feat, float scale, int R, int H, int W, int C, int PW,
+                         const float *rois, float *out, int *argmax, cudaStream_t stream)
+{
+    const int rowlen = W > 32 ? W : 32;
+    const int edge_words = (2 * kPH + 2 * PW + 3) & ~3;
+    const size_t smem = sizeof(int) * ((size_t)edge_words + (size_t)kPoolWarps * 2 * kPH * rowlen);
+    if (smem > 200 * 1024) return 2;  // caller falls back to the per-output kernel
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(roi_pool_fwd_warp_kernel<kPH>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return -(int)e;
+    }
+    dim3 grid(R, ceil_div(C, kPoolChunkC));
+    roi_pool_fwd_warp_kernel<kPH><<<grid, kPoolThreads, smem, stream>>>(
+        feat, scale, H, W, C, PW, rois, out, argmax, rowlen, edge_words);
+    return scda_launch_status();
+}
+
 template <bool kVec>
 __global__ void __launch_bounds__(256)
 roi_pool_bwd_scatter_kernel(const float *__restrict__ top_diff, const int *__restrict__ argmax,
@@ -150,6 +282,21 @@ SCDA_API int ROIPoolForwardLaucher(const float *bottom_data, const float spatial
         pooled_width <= 0 || !bottom_data || !bottom_rois || !top_data)
         return 0;
     if (num_rois == 0) return 1;
+    int st = 2;
+    switch (pooled_height) {
+#define SCDA_POOL_CASE(P)                                                                       \
+    case P:                                                                                     \
+        st = launch_pool_fwd_warp<P>(bottom_data, spatial_scale, num_rois, height, width,      \
+                                     channels, pooled_width, bottom_rois, top_data,            \
+                                     argmax_data, stream);                                     \
+        break;
+        SCDA_POOL_CASE(1) SCDA_POOL_CASE(2) SCDA_POOL_CASE(3) SCDA_POOL_CASE(4)
+        SCDA_POOL_CASE(5) SCDA_POOL_CASE(6) SCDA_POOL_CASE(7) SCDA_POOL_CASE(8)
+#undef SCDA_POOL_CASE
+    default: break;
+    }
+    if (st != 2) return st;
+    // generic form: pooled_height > 8 or a map too wide for the shared-memory rows
     dim3 grid(num_rois, ceil_div(channels, kPoolChunkC));
     const size_t smem = sizeof(int) * 2 * (pooled_height + pooled_width);
     const bool vec = channels % 4 == 0 && ((uintptr_t)top_data % 16 == 0) &&

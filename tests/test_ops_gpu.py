@@ -36,6 +36,9 @@ POOL_CASES = [
     ((2, 12, 20, 24), 33, (7, 7), 384, 320, (4, 300)),
     ((1, 6, 9, 13), 17, (3, 5), 208, 144, (2, 150)),       # C % 4 != 0 -> scalar store path
     ((1, 256, 64, 64), 128, (7, 7), 1024, 1024, (16, 512)),  # config 1 shape
+    ((1, 8, 21, 70), 40, (7, 7), 1120, 336, (8, 1100)),    # W not a multiple of 32, wide RoIs
+    ((1, 4, 40, 300), 24, (7, 9), 4800, 640, (8, 4800)),   # very wide map
+    ((2, 8, 16, 16), 30, (12, 3), 256, 256, (4, 250)),     # pooled_height > 8: generic kernel
 ]
 
 
