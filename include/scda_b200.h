@@ -121,6 +121,13 @@ int scda_abi_version(void);
 size_t scda_nms_workspace_bytes(int n);
 int scda_nms(int n, const float *boxes, float thresh, int max_keep, int64_t *keep_out,
              int64_t *num_out, void *workspace, size_t workspace_bytes, cudaStream_t stream);
+/* same, with the live box count read from device memory (int32 n_dev[0], clamped to
+ * [0, n_cap]): lets a pipeline whose earlier stages filter boxes on the device
+ * (min-size filter, functions/rpn_proposal.py:62-63) run NMS without a host
+ * round trip for the count.  Buffers and workspace are sized for n_cap. */
+int scda_nms_dyn(int n_cap, const int *n_dev, const float *boxes, float thresh, int max_keep,
+                 int64_t *keep_out, int64_t *num_out, void *workspace, size_t workspace_bytes,
+                 cudaStream_t stream);
 /* the bitmask alone, on a stream (the _nms symbol above is the stream-less form) */
 int scda_nms_mask(int n, const float *boxes, unsigned long long *mask, float thresh,
                   cudaStream_t stream);

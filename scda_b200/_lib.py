@@ -32,6 +32,7 @@ SIGNATURES = {
     "scda_abi_version": (_i, []),
     "scda_nms_workspace_bytes": (_z, [_i]),
     "scda_nms": (_i, [_i, _p, _f, _i, _p, _p, _p, _z, _p]),
+    "scda_nms_dyn": (_i, [_i, _p, _p, _f, _i, _p, _p, _p, _z, _p]),
     "scda_nms_mask": (_i, [_i, _p, _p, _f, _p]),
     "scda_bbox_overlaps": (_i, [_i, _p, _i, _p, _p, _p]),
     "scda_sigmoid_focal_loss_sum": (_i, [_i, _p, _p, _f, _f, _f, _i, _p, _p, _p]),

@@ -54,11 +54,15 @@ __device__ __forceinline__ bool suppresses(float ax1, float ay1, float ax2, floa
 //                      device scan pulls from with coalesced loads.
 template <bool kRowMajor>
 __global__ void __launch_bounds__(kMaskThreads)
-nms_mask_kernel(int n, float thresh, const float *__restrict__ boxes,
-                unsigned long long *__restrict__ mask, int cb)
+nms_mask_kernel(int n_cap, const int *__restrict__ n_dev, float thresh,
+                const float *__restrict__ boxes, unsigned long long *__restrict__ mask, int cb_cap)
 {
     __shared__ ColBox s_col[kColsPerCta][kTile];
+    // live box count: the capacity, or a device-resident count below it
+    const int n = n_dev ? max(0, min(n_cap, __ldg(n_dev))) : n_cap;
+    const int cb = (n + kTile - 1) / kTile;
     const int rb = blockIdx.y;
+    if (rb >= cb || blockIdx.x * kColsPerCta >= cb) return;
     const int sub = threadIdx.x / kTile, lane = threadIdx.x % kTile;
     const int colb = blockIdx.x * kColsPerCta + sub;
     // whole CTA below the diagonal: nothing to compute
@@ -95,9 +99,9 @@ nms_mask_kernel(int n, float thresh, const float *__restrict__ boxes,
         return;
     }
     if (kRowMajor)
-        mask[(long long)i * cb + colb] = word;
+        mask[(long long)i * cb_cap + colb] = word;
     else
-        mask[(long long)colb * n + i] = word;
+        mask[(long long)colb * n_cap + i] = word;
 }
 
 constexpr int kScanThreads = 1024;
@@ -119,10 +123,13 @@ __device__ __forceinline__ unsigned long long warp_or64(unsigned long long v)
 //   The kept bits live in shared memory; indices are expanded at the end
 //   (ordered compaction by popcount prefix), truncated to max_keep.
 __global__ void __launch_bounds__(kScanThreads)
-nms_scan_kernel(const unsigned long long *__restrict__ mask, int n, int cb, int max_keep,
-                long long *__restrict__ keep_out, long long *__restrict__ num_out)
+nms_scan_kernel(const unsigned long long *__restrict__ mask, int n_cap,
+                const int *__restrict__ n_dev, int max_keep, long long *__restrict__ keep_out,
+                long long *__restrict__ num_out)
 {
-    extern __shared__ unsigned long long s_kept[];  // cb words
+    extern __shared__ unsigned long long s_kept[];  // ceil(n_cap / 64) words
+    const int n = n_dev ? max(0, min(n_cap, __ldg(n_dev))) : n_cap;
+    const int cb = (n + kTile - 1) / kTile;
     __shared__ unsigned long long s_red[kScanThreads / 32];
     __shared__ int s_prefix[kScanThreads / 32];
     __shared__ int s_total, s_last;
@@ -132,7 +139,7 @@ nms_scan_kernel(const unsigned long long *__restrict__ mask, int n, int cb, int 
     __syncthreads();
 
     for (int b = 0; b < cb; ++b) {
-        const unsigned long long *__restrict__ col = mask + (long long)b * n;
+        const unsigned long long *__restrict__ col = mask + (long long)b * n_cap;
         const int before = b * kTile;
         const int rows = min(n - before, kTile);
         // diagonal words of this block: independent of the pull, issue them first
@@ -222,15 +229,43 @@ nms_scan_kernel(const unsigned long long *__restrict__ mask, int n, int cb, int 
     if (tid == 0) *num_out = (max_keep > 0 && base > max_keep) ? max_keep : base;
 }
 
-int launch_mask(int n, const float *boxes, unsigned long long *mask, float thresh, bool row_major,
-                cudaStream_t stream)
+int launch_mask(int n, const int *n_dev, const float *boxes, unsigned long long *mask, float thresh,
+                bool row_major, cudaStream_t stream)
 {
     const int cb = ceil_div(n, kTile);
     dim3 grid(ceil_div(cb, kColsPerCta), cb);
     if (row_major)
-        nms_mask_kernel<true><<<grid, kMaskThreads, 0, stream>>>(n, thresh, boxes, mask, cb);
+        nms_mask_kernel<true><<<grid, kMaskThreads, 0, stream>>>(n, n_dev, thresh, boxes, mask, cb);
     else
-        nms_mask_kernel<false><<<grid, kMaskThreads, 0, stream>>>(n, thresh, boxes, mask, cb);
+        nms_mask_kernel<false><<<grid, kMaskThreads, 0, stream>>>(n, n_dev, thresh, boxes, mask, cb);
+    return scda_launch_status();
+}
+
+int nms_impl(int n, const int *n_dev, const float *boxes, float thresh, int max_keep,
+             int64_t *keep_out, int64_t *num_out, void *workspace, size_t workspace_bytes,
+             cudaStream_t stream)
+{
+    if (n < 0 || !num_out) return 0;
+    if (n == 0) {
+        cudaError_t e = cudaMemsetAsync(num_out, 0, sizeof(int64_t), stream);
+        return e == cudaSuccess ? 1 : -(int)e;
+    }
+    if (!boxes || !keep_out || !workspace || workspace_bytes < scda_nms_workspace_bytes(n))
+        return 0;
+    const int cb = ceil_div(n, kTile);
+    const size_t smem = sizeof(unsigned long long) * (size_t)cb;
+    if (smem > 200 * 1024) return 0;  // n <= ~1.6 M boxes
+    unsigned long long *mask = (unsigned long long *)workspace;
+    int st = launch_mask(n, n_dev, boxes, mask, thresh, false, stream);
+    if (st != 1) return st;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(nms_scan_kernel,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return -(int)e;
+    }
+    nms_scan_kernel<<<1, kScanThreads, smem, stream>>>(mask, n, n_dev, max_keep,
+                                                       (long long *)keep_out,
+                                                       (long long *)num_out);
     return scda_launch_status();
 }
 
@@ -240,7 +275,7 @@ SCDA_API void _nms(int boxes_num, float *boxes_dev, unsigned long long *mask_dev
                    float nms_overlap_thresh)
 {
     if (boxes_num <= 0 || !boxes_dev || !mask_dev) return;
-    launch_mask(boxes_num, boxes_dev, mask_dev, nms_overlap_thresh, true, (cudaStream_t)0);
+    launch_mask(boxes_num, nullptr, boxes_dev, mask_dev, nms_overlap_thresh, true, (cudaStream_t)0);
 }
 
 SCDA_API int scda_nms_mask(int n, const float *boxes, unsigned long long *mask, float thresh,
@@ -248,7 +283,7 @@ SCDA_API int scda_nms_mask(int n, const float *boxes, unsigned long long *mask, 
 {
     if (n < 0 || (n > 0 && (!boxes || !mask))) return 0;
     if (n == 0) return 1;
-    return launch_mask(n, boxes, mask, thresh, true, stream);
+    return launch_mask(n, nullptr, boxes, mask, thresh, true, stream);
 }
 
 SCDA_API size_t scda_nms_workspace_bytes(int n)
@@ -262,26 +297,15 @@ SCDA_API int scda_nms(int n, const float *boxes, float thresh, int max_keep, int
                       int64_t *num_out, void *workspace, size_t workspace_bytes,
                       cudaStream_t stream)
 {
-    if (n < 0 || !num_out) return 0;
-    if (n == 0) {
-        cudaError_t e = cudaMemsetAsync(num_out, 0, sizeof(int64_t), stream);
-        return e == cudaSuccess ? 1 : -(int)e;
-    }
-    if (!boxes || !keep_out || !workspace || workspace_bytes < scda_nms_workspace_bytes(n))
-        return 0;
-    const int cb = ceil_div(n, kTile);
-    const size_t smem = sizeof(unsigned long long) * (size_t)cb;
-    if (smem > 200 * 1024) return 0;  // n <= ~1.6 M boxes
-    unsigned long long *mask = (unsigned long long *)workspace;
-    int st = launch_mask(n, boxes, mask, thresh, false, stream);
-    if (st != 1) return st;
-    if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(nms_scan_kernel,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return -(int)e;
-    }
-    nms_scan_kernel<<<1, kScanThreads, smem, stream>>>(mask, n, cb, max_keep,
-                                                       (long long *)keep_out,
-                                                       (long long *)num_out);
-    return scda_launch_status();
+    return nms_impl(n, nullptr, boxes, thresh, max_keep, keep_out, num_out, workspace,
+                    workspace_bytes, stream);
+}
+
+SCDA_API int scda_nms_dyn(int n_cap, const int *n_dev, const float *boxes, float thresh,
+                          int max_keep, int64_t *keep_out, int64_t *num_out, void *workspace,
+                          size_t workspace_bytes, cudaStream_t stream)
+{
+    if (!n_dev) return 0;
+    return nms_impl(n_cap, n_dev, boxes, thresh, max_keep, keep_out, num_out, workspace,
+                    workspace_bytes, stream);
 }

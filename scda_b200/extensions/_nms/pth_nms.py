@@ -17,8 +17,9 @@ import torch
 from ..._lib import check, load, require_cuda, stream_ptr
 
 
-def nms_device(dets, thresh, max_keep=0, workspace=None):
-    """dets: CUDA float32 [N, >=5] contiguous, sorted by descending score.
+def nms_device(dets, thresh, max_keep=0, workspace=None, n_dev=None):
+    """dets: CUDA float32 [N, 5] contiguous, sorted by descending score.
+    n_dev: optional int32 CUDA tensor [1]: only the first n_dev[0] rows are live.
 
     Returns (keep int64[N] device — first num_keep entries valid, num_keep int64[1] device).
     """
@@ -33,10 +34,18 @@ def nms_device(dets, thresh, max_keep=0, workspace=None):
     if workspace is None or workspace.numel() * workspace.element_size() < need:
         workspace = torch.empty(max(need, 8) // 8, dtype=torch.int64, device=dets.device)
     with torch.cuda.device(dets.device):
-        check(lib.scda_nms(n, dets.data_ptr(), float(thresh), int(max_keep), keep.data_ptr(),
-                           num.data_ptr(), workspace.data_ptr(),
-                           workspace.numel() * workspace.element_size(),
-                           stream_ptr(dets.device)), "scda_nms")
+        if n_dev is None:
+            check(lib.scda_nms(n, dets.data_ptr(), float(thresh), int(max_keep), keep.data_ptr(),
+                               num.data_ptr(), workspace.data_ptr(),
+                               workspace.numel() * workspace.element_size(),
+                               stream_ptr(dets.device)), "scda_nms")
+        else:
+            assert n_dev.is_cuda and n_dev.dtype == torch.int32 and n_dev.numel() == 1
+            check(lib.scda_nms_dyn(n, n_dev.data_ptr(), dets.data_ptr(), float(thresh),
+                                   int(max_keep), keep.data_ptr(), num.data_ptr(),
+                                   workspace.data_ptr(),
+                                   workspace.numel() * workspace.element_size(),
+                                   stream_ptr(dets.device)), "scda_nms_dyn")
     return keep, num
 
 

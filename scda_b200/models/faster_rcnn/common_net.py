@@ -1,0 +1,108 @@
+"""Building blocks of the reconstruction / discriminator networks (the subset of
+models/faster_rcnn/common_net.py the SCDA driver instantiates: :15-19 gaussian init,
+:59-80 INSResBlock, :107-129 LinUnsRes_cluster, :160-169 Interpolate, :205-245
+ResDis_cluster, :251-261 LeakyReLUConv2d, :279-293 LeakyReLUConvTranspose2d_2).
+Module / parameter names match the reference so state dicts are interchangeable."""
+import torch
+import torch.nn as nn
+
+
+def gaussian_weights_init(m):
+    name = m.__class__.__name__
+    if name.find('Conv') == 0:
+        m.weight.data.normal_(0.0, 0.02)
+
+
+class INSResBlock(nn.Module):
+    """conv3x3 - IN - ReLU - conv3x3 - IN (- Dropout) + identity."""
+
+    def __init__(self, inplanes, planes, stride=1, dropout=0.0):
+        super(INSResBlock, self).__init__()
+        model = [nn.Conv2d(inplanes, planes, kernel_size=3, stride=stride, padding=1),
+                 nn.InstanceNorm2d(planes),
+                 nn.ReLU(inplace=True),
+                 nn.Conv2d(planes, planes, kernel_size=3, stride=1, padding=1),
+                 nn.InstanceNorm2d(planes)]
+        if dropout > 0:
+            model += [nn.Dropout(p=dropout)]
+        self.model = nn.Sequential(*model)
+        self.model.apply(gaussian_weights_init)
+
+    def forward(self, x):
+        out = self.model(x)
+        out += x
+        return out
+
+
+class LinUnsRes_cluster(nn.Module):
+    """[cluster_num, threshold, 4096] -> view [cluster_num, channel, w, h]; no parameters."""
+
+    def __init__(self, channel=128, w=64, h=64, cluster_num=4):
+        super(LinUnsRes_cluster, self).__init__()
+        self.channel, self.w, self.h, self.cluster_num = channel, w, h, cluster_num
+
+    def forward(self, x):
+        return x.view(self.cluster_num, self.channel, self.w, self.h)
+
+
+class Interpolate(nn.Module):
+    def __init__(self, scale_factor, mode):
+        super(Interpolate, self).__init__()
+        self.scale_factor, self.mode = scale_factor, mode
+
+    def forward(self, x):
+        return nn.functional.interpolate(x, scale_factor=self.scale_factor, mode=self.mode,
+                                         align_corners=True)
+
+
+class ResDis_cluster(nn.Module):
+    """Feature-level (patch) discriminator trunk: three stride-2 3x3 convs (BN + LeakyReLU
+    after the first two), global average pool -> [cluster_num, 4 * n_in]."""
+
+    def __init__(self, n_in=128, n_out=256, kernel_size=3, stride=2, padding=1, w=64, h=64,
+                 cluster_num=4):
+        super(ResDis_cluster, self).__init__()
+        self.w, self.h, self.cluster_num, self.channel = w, h, cluster_num, n_in
+        model = [nn.Conv2d(n_in, n_out, kernel_size, stride, padding, bias=False),
+                 nn.BatchNorm2d(num_features=n_out),
+                 nn.LeakyReLU(inplace=True),
+                 nn.Conv2d(n_in * 2, n_out * 2, kernel_size, stride, padding, bias=False),
+                 nn.BatchNorm2d(num_features=n_out * 2),
+                 nn.LeakyReLU(inplace=True),
+                 nn.Conv2d(n_out * 2, n_out * 2, kernel_size, stride, padding, bias=False)]
+        self.model = nn.Sequential(*model)
+        self.model.apply(gaussian_weights_init)
+
+    def forward(self, x1):
+        out = self.model(x1.view(self.cluster_num, self.channel, self.w, self.h))
+        out = nn.functional.avg_pool2d(out, out.size()[2:])
+        return torch.squeeze(out)
+
+
+class LeakyReLUConv2d(nn.Module):
+    def __init__(self, n_in, n_out, kernel_size, stride, padding=0):
+        super(LeakyReLUConv2d, self).__init__()
+        self.model = nn.Sequential(
+            nn.Conv2d(n_in, n_out, kernel_size=kernel_size, stride=stride, padding=padding, bias=True),
+            nn.LeakyReLU(inplace=True))
+        self.model.apply(gaussian_weights_init)
+
+    def forward(self, x):
+        return self.model(x)
+
+
+class LeakyReLUConvTranspose2d_2(nn.Module):
+    """Despite the name: bilinear x2 upsample - conv - IN - LeakyReLU."""
+
+    def __init__(self, n_in, n_out, kernel_size, stride, padding=0, output_padding=0):
+        super(LeakyReLUConvTranspose2d_2, self).__init__()
+        self.model = nn.Sequential(
+            Interpolate(scale_factor=2, mode='bilinear'),
+            nn.Conv2d(in_channels=n_in, out_channels=n_out, kernel_size=kernel_size,
+                      padding=padding, stride=1, bias=True),
+            nn.InstanceNorm2d(num_features=n_out),
+            nn.LeakyReLU(inplace=True))
+        self.model.apply(gaussian_weights_init)
+
+    def forward(self, x):
+        return self.model(x)

@@ -1,0 +1,284 @@
+"""Detector graph and the adversarial / reconstruction networks (mirrors
+models/faster_rcnn/faster_rcnn_adver_expansion_reweight_cluster.py of the reference):
+`FasterRCNN_AdEx` (:19-234), `smooth_l1_loss_with_sigma` (:238-246), `accuracy` (:249-267),
+`GAN_dis_AE` (:270-308), `GAN_dis_AE_patch` (:312-333), `GAN_decoder_AE` (:336-399).
+
+What differs from the reference is where the plumbing between the networks runs: the
+reference hops to the host for anchors, proposals, NMS scan, targets and sampling
+(~10 H2D + ~8 D2H synchronous copies per image); here those stages run on
+the device through scda_b200.functions.* and the only host round trip left in the training
+forward is the 512 x 5 RoI table for the k-means of compute_cluster_targets.
+"""
+import functools
+import logging
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from ...functions.anchor_target import compute_anchor_targets
+from ...functions.mask import compute_cluster_targets
+from ...functions.predict_bbox import compute_predicted_bboxes
+from ...functions.proposal_target import compute_proposal_targets, proposal_targets_device
+from ...functions.rpn_proposal import compute_rpn_proposals, rpn_proposals_device
+from .common_net import (INSResBlock, LeakyReLUConv2d, LeakyReLUConvTranspose2d_2,
+                         LinUnsRes_cluster, ResDis_cluster, gaussian_weights_init)
+
+logger = logging.getLogger('global')
+
+
+def _host_info(image_info):
+    if torch.is_tensor(image_info):
+        return image_info.cpu().numpy() if image_info.is_cuda else image_info.numpy()
+    return image_info
+
+
+class FasterRCNN_AdEx(nn.Module):
+    def __init__(self, gan_model_flag):
+        super(FasterRCNN_AdEx, self).__init__()
+
+    def feature_extractor(self, x):
+        raise NotImplementedError
+
+    def rpn(self, x):
+        raise NotImplementedError
+
+    def rcnn(self, x, rois):
+        raise NotImplementedError
+
+    def _add_rpn_loss(self, compute_anchor_targets_fn, rpn_pred_cls, rpn_pred_loc):
+        cls_targets, loc_targets, loc_masks, loc_normalizer = \
+            compute_anchor_targets_fn(rpn_pred_loc.size())
+        rpn_pred_cls = rpn_pred_cls.permute(0, 2, 3, 1).contiguous().view(-1, 2)
+        cls_targets = cls_targets.permute(0, 2, 3, 1).contiguous().view(-1)
+        rpn_loss_cls = F.cross_entropy(rpn_pred_cls, cls_targets, ignore_index=-1)
+        rpn_loss_loc = smooth_l1_loss_with_sigma(rpn_pred_loc * loc_masks, loc_targets) / loc_normalizer
+        acc = accuracy(rpn_pred_cls.data, cls_targets.data)[0]
+        return rpn_loss_cls, rpn_loss_loc, acc
+
+    def _add_rcnn_loss(self, rcnn_pred_cls, rcnn_pred_loc, cls_targets, loc_targets, loc_weights):
+        rcnn_loss_cls = F.cross_entropy(rcnn_pred_cls, cls_targets)
+        loc_normalizer = cls_targets.shape[0]
+        rcnn_loss_loc = smooth_l1_loss_with_sigma(rcnn_pred_loc * loc_weights, loc_targets) / loc_normalizer
+        acc = accuracy(rcnn_pred_cls, cls_targets)[0]
+        return rcnn_loss_cls, rcnn_loss_loc, acc
+
+    def _pin_args_to_fn(self, cfg, ground_truth_bboxes, image_info, ignore_regions):
+        partial_fn = {}
+        if self.training:
+            partial_fn['anchor_target_fn'] = functools.partial(
+                compute_anchor_targets, cfg=cfg['train_anchor_target_cfg'],
+                ground_truth_bboxes=ground_truth_bboxes, ignore_regions=ignore_regions,
+                image_info=image_info)
+            partial_fn['proposal_target_fn'] = functools.partial(
+                compute_proposal_targets, cfg=cfg['train_proposal_target_cfg'],
+                ground_truth_bboxes=ground_truth_bboxes, ignore_regions=ignore_regions,
+                image_info=image_info)
+            partial_fn['rpn_proposal_fn'] = functools.partial(
+                compute_rpn_proposals, cfg=cfg['train_rpn_proposal_cfg'], image_info=image_info)
+        else:
+            partial_fn['rpn_proposal_fn'] = functools.partial(
+                compute_rpn_proposals, cfg=cfg['test_rpn_proposal_cfg'], image_info=image_info)
+            partial_fn['predict_bbox_fn'] = functools.partial(
+                compute_predicted_bboxes, image_info=image_info, cfg=cfg['test_predict_bbox_cfg'])
+        return partial_fn
+
+    @staticmethod
+    def _rpn_scores(rpn_pred_cls):
+        """2-way softmax over each anchor's (bg, fg) channel pair, NCHW in / NCHW out (:153-155)."""
+        x = rpn_pred_cls.permute(0, 2, 3, 1).contiguous()
+        x = F.softmax(x.view(-1, 2), dim=1).view_as(x)
+        return x.permute(0, 3, 1, 2)
+
+    def _train_rois(self, cfg, proposals_per_image, ground_truth_bboxes, image_info):
+        """proposal targets straight from the device-side proposal buffers (no host hop)."""
+        info = _host_info(image_info)
+        outs = []
+        for b, (boxes, n_keep) in enumerate(proposals_per_image):
+            outs.append(proposal_targets_device(
+                boxes, n_keep, ground_truth_bboxes[b].float(), cfg['train_proposal_target_cfg'],
+                (float(info[b][0]), float(info[b][1])), batch_ix=b))
+        return tuple(torch.cat([o[i] for o in outs], 0).contiguous() for i in range(4))
+
+    def forward(self, input, target=None):
+        '''
+        input: dict with 'cfg', 'image' [b,3,h,w], 'ground_truth_bboxes' [b,max_num_gts,5] or
+               None, 'image_info' [b,3], 'ignore_regions', and (training) 'cluster_num',
+               'threshold'.
+        target: the unlabelled target-domain image [b,3,h,w] (training only).
+        Return: dict of losses, predict, accuracy (+ cluster_features / cluster_centers).
+        '''
+        cfg = input['cfg']
+        x_input = input['image']
+        ground_truth_bboxes = input['ground_truth_bboxes']
+        image_info = input['image_info']
+        ignore_regions = input['ignore_regions']
+        if self.training and ground_truth_bboxes is not None and not ground_truth_bboxes.is_cuda:
+            ground_truth_bboxes = ground_truth_bboxes.to(x_input.device, non_blocking=True)
+        partial_fn = self._pin_args_to_fn(cfg, ground_truth_bboxes, image_info, ignore_regions)
+
+        outputs = {'losses': [], 'predict': [], 'accuracy': []}
+        x = self.feature_extractor(x_input)
+        rpn_pred_cls, rpn_pred_loc = self.rpn(x)
+
+        if self.training:
+            rpn_loss_cls, rpn_loss_loc, rpn_acc = self._add_rpn_loss(
+                partial_fn['anchor_target_fn'], rpn_pred_cls, rpn_pred_loc)
+            pcfg = cfg['train_rpn_proposal_cfg']
+            props = rpn_proposals_device(self._rpn_scores(rpn_pred_cls).data, rpn_pred_loc.data,
+                                         pcfg, image_info)
+            rois, cls_targets, loc_targets, loc_weights = self._train_rois(
+                cfg, props, ground_truth_bboxes, image_info)
+            assert rois.shape[1] == 5
+            x_fea, rcnn_pred_cls, rcnn_pred_loc = self.rcnn(x, rois)
+            x_cluster_fea, x_center_cluster = compute_cluster_targets(
+                rois, x_fea, N_cluster=input['cluster_num'], threshold=input['threshold'])
+
+            # RPN + RCNN on the target image: top-512 proposals, no ground truth (:171-189)
+            x_gan = self.feature_extractor(target)
+            rpn_pred_cls_gan, rpn_pred_loc_gan = self.rpn(x_gan)
+            props_gan = rpn_proposals_device(self._rpn_scores(rpn_pred_cls_gan).data,
+                                             rpn_pred_loc_gan.data, pcfg, image_info)
+            n_t = cfg['train_proposal_target_cfg']['batch_size']
+            gan_rows = []
+            for b, (boxes, n_keep) in enumerate(props_gan):
+                gan_rows.append((torch.cat([torch.full((boxes.shape[0], 1), float(b),
+                                                       device=boxes.device), boxes[:, :4]], 1),
+                                 n_keep))
+            if len(gan_rows) == 1 and gan_rows[0][0].shape[0] >= n_t:
+                proposals_gan = gan_rows[0][0][:n_t].contiguous()
+                enough = gan_rows[0][1] >= n_t           # 0-dim device flag, read by the caller
+            else:
+                ks = [int(n.item()) for _, n in gan_rows]
+                proposals_gan = torch.cat([r[:k] for (r, _), k in zip(gan_rows, ks)], 0)[:n_t].contiguous()
+                enough = torch.tensor(proposals_gan.shape[0] == n_t, device=x.device)
+            x_fea_gan, _, _ = self.rcnn(x_gan, proposals_gan)
+            assert x_gan.size() == x.size(), "gan_features does not match the backbone"
+
+            rcnn_loss_cls, rcnn_loss_loc, rcnn_acc = self._add_rcnn_loss(
+                rcnn_pred_cls, rcnn_pred_loc, cls_targets, loc_targets, loc_weights)
+            outputs['losses'] = [rpn_loss_cls, rpn_loss_loc, rcnn_loss_cls, rcnn_loss_loc]
+            outputs['accuracy'] = [rpn_acc, rcnn_acc]
+            outputs['predict'] = [props]
+            # fewer than 512 surviving target proposals: reuse the source clusters (:207-215)
+            if proposals_gan.shape[0] != n_t or not bool(enough):
+                logger.info("Different channels {} at target image".format(x_fea_gan.size(0)))
+                outputs['cluster_features'] = [x_cluster_fea, x_cluster_fea]
+                outputs['cluster_centers'] = [x_center_cluster, x_center_cluster]
+            else:
+                x_cluster_fea_gan, x_center_cluster_gan = compute_cluster_targets(
+                    proposals_gan, x_fea_gan, N_cluster=input['cluster_num'],
+                    threshold=input['threshold'])
+                outputs['cluster_features'] = [x_cluster_fea, x_cluster_fea_gan]
+                outputs['cluster_centers'] = [x_center_cluster, x_center_cluster_gan]
+        else:
+            proposals = partial_fn['rpn_proposal_fn'](self._rpn_scores(rpn_pred_cls).data,
+                                                      rpn_pred_loc.data)
+            proposals = proposals[:, :5].cuda().contiguous()
+            assert proposals.shape[1] == 5
+            x_fea, rcnn_pred_cls, rcnn_pred_loc = self.rcnn(x, proposals)
+            rcnn_pred_cls = F.softmax(rcnn_pred_cls, dim=1)
+            bboxes = partial_fn['predict_bbox_fn'](proposals, rcnn_pred_cls, rcnn_pred_loc)
+            outputs['predict'] = [proposals, bboxes]
+        return outputs
+
+
+def smooth_l1_loss_with_sigma(pred, targets, sigma=3.0):
+    sigma_2 = sigma ** 2
+    diff = pred - targets
+    abs_diff = torch.abs(diff)
+    smoothL1_sign = (abs_diff < 1. / sigma_2).detach().float()
+    loss = torch.pow(diff, 2) * sigma_2 / 2. * smoothL1_sign \
+        + (abs_diff - 0.5 / sigma_2) * (1. - smoothL1_sign)
+    return torch.sum(loss)
+
+
+def accuracy(output, target, topk=(1,), ignore_index=-1):
+    """precision@k in percent over the rows whose target != ignore_index.  Same values as the
+    reference's (:249-267) without its nonzero()/index host synchronisation."""
+    keep = target != ignore_index
+    maxk = max(topk)
+    _, pred = output.topk(maxk, 1, True, True)
+    correct = pred.eq(target.view(-1, 1)) & keep.view(-1, 1)
+    n = keep.sum().clamp(min=1).float()
+    return [correct[:, :k].reshape(-1).float().sum(0, keepdim=True) * (100.0 / n) for k in topk]
+
+
+class GAN_dis_AE(nn.Module):
+    """Image-level discriminators, one per domain: n_layer stride-2 LeakyReLU convs and a
+    1x1 conv to one channel; outputs are flattened to [clusters, H*W/4^n]."""
+
+    def __init__(self, params):
+        super(GAN_dis_AE, self).__init__()
+        ch, input_dim_a, n_layer = params['ch'], params['input_dim_a'], params['n_layer']
+        self.model_A = self._make_net(ch, input_dim_a, n_layer - 1)
+        self.model_A.apply(gaussian_weights_init)
+        self.model_B = self._make_net(ch, input_dim_a, n_layer - 1)
+        self.model_B.apply(gaussian_weights_init)
+
+    def _make_net(self, ch, input_dim, n_layer):
+        model = [LeakyReLUConv2d(input_dim, ch, kernel_size=3, stride=2, padding=1)]
+        tch = ch
+        for _ in range(n_layer):
+            model += [LeakyReLUConv2d(tch, tch * 2, kernel_size=3, stride=2, padding=1)]
+            tch *= 2
+        model += [nn.Conv2d(tch, 1, kernel_size=1, stride=1, padding=0)]
+        return nn.Sequential(*model)
+
+    def forward(self, x_aa, x_bb):
+        out_A = self.model_A(x_aa)
+        out_B = self.model_B(x_bb)
+        return out_A.view(out_A.size(0), -1), out_B.view(out_B.size(0), -1)
+
+
+class GAN_dis_AE_patch(nn.Module):
+    """Feature-level discriminator on the [clusters, threshold, 64, 64] RoI-feature image."""
+
+    def __init__(self, params=None):
+        super(GAN_dis_AE_patch, self).__init__()
+        if params:
+            self.n_in, self.n_out, cluster_num1 = params['n_in'], params['n_out'], params['cluster_num']
+        else:
+            self.n_in, self.n_out, cluster_num1 = 128, 256, 4
+        self.model_A_patch = nn.Sequential(
+            ResDis_cluster(n_in=self.n_in, n_out=self.n_out, kernel_size=3, stride=2, padding=1,
+                           w=64, h=64, cluster_num=cluster_num1))
+
+    def forward(self, rois_features):
+        return torch.sigmoid(self.model_A_patch(rois_features))
+
+
+class GAN_decoder_AE(nn.Module):
+    """Two decoders (source / target): view to [clusters, ch, 64, 64] -> n_gen_res_blk IN
+    res-blocks -> (n_gen_front_blk - 1) x [bilinear x2, conv3x3 halving channels, IN, LReLU]
+    -> 1x1 ConvTranspose to 3 channels -> tanh."""
+
+    def __init__(self, params):
+        super(GAN_decoder_AE, self).__init__()
+        input_dim_b, ch = params['input_dim_b'], params['ch']
+        n_gen_res_blk, n_gen_front_blk = params['n_gen_res_blk'], params['n_gen_front_blk']
+        res_dropout_ratio = params.get('res_dropout_ratio', 0)
+        neww, newh = params.get('neww', 64), params.get('newh', 64)
+        cluster_num = params.get('cluster_num', 4)
+
+        def make():
+            tch = ch
+            dec = [LinUnsRes_cluster(ch, neww, newh, cluster_num)]
+            for _ in range(n_gen_res_blk):
+                dec += [INSResBlock(tch, tch, dropout=res_dropout_ratio)]
+            for _ in range(n_gen_front_blk - 1):
+                dec += [LeakyReLUConvTranspose2d_2(tch, tch // 2, kernel_size=3, stride=1,
+                                                   padding=1, output_padding=0)]
+                tch = tch // 2
+            dec += [nn.ConvTranspose2d(tch, input_dim_b, kernel_size=1, stride=1, padding=0)]
+            dec += [nn.Tanh()]
+            return nn.Sequential(*dec)
+
+        # construction order B then A, as in the reference (it fixes the RNG stream of the init)
+        self.decode_B = make()
+        self.decode_B.apply(gaussian_weights_init)
+        self.decode_A = make()
+        self.decode_A.apply(gaussian_weights_init)
+
+    def forward(self, x_aa, x_bb):
+        return self.decode_A(x_aa), self.decode_B(x_bb)

@@ -1,0 +1,117 @@
+"""Data-parallel plumbing (mirrors utils/distributed_utils.py of the reference).
+
+Same three entry points — `dist_init`, `broadcast_params`, `average_gradients` — with the
+reference's semantics (SUM all-reduce of every gradient, loss pre-divided by world size by
+the caller, tools/faster_rcnn_train_val.py:604,736).  Differences in mechanism:
+  * rendezvous comes from the torchrun environment (RANK / WORLD_SIZE / LOCAL_RANK /
+    MASTER_ADDR / MASTER_PORT), falling back to the reference's SLURM variables;
+  * `average_gradients` reduces ONE flat buffer per network instead of one NCCL call per
+    parameter tensor (40 calls / 547 MB for the detector in the reference,
+    utils/distributed_utils.py:9-13): see FlatGradBucket.
+"""
+import os
+
+import torch
+import torch.distributed as dist
+
+
+def dist_init(port=None, backend="nccl"):
+    """Returns (rank, world_size).  One process per GPU."""
+    if "RANK" in os.environ and "WORLD_SIZE" in os.environ:
+        rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+        local = int(os.environ.get("LOCAL_RANK", rank))
+    elif "SLURM_PROCID" in os.environ:            # the reference's launch path (:26-45)
+        rank, world = int(os.environ["SLURM_PROCID"]), int(os.environ["SLURM_NTASKS"])
+        local = rank % max(torch.cuda.device_count(), 1)
+        node_list = os.environ["SLURM_NODELIST"]
+        if "[" in node_list:
+            beg = node_list.find("[")
+            ends = [p for p in (node_list.find("-", beg), node_list.find(",", beg)) if p >= 0]
+            node_list = node_list[:min(ends) if ends else 1000].replace("[", "")
+        os.environ.setdefault("MASTER_ADDR", node_list[8:].replace("-", "."))
+        os.environ["RANK"], os.environ["WORLD_SIZE"] = str(rank), str(world)
+    else:
+        rank, world, local = 0, 1, 0
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ["RANK"], os.environ["WORLD_SIZE"] = "0", "1"
+    if port is not None:
+        os.environ.setdefault("MASTER_PORT", str(port))
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", "29500")
+    if backend == "nccl":
+        torch.cuda.set_device(local)
+    if not dist.is_initialized():
+        dist.init_process_group(backend=backend, rank=rank, world_size=world)
+    return dist.get_rank(), dist.get_world_size()
+
+
+def broadcast_params(model):
+    """Rank 0's state to everyone (:15-19), coalesced into one broadcast per dtype."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return
+    by_dtype = {}
+    for p in model.state_dict().values():
+        by_dtype.setdefault((p.dtype, p.device), []).append(p)
+    for tensors in by_dtype.values():
+        flat = torch.cat([t.reshape(-1) for t in tensors])
+        dist.broadcast(flat, 0)
+        off = 0
+        for t in tensors:
+            t.copy_(flat[off:off + t.numel()].view_as(t))
+            off += t.numel()
+
+
+class FlatGradBucket(object):
+    """All gradients of one network as views into one contiguous fp32 buffer, so the
+    data-parallel exchange is a single all-reduce and the optimiser can sweep one array."""
+
+    def __init__(self, params):
+        self.params = [p for p in params if p.requires_grad]
+        n = sum(p.numel() for p in self.params)
+        dev = self.params[0].device if self.params else "cpu"
+        self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
+        off = 0
+        for p in self.params:
+            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+
+    def zero(self):
+        self.flat.zero_()
+
+    def rebind(self):
+        """Re-point p.grad at the flat buffer if something replaced it."""
+        off = 0
+        for p in self.params:
+            view = self.flat[off:off + p.numel()].view_as(p)
+            if p.grad is None or p.grad.data_ptr() != view.data_ptr():
+                if p.grad is not None:
+                    view.copy_(p.grad)
+                p.grad = view
+            off += p.numel()
+
+    def all_reduce(self, async_op=False):
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            return dist.all_reduce(self.flat, async_op=async_op)
+        return None
+
+
+def average_gradients(model):
+    """SUM all-reduce of the model's gradients (:9-13).  If the model carries a
+    FlatGradBucket (attribute `_scda_bucket`) that single buffer is reduced; otherwise the
+    gradients are coalesced into one message."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return
+    bucket = getattr(model, "_scda_bucket", None)
+    if bucket is not None:
+        bucket.rebind()
+        bucket.all_reduce()
+        return
+    grads = [p.grad.data for p in model.parameters() if p.requires_grad and p.grad is not None]
+    if not grads:
+        return
+    flat = torch.cat([g.reshape(-1) for g in grads])
+    dist.all_reduce(flat)
+    off = 0
+    for g in grads:
+        g.copy_(flat[off:off + g.numel()].view_as(g))
+        off += g.numel()

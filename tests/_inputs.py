@@ -73,3 +73,24 @@ def focal_inputs(m, k, seed, softmax=False):
     hi = k if softmax else k + 1     # softmax labels 0..k-1, sigmoid labels 0..k (d+1 <-> column d)
     targets = r.randint(lo, hi, m).astype(np.int32)
     return logits, targets
+
+
+def synth_rpn_outputs(seed, fh=32, fw=64, A=15):
+    """RPN head outputs as the proposal stage sees them: class map already soft-maxed
+    over each anchor's (bg, fg) channel pair, [1, 2A, fh, fw]; deltas [1, 4A, fh, fw]."""
+    import torch
+    r = np.random.RandomState(seed)
+    logits = r.standard_normal((1, 2 * A, fh, fw)).astype(np.float32) * 2
+    x = torch.from_numpy(logits).permute(0, 2, 3, 1).contiguous()
+    p = torch.softmax(x.view(-1, 2), dim=1).view_as(x).permute(0, 3, 1, 2).contiguous()
+    loc = (r.standard_normal((1, 4 * A, fh, fw)) * 0.3).astype(np.float32)
+    return p.numpy(), loc
+
+
+def load_cfg():
+    """The reference's config_512.json with `shared` merged into every section
+    (tools/faster_rcnn_train_val.py:183-189), committed by make_golden_host.py."""
+    import json
+    import os
+    return json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden",
+                                       "config_512_merged.json")))
