@@ -1,0 +1,297 @@
+#!/usr/bin/env python
+"""Headline benchmark: images/sec of one SCDA training iteration (512x1024, bs 1 per GPU).
+
+    python bench.py --gpus N --steps K --warmup W            # this build, N GPUs of one node
+    python bench.py --impl reference --gpus N --steps K ...   # the reference's CPU path
+
+Under `python -m torch.distributed.run --nproc-per-node N ...` each rank owns one GPU
+(RANK / LOCAL_RANK / WORLD_SIZE / MASTER_* from the environment); rank 0 prints ONE JSON line.
+
+A "step" = one full iteration of the reference's train() on one synthetic source image, one
+synthetic target image and 20 random ground-truth boxes per rank: detector forward on both
+images, the four-phase discriminator / decoder / detector update, gradient all-reduce and
+Adam on all four networks (BASELINE.json configs[3]; on one GPU this is configs[2] plus the
+reconstruction networks).  value = images/s with the inputs already resident in HBM;
+e2e = the same through the public step call with HOST (pinned) inputs copied in and the loss
+read back every step.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+IMG_H, IMG_W, NUM_GT = 512, 1024, 20
+METRIC, UNIT = "images/sec (512x1024, bs=1/GPU) fwd+bwd", "images/s"
+WORKLOAD = "SCDA type-2 train iteration (cluster_num=4, threshold=128, recon_size=256): " \
+           "vgg16 Faster R-CNN fwd(source)+fwd(target)+bwd + decoder/discriminators, Adam x4, " \
+           "1x3x512x1024 source + target per GPU, 20 GT boxes"
+# algorithmic work per image (SURVEY.md §8d / BASELINE.md §3)
+CONV3x3_FWD_GFLOP_AT_MODEL_SHAPE = 38.65   # one 512->512 (or 64->64 @512x1024) 3x3 layer
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d["hbm_gbs"], d["bf16_tflops"], d.get("bf16_tflops_sustained", d["bf16_tflops"]), "measured"
+    return 6650.0, 1590.0, 1400.0, "fallback"
+
+
+def load_cfg():
+    import _inputs
+    return _inputs.load_cfg()
+
+
+def synth_batch(rank, pinned):
+    import _inputs
+    r = np.random.RandomState(1000 + rank)
+    mk = lambda: torch.from_numpy(r.standard_normal((1, 3, IMG_H, IMG_W)).astype(np.float32))
+    image, target = mk(), mk()
+    gts = torch.from_numpy(_inputs.gt_boxes(NUM_GT, rank, img_w=IMG_W, img_h=IMG_H)[None])
+    info = torch.tensor([[IMG_H, IMG_W, 0.5]])
+    if pinned:
+        image, target, gts = image.pin_memory(), target.pin_memory(), gts.pin_memory()
+    return image, target, gts, info
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True,
+                                     timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([s.strip() for s in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        self.stop_flag = True
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None,
+                "sm_max_mhz": float(self.samples[0][1]) if self.samples[0][1].replace(".", "").isdigit() else None,
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+def cpu_reference_run(steps, warmup, budget_s, threads=None):
+    """The reference CPU-extension path (oracle/model_cpu.py) timed on the host cores."""
+    from oracle.model_cpu import CPUTrainer
+    if threads:
+        torch.set_num_threads(threads)
+    cores = torch.get_num_threads()
+    cfg = load_cfg()
+    tr = CPUTrainer(cfg)
+    image, target, gts, info = synth_batch(0, pinned=False)
+    t_all = time.perf_counter()
+    done_w = 0
+    for _ in range(max(warmup, 1)):
+        tr.iteration(image, info, gts, target)
+        done_w += 1
+        if time.perf_counter() - t_all > budget_s * 0.35:
+            break
+    times = []
+    for _ in range(max(steps, 1)):
+        t0 = time.perf_counter()
+        tr.iteration(image, info, gts, target)
+        times.append(time.perf_counter() - t0)
+        if time.perf_counter() - t_all > budget_s and len(times) >= 1:
+            break
+    sec = float(np.mean(times))
+    return {"value": 1.0 / sec, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "%d warm-up + %d timed full iterations of the same workload (1 image each) on the "
+                      "host, torch CPU fp32 + OpenMP C restatements of the reference's CUDA ops + the "
+                      "reference's numpy/sklearn plumbing (time-boxed to %ds)" % (done_w, len(times), budget_s),
+            "ms_per_step": sec * 1e3, "steps_done": len(times), "warmup_done": done_w}
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    r = cpu_reference_run(args.steps, args.warmup, budget_s=args.cpu_budget)
+    line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT,
+            "n_gpus": args.gpus, "steps": r["steps_done"], "warmup": r["warmup_done"],
+            "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "note": "CPU path runs one image stream regardless of --gpus"},
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def roofline_probe(dev):
+    """Dominant hand-written kernel timed alone with CUDA events on its launch stream."""
+    import _inputs
+    from scda_b200 import _lib
+    lib = _lib.load()
+    hbm, tf, tf_sus, src = peaks()
+    st = torch.cuda.current_stream().cuda_stream
+    feat = torch.from_numpy(_inputs.features((1, 512, 32, 64), 0)).to(dev)
+    rois = torch.from_numpy(_inputs.rois_uniform(512, 1, img_w=IMG_W, img_h=IMG_H)).to(dev)
+    out = torch.empty(512, 512, 7, 7, device=dev)
+    arg = torch.empty(512, 512, 7, 7, dtype=torch.int32, device=dev)
+    g = torch.randn_like(out)
+    gi = torch.empty_like(feat)
+    flush = torch.zeros(64 * 1024 * 1024, device=dev)
+    fn = lambda: lib.ROIPoolBackwardLaucher(g.data_ptr(), 1 / 16., 1, 512, 32, 64, 512, 7, 7,
+                                            rois.data_ptr(), gi.data_ptr(), arg.data_ptr(), st)
+    lib.ROIPoolForwardLaucher(feat.data_ptr(), 1 / 16., 512, 32, 64, 512, 7, 7, rois.data_ptr(),
+                              out.data_ptr(), arg.data_ptr(), st)
+    ts = []
+    for i in range(8):
+        flush.add_(1.0)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        b.synchronize()
+        if i >= 3:
+            ts.append(a.elapsed_time(b) * 1e-3)
+    t = float(np.mean(ts))
+    alg = out.numel() * 8 + feat.numel() * 4     # gradient + argmax read once, input gradient written
+    return {"bound": "hbm", "achieved": alg / t / 1e9, "peak": hbm, "unit": "GB/s",
+            "frac": alg / t / 1e9 / hbm, "traffic": None, "kernel": "roi_pool_bwd_scatter_kernel",
+            "peak_source": src + " (MEASURED_PEAKS.json hbm_gbs, burst: kernel timed alone)",
+            "algorithmic_bytes_per_launch": alg}
+
+
+def our_arm(args):
+    import torch.distributed as dist
+    from scda_b200 import _lib
+    from scda_b200.engine import build_trainer
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU path in scda_b200)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.load()
+    cfg = load_cfg()
+    tr = build_trainer(cfg, world_size=world, seed=0)
+    if world > 1:
+        from scda_b200.utils.distributed_utils import broadcast_params
+        for net in tr.nets():
+            broadcast_params(net)
+    h_image, h_target, h_gts, info = synth_batch(rank, pinned=True)
+    d_image, d_target, d_gts = h_image.to(dev), h_target.to(dev), h_gts.to(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        return tr.iteration(cfg, d_image, info, d_gts, d_target)
+
+    def step_e2e():
+        img = h_image.to(dev, non_blocking=True)
+        tgt = h_target.to(dev, non_blocking=True)
+        gts = h_gts.to(dev, non_blocking=True)
+        out = tr.iteration(cfg, img, info, gts, tgt)
+        return float(out['loss'].item())           # D2H read of the step's result
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    n0 = _lib.LAUNCHES
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(args.steps):
+        step_resident()
+    b.record()
+    barrier()
+    launches = _lib.LAUNCHES - n0
+    ms = a.elapsed_time(b)
+    clocks = sampler.summary()
+
+    step_e2e()
+    barrier()
+    a2, b2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a2.record()
+    for _ in range(args.steps):
+        last = step_e2e()
+    b2.record()
+    barrier()
+    ms2 = a2.elapsed_time(b2)
+
+    if world > 1:
+        t = torch.tensor([ms, ms2], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms2 = float(t[0]), float(t[1])
+    if rank == 0:
+        roof = roofline_probe(dev)
+        line = {"metric": METRIC, "value": world * args.steps / (ms / 1e3), "unit": UNIT,
+                "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": WORKLOAD, "parallelism": "dp%d" % world,
+                           "l2": "per-step working set (547 MB of fp32 weights + activations) exceeds the "
+                                 "126 MB L2; no explicit flush"},
+                "clocks": clocks,
+                "e2e": {"value": world * args.steps / (ms2 / 1e3), "unit": UNIT,
+                        "h2d_bytes_per_step": int(h_image.numel() * 4 + h_target.numel() * 4 + h_gts.numel() * 4),
+                        "d2h_bytes_per_step": 4 + 512 * 5 * 4 * 2, "last_loss": last},
+                "gpu_launches": launches, "roofline": roof}
+        if world == 1 and not args.no_cpu_baseline:
+            r = cpu_reference_run(2, 1, budget_s=args.cpu_budget_inline)
+            line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-budget", type=int, default=150, help="seconds for the --impl reference arm")
+    ap.add_argument("--cpu-budget-inline", type=int, default=45)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        reference_arm(args)
+        return
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.gpus > 1 and world == 1:
+        # convenience: re-launch under torchrun
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
+               "--master-addr", "127.0.0.1", "--master-port", "29511", os.path.abspath(__file__)] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
+    our_arm(args)
+
+
+if __name__ == "__main__":
+    main()

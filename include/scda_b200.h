@@ -154,6 +154,17 @@ int scda_softmax_focal_loss_sum(const int N, const float *logits, const int *tar
                                 const int num_classes, float *losses, float *priors,
                                 float *loss_sum, cudaStream_t stream);
 
+/* --- optimiser -------------------------------------------------------- */
+/* replaces torch.optim.Adam(...).step() on each of the four networks
+ * (tools/faster_rcnn_train_val.py:305-316 construct, :616,:635,:704,:750 step): one pass
+ * over a network's FLAT fp32 parameter / gradient / moment buffers (torch 0.4.1 update
+ * rule, weight decay added to the gradient).  grad_scale multiplies the gradient first
+ * (1 when the loss was already divided by world size).  bf16_shadow, if not NULL, receives
+ * the updated parameters rounded to bf16 for the tensor-core kernels.  step counts from 1. */
+int scda_adam_step(float *param, const float *grad, float *exp_avg, float *exp_avg_sq,
+                   void *bf16_shadow, long long n, int step, float lr, float beta1, float beta2,
+                   float eps, float weight_decay, float grad_scale, cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

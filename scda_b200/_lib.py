@@ -37,6 +37,7 @@ SIGNATURES = {
     "scda_bbox_overlaps": (_i, [_i, _p, _i, _p, _p, _p]),
     "scda_sigmoid_focal_loss_sum": (_i, [_i, _p, _p, _f, _f, _f, _i, _p, _p, _p]),
     "scda_softmax_focal_loss_sum": (_i, [_i, _p, _p, _f, _f, _f, _i, _p, _p, _p, _p]),
+    "scda_adam_step": (_i, [_p, _p, _p, _p, _p, C.c_longlong, _i, _f, _f, _f, _f, _f, _f, _p]),
 }
 
 _LIB = None
@@ -69,9 +70,20 @@ def load(path: str | None = None) -> C.CDLL:
     return lib
 
 
+# kernels launched per successful entry-point call (memsets not counted); bench.py reports
+# the total inside its timed region as `gpu_launches`
+KERNELS_PER_CALL = {
+    "scda_nms": 2, "scda_nms_dyn": 2, "SoftmaxFocalLossForwardLaucher": 1,
+    "SoftmaxFocalLossBackwardLaucher": 1,
+}
+LAUNCHES = 0
+
+
 def check(status: int, what: str) -> None:
     """Status convention of include/scda_b200.h: 1 ok, 0 bad arguments, <0 = -cudaError_t."""
+    global LAUNCHES
     if status == 1:
+        LAUNCHES += KERNELS_PER_CALL.get(what, 1)
         return
     if status == 0:
         raise ValueError("%s: arguments rejected by libscda_b200" % what)

@@ -1,0 +1,242 @@
+"""One SCDA training iteration on one rank — the body of `train()` in the reference driver
+(tools/faster_rcnn_train_val.py:507-770), kept as a function so the driver, bench.py and
+the tests run the same code.
+
+Four networks, four Adam optimisers stepping in sequence, as the reference does:
+  detector forward on the source AND target image            (:526)
+  crops around the cluster centres, decoder                   (:528-560)
+  (1) image discriminator update                              (:567-616)
+  (2) patch (feature) discriminator update                    (:623-635)
+  (3) decoder update                                          (:642-704)
+  (4) detector update                                         (:716-750)
+
+Mechanism differences (results are the same):
+  * each network's parameters, gradients and Adam moments live in ONE flat fp32 buffer
+    (FlatAdam): one NCCL all-reduce and one fused optimiser launch per network instead of
+    one collective and ~10 elementwise kernels per parameter tensor;
+  * every backward names the parameters it is for (`inputs=`), so autograd does not
+    compute the stray gradients the reference accumulates into the other networks and
+    then discards with the next zero_grad();
+  * the "Max Grad" logging loops (:607-611, 695-699, 741-745: one host sync per parameter
+    tensor) are off unless asked for.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from ._lib import check, load, stream_ptr
+from .utils.distributed_utils import FlatGradBucket
+
+
+class FlatAdam(object):
+    """Adam(lr, betas, eps, weight_decay) of torch 0.4.1 over one network, flat storage,
+    stepped by libscda_b200's scda_adam_step."""
+
+    def __init__(self, module, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-4):
+        self.params = [p for p in module.parameters() if p.requires_grad]
+        assert self.params and all(p.is_cuda and p.dtype == torch.float32 for p in self.params)
+        dev = self.params[0].device
+        n = sum(p.numel() for p in self.params)
+        pad = (-n) % 4
+        self.flat = torch.zeros(n + pad, dtype=torch.float32, device=dev)
+        off = 0
+        for p in self.params:
+            self.flat[off:off + p.numel()].copy_(p.data.reshape(-1))
+            p.data = self.flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+        self.n = n
+        self.bucket = FlatGradBucket(self.params)
+        module._scda_bucket = self.bucket
+        self.exp_avg = torch.zeros_like(self.flat)
+        self.exp_avg_sq = torch.zeros_like(self.flat)
+        self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
+        self.t = 0
+
+    def zero_grad(self):
+        self.bucket.zero()
+
+    def all_reduce(self):
+        self.bucket.rebind()
+        self.bucket.all_reduce()
+
+    def step(self, lr=None, grad_scale=1.0):
+        self.t += 1
+        self.bucket.rebind()
+        with torch.cuda.device(self.flat.device):
+            check(load().scda_adam_step(
+                self.flat.data_ptr(), self.bucket.flat.data_ptr(), self.exp_avg.data_ptr(),
+                self.exp_avg_sq.data_ptr(), None, self.n, self.t,
+                float(self.lr if lr is None else lr), self.betas[0], self.betas[1], self.eps,
+                self.weight_decay, float(grad_scale), stream_ptr(self.flat.device)),
+                "scda_adam_step")
+
+
+def get_corner_from_center(center, recon_size, new_w, new_h):
+    """(cluster_num, 2) centres -> recon_size windows shifted to stay inside new_w x new_h
+    (tools/faster_rcnn_train_val.py:411-438)."""
+    half = recon_size // 2
+    corner = []
+    for cx, cy in center:
+        x_1 = max(int(cx) - half, 0)
+        y_1 = max(int(cy) - half, 0)
+        if x_1 == 0:
+            x_2 = recon_size
+        else:
+            x_2 = min(int(cx) + half, new_w)
+            if x_2 == new_w:
+                x_1 = new_w - recon_size
+        if y_1 == 0:
+            y_2 = recon_size
+        else:
+            y_2 = min(int(cy) + half, new_h)
+            if y_2 == new_h:
+                y_1 = new_h - recon_size
+        corner.append([x_1, y_1, x_2, y_2])
+    return corner
+
+
+def _crops(image, corners, recon_size):
+    out = []
+    for x1, y1, x2, y2 in corners:
+        assert x2 - x1 == recon_size and y2 - y1 == recon_size, "crop size does not match recon_size"
+        out.append(image[:, :, y1:y2, x1:x2])
+    return torch.cat(out, 0)
+
+
+def soft_label(flag, like, generator=None):
+    """U(0.8, 1) for 1, U(0, 0.3) for 0 (:440-448), drawn on the device."""
+    u = torch.rand(like.shape, device=like.device, generator=generator)
+    return 0.8 + 0.2 * u if flag == 1 else 0.3 * u
+
+
+def _bce_rows(p, label_row):
+    """sum over clusters of F.binary_cross_entropy(p[c:c+1], label_row) -> per-cluster vector."""
+    return F.binary_cross_entropy(p, label_row.expand_as(p), reduction='none').mean(dim=1)
+
+
+class SCDATrainer(object):
+    """The reference's four networks + optimisers for one rank."""
+
+    def __init__(self, model, dec_model, dis_model, dis_model_patch, lr, cluster_num=4,
+                 threshold=128, recon_size=256, new_w=1024, new_h=512, world_size=1,
+                 weight_decay=1e-4):
+        self.model, self.dec_model = model, dec_model
+        self.dis_model, self.dis_model_patch = dis_model, dis_model_patch
+        self.opt = FlatAdam(model, lr, weight_decay=weight_decay)
+        self.opt_dec = FlatAdam(dec_model, lr, weight_decay=weight_decay)
+        self.opt_dis = FlatAdam(dis_model, lr, weight_decay=weight_decay)
+        self.opt_dis_patch = FlatAdam(dis_model_patch, lr, weight_decay=weight_decay)
+        self.cluster_num, self.threshold, self.recon_size = cluster_num, threshold, recon_size
+        self.new_w, self.new_h, self.world_size = new_w, new_h, world_size
+
+    def nets(self):
+        return (self.model, self.dec_model, self.dis_model, self.dis_model_patch)
+
+    def train_mode(self):
+        for n in self.nets():
+            n.train()
+
+    def iteration(self, cfg, image, image_info, gts, target, lr=None):
+        """One iteration; returns a dict of 0-dim loss tensors (no host sync here)."""
+        ws = float(self.world_size)
+        x = {'cfg': cfg, 'image': image, 'image_info': image_info, 'ground_truth_bboxes': gts,
+             'ignore_regions': None, 'cluster_num': self.cluster_num, 'threshold': self.threshold}
+        outputs = self.model(x, target)
+        centers_source, centers_target = outputs['cluster_centers']
+        x_small = _crops(image, get_corner_from_center(centers_source, self.recon_size,
+                                                       self.new_w, self.new_h), self.recon_size)
+        target_small = _crops(target, get_corner_from_center(centers_target, self.recon_size,
+                                                             self.new_w, self.new_h), self.recon_size)
+        x_source_patch, x_target_patch = outputs['cluster_features']
+        x_source_recon, x_target_recon = self.dec_model(x_source_patch, x_target_patch)
+
+        # ---- (1) image discriminator
+        self.opt_dis.zero_grad()
+        s_dis, t_dis = [torch.sigmoid(o) for o in self.dis_model(x_source_recon, x_target_recon)]
+        s_real, t_real = [torch.sigmoid(o) for o in self.dis_model(x_small, target_small)]
+        score_1 = soft_label(1, s_real[:1])
+        score_0 = soft_label(0, s_dis[:1])
+        adloss_source = (_bce_rows(s_dis, score_1) + _bce_rows(s_real, score_0)).sum()
+        t_patch_pro = self.dis_model_patch(x_target_patch)
+        t_patch_mean = torch.mean(t_patch_pro, 1)
+        s_patch_pro = self.dis_model_patch(x_source_patch)
+        adloss_target = (t_patch_mean * _bce_rows(t_dis, score_0) + _bce_rows(t_real, score_1)).sum()
+        adloss = (adloss_source + adloss_target) / ws
+        adloss.backward(retain_graph=True, inputs=self.opt_dis.params)
+        self.opt_dis.all_reduce()
+        self.opt_dis.step(lr)
+
+        # ---- (2) patch discriminator
+        self.opt_dis_patch.zero_grad()
+        score_0_patch = soft_label(0, t_patch_pro)
+        score_1_patch = soft_label(1, s_patch_pro)
+        dis_patch_loss = (F.binary_cross_entropy(s_patch_pro, score_1_patch)
+                          + F.binary_cross_entropy(t_patch_pro, score_0_patch)) / ws
+        dis_patch_loss.backward(retain_graph=True, inputs=self.opt_dis_patch.params)
+        self.opt_dis_patch.all_reduce()
+        self.opt_dis_patch.step(lr)
+
+        # ---- (3) decoder
+        self.opt_dec.zero_grad()
+        s_dis2, t_dis2 = self.dis_model(x_source_recon, x_target_recon)
+        s_dis2, t_dis2 = torch.sigmoid(s_dis2), torch.sigmoid(t_dis2)
+        s_real2, t_real2 = [torch.sigmoid(o) for o in self.dis_model(x_small, target_small)]
+        t_patch_mean2 = torch.mean(self.dis_model_patch(x_target_patch), 1)
+        ones, zeros = torch.ones_like(t_dis2[:1]), torch.zeros_like(t_dis2[:1])
+        fake_loss1_target = (t_patch_mean2 * (_bce_rows(t_dis2, ones) + _bce_rows(t_real2, zeros))).sum()
+        fake_loss1_source = (_bce_rows(s_dis2, ones) + _bce_rows(s_real2, zeros)).sum()
+        recon_loss = (fake_loss1_source + fake_loss1_target) / ws
+        recon_loss.backward(retain_graph=True, inputs=self.opt_dec.params)
+        self.opt_dec.all_reduce()
+        self.opt_dec.step(lr)
+
+        # ---- (4) detector: decoders swapped (target features -> source reconstruction)
+        x_source_recon2, x_target_recon2 = self.dec_model(x_target_patch, x_source_patch)
+        s_dis3, t_dis3 = self.dis_model(x_source_recon2, x_target_recon2)
+        fake_dis = torch.sigmoid(t_dis3)
+        fake_loss_source = F.binary_cross_entropy(fake_dis, torch.ones_like(fake_dis))
+        fake_dis2 = torch.sigmoid(s_dis3)
+        fake_loss_target = (t_patch_mean2 * _bce_rows(fake_dis2, torch.ones_like(fake_dis2[:1]))).sum()
+        rpn_cls_loss, rpn_loc_loss, rcnn_cls_loss, rcnn_loc_loss = outputs['losses']
+        loss = (rpn_cls_loss + rpn_loc_loss + rcnn_cls_loss + rcnn_loc_loss
+                + 0.1 * (fake_loss_source + fake_loss_target)) / ws
+        self.opt.zero_grad()
+        loss.backward(inputs=self.opt.params)
+        self.opt.all_reduce()
+        self.opt.step(lr)
+        return {'loss': loss.detach() * ws, 'rpn_cls': rpn_cls_loss.detach(),
+                'rpn_loc': rpn_loc_loss.detach(), 'rcnn_cls': rcnn_cls_loss.detach(),
+                'rcnn_loc': rcnn_loc_loss.detach(), 'fake_loss': fake_loss_target.detach(),
+                'dec_loss': recon_loss.detach(), 'dis_loss': adloss.detach(),
+                'dis_patch_loss': dis_patch_loss.detach(),
+                'rpn_acc': outputs['accuracy'][0], 'rcnn_acc': outputs['accuracy'][1]}
+
+
+def builder_gan(cluster_num=4, threshold=128, recon_size=256, neww=64, newh=64):
+    """The three GAN networks with the hyper-parameters of the reference's builder_gan
+    (tools/faster_rcnn_train_val.py:255-273)."""
+    from .models.faster_rcnn.faster_rcnn_adver_expansion_reweight_cluster import (
+        GAN_decoder_AE, GAN_dis_AE, GAN_dis_AE_patch)
+    size2layers = {256: 3, 512: 4, 128: 2}
+    params_dec = {'ch': threshold, 'input_dim_a': 3, 'input_dim_b': 3, 'n_gen_res_blk': 3,
+                  'n_gen_front_blk': size2layers[recon_size], 'res_dropout_ratio': 0.5,
+                  'neww': neww, 'newh': newh, 'cluster_num': cluster_num, 'threshold': threshold}
+    params_dis = {'input_dim_a': 3, 'input_dim_b': 3, 'ch': 32, 'n_gen_res_blk': 3,
+                  'n_layer': size2layers[recon_size]}
+    params_patch_dis = {'n_in': threshold, 'n_out': threshold * 2, 'cluster_num': cluster_num}
+    return GAN_dis_AE(params_dis), GAN_decoder_AE(params_dec), GAN_dis_AE_patch(params_patch_dis)
+
+
+def build_trainer(cfg, lr=1.25e-5, device="cuda", cluster_num=4, threshold=128, recon_size=256,
+                  new_w=1024, new_h=512, world_size=1, seed=0):
+    from .models.faster_rcnn.vgg_adver_expansion_cluster import vgg16
+    torch.manual_seed(seed)
+    np.random.seed(seed)
+    model = vgg16(pretrained=False, cfg=cfg['shared']).to(device)
+    dis_model, dec_model, dis_model_patch = builder_gan(cluster_num, threshold, recon_size)
+    tr = SCDATrainer(model, dec_model.to(device), dis_model.to(device), dis_model_patch.to(device),
+                     lr, cluster_num, threshold, recon_size, new_w, new_h, world_size)
+    tr.train_mode()
+    return tr
