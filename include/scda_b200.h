@@ -154,6 +154,30 @@ int scda_softmax_focal_loss_sum(const int N, const float *logits, const int *tar
                                 const int num_classes, float *losses, float *priors,
                                 float *loss_sum, cudaStream_t stream);
 
+/* --- tensor-core GEMM / 3x3 convolution (tcgen05 + TMA) ----------------- */
+/* flags for both entry points */
+#define SCDA_TC_RELU        1   /* y = max(y, 0)                                        */
+#define SCDA_TC_OUT_F32     2   /* output fp32 (default bf16)                            */
+#define SCDA_TC_MASK_POS    4   /* y = mask_src > 0 ? y : 0  (ReLU backward, bf16 mask)  */
+#define SCDA_TC_ACCUMULATE  8   /* y += old y (fp32 output only)                         */
+/* replaces the cuBLAS GEMM behind nn.Linear (fc6 / fc7 / fc_rcnn_cls / fc_rcnn_loc,
+ * models/faster_rcnn/vgg_adver_expansion_cluster.py:46-60,73-80) and behind 1x1 convs
+ * (models/head.py:15-18):  C[M,N] = A[M,K] . B[N,K]^T + bias[N].
+ * A, B bf16 row-major with leading dimensions lda, ldb (elements, multiples of 8, 16 B
+ * aligned bases); C bf16 or fp32 with leading dimension ldc; bias fp32 or NULL. */
+int scda_gemm_bf16_tn(int M, int N, int K, const void *A, long long lda, const void *B, long long ldb,
+                      const float *bias, void *C, long long ldc, int flags, const void *mask_src,
+                      cudaStream_t stream);
+/* replaces the cuDNN convolution behind nn.Conv2d(k=3, s=1, p=1) (VGG backbone,
+ * vgg_adver_expansion_cluster.py:101-114; RPN conv3x3, models/head.py:13):
+ * x NHWC bf16 [NB,H,W,Cin], w bf16 [Cout][3][3][Cin], y NHWC [NB,H,W,Cout] bf16 or fp32.
+ * Cin % 64 == 0, W % 8 == 0.  With the weights flipped and transposed by the caller the same
+ * entry point computes the data gradient; SCDA_TC_MASK_POS then applies the ReLU gradient of
+ * the layer input (mask_src = that input, same shape as y). */
+int scda_conv3x3_bf16_nhwc(int NB, int H, int W, int Cin, int Cout, const void *x, const void *w_krsc,
+                           const float *bias, void *y, int flags, const void *mask_src,
+                           cudaStream_t stream);
+
 /* --- optimiser -------------------------------------------------------- */
 /* replaces torch.optim.Adam(...).step() on each of the four networks
  * (tools/faster_rcnn_train_val.py:305-316 construct, :616,:635,:704,:750 step): one pass

@@ -37,6 +37,8 @@ SIGNATURES = {
     "scda_bbox_overlaps": (_i, [_i, _p, _i, _p, _p, _p]),
     "scda_sigmoid_focal_loss_sum": (_i, [_i, _p, _p, _f, _f, _f, _i, _p, _p, _p]),
     "scda_softmax_focal_loss_sum": (_i, [_i, _p, _p, _f, _f, _f, _i, _p, _p, _p, _p]),
+    "scda_gemm_bf16_tn": (_i, [_i, _i, _i, _p, C.c_longlong, _p, C.c_longlong, _p, _p, C.c_longlong, _i, _p, _p]),
+    "scda_conv3x3_bf16_nhwc": (_i, [_i, _i, _i, _i, _i, _p, _p, _p, _p, _i, _p, _p]),
     "scda_adam_step": (_i, [_p, _p, _p, _p, _p, C.c_longlong, _i, _f, _f, _f, _f, _f, _f, _p]),
 }
 

@@ -1,0 +1,455 @@
+// tcgen05 tensor-core kernels for sm_100a: bf16 x bf16 -> fp32 (TMEM) GEMM and 3x3
+// implicit-GEMM convolution with im2col folded into the TMA staging.
+//
+// Replaces the cuDNN / cuBLAS calls behind the reference's nn.Conv2d / nn.Linear on the
+// detector's hot path (13 VGG convs: models/faster_rcnn/vgg_adver_expansion_cluster.py:101-114;
+// RPN head: models/head.py:13-18; fc6/fc7/cls/loc: vgg_adver_expansion_cluster.py:46-60).
+//
+// One kernel, two A-operand addressing modes:
+//   GEMM  C[M,N] = A[M,K] . B[N,K]^T      A tile = 2-D TMA box {64 k, 128 rows}
+//   CONV  Y[n,h,w,co] = sum_{r,s,ci} X[n,h+r-1,w+s-1,ci] W[co,r,s,ci]   (NHWC, pad 1)
+//         M = pixels of an 8x16 (TH x TW) spatial tile, K = 9 taps x Cin.  For k-block
+//         (tap r,s ; channel block c0) the A tile is ONE 4-D TMA box {64 ch, TW, TH, 1}
+//         at coordinates {c0, w0+s-1, h0+r-1, n}: the shifted window lands in shared
+//         memory already in the K-major 128-byte-swizzled layout the MMA wants, and TMA's
+//         out-of-bounds zero fill IS the padding.  No im2col buffer ever exists.
+// Both operands are K-major bf16, 128B swizzle; accumulators are 128 x BLOCK_N fp32 in TMEM.
+//
+// Warp roles (256 threads, 1 CTA / SM):
+//   warp 0   : TMA producer (one elected lane), kStages-deep mbarrier ring
+//   warp 1   : MMA issuer (one elected lane): 4 x tcgen05.mma (K=16) per 64-wide k-block,
+//              tcgen05.commit releases the smem stage / signals the epilogue
+//   warp 2   : TMEM allocate / free
+//   warps 4-7: epilogue: tcgen05.ld 32 lanes x 32 columns at a time -> bias, ReLU or the
+//              ReLU-gradient mask of the layer input, bf16/fp32 pack -> global
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;        // 64 bf16 = 128 B = one swizzle row
+constexpr int kUmmaK = 16;
+constexpr int kThreads = 256;
+
+enum : int {
+    kFlagRelu = 1,        // y = max(y, 0)
+    kFlagOutF32 = 2,      // write fp32 instead of bf16
+    kFlagMaskPos = 4,     // y = (mask_src > 0) ? y : 0     (ReLU backward fused into dgrad)
+    kFlagAccumulate = 8,  // y += previous contents (fp32 output only)
+};
+
+struct TcParams {
+    int M, N, K;                 // GEMM view (CONV: M = NB*H*W, K = 9*Cin)
+    int num_k_blocks;
+    int conv;                    // 0 GEMM, 1 CONV
+    int H, W, Cin, TH, TW;       // CONV geometry
+    int tiles_w, tiles_h;
+    const float *bias;           // [N] or null
+    void *out;                   // [M, ldc]
+    long long ldc;
+    const __nv_bfloat16 *mask_src;   // [M, ldc] (kFlagMaskPos)
+    int flags;
+};
+
+// ----------------------------------------------------------------------------- PTX
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}\n" ::"r"(bar), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1,
+                                            int c2, int c3)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, 128B-swizzled operand tile: rows of 128 B, 8-row groups 1024 B apart
+// (cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46),
+//  version=1 [46,48), layout SWIZZLE_128B=2 [61,64)).
+__device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t saddr)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;                  // LBO (unused for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;        // SBO
+    d |= (uint64_t)1 << 46;                  // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                  // SWIZZLE_128B
+    return d;
+}
+// cute::UMMA::InstrDescriptor, kind::f16: D=F32 [4,6)=1, A=BF16 [7,10)=1, B=BF16 [10,13)=1,
+// both K-major, N>>3 at [17,23), M>>4 at [24,29)
+__host__ __device__ constexpr uint32_t make_idesc(int m, int n)
+{
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+template <int kBlockN, int kStages>
+struct SmemLayout {
+    static constexpr int kABytes = kBlockM * kBlockK * 2;   // 16 KB
+    static constexpr int kBBytes = kBlockN * kBlockK * 2;
+    static constexpr int kStageBytes = kABytes + kBBytes;
+    static constexpr int kTileBytes = kStages * kStageBytes;
+    static constexpr int kBarOffset = kTileBytes;           // full[kStages], empty[kStages], tmem_full
+    static constexpr int kTotal = kTileBytes + (2 * kStages + 1) * 8 + 16 + 1024;  // + tmem ptr + align slack
+};
+
+template <int kBlockN, int kStages>
+__global__ void __launch_bounds__(kThreads, 1)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+               const TcParams p)
+{
+    using L = SmemLayout<kBlockN, kStages>;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B needs 1024 B alignment
+    uint8_t *gen = smem_raw + (base - smem_u32(smem_raw));
+    const uint32_t bar_full = base + L::kBarOffset;
+    const uint32_t bar_empty = bar_full + kStages * 8;
+    const uint32_t bar_tmem = bar_empty + kStages * 8;
+    volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(gen + L::kBarOffset + (2 * kStages + 1) * 8);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m_tile = blockIdx.x, n_tile = blockIdx.y;
+    const int n0 = n_tile * kBlockN;
+
+    // CONV: decompose the m tile into (image, tile row, tile col)
+    int img = 0, h0 = 0, w0 = 0;
+    if (p.conv) {
+        const int per_img = p.tiles_h * p.tiles_w;
+        img = m_tile / per_img;
+        const int t = m_tile - img * per_img;
+        h0 = (t / p.tiles_w) * p.TH;
+        w0 = (t % p.tiles_w) * p.TW;
+    }
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(bar_full + s * 8, 1);
+            mbar_init(bar_empty + s * 8, 1);
+        }
+        mbar_init(bar_tmem, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        const uint32_t ncols = kBlockN;
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                         smem_u32((const void *)tmem_slot)),
+                     "r"(ncols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            const int cblocks = p.conv ? p.Cin / kBlockK : 0;
+            for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+                const int s = kb % kStages;
+                const uint32_t ph = (kb / kStages) & 1;
+                mbar_wait(bar_empty + s * 8, ph ^ 1);
+                const uint32_t a_dst = base + s * L::kStageBytes;
+                const uint32_t b_dst = a_dst + L::kABytes;
+                mbar_expect_tx(bar_full + s * 8, L::kStageBytes);
+                if (p.conv) {
+                    const int tap = kb / cblocks, cb = kb - tap * cblocks;
+                    const int r = tap / 3, sx = tap - r * 3;
+                    tma_load_4d(a_dst, &map_a, bar_full + s * 8, cb * kBlockK, w0 + sx - 1, h0 + r - 1, img);
+                    tma_load_2d(b_dst, &map_b, bar_full + s * 8, tap * p.Cin + cb * kBlockK, n0);
+                } else {
+                    tma_load_2d(a_dst, &map_a, bar_full + s * 8, kb * kBlockK, m_tile * kBlockM);
+                    tma_load_2d(b_dst, &map_b, bar_full + s * 8, kb * kBlockK, n0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(kBlockM, kBlockN);
+            for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+                const int s = kb % kStages;
+                const uint32_t ph = (kb / kStages) & 1;
+                mbar_wait(bar_full + s * 8, ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t a_src = base + s * L::kStageBytes;
+                const uint32_t b_src = a_src + L::kABytes;
+#pragma unroll
+                for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+                    const uint64_t ad = make_kmajor_desc(a_src + k * kUmmaK * 2);
+                    const uint64_t bd = make_kmajor_desc(b_src + k * kUmmaK * 2);
+                    umma_bf16(tmem_base, ad, bd, idesc, (kb | k) != 0);
+                }
+                umma_commit(bar_empty + s * 8);   // frees the stage when these MMAs retire
+            }
+            umma_commit(bar_tmem);                // accumulator complete
+        }
+    } else if (warp >= 4) {
+        const int ew = warp - 4;                  // TMEM lane quarter this warp may read
+        mbar_wait(bar_tmem, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int row = ew * 32 + lane;           // accumulator row = TMEM lane
+        long long out_row;
+        bool row_ok;
+        if (p.conv) {
+            const int th = row / p.TW, tw = row - th * p.TW;
+            const int h = h0 + th, w = w0 + tw;
+            row_ok = h < p.H && w < p.W;
+            out_row = ((long long)img * p.H + h) * p.W + w;
+        } else {
+            out_row = (long long)m_tile * kBlockM + row;
+            row_ok = out_row < p.M;
+        }
+        const bool f32 = p.flags & kFlagOutF32;
+        const bool vec_ok = (p.ldc % 8 == 0) && (n0 % 8 == 0);
+#pragma unroll 1
+        for (int c0 = 0; c0 < kBlockN; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)c0, v);
+            if (!row_ok) continue;
+            const int ncol = min(32, p.N - (n0 + c0));
+            if (ncol <= 0) continue;
+            float f[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                float x = __uint_as_float(v[j]);
+                if (p.bias && j < ncol) x += __ldg(p.bias + n0 + c0 + j);
+                if (p.flags & kFlagRelu) x = fmaxf(x, 0.f);
+                f[j] = x;
+            }
+            const long long o = out_row * p.ldc + n0 + c0;
+            if (p.flags & kFlagMaskPos) {
+                const __nv_bfloat16 *ms = p.mask_src + o;
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (j < ncol && !(__bfloat162float(ms[j]) > 0.f)) f[j] = 0.f;
+            }
+            if (f32) {
+                float *dst = reinterpret_cast<float *>(p.out) + o;
+                if (p.flags & kFlagAccumulate) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (j < ncol) dst[j] += f[j];
+                } else if (ncol == 32 && vec_ok) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4)
+                        *reinterpret_cast<float4 *>(dst + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (j < ncol) dst[j] = f[j];
+                }
+            } else {
+                __nv_bfloat16 *dst = reinterpret_cast<__nv_bfloat16 *>(p.out) + o;
+                if (ncol == 32 && vec_ok) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 8) {
+                        uint4 pk;
+                        __nv_bfloat162 b0 = __floats2bfloat162_rn(f[j], f[j + 1]);
+                        __nv_bfloat162 b1 = __floats2bfloat162_rn(f[j + 2], f[j + 3]);
+                        __nv_bfloat162 b2 = __floats2bfloat162_rn(f[j + 4], f[j + 5]);
+                        __nv_bfloat162 b3 = __floats2bfloat162_rn(f[j + 6], f[j + 7]);
+                        pk.x = *reinterpret_cast<uint32_t *>(&b0);
+                        pk.y = *reinterpret_cast<uint32_t *>(&b1);
+                        pk.z = *reinterpret_cast<uint32_t *>(&b2);
+                        pk.w = *reinterpret_cast<uint32_t *>(&b3);
+                        *reinterpret_cast<uint4 *>(dst + j) = pk;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (j < ncol) dst[j] = __float2bfloat16_rn(f[j]);
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 2) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t ncols = kBlockN;
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ncols)
+                     : "memory");
+    }
+}
+
+// ------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn()
+{
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *ptr = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)ptr;
+    }
+    return fn;
+}
+
+// bf16 tensor, dims/strides innermost first; box innermost = 64 elements (128 B), 128B swizzle
+bool make_map(CUtensorMap *map, const void *ptr, int rank, const cuuint64_t *dims, const cuuint64_t *strides_bytes,
+              const cuuint32_t *box)
+{
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return false;
+    cuuint32_t ones[5] = {1, 1, 1, 1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void *>(ptr), dims,
+                    strides_bytes, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+template <int kBlockN, int kStages>
+int launch_tc(const CUtensorMap &ma, const CUtensorMap &mb, const TcParams &p, int m_tiles, cudaStream_t stream)
+{
+    using L = SmemLayout<kBlockN, kStages>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<kBlockN, kStages>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
+        if (e != cudaSuccess) return -(int)e;
+        attr_done = true;
+    }
+    dim3 grid(m_tiles, ceil_div(p.N, kBlockN));
+    tc_gemm_kernel<kBlockN, kStages><<<grid, kThreads, L::kTotal, stream>>>(ma, mb, p);
+    return scda_launch_status();
+}
+
+int dispatch_tc(const CUtensorMap &ma, const CUtensorMap &mb, const TcParams &p, int m_tiles, int block_n,
+                cudaStream_t stream)
+{
+    if (block_n == 64) return launch_tc<64, 8>(ma, mb, p, m_tiles, stream);
+    return launch_tc<128, 6>(ma, mb, p, m_tiles, stream);
+}
+
+int pick_block_n(int N) { return N <= 64 ? 64 : 128; }
+
+}  // namespace
+
+SCDA_API int scda_gemm_bf16_tn(int M, int N, int K, const void *A, long long lda, const void *B, long long ldb,
+                               const float *bias, void *C, long long ldc, int flags, const void *mask_src,
+                               cudaStream_t stream)
+{
+    if (M <= 0 || N <= 0 || K <= 0 || !A || !B || !C) return 0;
+    if (lda % 8 || ldb % 8 || ((uintptr_t)A % 16) || ((uintptr_t)B % 16)) return 0;
+    if ((flags & kFlagMaskPos) && !mask_src) return 0;
+    if ((flags & kFlagAccumulate) && !(flags & kFlagOutF32)) return 0;
+    const int bn = pick_block_n(N);
+    CUtensorMap ma, mb;
+    cuuint64_t da[2] = {(cuuint64_t)K, (cuuint64_t)M}, sa[1] = {(cuuint64_t)lda * 2};
+    cuuint32_t ba[2] = {kBlockK, kBlockM};
+    cuuint64_t db[2] = {(cuuint64_t)K, (cuuint64_t)N}, sb[1] = {(cuuint64_t)ldb * 2};
+    cuuint32_t bb[2] = {kBlockK, (cuuint32_t)bn};
+    if (!make_map(&ma, A, 2, da, sa, ba) || !make_map(&mb, B, 2, db, sb, bb)) return 0;
+    TcParams p = {};
+    p.M = M; p.N = N; p.K = K;
+    p.num_k_blocks = ceil_div(K, kBlockK);
+    p.conv = 0;
+    p.bias = bias; p.out = C; p.ldc = ldc;
+    p.mask_src = (const __nv_bfloat16 *)mask_src;
+    p.flags = flags;
+    return dispatch_tc(ma, mb, p, ceil_div(M, kBlockM), bn, stream);
+}
+
+SCDA_API int scda_conv3x3_bf16_nhwc(int NB, int H, int W, int Cin, int Cout, const void *x, const void *w_krsc,
+                                    const float *bias, void *y, int flags, const void *mask_src,
+                                    cudaStream_t stream)
+{
+    if (NB <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0 || !x || !w_krsc || !y) return 0;
+    if (Cin % kBlockK) return 0;               // channel blocks of 64 (conv1_1 has its own kernel)
+    if ((flags & kFlagMaskPos) && !mask_src) return 0;
+    if ((flags & kFlagAccumulate) && !(flags & kFlagOutF32)) return 0;
+    int TW = 16, TH = 8;
+    if (W % 16) {                                 // narrow maps: 8 x 16 tile turned around
+        if (W % 8 == 0) { TW = 8; TH = 16; } else return 0;
+    }
+    const int tiles_w = W / TW, tiles_h = ceil_div(H, TH);
+    const int bn = pick_block_n(Cout);
+    CUtensorMap ma, mb;
+    cuuint64_t da[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)NB};
+    cuuint64_t sa[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)W * Cin * 2, (cuuint64_t)H * W * Cin * 2};
+    cuuint32_t ba[4] = {kBlockK, (cuuint32_t)TW, (cuuint32_t)TH, 1};
+    cuuint64_t db[2] = {(cuuint64_t)9 * Cin, (cuuint64_t)Cout}, sb[1] = {(cuuint64_t)9 * Cin * 2};
+    cuuint32_t bb[2] = {kBlockK, (cuuint32_t)bn};
+    if (!make_map(&ma, x, 4, da, sa, ba) || !make_map(&mb, w_krsc, 2, db, sb, bb)) return 0;
+    TcParams p = {};
+    p.M = NB * H * W; p.N = Cout; p.K = 9 * Cin;
+    p.num_k_blocks = 9 * (Cin / kBlockK);
+    p.conv = 1;
+    p.H = H; p.W = W; p.Cin = Cin; p.TH = TH; p.TW = TW; p.tiles_w = tiles_w; p.tiles_h = tiles_h;
+    p.bias = bias; p.out = y; p.ldc = Cout;
+    p.mask_src = (const __nv_bfloat16 *)mask_src;
+    p.flags = flags;
+    return dispatch_tc(ma, mb, p, NB * tiles_h * tiles_w, bn, stream);
+}

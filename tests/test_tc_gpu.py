@@ -1,0 +1,96 @@
+"""tcgen05 GEMM / implicit-GEMM convolution against a plain PyTorch fp32 reference of the
+same op on the same bf16-rounded operands.  Tolerance: the kernels accumulate in fp32 and
+round the OUTPUT to bf16 (rel 2^-8), so |err| <= 1e-2 * |ref| + 1e-2 * rms(ref)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _close(out, ref, rtol=1e-2):
+    import torch
+    out, ref = out.float(), ref.float()
+    tol = rtol * ref.abs() + rtol * ref.pow(2).mean().sqrt()
+    bad = (out - ref).abs() > tol
+    assert not bool(bad.any()), "mismatch: %d / %d, max abs err %g (ref rms %g)" % (
+        int(bad.sum()), bad.numel(), float((out - ref).abs().max()), float(ref.pow(2).mean().sqrt()))
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (128, 128, 256), (256, 384, 512), (512, 4096, 1024),
+                                   (512, 36, 4096), (512, 9, 4096), (300, 4096, 512), (2048, 30, 512),
+                                   (130, 70, 72), (512, 4096, 25088)])
+def test_gemm_tn(cuda_lib, M, N, K):
+    import torch
+    from scda_b200 import tc
+    g = torch.Generator(device="cuda").manual_seed(M * 7 + N * 3 + K)
+    a = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    b = (torch.randn(N, K, device="cuda", generator=g) / K ** 0.5).bfloat16()
+    bias = torch.randn(N, device="cuda", generator=g)
+    ref = a.float() @ b.float().t() + bias
+    out = tc.gemm_tn(a, b, bias)
+    _close(out, ref)
+    out32 = tc.gemm_tn(a, b, bias, relu=True, out_dtype=torch.float32)
+    _close(out32, ref.clamp(min=0), rtol=2e-3)
+    # strided A (a row-slice view with a larger leading dimension)
+    if K % 16 == 0 and K >= 128:
+        big = torch.randn(M, K + 64, device="cuda", generator=g).bfloat16()
+        av = big[:, :K]
+        _close(tc.gemm_tn(av, b), av.float() @ b.float().t())
+
+
+def test_gemm_mask_and_accumulate(cuda_lib):
+    import torch
+    from scda_b200 import tc
+    g = torch.Generator(device="cuda").manual_seed(1)
+    a = torch.randn(256, 320, device="cuda", generator=g).bfloat16()
+    b = (torch.randn(192, 320, device="cuda", generator=g) / 18).bfloat16()
+    mask = torch.randn(256, 192, device="cuda", generator=g).bfloat16()
+    ref = a.float() @ b.float().t()
+    _close(tc.gemm_tn(a, b, mask_src=mask), torch.where(mask.float() > 0, ref, torch.zeros_like(ref)))
+    acc = torch.ones(256, 192, device="cuda")
+    tc.gemm_tn(a, b, out=acc, accumulate=True)
+    _close(acc, ref + 1, rtol=2e-3)
+
+
+@pytest.mark.parametrize("NB,H,W,Cin,Cout", [(1, 8, 16, 64, 64), (1, 16, 32, 64, 128), (2, 32, 64, 128, 64),
+                                             (1, 32, 64, 512, 512), (1, 64, 128, 256, 512),
+                                             (4, 64, 64, 128, 128), (1, 24, 40, 64, 192),
+                                             (1, 128, 256, 128, 256)])
+def test_conv3x3(cuda_lib, NB, H, W, Cin, Cout):
+    import torch
+    import torch.nn.functional as F
+    from scda_b200 import tc
+    g = torch.Generator(device="cuda").manual_seed(H * W + Cin)
+    x = torch.randn(NB, H, W, Cin, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(Cout, 3, 3, Cin, device="cuda", generator=g) / (9 * Cin) ** 0.5).bfloat16()
+    bias = torch.randn(Cout, device="cuda", generator=g)
+    torch.backends.cudnn.allow_tf32 = False
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float().permute(0, 3, 1, 2), bias, padding=1)
+    ref = ref.permute(0, 2, 3, 1)
+    y = tc.conv3x3_nhwc(x, w, bias)
+    _close(y, ref)
+    y2 = tc.conv3x3_nhwc(x, w, bias, relu=True)
+    _close(y2, ref.clamp(min=0))
+    assert float(y2.float().min()) >= 0
+
+
+def test_conv3x3_backbone_full_size(cuda_lib):
+    """conv1_2 at the benchmark resolution (64 -> 64 @ 512 x 1024): linearity in the input
+    (size-independent property) + a corner / edge spot check against PyTorch."""
+    import torch
+    import torch.nn.functional as F
+    from scda_b200 import tc
+    g = torch.Generator(device="cuda").manual_seed(0)
+    x1 = torch.randn(1, 512, 1024, 64, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(64, 3, 3, 64, device="cuda", generator=g) / 24).bfloat16()
+    y1 = tc.conv3x3_nhwc(x1, w, out_dtype=torch.float32)
+    y2 = tc.conv3x3_nhwc((x1.float() * 2).bfloat16(), w, out_dtype=torch.float32)   # exact in bf16
+    assert float((y2 - 2 * y1).abs().max()) <= 1e-3 * float(y1.abs().max())
+    torch.backends.cudnn.allow_tf32 = False
+    for hs, ws in ((slice(0, 24), slice(0, 40)), (slice(488, 512), slice(984, 1024))):
+        h0 = max(hs.start - 1, 0)
+        w0 = max(ws.start - 1, 0)
+        patch = x1[:, h0:min(hs.stop + 1, 512), w0:min(ws.stop + 1, 1024)].float().permute(0, 3, 1, 2)
+        ref = F.conv2d(patch, w.float().permute(0, 3, 1, 2), padding=1).permute(0, 2, 3, 1)
+        ref = ref[:, hs.start - h0:hs.start - h0 + 24, ws.start - w0:ws.start - w0 + 40]
+        _close(y1[:, hs, ws], ref, rtol=2e-3)
