@@ -178,6 +178,22 @@ int scda_conv3x3_bf16_nhwc(int NB, int H, int W, int Cin, int Cout, const void *
                            const float *bias, void *y, int flags, const void *mask_src,
                            cudaStream_t stream);
 
+/* C[M,N] = A[M,K] . B[K,N] + bias: B row-major with N contiguous (the data gradient of
+ * nn.Linear, dX = dY . W, reads W[out,in] this way; no transposed weight copy is kept). */
+int scda_gemm_bf16_nn(int M, int N, int K, const void *A, long long lda, const void *B, long long ldb,
+                      const float *bias, void *C, long long ldc, int flags, const void *mask_src,
+                      cudaStream_t stream);
+/* weight gradient of nn.Linear: dW[Nout,Kin] (fp32, leading dimension lddw) =
+ * dY[rows,Nout]^T . X[rows,Kin], both bf16 row-major. */
+int scda_linear_wgrad_bf16(int rows, int Nout, int Kin, const void *dY, long long lddy, const void *X,
+                           long long ldx, float *dW, long long lddw, cudaStream_t stream);
+/* weight gradient of the 3x3 convolution: x NHWC bf16 [NB,H,W,Cin], dy NHWC bf16
+ * [NB,H,W,Cout] -> dw_partials fp32 [splits][Cout][3][3][Cin]; the pixel reduction is cut
+ * into `splits` equal ranges of 128-pixel tiles (every slab is written; the caller sums
+ * them, so the result does not depend on scheduling).  Cin, Cout % 64 == 0. */
+int scda_conv3x3_wgrad_bf16_nhwc(int NB, int H, int W, int Cin, int Cout, const void *x, const void *dy,
+                                 float *dw_partials, int splits, cudaStream_t stream);
+
 /* --- optimiser -------------------------------------------------------- */
 /* replaces torch.optim.Adam(...).step() on each of the four networks
  * (tools/faster_rcnn_train_val.py:305-316 construct, :616,:635,:704,:750 step): one pass

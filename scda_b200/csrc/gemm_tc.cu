@@ -138,11 +138,26 @@ __device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t saddr)
     d |= (uint64_t)2 << 61;                  // SWIZZLE_128B
     return d;
 }
-// cute::UMMA::InstrDescriptor, kind::f16: D=F32 [4,6)=1, A=BF16 [7,10)=1, B=BF16 [10,13)=1,
-// both K-major, N>>3 at [17,23), M>>4 at [24,29)
-__host__ __device__ constexpr uint32_t make_idesc(int m, int n)
+// MN-major, 128B-swizzled operand: the tile is stored [k rows][64 mn] (128 B per k row, the
+// image a TMA box {64 mn, rows} leaves in shared memory); 8-k-row groups are 1024 B apart
+// (SBO) and successive 64-wide mn chunks are `chunk_bytes` apart (LBO).
+// Canonical form ((T,8,m),(8,k)):((1,T,LBO),(8T,SBO)), cute mma_traits_sm100.hpp.
+__device__ __forceinline__ uint64_t make_mnmajor_desc(uint32_t saddr, uint32_t chunk_bytes)
 {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)((chunk_bytes >> 4) & 0x3FFF) << 16;   // LBO
+    d |= (uint64_t)(1024 >> 4) << 32;                     // SBO
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// cute::UMMA::InstrDescriptor, kind::f16: D=F32 [4,6)=1, A=BF16 [7,10)=1, B=BF16 [10,13)=1,
+// A major [15], B major [16] (0 = K, 1 = MN), N>>3 at [17,23), M>>4 at [24,29)
+__host__ __device__ constexpr uint32_t make_idesc(int m, int n, int a_mn = 0, int b_mn = 0)
+{
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
+           ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
 template <int kBlockN, int kStages>
@@ -155,7 +170,7 @@ struct SmemLayout {
     static constexpr int kTotal = kTileBytes + (2 * kStages + 1) * 8 + 16 + 1024;  // + tmem ptr + align slack
 };
 
-template <int kBlockN, int kStages>
+template <int kBlockN, int kStages, bool kBMn>
 __global__ void __launch_bounds__(kThreads, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const TcParams p)
@@ -225,13 +240,21 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     tma_load_2d(b_dst, &map_b, bar_full + s * 8, tap * p.Cin + cb * kBlockK, n0);
                 } else {
                     tma_load_2d(a_dst, &map_a, bar_full + s * 8, kb * kBlockK, m_tile * kBlockM);
-                    tma_load_2d(b_dst, &map_b, bar_full + s * 8, kb * kBlockK, n0);
+                    if (kBMn) {
+                        // B given as [K rows][N contiguous]: one {64 n, 64 k} box per 64-wide n chunk
+#pragma unroll
+                        for (int c = 0; c < kBlockN / 64; ++c)
+                            tma_load_2d(b_dst + c * (kBlockK * 128), &map_b, bar_full + s * 8, n0 + c * 64,
+                                        kb * kBlockK);
+                    } else {
+                        tma_load_2d(b_dst, &map_b, bar_full + s * 8, kb * kBlockK, n0);
+                    }
                 }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc(kBlockM, kBlockN);
+            constexpr uint32_t idesc = make_idesc(kBlockM, kBlockN, 0, kBMn ? 1 : 0);
             for (int kb = 0; kb < p.num_k_blocks; ++kb) {
                 const int s = kb % kStages;
                 const uint32_t ph = (kb / kStages) & 1;
@@ -242,7 +265,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
                 for (int k = 0; k < kBlockK / kUmmaK; ++k) {
                     const uint64_t ad = make_kmajor_desc(a_src + k * kUmmaK * 2);
-                    const uint64_t bd = make_kmajor_desc(b_src + k * kUmmaK * 2);
+                    const uint64_t bd = kBMn ? make_mnmajor_desc(b_src + k * kUmmaK * 128, kBlockK * 128)
+                                             : make_kmajor_desc(b_src + k * kUmmaK * 2);
                     umma_bf16(tmem_base, ad, bd, idesc, (kb | k) != 0);
                 }
                 umma_commit(bar_empty + s * 8);   // frees the stage when these MMAs retire
@@ -370,30 +394,211 @@ bool make_map(CUtensorMap *map, const void *ptr, int rank, const cuuint64_t *dim
     return r == CUDA_SUCCESS;
 }
 
-template <int kBlockN, int kStages>
+template <int kBlockN, int kStages, bool kBMn>
 int launch_tc(const CUtensorMap &ma, const CUtensorMap &mb, const TcParams &p, int m_tiles, cudaStream_t stream)
 {
     using L = SmemLayout<kBlockN, kStages>;
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<kBlockN, kStages>,
+        cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<kBlockN, kStages, kBMn>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
         if (e != cudaSuccess) return -(int)e;
         attr_done = true;
     }
     dim3 grid(m_tiles, ceil_div(p.N, kBlockN));
-    tc_gemm_kernel<kBlockN, kStages><<<grid, kThreads, L::kTotal, stream>>>(ma, mb, p);
+    tc_gemm_kernel<kBlockN, kStages, kBMn><<<grid, kThreads, L::kTotal, stream>>>(ma, mb, p);
     return scda_launch_status();
 }
 
 int dispatch_tc(const CUtensorMap &ma, const CUtensorMap &mb, const TcParams &p, int m_tiles, int block_n,
-                cudaStream_t stream)
+                cudaStream_t stream, bool b_mn = false)
 {
-    if (block_n == 64) return launch_tc<64, 8>(ma, mb, p, m_tiles, stream);
-    return launch_tc<128, 6>(ma, mb, p, m_tiles, stream);
+    if (b_mn) {
+        if (block_n == 64) return launch_tc<64, 8, true>(ma, mb, p, m_tiles, stream);
+        return launch_tc<128, 6, true>(ma, mb, p, m_tiles, stream);
+    }
+    if (block_n == 64) return launch_tc<64, 8, false>(ma, mb, p, m_tiles, stream);
+    return launch_tc<128, 6, false>(ma, mb, p, m_tiles, stream);
 }
 
 int pick_block_n(int N) { return N <= 64 ? 64 : 128; }
+
+// ---------------------------------------------------------------------------------------
+// Weight-gradient kernel: C[Mo, No] (+)= sum_k A[k, Mo] B[k, No], both operands given with
+// the REDUCTION index as the row (slow) dimension, i.e. MN-major for the MMA:
+//   linear : dW[out, in]      = sum_rows  dY[row, out]      X[row, in]          (2-D boxes)
+//   conv   : dW[co, r, s, ci] = sum_pixel dY[pixel, co]     X[pixel + (r-1, s-1), ci]
+//            one (tap, co tile, ci tile, k split) per CTA; the shifted X window is one 4-D
+//            TMA box per 64-channel chunk, zero-filled outside the image.
+// k-block = 128 reduction rows (one 8x16 pixel tile) -> 8 MMAs of K = 16.
+// Partial sums of a k split go to their own fp32 slab (deterministic); the caller reduces.
+struct WgParams {
+    int Mo, No;                  // output tile space (Cout, Cin)
+    int conv;
+    int H, W, TH, TW, tiles_w, tiles_h;
+    int total_k_blocks, k_per_split;
+    float *out;                  // [splits][Mo][ldo]
+    long long ldo;               // row stride of the output (conv: 9*Cin)
+    long long split_stride;
+};
+
+template <int kBlockN, int kStages>
+struct WgSmem {
+    static constexpr int kChunk = 128 * 128;                 // [128 k rows][64 mn] bf16
+    static constexpr int kABytes = 2 * kChunk;               // Mo tile 128 = 2 chunks
+    static constexpr int kBBytes = (kBlockN / 64) * kChunk;
+    static constexpr int kStageBytes = kABytes + kBBytes;
+    static constexpr int kBarOffset = kStages * kStageBytes;
+    static constexpr int kTotal = kBarOffset + (2 * kStages + 1) * 8 + 16 + 1024;
+};
+
+template <int kBlockN, int kStages>
+__global__ void __launch_bounds__(kThreads, 1)
+tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                const WgParams p)
+{
+    using L = WgSmem<kBlockN, kStages>;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t *gen = smem_raw + (base - smem_u32(smem_raw));
+    const uint32_t bar_full = base + L::kBarOffset;
+    const uint32_t bar_empty = bar_full + kStages * 8;
+    const uint32_t bar_tmem = bar_empty + kStages * 8;
+    volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(gen + L::kBarOffset + (2 * kStages + 1) * 8);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.x * kBlockM;                 // Cout offset
+    const int n_tiles = (p.No + kBlockN - 1) / kBlockN;
+    const int tap = p.conv ? blockIdx.y / n_tiles : 0;
+    const int n0 = (blockIdx.y - tap * n_tiles) * kBlockN;   // Cin offset
+    const int split = blockIdx.z;
+    const int kb0 = split * p.k_per_split;
+    const int kb1 = min(kb0 + p.k_per_split, p.total_k_blocks);
+    const int r = tap / 3, sx = tap - r * 3;
+
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(bar_full + s * 8, 1);
+            mbar_init(bar_empty + s * 8, 1);
+        }
+        mbar_init(bar_tmem, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        const uint32_t ncols = kBlockN;
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                         smem_u32((const void *)tmem_slot)), "r"(ncols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int kb = kb0; kb < kb1; ++kb) {
+                const int it = kb - kb0, s = it % kStages;
+                const uint32_t ph = (it / kStages) & 1;
+                mbar_wait(bar_empty + s * 8, ph ^ 1);
+                const uint32_t a_dst = base + s * L::kStageBytes;
+                const uint32_t b_dst = a_dst + L::kABytes;
+                mbar_expect_tx(bar_full + s * 8, L::kStageBytes);
+                if (p.conv) {
+                    const int per_img = p.tiles_h * p.tiles_w;
+                    const int img = kb / per_img, t = kb - img * per_img;
+                    const int h0 = (t / p.tiles_w) * p.TH, w0 = (t % p.tiles_w) * p.TW;
+#pragma unroll
+                    for (int c = 0; c < 2; ++c)
+                        tma_load_4d(a_dst + c * L::kChunk, &map_a, bar_full + s * 8, m0 + c * 64, w0, h0, img);
+#pragma unroll
+                    for (int c = 0; c < kBlockN / 64; ++c)
+                        tma_load_4d(b_dst + c * L::kChunk, &map_b, bar_full + s * 8, n0 + c * 64, w0 + sx - 1,
+                                    h0 + r - 1, img);
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 2; ++c)
+                        tma_load_2d(a_dst + c * L::kChunk, &map_a, bar_full + s * 8, m0 + c * 64, kb * 128);
+#pragma unroll
+                    for (int c = 0; c < kBlockN / 64; ++c)
+                        tma_load_2d(b_dst + c * L::kChunk, &map_b, bar_full + s * 8, n0 + c * 64, kb * 128);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(kBlockM, kBlockN, 1, 1);
+            for (int kb = kb0; kb < kb1; ++kb) {
+                const int it = kb - kb0, s = it % kStages;
+                const uint32_t ph = (it / kStages) & 1;
+                mbar_wait(bar_full + s * 8, ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t a_src = base + s * L::kStageBytes;
+                const uint32_t b_src = a_src + L::kABytes;
+#pragma unroll
+                for (int k = 0; k < 128 / kUmmaK; ++k) {
+                    const uint64_t ad = make_mnmajor_desc(a_src + k * kUmmaK * 128, L::kChunk);
+                    const uint64_t bd = make_mnmajor_desc(b_src + k * kUmmaK * 128, L::kChunk);
+                    umma_bf16(tmem_base, ad, bd, idesc, (it | k) != 0);
+                }
+                umma_commit(bar_empty + s * 8);
+            }
+            umma_commit(bar_tmem);
+        }
+    } else if (warp >= 4) {
+        const int ew = warp - 4;
+        mbar_wait(bar_tmem, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int row = m0 + ew * 32 + lane;
+        float *dst_row = p.out + (long long)split * p.split_stride + (long long)row * p.ldo +
+                         (p.conv ? (long long)tap * p.No : 0);
+        const bool vec_ok = (p.ldo % 4 == 0) && (p.No % 4 == 0);
+#pragma unroll 1
+        for (int c0 = 0; c0 < kBlockN; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)c0, v);
+            if (row >= p.Mo) continue;
+            const int ncol = min(32, p.No - (n0 + c0));
+            if (ncol <= 0) continue;
+            float *dst = dst_row + n0 + c0;
+            if (ncol == 32 && vec_ok) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                    *reinterpret_cast<float4 *>(dst + j) =
+                        make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                                    __uint_as_float(v[j + 3]));
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (j < ncol) dst[j] = __uint_as_float(v[j]);
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 2) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t ncols = kBlockN;
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ncols) : "memory");
+    }
+}
+
+template <int kBlockN, int kStages>
+int launch_wg(const CUtensorMap &ma, const CUtensorMap &mb, const WgParams &p, int taps, int splits,
+              cudaStream_t stream)
+{
+    using L = WgSmem<kBlockN, kStages>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(tc_wgrad_kernel<kBlockN, kStages>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
+        if (e != cudaSuccess) return -(int)e;
+        attr_done = true;
+    }
+    dim3 grid(ceil_div(p.Mo, kBlockM), taps * ceil_div(p.No, kBlockN), splits);
+    tc_wgrad_kernel<kBlockN, kStages><<<grid, kThreads, L::kTotal, stream>>>(ma, mb, p);
+    return scda_launch_status();
+}
 
 }  // namespace
 
@@ -452,4 +657,82 @@ SCDA_API int scda_conv3x3_bf16_nhwc(int NB, int H, int W, int Cin, int Cout, con
     p.mask_src = (const __nv_bfloat16 *)mask_src;
     p.flags = flags;
     return dispatch_tc(ma, mb, p, NB * tiles_h * tiles_w, bn, stream);
+}
+
+SCDA_API int scda_gemm_bf16_nn(int M, int N, int K, const void *A, long long lda, const void *B, long long ldb,
+                               const float *bias, void *C, long long ldc, int flags, const void *mask_src,
+                               cudaStream_t stream)
+{
+    // C[M,N] = A[M,K] . B[K,N]   (B row-major with N contiguous: the MN-major operand form)
+    if (M <= 0 || N <= 0 || K <= 0 || !A || !B || !C) return 0;
+    if (lda % 8 || ldb % 8 || ((uintptr_t)A % 16) || ((uintptr_t)B % 16)) return 0;
+    if ((flags & kFlagMaskPos) && !mask_src) return 0;
+    if ((flags & kFlagAccumulate) && !(flags & kFlagOutF32)) return 0;
+    const int bn = pick_block_n(N);
+    CUtensorMap ma, mb;
+    cuuint64_t da[2] = {(cuuint64_t)K, (cuuint64_t)M}, sa[1] = {(cuuint64_t)lda * 2};
+    cuuint32_t ba[2] = {kBlockK, kBlockM};
+    cuuint64_t db[2] = {(cuuint64_t)N, (cuuint64_t)K}, sb[1] = {(cuuint64_t)ldb * 2};
+    cuuint32_t bb[2] = {64, kBlockK};
+    if (!make_map(&ma, A, 2, da, sa, ba) || !make_map(&mb, B, 2, db, sb, bb)) return 0;
+    TcParams p = {};
+    p.M = M; p.N = N; p.K = K;
+    p.num_k_blocks = ceil_div(K, kBlockK);
+    p.bias = bias; p.out = C; p.ldc = ldc;
+    p.mask_src = (const __nv_bfloat16 *)mask_src;
+    p.flags = flags;
+    return dispatch_tc(ma, mb, p, ceil_div(M, kBlockM), bn, stream, true);
+}
+
+SCDA_API int scda_linear_wgrad_bf16(int rows, int Nout, int Kin, const void *dY, long long lddy, const void *X,
+                                    long long ldx, float *dW, long long lddw, cudaStream_t stream)
+{
+    // dW[Nout, Kin] = dY[rows, Nout]^T . X[rows, Kin]
+    if (rows <= 0 || Nout <= 0 || Kin <= 0 || !dY || !X || !dW) return 0;
+    if (lddy % 8 || ldx % 8 || ((uintptr_t)dY % 16) || ((uintptr_t)X % 16)) return 0;
+    const int bn = pick_block_n(Kin);
+    CUtensorMap ma, mb;
+    cuuint64_t da[2] = {(cuuint64_t)Nout, (cuuint64_t)rows}, sa[1] = {(cuuint64_t)lddy * 2};
+    cuuint64_t db[2] = {(cuuint64_t)Kin, (cuuint64_t)rows}, sb[1] = {(cuuint64_t)ldx * 2};
+    cuuint32_t box[2] = {64, 128};
+    if (!make_map(&ma, dY, 2, da, sa, box) || !make_map(&mb, X, 2, db, sb, box)) return 0;
+    WgParams p = {};
+    p.Mo = Nout; p.No = Kin; p.conv = 0;
+    p.total_k_blocks = ceil_div(rows, 128);
+    p.k_per_split = p.total_k_blocks;
+    p.out = dW; p.ldo = lddw; p.split_stride = 0;
+    if (bn == 64) return launch_wg<64, 4>(ma, mb, p, 1, 1, stream);
+    return launch_wg<128, 3>(ma, mb, p, 1, 1, stream);
+}
+
+SCDA_API int scda_conv3x3_wgrad_bf16_nhwc(int NB, int H, int W, int Cin, int Cout, const void *x, const void *dy,
+                                          float *dw_partials, int splits, cudaStream_t stream)
+{
+    // dw_partials: [splits][Cout][3][3][Cin] fp32; the caller sums the slabs
+    if (NB <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0 || !x || !dy || !dw_partials || splits < 1) return 0;
+    if (Cin % 64 || Cout % 64) return 0;
+    int TW = 16, TH = 8;
+    if (W % 16) {
+        if (W % 8 == 0) { TW = 8; TH = 16; } else return 0;
+    }
+    if (H % TH) return 0;
+    const int tiles_w = W / TW, tiles_h = H / TH;
+    const int bn = pick_block_n(Cin);
+    CUtensorMap ma, mb;
+    cuuint64_t da[4] = {(cuuint64_t)Cout, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)NB};
+    cuuint64_t sa[3] = {(cuuint64_t)Cout * 2, (cuuint64_t)W * Cout * 2, (cuuint64_t)H * W * Cout * 2};
+    cuuint64_t db[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)NB};
+    cuuint64_t sb[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)W * Cin * 2, (cuuint64_t)H * W * Cin * 2};
+    cuuint32_t box[4] = {64, (cuuint32_t)TW, (cuuint32_t)TH, 1};
+    if (!make_map(&ma, dy, 4, da, sa, box) || !make_map(&mb, x, 4, db, sb, box)) return 0;
+    WgParams p = {};
+    p.Mo = Cout; p.No = Cin; p.conv = 1;
+    p.H = H; p.W = W; p.TH = TH; p.TW = TW; p.tiles_w = tiles_w; p.tiles_h = tiles_h;
+    p.total_k_blocks = NB * tiles_h * tiles_w;
+    if (splits > p.total_k_blocks) return 0;
+    p.k_per_split = ceil_div(p.total_k_blocks, splits);
+    if (ceil_div(p.total_k_blocks, p.k_per_split) != splits) return 0;   // every slab must be written
+    p.out = dw_partials; p.ldo = 9ll * Cin; p.split_stride = (long long)Cout * 9 * Cin;
+    if (bn == 64) return launch_wg<64, 4>(ma, mb, p, 9, splits, stream);
+    return launch_wg<128, 3>(ma, mb, p, 9, splits, stream);
 }

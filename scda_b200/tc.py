@@ -59,3 +59,62 @@ def conv3x3_nhwc(x, w_krsc, bias=None, relu=False, out_dtype=torch.bfloat16, mas
                                             flags, mask_src.data_ptr() if mask_src is not None else None,
                                             stream_ptr(x.device)), "scda_conv3x3_bf16_nhwc")
     return y
+
+
+def gemm_nn(a, b, bias=None, relu=False, out_dtype=torch.bfloat16, mask_src=None):
+    """out[M, N] = a[M, K] @ b[K, N] — b row-major with N contiguous (e.g. dX = dY @ W)."""
+    require_cuda(a, b)
+    assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16
+    assert a.dim() == 2 and b.dim() == 2 and a.shape[1] == b.shape[0]
+    assert a.stride(1) == 1 and b.stride(1) == 1
+    M, K = a.shape
+    N = b.shape[1]
+    out = torch.empty(M, N, dtype=out_dtype, device=a.device)
+    flags = (RELU if relu else 0) | (OUT_F32 if out_dtype == torch.float32 else 0) \
+        | (MASK_POS if mask_src is not None else 0)
+    if mask_src is not None:
+        assert mask_src.dtype == torch.bfloat16 and mask_src.shape == out.shape and mask_src.is_contiguous()
+    with torch.cuda.device(a.device):
+        check(load().scda_gemm_bf16_nn(M, N, K, a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0),
+                                       bias.data_ptr() if bias is not None else None, out.data_ptr(),
+                                       out.stride(0), flags,
+                                       mask_src.data_ptr() if mask_src is not None else None,
+                                       stream_ptr(a.device)), "scda_gemm_bf16_nn")
+    return out
+
+
+def linear_wgrad(dy, x, out=None):
+    """dW[Nout, Kin] fp32 = dy[rows, Nout]^T @ x[rows, Kin]."""
+    require_cuda(dy, x)
+    assert dy.dtype == torch.bfloat16 and x.dtype == torch.bfloat16
+    assert dy.shape[0] == x.shape[0] and dy.stride(1) == 1 and x.stride(1) == 1
+    rows, nout = dy.shape
+    kin = x.shape[1]
+    if out is None:
+        out = torch.empty(nout, kin, dtype=torch.float32, device=x.device)
+    assert out.dtype == torch.float32 and out.shape == (nout, kin) and out.stride(1) == 1
+    with torch.cuda.device(x.device):
+        check(load().scda_linear_wgrad_bf16(rows, nout, kin, dy.data_ptr(), dy.stride(0), x.data_ptr(),
+                                            x.stride(0), out.data_ptr(), out.stride(0),
+                                            stream_ptr(x.device)), "scda_linear_wgrad_bf16")
+    return out
+
+
+def conv3x3_wgrad_nhwc(x, dy, target_ctas=296):
+    """dW[Cout, 3, 3, Cin] fp32 from x[N,H,W,Cin], dy[N,H,W,Cout] (both bf16 NHWC)."""
+    require_cuda(x, dy)
+    assert x.dtype == torch.bfloat16 and dy.dtype == torch.bfloat16
+    assert x.is_contiguous() and dy.is_contiguous() and x.shape[:3] == dy.shape[:3]
+    NB, H, W, Cin = x.shape
+    Cout = dy.shape[3]
+    tiles = NB * H * W // 128
+    base = 9 * ((Cout + 127) // 128) * ((Cin + (63 if Cin <= 64 else 127)) // (64 if Cin <= 64 else 128))
+    splits = max(1, min(tiles, target_ctas // max(base, 1)))
+    per = -(-tiles // splits)
+    splits = -(-tiles // per)
+    part = torch.empty(splits, Cout, 3, 3, Cin, dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        check(load().scda_conv3x3_wgrad_bf16_nhwc(NB, H, W, Cin, Cout, x.data_ptr(), dy.data_ptr(),
+                                                  part.data_ptr(), splits, stream_ptr(x.device)),
+              "scda_conv3x3_wgrad_bf16_nhwc")
+    return part[0] if splits == 1 else part.sum(0)

@@ -94,3 +94,66 @@ def test_conv3x3_backbone_full_size(cuda_lib):
         ref = F.conv2d(patch, w.float().permute(0, 3, 1, 2), padding=1).permute(0, 2, 3, 1)
         ref = ref[:, hs.start - h0:hs.start - h0 + 24, ws.start - w0:ws.start - w0 + 40]
         _close(y1[:, hs, ws], ref, rtol=2e-3)
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (512, 25088, 4096), (512, 4096, 36), (300, 512, 72),
+                                   (512, 4096, 9)])
+def test_gemm_nn(cuda_lib, M, N, K):
+    """dX = dY @ W with W read as stored ([out, in], `in` contiguous)."""
+    import torch
+    from scda_b200 import tc
+    if K % 8:
+        pytest.skip("leading dimension must be a multiple of 8 elements")
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    a = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    b = (torch.randn(K, N, device="cuda", generator=g) / K ** 0.5).bfloat16()
+    _close(tc.gemm_nn(a, b), a.float() @ b.float())
+
+
+@pytest.mark.parametrize("rows,nout,kin", [(128, 128, 64), (512, 4096, 4096), (512, 4096, 25088),
+                                           (300, 256, 192), (512, 40, 4096)])
+def test_linear_wgrad(cuda_lib, rows, nout, kin):
+    import torch
+    from scda_b200 import tc
+    if nout % 8:
+        pytest.skip("leading dimension must be a multiple of 8 elements")
+    g = torch.Generator(device="cuda").manual_seed(rows + nout)
+    dy = (torch.randn(rows, nout, device="cuda", generator=g) / rows ** 0.5).bfloat16()
+    x = torch.randn(rows, kin, device="cuda", generator=g).bfloat16()
+    ref = dy.float().t() @ x.float()
+    _close(tc.linear_wgrad(dy, x), ref, rtol=2e-3)
+
+
+@pytest.mark.parametrize("NB,H,W,Cin,Cout", [(1, 8, 16, 64, 128), (1, 32, 64, 512, 512), (2, 32, 32, 128, 64),
+                                             (1, 64, 128, 64, 64), (1, 128, 256, 128, 256)])
+def test_conv3x3_wgrad(cuda_lib, NB, H, W, Cin, Cout):
+    import torch
+    from scda_b200 import tc
+    g = torch.Generator(device="cuda").manual_seed(H + W + Cin)
+    x = torch.randn(NB, H, W, Cin, device="cuda", generator=g).bfloat16()
+    dy = (torch.randn(NB, H, W, Cout, device="cuda", generator=g) / (H * W) ** 0.5).bfloat16()
+    torch.backends.cudnn.allow_tf32 = False
+    ref = torch.nn.grad.conv2d_weight(x.float().permute(0, 3, 1, 2), (Cout, Cin, 3, 3),
+                                      dy.float().permute(0, 3, 1, 2), padding=1).permute(0, 2, 3, 1)
+    _close(tc.conv3x3_wgrad_nhwc(x, dy), ref, rtol=3e-3)
+    _close(tc.conv3x3_wgrad_nhwc(x, dy, target_ctas=9), ref, rtol=3e-3)       # no split
+
+
+def test_conv3x3_dgrad_via_flipped_weights(cuda_lib):
+    """The data gradient is the same kernel on flipped / transposed weights, with the ReLU
+    gradient of the layer input fused (mask)."""
+    import torch
+    import torch.nn.functional as F
+    from scda_b200 import tc
+    g = torch.Generator(device="cuda").manual_seed(3)
+    NB, H, W, Cin, Cout = 1, 32, 64, 128, 256
+    x = torch.randn(NB, H, W, Cin, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(Cout, 3, 3, Cin, device="cuda", generator=g) / 34).bfloat16()
+    dy = torch.randn(NB, H, W, Cout, device="cuda", generator=g).bfloat16()
+    wd = w.flip(1, 2).permute(3, 1, 2, 0).contiguous()            # [Cin][3][3][Cout]
+    dx = tc.conv3x3_nhwc(dy, wd, mask_src=x)
+    torch.backends.cudnn.allow_tf32 = False
+    ref = torch.nn.grad.conv2d_input((NB, Cin, H, W), w.float().permute(0, 3, 1, 2),
+                                     dy.float().permute(0, 3, 1, 2), padding=1).permute(0, 2, 3, 1)
+    ref = torch.where(x.float() > 0, ref, torch.zeros_like(ref))
+    _close(dx, ref)
