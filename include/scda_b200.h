@@ -160,6 +160,7 @@ int scda_softmax_focal_loss_sum(const int N, const float *logits, const int *tar
 #define SCDA_TC_OUT_F32     2   /* output fp32 (default bf16)                            */
 #define SCDA_TC_MASK_POS    4   /* y = mask_src > 0 ? y : 0  (ReLU backward, bf16 mask)  */
 #define SCDA_TC_ACCUMULATE  8   /* y += old y (fp32 output only)                         */
+#define SCDA_TC_MUL_SRC     16  /* y *= mul_src (bf16, e.g. the dropout keep/scale tensor) */
 /* replaces the cuBLAS GEMM behind nn.Linear (fc6 / fc7 / fc_rcnn_cls / fc_rcnn_loc,
  * models/faster_rcnn/vgg_adver_expansion_cluster.py:46-60,73-80) and behind 1x1 convs
  * (models/head.py:15-18):  C[M,N] = A[M,K] . B[N,K]^T + bias[N].
@@ -167,7 +168,7 @@ int scda_softmax_focal_loss_sum(const int N, const float *logits, const int *tar
  * aligned bases); C bf16 or fp32 with leading dimension ldc; bias fp32 or NULL. */
 int scda_gemm_bf16_tn(int M, int N, int K, const void *A, long long lda, const void *B, long long ldb,
                       const float *bias, void *C, long long ldc, int flags, const void *mask_src,
-                      cudaStream_t stream);
+                      const void *mul_src, cudaStream_t stream);
 /* replaces the cuDNN convolution behind nn.Conv2d(k=3, s=1, p=1) (VGG backbone,
  * vgg_adver_expansion_cluster.py:101-114; RPN conv3x3, models/head.py:13):
  * x NHWC bf16 [NB,H,W,Cin], w bf16 [Cout][3][3][Cin], y NHWC [NB,H,W,Cout] bf16 or fp32.
@@ -178,21 +179,49 @@ int scda_conv3x3_bf16_nhwc(int NB, int H, int W, int Cin, int Cout, const void *
                            const float *bias, void *y, int flags, const void *mask_src,
                            cudaStream_t stream);
 
+/* data gradient of that convolution read straight from the FORWARD weights (no flipped /
+ * transposed copy is kept): dy NHWC bf16 [NB,H,W,Cout], w bf16 [Cout][3][3][Cin] ->
+ * dx NHWC [NB,H,W,Cin] (bf16, or fp32 with SCDA_TC_OUT_F32).  The weights enter the MMA as an
+ * MN-major operand with the tap mirrored.  SCDA_TC_MASK_POS applies the ReLU gradient of the
+ * layer input (mask_src = that input).  Cin, Cout % 64 == 0, W % 8 == 0. */
+int scda_conv3x3_dgrad_bf16_nhwc(int NB, int H, int W, int Cin, int Cout, const void *dy,
+                                 const void *w_krsc, void *dx, int flags, const void *mask_src,
+                                 cudaStream_t stream);
+
 /* C[M,N] = A[M,K] . B[K,N] + bias: B row-major with N contiguous (the data gradient of
  * nn.Linear, dX = dY . W, reads W[out,in] this way; no transposed weight copy is kept). */
 int scda_gemm_bf16_nn(int M, int N, int K, const void *A, long long lda, const void *B, long long ldb,
                       const float *bias, void *C, long long ldc, int flags, const void *mask_src,
-                      cudaStream_t stream);
+                      const void *mul_src, cudaStream_t stream);
 /* weight gradient of nn.Linear: dW[Nout,Kin] (fp32, leading dimension lddw) =
  * dY[rows,Nout]^T . X[rows,Kin], both bf16 row-major. */
 int scda_linear_wgrad_bf16(int rows, int Nout, int Kin, const void *dY, long long lddy, const void *X,
-                           long long ldx, float *dW, long long lddw, cudaStream_t stream);
+                           long long ldx, float *dW, long long lddw, int accumulate,
+                           cudaStream_t stream);
 /* weight gradient of the 3x3 convolution: x NHWC bf16 [NB,H,W,Cin], dy NHWC bf16
  * [NB,H,W,Cout] -> dw_partials fp32 [splits][Cout][3][3][Cin]; the pixel reduction is cut
  * into `splits` equal ranges of 128-pixel tiles (every slab is written; the caller sums
  * them, so the result does not depend on scheduling).  Cin, Cout % 64 == 0. */
 int scda_conv3x3_wgrad_bf16_nhwc(int NB, int H, int W, int Cin, int Cout, const void *x, const void *dy,
                                  float *dw_partials, int splits, cudaStream_t stream);
+
+/* --- bf16 NHWC companions of the tensor-core kernels (HBM bound) --------- */
+/* nn.MaxPool2d(2, 2) of the VGG stack (vgg_adver_expansion_cluster.py:105-106) on NHWC bf16 */
+int scda_maxpool2x2_nhwc_bf16(int NB, int H, int W, int C, const void *x, void *y, cudaStream_t stream);
+/* its backward (gradient to the first maximum of each window, PyTorch's tie rule); with
+ * relu_mask != 0 also the backward of the nn.ReLU below it (x = that ReLU's output) */
+int scda_maxpool2x2_bwd_nhwc_bf16(int NB, int H, int W, int C, const void *x, const void *dy, void *dx,
+                                  int relu_mask, cudaStream_t stream);
+/* image NCHW fp32 -> NHWC bf16 with the channel dimension zero-padded to Cpad */
+int scda_nchw_f32_to_nhwc_bf16(int NB, int C, int H, int W, int Cpad, const float *x, void *y,
+                               cudaStream_t stream);
+/* feature map NHWC bf16 -> NCHW fp32 (the layout of the reference's RoI operators) */
+int scda_nhwc_bf16_to_nchw_f32(int NB, int C, int H, int W, const void *x, float *y, cudaStream_t stream);
+/* dst[n] (+)= sum of n_slabs fp32 slabs (split-K partial weight gradients) */
+int scda_reduce_slabs_f32(const float *slabs, long long slab_stride, int n_slabs, float *dst,
+                          long long n, int accumulate, cudaStream_t stream);
+/* bias gradient: out[N] += column sums of x[M, ld] (bf16) */
+int scda_colsum_bf16(long long M, int N, const void *x, long long ld, float *out, cudaStream_t stream);
 
 /* --- optimiser -------------------------------------------------------- */
 /* replaces torch.optim.Adam(...).step() on each of the four networks

@@ -37,10 +37,17 @@ SIGNATURES = {
     "scda_bbox_overlaps": (_i, [_i, _p, _i, _p, _p, _p]),
     "scda_sigmoid_focal_loss_sum": (_i, [_i, _p, _p, _f, _f, _f, _i, _p, _p, _p]),
     "scda_softmax_focal_loss_sum": (_i, [_i, _p, _p, _f, _f, _f, _i, _p, _p, _p, _p]),
-    "scda_gemm_bf16_tn": (_i, [_i, _i, _i, _p, C.c_longlong, _p, C.c_longlong, _p, _p, C.c_longlong, _i, _p, _p]),
+    "scda_gemm_bf16_tn": (_i, [_i, _i, _i, _p, C.c_longlong, _p, C.c_longlong, _p, _p, C.c_longlong, _i, _p, _p, _p]),
+    "scda_conv3x3_dgrad_bf16_nhwc": (_i, [_i, _i, _i, _i, _i, _p, _p, _p, _i, _p, _p]),
+    "scda_maxpool2x2_nhwc_bf16": (_i, [_i, _i, _i, _i, _p, _p, _p]),
+    "scda_maxpool2x2_bwd_nhwc_bf16": (_i, [_i, _i, _i, _i, _p, _p, _p, _i, _p]),
+    "scda_nchw_f32_to_nhwc_bf16": (_i, [_i, _i, _i, _i, _i, _p, _p, _p]),
+    "scda_nhwc_bf16_to_nchw_f32": (_i, [_i, _i, _i, _i, _p, _p, _p]),
+    "scda_reduce_slabs_f32": (_i, [_p, C.c_longlong, _i, _p, C.c_longlong, _i, _p]),
+    "scda_colsum_bf16": (_i, [C.c_longlong, _i, _p, C.c_longlong, _p, _p]),
     "scda_conv3x3_bf16_nhwc": (_i, [_i, _i, _i, _i, _i, _p, _p, _p, _p, _i, _p, _p]),
-    "scda_gemm_bf16_nn": (_i, [_i, _i, _i, _p, C.c_longlong, _p, C.c_longlong, _p, _p, C.c_longlong, _i, _p, _p]),
-    "scda_linear_wgrad_bf16": (_i, [_i, _i, _i, _p, C.c_longlong, _p, C.c_longlong, _p, C.c_longlong, _p]),
+    "scda_gemm_bf16_nn": (_i, [_i, _i, _i, _p, C.c_longlong, _p, C.c_longlong, _p, _p, C.c_longlong, _i, _p, _p, _p]),
+    "scda_linear_wgrad_bf16": (_i, [_i, _i, _i, _p, C.c_longlong, _p, C.c_longlong, _p, C.c_longlong, _i, _p]),
     "scda_conv3x3_wgrad_bf16_nhwc": (_i, [_i, _i, _i, _i, _i, _p, _p, _p, _i, _p]),
     "scda_adam_step": (_i, [_p, _p, _p, _p, _p, C.c_longlong, _i, _f, _f, _f, _f, _f, _f, _p]),
 }

@@ -279,4 +279,4 @@ SCDA_API int SoftmaxFocalLossBackwardLaucher(const int N, const float *logits, c
     return scda_launch_status();
 }
 
-SCDA_API int scda_abi_version(void) { return 1; }
+SCDA_API int scda_abi_version(void) { return 2; }

@@ -39,6 +39,7 @@ enum : int {
     kFlagOutF32 = 2,      // write fp32 instead of bf16
     kFlagMaskPos = 4,     // y = (mask_src > 0) ? y : 0     (ReLU backward fused into dgrad)
     kFlagAccumulate = 8,  // y += previous contents (fp32 output only)
+    kFlagMulSrc = 16,     // y *= mul_src            (dropout keep/scale tensor, bf16)
 };
 
 struct TcParams {
@@ -51,6 +52,7 @@ struct TcParams {
     void *out;                   // [M, ldc]
     long long ldc;
     const __nv_bfloat16 *mask_src;   // [M, ldc] (kFlagMaskPos)
+    const __nv_bfloat16 *mul_src;    // [M, ldc] (kFlagMulSrc)
     int flags;
 };
 
@@ -66,6 +68,10 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 {
@@ -166,14 +172,40 @@ struct SmemLayout {
     static constexpr int kBBytes = kBlockN * kBlockK * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
     static constexpr int kTileBytes = kStages * kStageBytes;
-    static constexpr int kBarOffset = kTileBytes;           // full[kStages], empty[kStages], tmem_full
-    static constexpr int kTotal = kTileBytes + (2 * kStages + 1) * 8 + 16 + 1024;  // + tmem ptr + align slack
+    static constexpr int kBarOffset = kTileBytes;           // full[kStages], empty[kStages], tmem_full[2], tmem_empty[2]
+    static constexpr int kNumBars = 2 * kStages + 4;
+    static constexpr int kTotal = kTileBytes + kNumBars * 8 + 16 + 1024;  // + tmem ptr + align slack
 };
 
+struct TileCoord {
+    int m_tile, n0;
+    int img, h0, w0;
+};
+
+__device__ __forceinline__ TileCoord tile_coord(const TcParams &p, int tile, int n_tiles, int block_n)
+{
+    TileCoord t;
+    t.m_tile = tile / n_tiles;
+    t.n0 = (tile - t.m_tile * n_tiles) * block_n;
+    t.img = 0; t.h0 = 0; t.w0 = 0;
+    if (p.conv) {
+        const int per_img = p.tiles_h * p.tiles_w;
+        t.img = t.m_tile / per_img;
+        const int r = t.m_tile - t.img * per_img;
+        t.h0 = (r / p.tiles_w) * p.TH;
+        t.w0 = (r % p.tiles_w) * p.TW;
+    }
+    return t;
+}
+
+// Persistent kernel: grid = min(#tiles, #SMs); every CTA walks tiles blockIdx.x, +gridDim.x, ...
+// (n tile fastest, so CTAs running side by side share the A tile in L2).  The accumulator is
+// double-buffered in TMEM (2 x kBlockN columns): the epilogue warps drain tile i while the MMA
+// warp is already accumulating tile i+1 and the TMA warp is loading ahead of both.
 template <int kBlockN, int kStages, bool kBMn>
 __global__ void __launch_bounds__(kThreads, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-               const TcParams p)
+               const TcParams p, const int m_tiles, const int n_tiles)
 {
     using L = SmemLayout<kBlockN, kStages>;
     extern __shared__ uint8_t smem_raw[];
@@ -181,22 +213,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     uint8_t *gen = smem_raw + (base - smem_u32(smem_raw));
     const uint32_t bar_full = base + L::kBarOffset;
     const uint32_t bar_empty = bar_full + kStages * 8;
-    const uint32_t bar_tmem = bar_empty + kStages * 8;
-    volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(gen + L::kBarOffset + (2 * kStages + 1) * 8);
+    const uint32_t bar_tfull = bar_empty + kStages * 8;     // [2] accumulator ready
+    const uint32_t bar_tempty = bar_tfull + 2 * 8;          // [2] accumulator drained
+    volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(gen + L::kBarOffset + L::kNumBars * 8);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m_tile = blockIdx.x, n_tile = blockIdx.y;
-    const int n0 = n_tile * kBlockN;
-
-    // CONV: decompose the m tile into (image, tile row, tile col)
-    int img = 0, h0 = 0, w0 = 0;
-    if (p.conv) {
-        const int per_img = p.tiles_h * p.tiles_w;
-        img = m_tile / per_img;
-        const int t = m_tile - img * per_img;
-        h0 = (t / p.tiles_w) * p.TH;
-        w0 = (t % p.tiles_w) * p.TW;
-    }
+    const int total_tiles = m_tiles * n_tiles;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
@@ -207,11 +229,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             mbar_init(bar_full + s * 8, 1);
             mbar_init(bar_empty + s * 8, 1);
         }
-        mbar_init(bar_tmem, 1);
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(bar_tfull + a * 8, 1);
+            mbar_init(bar_tempty + a * 8, 4);    // one arrival per epilogue warp
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
-        const uint32_t ncols = kBlockN;
+        const uint32_t ncols = 2 * kBlockN;
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
                          smem_u32((const void *)tmem_slot)),
                      "r"(ncols)
@@ -226,28 +251,43 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     if (warp == 0) {
         if (lane == 0) {
             const int cblocks = p.conv ? p.Cin / kBlockK : 0;
-            for (int kb = 0; kb < p.num_k_blocks; ++kb) {
-                const int s = kb % kStages;
-                const uint32_t ph = (kb / kStages) & 1;
-                mbar_wait(bar_empty + s * 8, ph ^ 1);
-                const uint32_t a_dst = base + s * L::kStageBytes;
-                const uint32_t b_dst = a_dst + L::kABytes;
-                mbar_expect_tx(bar_full + s * 8, L::kStageBytes);
-                if (p.conv) {
-                    const int tap = kb / cblocks, cb = kb - tap * cblocks;
-                    const int r = tap / 3, sx = tap - r * 3;
-                    tma_load_4d(a_dst, &map_a, bar_full + s * 8, cb * kBlockK, w0 + sx - 1, h0 + r - 1, img);
-                    tma_load_2d(b_dst, &map_b, bar_full + s * 8, tap * p.Cin + cb * kBlockK, n0);
-                } else {
-                    tma_load_2d(a_dst, &map_a, bar_full + s * 8, kb * kBlockK, m_tile * kBlockM);
-                    if (kBMn) {
-                        // B given as [K rows][N contiguous]: one {64 n, 64 k} box per 64-wide n chunk
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const TileCoord t = tile_coord(p, tile, n_tiles, kBlockN);
+                for (int kb = 0; kb < p.num_k_blocks; ++kb, ++it) {
+                    const int s = it % kStages;
+                    const uint32_t ph = (it / kStages) & 1;
+                    mbar_wait(bar_empty + s * 8, ph ^ 1);
+                    const uint32_t a_dst = base + s * L::kStageBytes;
+                    const uint32_t b_dst = a_dst + L::kABytes;
+                    mbar_expect_tx(bar_full + s * 8, L::kStageBytes);
+                    if (p.conv) {
+                        const int tap = kb / cblocks, cb = kb - tap * cblocks;
+                        const int r = tap / 3, sx = tap - r * 3;
+                        tma_load_4d(a_dst, &map_a, bar_full + s * 8, cb * kBlockK, t.w0 + sx - 1, t.h0 + r - 1,
+                                    t.img);
+                        if (kBMn) {
+                            // data gradient straight from the forward weights W[co][tap][ci] seen as
+                            // [co rows][9*N cols]: reduction index = co (rows), output channel = ci
+                            // (contiguous), tap mirrored (r, s) -> (2 - r, 2 - s)
 #pragma unroll
-                        for (int c = 0; c < kBlockN / 64; ++c)
-                            tma_load_2d(b_dst + c * (kBlockK * 128), &map_b, bar_full + s * 8, n0 + c * 64,
-                                        kb * kBlockK);
+                            for (int c = 0; c < kBlockN / 64; ++c)
+                                tma_load_2d(b_dst + c * (kBlockK * 128), &map_b, bar_full + s * 8,
+                                            (8 - tap) * p.N + t.n0 + c * 64, cb * kBlockK);
+                        } else {
+                            tma_load_2d(b_dst, &map_b, bar_full + s * 8, tap * p.Cin + cb * kBlockK, t.n0);
+                        }
                     } else {
-                        tma_load_2d(b_dst, &map_b, bar_full + s * 8, kb * kBlockK, n0);
+                        tma_load_2d(a_dst, &map_a, bar_full + s * 8, kb * kBlockK, t.m_tile * kBlockM);
+                        if (kBMn) {
+                            // B given as [K rows][N contiguous]: one {64 n, 64 k} box per 64-wide n chunk
+#pragma unroll
+                            for (int c = 0; c < kBlockN / 64; ++c)
+                                tma_load_2d(b_dst + c * (kBlockK * 128), &map_b, bar_full + s * 8,
+                                            t.n0 + c * 64, kb * kBlockK);
+                        } else {
+                            tma_load_2d(b_dst, &map_b, bar_full + s * 8, kb * kBlockK, t.n0);
+                        }
                     }
                 }
             }
@@ -255,99 +295,146 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     } else if (warp == 1) {
         if (lane == 0) {
             constexpr uint32_t idesc = make_idesc(kBlockM, kBlockN, 0, kBMn ? 1 : 0);
-            for (int kb = 0; kb < p.num_k_blocks; ++kb) {
-                const int s = kb % kStages;
-                const uint32_t ph = (kb / kStages) & 1;
-                mbar_wait(bar_full + s * 8, ph);
+            uint32_t it = 0, ti = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
+                const uint32_t acc = ti & 1, acc_ph = (ti >> 1) & 1;
+                mbar_wait(bar_tempty + acc * 8, acc_ph ^ 1);     // epilogue has drained this buffer
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t a_src = base + s * L::kStageBytes;
-                const uint32_t b_src = a_src + L::kABytes;
+                const uint32_t tmem_d = tmem_base + acc * kBlockN;
+                for (int kb = 0; kb < p.num_k_blocks; ++kb, ++it) {
+                    const int s = it % kStages;
+                    const uint32_t ph = (it / kStages) & 1;
+                    mbar_wait(bar_full + s * 8, ph);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t a_src = base + s * L::kStageBytes;
+                    const uint32_t b_src = a_src + L::kABytes;
 #pragma unroll
-                for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-                    const uint64_t ad = make_kmajor_desc(a_src + k * kUmmaK * 2);
-                    const uint64_t bd = kBMn ? make_mnmajor_desc(b_src + k * kUmmaK * 128, kBlockK * 128)
-                                             : make_kmajor_desc(b_src + k * kUmmaK * 2);
-                    umma_bf16(tmem_base, ad, bd, idesc, (kb | k) != 0);
+                    for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+                        const uint64_t ad = make_kmajor_desc(a_src + k * kUmmaK * 2);
+                        const uint64_t bd = kBMn ? make_mnmajor_desc(b_src + k * kUmmaK * 128, kBlockK * 128)
+                                                 : make_kmajor_desc(b_src + k * kUmmaK * 2);
+                        umma_bf16(tmem_d, ad, bd, idesc, (kb | k) != 0);
+                    }
+                    umma_commit(bar_empty + s * 8);   // frees the stage when these MMAs retire
                 }
-                umma_commit(bar_empty + s * 8);   // frees the stage when these MMAs retire
+                umma_commit(bar_tfull + acc * 8);     // accumulator complete
             }
-            umma_commit(bar_tmem);                // accumulator complete
         }
     } else if (warp >= 4) {
         const int ew = warp - 4;                  // TMEM lane quarter this warp may read
-        mbar_wait(bar_tmem, 0);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const int row = ew * 32 + lane;           // accumulator row = TMEM lane
-        long long out_row;
-        bool row_ok;
-        if (p.conv) {
-            const int th = row / p.TW, tw = row - th * p.TW;
-            const int h = h0 + th, w = w0 + tw;
-            row_ok = h < p.H && w < p.W;
-            out_row = ((long long)img * p.H + h) * p.W + w;
-        } else {
-            out_row = (long long)m_tile * kBlockM + row;
-            row_ok = out_row < p.M;
-        }
         const bool f32 = p.flags & kFlagOutF32;
-        const bool vec_ok = (p.ldc % 8 == 0) && (n0 % 8 == 0);
-#pragma unroll 1
-        for (int c0 = 0; c0 < kBlockN; c0 += 32) {
-            uint32_t v[32];
-            tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)c0, v);
-            if (!row_ok) continue;
-            const int ncol = min(32, p.N - (n0 + c0));
-            if (ncol <= 0) continue;
-            float f[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                float x = __uint_as_float(v[j]);
-                if (p.bias && j < ncol) x += __ldg(p.bias + n0 + c0 + j);
-                if (p.flags & kFlagRelu) x = fmaxf(x, 0.f);
-                f[j] = x;
-            }
-            const long long o = out_row * p.ldc + n0 + c0;
-            if (p.flags & kFlagMaskPos) {
-                const __nv_bfloat16 *ms = p.mask_src + o;
-#pragma unroll
-                for (int j = 0; j < 32; ++j)
-                    if (j < ncol && !(__bfloat162float(ms[j]) > 0.f)) f[j] = 0.f;
-            }
-            if (f32) {
-                float *dst = reinterpret_cast<float *>(p.out) + o;
-                if (p.flags & kFlagAccumulate) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (j < ncol) dst[j] += f[j];
-                } else if (ncol == 32 && vec_ok) {
-#pragma unroll
-                    for (int j = 0; j < 32; j += 4)
-                        *reinterpret_cast<float4 *>(dst + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (j < ncol) dst[j] = f[j];
-                }
+        uint32_t ti = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
+            const TileCoord t = tile_coord(p, tile, n_tiles, kBlockN);
+            const uint32_t acc = ti & 1, acc_ph = (ti >> 1) & 1;
+            const int n0 = t.n0;
+            mbar_wait(bar_tfull + acc * 8, acc_ph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const int row = ew * 32 + lane;           // accumulator row = TMEM lane
+            long long out_row;
+            bool row_ok;
+            if (p.conv) {
+                const int th = row / p.TW, tw = row - th * p.TW;
+                const int h = t.h0 + th, w = t.w0 + tw;
+                row_ok = h < p.H && w < p.W;
+                out_row = ((long long)t.img * p.H + h) * p.W + w;
             } else {
-                __nv_bfloat16 *dst = reinterpret_cast<__nv_bfloat16 *>(p.out) + o;
-                if (ncol == 32 && vec_ok) {
+                out_row = (long long)t.m_tile * kBlockM + row;
+                row_ok = out_row < p.M;
+            }
+            const bool vec_ok = (p.ldc % 8 == 0) && (n0 % 8 == 0);
+#pragma unroll 1
+            for (int c0 = 0; c0 < kBlockN; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * kBlockN + c0), v);
+                if (c0 + 32 >= kBlockN) {
+                    // the whole accumulator of this warp's lanes is in registers: hand the buffer back
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_tempty + acc * 8);
+                }
+                if (!row_ok) continue;
+                const int ncol = min(32, p.N - (n0 + c0));
+                if (ncol <= 0) continue;
+                const bool full = ncol == 32 && vec_ok;
+                float f[32];
 #pragma unroll
-                    for (int j = 0; j < 32; j += 8) {
-                        uint4 pk;
-                        __nv_bfloat162 b0 = __floats2bfloat162_rn(f[j], f[j + 1]);
-                        __nv_bfloat162 b1 = __floats2bfloat162_rn(f[j + 2], f[j + 3]);
-                        __nv_bfloat162 b2 = __floats2bfloat162_rn(f[j + 4], f[j + 5]);
-                        __nv_bfloat162 b3 = __floats2bfloat162_rn(f[j + 6], f[j + 7]);
-                        pk.x = *reinterpret_cast<uint32_t *>(&b0);
-                        pk.y = *reinterpret_cast<uint32_t *>(&b1);
-                        pk.z = *reinterpret_cast<uint32_t *>(&b2);
-                        pk.w = *reinterpret_cast<uint32_t *>(&b3);
-                        *reinterpret_cast<uint4 *>(dst + j) = pk;
+                for (int j = 0; j < 32; ++j) {
+                    float x = __uint_as_float(v[j]);
+                    if (p.bias && j < ncol) x += __ldg(p.bias + n0 + c0 + j);
+                    if (p.flags & kFlagRelu) x = fmaxf(x, 0.f);
+                    f[j] = x;
+                }
+                const long long o = out_row * p.ldc + n0 + c0;
+                if (p.flags & kFlagMaskPos) {
+                    const __nv_bfloat16 *ms = p.mask_src + o;
+                    if (full) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 8) {
+                            const uint4 q = __ldg(reinterpret_cast<const uint4 *>(ms + j));
+                            const __nv_bfloat16 *qb = reinterpret_cast<const __nv_bfloat16 *>(&q);
+#pragma unroll
+                            for (int e = 0; e < 8; ++e)
+                                if (!(__bfloat162float(qb[e]) > 0.f)) f[j + e] = 0.f;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (j < ncol && !(__bfloat162float(ms[j]) > 0.f)) f[j] = 0.f;
+                    }
+                }
+                if (p.flags & kFlagMulSrc) {
+                    const __nv_bfloat16 *ms = p.mul_src + o;
+                    if (full) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 8) {
+                            const uint4 q = __ldg(reinterpret_cast<const uint4 *>(ms + j));
+                            const __nv_bfloat16 *qb = reinterpret_cast<const __nv_bfloat16 *>(&q);
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) f[j + e] *= __bfloat162float(qb[e]);
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (j < ncol) f[j] *= __bfloat162float(ms[j]);
+                    }
+                }
+                if (f32) {
+                    float *dst = reinterpret_cast<float *>(p.out) + o;
+                    if (p.flags & kFlagAccumulate) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (j < ncol) dst[j] += f[j];
+                    } else if (full) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4)
+                            *reinterpret_cast<float4 *>(dst + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (j < ncol) dst[j] = f[j];
                     }
                 } else {
+                    __nv_bfloat16 *dst = reinterpret_cast<__nv_bfloat16 *>(p.out) + o;
+                    if (full) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (j < ncol) dst[j] = __float2bfloat16_rn(f[j]);
+                        for (int j = 0; j < 32; j += 8) {
+                            uint4 pk;
+                            __nv_bfloat162 b0 = __floats2bfloat162_rn(f[j], f[j + 1]);
+                            __nv_bfloat162 b1 = __floats2bfloat162_rn(f[j + 2], f[j + 3]);
+                            __nv_bfloat162 b2 = __floats2bfloat162_rn(f[j + 4], f[j + 5]);
+                            __nv_bfloat162 b3 = __floats2bfloat162_rn(f[j + 6], f[j + 7]);
+                            pk.x = *reinterpret_cast<uint32_t *>(&b0);
+                            pk.y = *reinterpret_cast<uint32_t *>(&b1);
+                            pk.z = *reinterpret_cast<uint32_t *>(&b2);
+                            pk.w = *reinterpret_cast<uint32_t *>(&b3);
+                            *reinterpret_cast<uint4 *>(dst + j) = pk;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (j < ncol) dst[j] = __float2bfloat16_rn(f[j]);
+                    }
                 }
             }
         }
@@ -356,7 +443,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     __syncthreads();
     if (warp == 2) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t ncols = kBlockN;
+        const uint32_t ncols = 2 * kBlockN;
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ncols)
                      : "memory");
     }
@@ -379,6 +466,18 @@ EncodeTiledFn encode_fn()
             fn = (EncodeTiledFn)ptr;
     }
     return fn;
+}
+
+int num_sms()
+{
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess ||
+            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+            n = kNumSMs;
+    }
+    return n;
 }
 
 // bf16 tensor, dims/strides innermost first; box innermost = 64 elements (128 B), 128B swizzle
@@ -405,8 +504,10 @@ int launch_tc(const CUtensorMap &ma, const CUtensorMap &mb, const TcParams &p, i
         if (e != cudaSuccess) return -(int)e;
         attr_done = true;
     }
-    dim3 grid(m_tiles, ceil_div(p.N, kBlockN));
-    tc_gemm_kernel<kBlockN, kStages, kBMn><<<grid, kThreads, L::kTotal, stream>>>(ma, mb, p);
+    const int n_tiles = ceil_div(p.N, kBlockN);
+    const long long total = (long long)m_tiles * n_tiles;
+    const int grid = (int)(total < num_sms() ? total : num_sms());
+    tc_gemm_kernel<kBlockN, kStages, kBMn><<<grid, kThreads, L::kTotal, stream>>>(ma, mb, p, m_tiles, n_tiles);
     return scda_launch_status();
 }
 
@@ -415,13 +516,22 @@ int dispatch_tc(const CUtensorMap &ma, const CUtensorMap &mb, const TcParams &p,
 {
     if (b_mn) {
         if (block_n == 64) return launch_tc<64, 8, true>(ma, mb, p, m_tiles, stream);
-        return launch_tc<128, 6, true>(ma, mb, p, m_tiles, stream);
+        if (block_n == 128) return launch_tc<128, 6, true>(ma, mb, p, m_tiles, stream);
+        return launch_tc<256, 4, true>(ma, mb, p, m_tiles, stream);
     }
     if (block_n == 64) return launch_tc<64, 8, false>(ma, mb, p, m_tiles, stream);
-    return launch_tc<128, 6, false>(ma, mb, p, m_tiles, stream);
+    if (block_n == 128) return launch_tc<128, 6, false>(ma, mb, p, m_tiles, stream);
+    return launch_tc<256, 4, false>(ma, mb, p, m_tiles, stream);
 }
 
-int pick_block_n(int N) { return N <= 64 ? 64 : 128; }
+// N tile: 64 for narrow outputs; 256 when that still leaves every SM a tile (fewer bytes
+// staged per flop), else 128.
+int pick_block_n(int N, long long m_tiles = 1 << 30)
+{
+    if (N <= 64) return 64;
+    if (N % 256 == 0 && m_tiles * (N / 256) >= num_sms()) return 256;
+    return 128;
+}
 
 // ---------------------------------------------------------------------------------------
 // Weight-gradient kernel: C[Mo, No] (+)= sum_k A[k, Mo] B[k, No], both operands given with
@@ -440,6 +550,7 @@ struct WgParams {
     float *out;                  // [splits][Mo][ldo]
     long long ldo;               // row stride of the output (conv: 9*Cin)
     long long split_stride;
+    int accumulate;              // dst += (linear form only)
 };
 
 template <int kBlockN, int kStages>
@@ -561,7 +672,11 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             const int ncol = min(32, p.No - (n0 + c0));
             if (ncol <= 0) continue;
             float *dst = dst_row + n0 + c0;
-            if (ncol == 32 && vec_ok) {
+            if (p.accumulate) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (j < ncol) dst[j] += __uint_as_float(v[j]);
+            } else if (ncol == 32 && vec_ok) {
 #pragma unroll
                 for (int j = 0; j < 32; j += 4)
                     *reinterpret_cast<float4 *>(dst + j) =
@@ -604,13 +719,14 @@ int launch_wg(const CUtensorMap &ma, const CUtensorMap &mb, const WgParams &p, i
 
 SCDA_API int scda_gemm_bf16_tn(int M, int N, int K, const void *A, long long lda, const void *B, long long ldb,
                                const float *bias, void *C, long long ldc, int flags, const void *mask_src,
-                               cudaStream_t stream)
+                               const void *mul_src, cudaStream_t stream)
 {
     if (M <= 0 || N <= 0 || K <= 0 || !A || !B || !C) return 0;
     if (lda % 8 || ldb % 8 || ((uintptr_t)A % 16) || ((uintptr_t)B % 16)) return 0;
     if ((flags & kFlagMaskPos) && !mask_src) return 0;
+    if ((flags & kFlagMulSrc) && !mul_src) return 0;
     if ((flags & kFlagAccumulate) && !(flags & kFlagOutF32)) return 0;
-    const int bn = pick_block_n(N);
+    const int bn = pick_block_n(N, ceil_div(M, kBlockM));
     CUtensorMap ma, mb;
     cuuint64_t da[2] = {(cuuint64_t)K, (cuuint64_t)M}, sa[1] = {(cuuint64_t)lda * 2};
     cuuint32_t ba[2] = {kBlockK, kBlockM};
@@ -623,6 +739,7 @@ SCDA_API int scda_gemm_bf16_tn(int M, int N, int K, const void *A, long long lda
     p.conv = 0;
     p.bias = bias; p.out = C; p.ldc = ldc;
     p.mask_src = (const __nv_bfloat16 *)mask_src;
+    p.mul_src = (const __nv_bfloat16 *)mul_src;
     p.flags = flags;
     return dispatch_tc(ma, mb, p, ceil_div(M, kBlockM), bn, stream);
 }
@@ -640,7 +757,7 @@ SCDA_API int scda_conv3x3_bf16_nhwc(int NB, int H, int W, int Cin, int Cout, con
         if (W % 8 == 0) { TW = 8; TH = 16; } else return 0;
     }
     const int tiles_w = W / TW, tiles_h = ceil_div(H, TH);
-    const int bn = pick_block_n(Cout);
+    const int bn = pick_block_n(Cout, (long long)NB * tiles_h * tiles_w);
     CUtensorMap ma, mb;
     cuuint64_t da[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)NB};
     cuuint64_t sa[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)W * Cin * 2, (cuuint64_t)H * W * Cin * 2};
@@ -659,16 +776,51 @@ SCDA_API int scda_conv3x3_bf16_nhwc(int NB, int H, int W, int Cin, int Cout, con
     return dispatch_tc(ma, mb, p, NB * tiles_h * tiles_w, bn, stream);
 }
 
+SCDA_API int scda_conv3x3_dgrad_bf16_nhwc(int NB, int H, int W, int Cin, int Cout, const void *dy,
+                                          const void *w_krsc, void *dx, int flags, const void *mask_src,
+                                          cudaStream_t stream)
+{
+    // dx[n,h,w,ci] = sum_{r,s,co} dy[n,h-(r-1),w-(s-1),co] W[co][r][s][ci]: the forward kernel with
+    // A = dy, reduction over (tap, co), and B read from the FORWARD weights as an MN-major operand.
+    if (NB <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0 || !dy || !w_krsc || !dx) return 0;
+    if (Cin % 64 || Cout % kBlockK) return 0;
+    if ((flags & kFlagMaskPos) && !mask_src) return 0;
+    if (flags & (kFlagAccumulate | kFlagMulSrc | kFlagRelu)) return 0;
+    int TW = 16, TH = 8;
+    if (W % 16) {
+        if (W % 8 == 0) { TW = 8; TH = 16; } else return 0;
+    }
+    const int tiles_w = W / TW, tiles_h = ceil_div(H, TH);
+    const int bn = pick_block_n(Cin, (long long)NB * tiles_h * tiles_w);
+    CUtensorMap ma, mb;
+    cuuint64_t da[4] = {(cuuint64_t)Cout, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)NB};
+    cuuint64_t sa[3] = {(cuuint64_t)Cout * 2, (cuuint64_t)W * Cout * 2, (cuuint64_t)H * W * Cout * 2};
+    cuuint32_t ba[4] = {kBlockK, (cuuint32_t)TW, (cuuint32_t)TH, 1};
+    cuuint64_t db[2] = {(cuuint64_t)9 * Cin, (cuuint64_t)Cout}, sb[1] = {(cuuint64_t)9 * Cin * 2};
+    cuuint32_t bb[2] = {64, kBlockK};
+    if (!make_map(&ma, dy, 4, da, sa, ba) || !make_map(&mb, w_krsc, 2, db, sb, bb)) return 0;
+    TcParams p = {};
+    p.M = NB * H * W; p.N = Cin; p.K = 9 * Cout;
+    p.num_k_blocks = 9 * (Cout / kBlockK);
+    p.conv = 1;
+    p.H = H; p.W = W; p.Cin = Cout; p.TH = TH; p.TW = TW; p.tiles_w = tiles_w; p.tiles_h = tiles_h;
+    p.bias = nullptr; p.out = dx; p.ldc = Cin;
+    p.mask_src = (const __nv_bfloat16 *)mask_src;
+    p.flags = flags;
+    return dispatch_tc(ma, mb, p, NB * tiles_h * tiles_w, bn, stream, true);
+}
+
 SCDA_API int scda_gemm_bf16_nn(int M, int N, int K, const void *A, long long lda, const void *B, long long ldb,
                                const float *bias, void *C, long long ldc, int flags, const void *mask_src,
-                               cudaStream_t stream)
+                               const void *mul_src, cudaStream_t stream)
 {
     // C[M,N] = A[M,K] . B[K,N]   (B row-major with N contiguous: the MN-major operand form)
     if (M <= 0 || N <= 0 || K <= 0 || !A || !B || !C) return 0;
     if (lda % 8 || ldb % 8 || ((uintptr_t)A % 16) || ((uintptr_t)B % 16)) return 0;
     if ((flags & kFlagMaskPos) && !mask_src) return 0;
+    if ((flags & kFlagMulSrc) && !mul_src) return 0;
     if ((flags & kFlagAccumulate) && !(flags & kFlagOutF32)) return 0;
-    const int bn = pick_block_n(N);
+    const int bn = pick_block_n(N, ceil_div(M, kBlockM));
     CUtensorMap ma, mb;
     cuuint64_t da[2] = {(cuuint64_t)K, (cuuint64_t)M}, sa[1] = {(cuuint64_t)lda * 2};
     cuuint32_t ba[2] = {kBlockK, kBlockM};
@@ -680,17 +832,19 @@ SCDA_API int scda_gemm_bf16_nn(int M, int N, int K, const void *A, long long lda
     p.num_k_blocks = ceil_div(K, kBlockK);
     p.bias = bias; p.out = C; p.ldc = ldc;
     p.mask_src = (const __nv_bfloat16 *)mask_src;
+    p.mul_src = (const __nv_bfloat16 *)mul_src;
     p.flags = flags;
     return dispatch_tc(ma, mb, p, ceil_div(M, kBlockM), bn, stream, true);
 }
 
 SCDA_API int scda_linear_wgrad_bf16(int rows, int Nout, int Kin, const void *dY, long long lddy, const void *X,
-                                    long long ldx, float *dW, long long lddw, cudaStream_t stream)
+                                    long long ldx, float *dW, long long lddw, int accumulate,
+                                    cudaStream_t stream)
 {
     // dW[Nout, Kin] = dY[rows, Nout]^T . X[rows, Kin]
     if (rows <= 0 || Nout <= 0 || Kin <= 0 || !dY || !X || !dW) return 0;
     if (lddy % 8 || ldx % 8 || ((uintptr_t)dY % 16) || ((uintptr_t)X % 16)) return 0;
-    const int bn = pick_block_n(Kin);
+    const int bn = Kin <= 64 ? 64 : 128;
     CUtensorMap ma, mb;
     cuuint64_t da[2] = {(cuuint64_t)Nout, (cuuint64_t)rows}, sa[1] = {(cuuint64_t)lddy * 2};
     cuuint64_t db[2] = {(cuuint64_t)Kin, (cuuint64_t)rows}, sb[1] = {(cuuint64_t)ldx * 2};
@@ -701,6 +855,7 @@ SCDA_API int scda_linear_wgrad_bf16(int rows, int Nout, int Kin, const void *dY,
     p.total_k_blocks = ceil_div(rows, 128);
     p.k_per_split = p.total_k_blocks;
     p.out = dW; p.ldo = lddw; p.split_stride = 0;
+    p.accumulate = accumulate ? 1 : 0;
     if (bn == 64) return launch_wg<64, 4>(ma, mb, p, 1, 1, stream);
     return launch_wg<128, 3>(ma, mb, p, 1, 1, stream);
 }
@@ -717,7 +872,7 @@ SCDA_API int scda_conv3x3_wgrad_bf16_nhwc(int NB, int H, int W, int Cin, int Cou
     }
     if (H % TH) return 0;
     const int tiles_w = W / TW, tiles_h = H / TH;
-    const int bn = pick_block_n(Cin);
+    const int bn = Cin <= 64 ? 64 : 128;
     CUtensorMap ma, mb;
     cuuint64_t da[4] = {(cuuint64_t)Cout, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)NB};
     cuuint64_t sa[3] = {(cuuint64_t)Cout * 2, (cuuint64_t)W * Cout * 2, (cuuint64_t)H * W * Cout * 2};

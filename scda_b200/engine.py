@@ -32,25 +32,42 @@ from .utils.distributed_utils import FlatGradBucket
 
 class FlatAdam(object):
     """Adam(lr, betas, eps, weight_decay) of torch 0.4.1 over one network, flat storage,
-    stepped by libscda_b200's scda_adam_step."""
+    stepped by libscda_b200's scda_adam_step.
 
-    def __init__(self, module, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-4):
+    Parameters, gradients, both moments and (tensor_core=True) a bf16 shadow of the
+    parameters live in flat buffers with one 64-element-aligned segment per parameter; 4-D
+    weights are stored [O][kh][kw][I] (the parameter keeps its [O,I,kh,kw] shape with
+    channels_last strides), so the shadow segment of a conv weight IS the KRSC operand of the
+    tcgen05 kernels and is refreshed by the optimiser kernel itself."""
+
+    def __init__(self, module, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-4, tensor_core=False):
+        from .utils.distributed_utils import flat_layout, flat_view
         self.params = [p for p in module.parameters() if p.requires_grad]
         assert self.params and all(p.is_cuda and p.dtype == torch.float32 for p in self.params)
         dev = self.params[0].device
-        n = sum(p.numel() for p in self.params)
-        pad = (-n) % 4
-        self.flat = torch.zeros(n + pad, dtype=torch.float32, device=dev)
-        off = 0
-        for p in self.params:
-            self.flat[off:off + p.numel()].copy_(p.data.reshape(-1))
-            p.data = self.flat[off:off + p.numel()].view_as(p)
-            off += p.numel()
+        self.offsets, n = flat_layout(self.params, 64)
+        self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
+        for p, off in zip(self.params, self.offsets):
+            view = flat_view(self.flat, off, p) if tensor_core else self.flat[off:off + p.numel()].view_as(p)
+            view.copy_(p.data)
+            p.data = view
         self.n = n
-        self.bucket = FlatGradBucket(self.params)
+        self.bucket = FlatGradBucket(self.params, self.offsets, n, channels_last=tensor_core)
         module._scda_bucket = self.bucket
         self.exp_avg = torch.zeros_like(self.flat)
         self.exp_avg_sq = torch.zeros_like(self.flat)
+        self.shadow = None
+        if tensor_core:
+            self.shadow = self.flat.to(torch.bfloat16)
+            for p, off in zip(self.params, self.offsets):
+                seg = self.shadow[off:off + p.numel()]
+                if p.dim() == 4:
+                    o, i, kh, kw = p.shape
+                    p._scda_shadow = seg.view(o, kh, kw, i)
+                else:
+                    p._scda_shadow = seg.view(p.shape)
+                p._scda_shadow_version = p._version
+                p._scda_direct_grad = True
         self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
         self.t = 0
 
@@ -59,18 +76,28 @@ class FlatAdam(object):
 
     def all_reduce(self):
         self.bucket.rebind()
+        self.bucket.settle()
         self.bucket.all_reduce()
 
     def step(self, lr=None, grad_scale=1.0):
         self.t += 1
         self.bucket.rebind()
+        self.bucket.settle()
         with torch.cuda.device(self.flat.device):
             check(load().scda_adam_step(
                 self.flat.data_ptr(), self.bucket.flat.data_ptr(), self.exp_avg.data_ptr(),
-                self.exp_avg_sq.data_ptr(), None, self.n, self.t,
+                self.exp_avg_sq.data_ptr(), self.shadow.data_ptr() if self.shadow is not None else None,
+                self.n, self.t,
                 float(self.lr if lr is None else lr), self.betas[0], self.betas[1], self.eps,
                 self.weight_decay, float(grad_scale), stream_ptr(self.flat.device)),
                 "scda_adam_step")
+        # the kernel wrote the parameters through raw pointers: stamp what is (not) in sync
+        for p in self.params:
+            p._scda_epoch = getattr(p, "_scda_epoch", 0) + 1
+            if self.shadow is not None:
+                p._scda_shadow_version = p._version
+            elif hasattr(p, "_scda_shadow_version"):
+                p._scda_shadow_version = -1
 
 
 def get_corner_from_center(center, recon_size, new_w, new_h):
@@ -124,7 +151,7 @@ class SCDATrainer(object):
                  weight_decay=1e-4):
         self.model, self.dec_model = model, dec_model
         self.dis_model, self.dis_model_patch = dis_model, dis_model_patch
-        self.opt = FlatAdam(model, lr, weight_decay=weight_decay)
+        self.opt = FlatAdam(model, lr, weight_decay=weight_decay, tensor_core=True)
         self.opt_dec = FlatAdam(dec_model, lr, weight_decay=weight_decay)
         self.opt_dis = FlatAdam(dis_model, lr, weight_decay=weight_decay)
         self.opt_dis_patch = FlatAdam(dis_model_patch, lr, weight_decay=weight_decay)

@@ -135,8 +135,11 @@ class FasterRCNN_AdEx(nn.Module):
                 rois, x_fea, N_cluster=input['cluster_num'], threshold=input['threshold'])
 
             # RPN + RCNN on the target image: top-512 proposals, no ground truth (:171-189)
-            x_gan = self.feature_extractor(target)
-            rpn_pred_cls_gan, rpn_pred_loc_gan = self.rpn(x_gan)
+            # (nothing downstream differentiates through this branch: its only product, the
+            #  cluster features, is detached by compute_cluster_targets — functions/mask.py:234)
+            with torch.no_grad():
+                x_gan = self.feature_extractor(target)
+                rpn_pred_cls_gan, rpn_pred_loc_gan = self.rpn(x_gan)
             props_gan = rpn_proposals_device(self._rpn_scores(rpn_pred_cls_gan).data,
                                              rpn_pred_loc_gan.data, pcfg, image_info)
             n_t = cfg['train_proposal_target_cfg']['batch_size']
@@ -152,7 +155,8 @@ class FasterRCNN_AdEx(nn.Module):
                 ks = [int(n.item()) for _, n in gan_rows]
                 proposals_gan = torch.cat([r[:k] for (r, _), k in zip(gan_rows, ks)], 0)[:n_t].contiguous()
                 enough = torch.tensor(proposals_gan.shape[0] == n_t, device=x.device)
-            x_fea_gan, _, _ = self.rcnn(x_gan, proposals_gan)
+            with torch.no_grad():
+                x_fea_gan, _, _ = self.rcnn(x_gan, proposals_gan)
             assert x_gan.size() == x.size(), "gan_features does not match the backbone"
 
             rcnn_loss_cls, rcnn_loss_loc, rcnn_acc = self._add_rcnn_loss(

@@ -39,14 +39,34 @@ class VGG(FasterRCNN_AdEx):
         self.fc_rcnn_loc = nn.Linear(4096, cfg['num_classes'] * 4)
         self._initialize_weights()
 
+    # The three stages run on the tcgen05 kernels (scda_b200/tc_detector.py): the feature
+    # map between them is NHWC bf16.  `_fp32_graph = True` runs the same modules through
+    # torch.nn in fp32 NCHW instead — the plain-PyTorch reference the numerics tests
+    # compare the kernels with, not a production path.
+    _fp32_graph = False
+
+    def _tc(self):
+        rt = self.__dict__.get('_tc_runtime')
+        if rt is None:
+            from ...tc_detector import TcDetector
+            rt = TcDetector(self)
+            self.__dict__['_tc_runtime'] = rt
+        return rt
+
     def feature_extractor(self, x):
-        return self.features(x)
+        if self._fp32_graph:
+            return self.features(x)
+        return self._tc().features(x)
 
     def rpn(self, x):
-        return self.rpn_head(x)
+        if self._fp32_graph:
+            return self.rpn_head(x)
+        return self._tc().rpn(x)
 
     def rcnn(self, x, rois):
         assert rois.shape[1] == 5
+        if not self._fp32_graph:
+            return self._tc().rcnn(x, rois)
         x = self.roipooling(x, rois)          # [R, 512, 7, 7]
         x = x.view(x.size(0), -1)
         x_fea = self.classifier(x)            # [R, 4096]

@@ -1,4 +1,5 @@
-"""Python entry points of the tcgen05 GEMM / 3x3-convolution kernels (csrc/gemm_tc.cu).
+"""Python entry points of the tcgen05 GEMM / 3x3-convolution kernels (csrc/gemm_tc.cu) and
+their bf16 NHWC companions (csrc/nhwc_ops.cu).
 
 Tensors are bf16 CUDA tensors; activations are NHWC ([N, H, W, C] contiguous), conv
 weights [Cout, 3, 3, Cin] ("KRSC").  Outputs are allocated here, the kernels only borrow
@@ -7,12 +8,27 @@ import torch
 
 from ._lib import check, load, require_cuda, stream_ptr
 
-RELU, OUT_F32, MASK_POS, ACCUMULATE = 1, 2, 4, 8
+RELU, OUT_F32, MASK_POS, ACCUMULATE, MUL_SRC = 1, 2, 4, 8, 16
+
+
+def _ptr(t):
+    return t.data_ptr() if t is not None else None
+
+
+def _flags(relu, out_dtype, mask_src, accumulate=False, mul_src=None):
+    return (RELU if relu else 0) | (OUT_F32 if out_dtype == torch.float32 else 0) \
+        | (MASK_POS if mask_src is not None else 0) | (ACCUMULATE if accumulate else 0) \
+        | (MUL_SRC if mul_src is not None else 0)
+
+
+def _check_side(t, out, what):
+    assert t.dtype == torch.bfloat16 and t.shape == out.shape and t.stride() == out.stride(), what
 
 
 def gemm_tn(a, b, bias=None, relu=False, out_dtype=torch.bfloat16, mask_src=None, out=None,
-            accumulate=False):
-    """out[M, N] = a[M, K] @ b[N, K]^T (+ bias) — a, b bf16 row-major (last dim contiguous)."""
+            accumulate=False, mul_src=None):
+    """out[M, N] = a[M, K] @ b[N, K]^T (+ bias) — a, b bf16 row-major (last dim contiguous).
+    Epilogue order: bias, ReLU, mask (mask_src > 0), multiply (mul_src)."""
     require_cuda(a, b)
     assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16
     assert a.dim() == 2 and b.dim() == 2 and a.shape[1] == b.shape[1]
@@ -22,19 +38,40 @@ def gemm_tn(a, b, bias=None, relu=False, out_dtype=torch.bfloat16, mask_src=None
     if out is None:
         out = torch.empty(M, N, dtype=out_dtype, device=a.device)
     assert out.shape == (M, N) and out.stride(1) == 1
-    flags = (RELU if relu else 0) | (OUT_F32 if out.dtype == torch.float32 else 0) \
-        | (MASK_POS if mask_src is not None else 0) | (ACCUMULATE if accumulate else 0)
+    flags = _flags(relu, out.dtype, mask_src, accumulate, mul_src)
     if bias is not None:
         assert bias.dtype == torch.float32 and bias.numel() == N and bias.is_contiguous()
     if mask_src is not None:
-        assert mask_src.dtype == torch.bfloat16 and mask_src.shape == out.shape \
-            and mask_src.stride() == out.stride()
+        _check_side(mask_src, out, "mask_src must match the output")
+    if mul_src is not None:
+        _check_side(mul_src, out, "mul_src must match the output")
     with torch.cuda.device(a.device):
         check(load().scda_gemm_bf16_tn(M, N, K, a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0),
-                                       bias.data_ptr() if bias is not None else None, out.data_ptr(),
-                                       out.stride(0), flags,
-                                       mask_src.data_ptr() if mask_src is not None else None,
-                                       stream_ptr(a.device)), "scda_gemm_bf16_tn")
+                                       _ptr(bias), out.data_ptr(), out.stride(0), flags,
+                                       _ptr(mask_src), _ptr(mul_src), stream_ptr(a.device)),
+              "scda_gemm_bf16_tn")
+    return out
+
+
+def gemm_nn(a, b, bias=None, relu=False, out_dtype=torch.bfloat16, mask_src=None, mul_src=None):
+    """out[M, N] = a[M, K] @ b[K, N] — b row-major with N contiguous (e.g. dX = dY @ W)."""
+    require_cuda(a, b)
+    assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16
+    assert a.dim() == 2 and b.dim() == 2 and a.shape[1] == b.shape[0]
+    assert a.stride(1) == 1 and b.stride(1) == 1
+    M, K = a.shape
+    N = b.shape[1]
+    out = torch.empty(M, N, dtype=out_dtype, device=a.device)
+    flags = _flags(relu, out_dtype, mask_src, False, mul_src)
+    if mask_src is not None:
+        _check_side(mask_src, out, "mask_src must match the output")
+    if mul_src is not None:
+        _check_side(mul_src, out, "mul_src must match the output")
+    with torch.cuda.device(a.device):
+        check(load().scda_gemm_bf16_nn(M, N, K, a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0),
+                                       _ptr(bias), out.data_ptr(), out.stride(0), flags,
+                                       _ptr(mask_src), _ptr(mul_src), stream_ptr(a.device)),
+              "scda_gemm_bf16_nn")
     return out
 
 
@@ -47,74 +84,151 @@ def conv3x3_nhwc(x, w_krsc, bias=None, relu=False, out_dtype=torch.bfloat16, mas
     Cout = w_krsc.shape[0]
     assert tuple(w_krsc.shape[1:]) == (3, 3, Cin)
     y = torch.empty(NB, H, W, Cout, dtype=out_dtype, device=x.device)
-    flags = (RELU if relu else 0) | (OUT_F32 if out_dtype == torch.float32 else 0) \
-        | (MASK_POS if mask_src is not None else 0)
+    flags = _flags(relu, out_dtype, mask_src)
     if bias is not None:
         assert bias.dtype == torch.float32 and bias.numel() == Cout and bias.is_contiguous()
     if mask_src is not None:
         assert mask_src.dtype == torch.bfloat16 and mask_src.shape == y.shape and mask_src.is_contiguous()
     with torch.cuda.device(x.device):
         check(load().scda_conv3x3_bf16_nhwc(NB, H, W, Cin, Cout, x.data_ptr(), w_krsc.data_ptr(),
-                                            bias.data_ptr() if bias is not None else None, y.data_ptr(),
-                                            flags, mask_src.data_ptr() if mask_src is not None else None,
+                                            _ptr(bias), y.data_ptr(), flags, _ptr(mask_src),
                                             stream_ptr(x.device)), "scda_conv3x3_bf16_nhwc")
     return y
 
 
-def gemm_nn(a, b, bias=None, relu=False, out_dtype=torch.bfloat16, mask_src=None):
-    """out[M, N] = a[M, K] @ b[K, N] — b row-major with N contiguous (e.g. dX = dY @ W)."""
-    require_cuda(a, b)
-    assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16
-    assert a.dim() == 2 and b.dim() == 2 and a.shape[1] == b.shape[0]
-    assert a.stride(1) == 1 and b.stride(1) == 1
-    M, K = a.shape
-    N = b.shape[1]
-    out = torch.empty(M, N, dtype=out_dtype, device=a.device)
-    flags = (RELU if relu else 0) | (OUT_F32 if out_dtype == torch.float32 else 0) \
-        | (MASK_POS if mask_src is not None else 0)
+def conv3x3_dgrad_nhwc(dy, w_krsc, mask_src=None, out_dtype=torch.bfloat16):
+    """dx[N,H,W,Cin] from dy[N,H,W,Cout] and the FORWARD weights w[Cout,3,3,Cin]; with
+    mask_src (= the layer input, a ReLU output) the ReLU gradient is applied as well."""
+    require_cuda(dy, w_krsc)
+    assert dy.dtype == torch.bfloat16 and w_krsc.dtype == torch.bfloat16
+    assert dy.is_contiguous() and w_krsc.is_contiguous() and dy.dim() == 4 and w_krsc.dim() == 4
+    NB, H, W, Cout = dy.shape
+    Cin = w_krsc.shape[3]
+    assert tuple(w_krsc.shape[:3]) == (Cout, 3, 3)
+    dx = torch.empty(NB, H, W, Cin, dtype=out_dtype, device=dy.device)
+    flags = _flags(False, out_dtype, mask_src)
     if mask_src is not None:
-        assert mask_src.dtype == torch.bfloat16 and mask_src.shape == out.shape and mask_src.is_contiguous()
-    with torch.cuda.device(a.device):
-        check(load().scda_gemm_bf16_nn(M, N, K, a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0),
-                                       bias.data_ptr() if bias is not None else None, out.data_ptr(),
-                                       out.stride(0), flags,
-                                       mask_src.data_ptr() if mask_src is not None else None,
-                                       stream_ptr(a.device)), "scda_gemm_bf16_nn")
-    return out
+        assert mask_src.dtype == torch.bfloat16 and mask_src.shape == dx.shape and mask_src.is_contiguous()
+    with torch.cuda.device(dy.device):
+        check(load().scda_conv3x3_dgrad_bf16_nhwc(NB, H, W, Cin, Cout, dy.data_ptr(), w_krsc.data_ptr(),
+                                                  dx.data_ptr(), flags, _ptr(mask_src),
+                                                  stream_ptr(dy.device)), "scda_conv3x3_dgrad_bf16_nhwc")
+    return dx
 
 
-def linear_wgrad(dy, x, out=None):
-    """dW[Nout, Kin] fp32 = dy[rows, Nout]^T @ x[rows, Kin]."""
+def linear_wgrad(dy, x, out=None, accumulate=False):
+    """dW[Nout, Kin] fp32 (+)= dy[rows, Nout]^T @ x[rows, Kin]."""
     require_cuda(dy, x)
     assert dy.dtype == torch.bfloat16 and x.dtype == torch.bfloat16
     assert dy.shape[0] == x.shape[0] and dy.stride(1) == 1 and x.stride(1) == 1
     rows, nout = dy.shape
     kin = x.shape[1]
     if out is None:
+        assert not accumulate
         out = torch.empty(nout, kin, dtype=torch.float32, device=x.device)
     assert out.dtype == torch.float32 and out.shape == (nout, kin) and out.stride(1) == 1
     with torch.cuda.device(x.device):
         check(load().scda_linear_wgrad_bf16(rows, nout, kin, dy.data_ptr(), dy.stride(0), x.data_ptr(),
                                             x.stride(0), out.data_ptr(), out.stride(0),
-                                            stream_ptr(x.device)), "scda_linear_wgrad_bf16")
+                                            1 if accumulate else 0, stream_ptr(x.device)),
+              "scda_linear_wgrad_bf16")
     return out
 
 
-def conv3x3_wgrad_nhwc(x, dy, target_ctas=296):
-    """dW[Cout, 3, 3, Cin] fp32 from x[N,H,W,Cin], dy[N,H,W,Cout] (both bf16 NHWC)."""
+def _wgrad_splits(NB, H, W, Cin, Cout, target_ctas):
+    tiles = NB * H * W // 128
+    base = 9 * ((Cout + 127) // 128) * ((Cin + (63 if Cin <= 64 else 127)) // (64 if Cin <= 64 else 128))
+    splits = max(1, min(tiles, target_ctas // max(base, 1)))
+    per = -(-tiles // splits)
+    return -(-tiles // per)
+
+
+def conv3x3_wgrad_nhwc(x, dy, target_ctas=296, out=None, accumulate=False):
+    """dW[Cout, 3, 3, Cin] fp32 from x[N,H,W,Cin], dy[N,H,W,Cout] (both bf16 NHWC).  With
+    `out` (a contiguous fp32 [Cout,3,3,Cin] buffer) the split-K slabs are reduced straight
+    into it (overwriting, or adding when accumulate)."""
     require_cuda(x, dy)
     assert x.dtype == torch.bfloat16 and dy.dtype == torch.bfloat16
     assert x.is_contiguous() and dy.is_contiguous() and x.shape[:3] == dy.shape[:3]
     NB, H, W, Cin = x.shape
     Cout = dy.shape[3]
-    tiles = NB * H * W // 128
-    base = 9 * ((Cout + 127) // 128) * ((Cin + (63 if Cin <= 64 else 127)) // (64 if Cin <= 64 else 128))
-    splits = max(1, min(tiles, target_ctas // max(base, 1)))
-    per = -(-tiles // splits)
-    splits = -(-tiles // per)
+    splits = _wgrad_splits(NB, H, W, Cin, Cout, target_ctas)
     part = torch.empty(splits, Cout, 3, 3, Cin, dtype=torch.float32, device=x.device)
     with torch.cuda.device(x.device):
         check(load().scda_conv3x3_wgrad_bf16_nhwc(NB, H, W, Cin, Cout, x.data_ptr(), dy.data_ptr(),
                                                   part.data_ptr(), splits, stream_ptr(x.device)),
               "scda_conv3x3_wgrad_bf16_nhwc")
-    return part[0] if splits == 1 else part.sum(0)
+    if out is None:
+        return part[0] if splits == 1 else part.sum(0)
+    assert out.dtype == torch.float32 and out.numel() == part[0].numel()
+    reduce_slabs(part, out, accumulate)
+    return out
+
+
+def reduce_slabs(part, out, accumulate=False):
+    """out (+)= part.sum(0); `out` is any fp32 tensor whose storage order matches a slab."""
+    n = part[0].numel()
+    with torch.cuda.device(part.device):
+        check(load().scda_reduce_slabs_f32(part.data_ptr(), n, part.shape[0], out.data_ptr(), n,
+                                           1 if accumulate else 0, stream_ptr(part.device)),
+              "scda_reduce_slabs_f32")
+    return out
+
+
+def maxpool2x2_nhwc(x):
+    require_cuda(x)
+    assert x.dtype == torch.bfloat16 and x.is_contiguous() and x.dim() == 4
+    NB, H, W, C = x.shape
+    y = torch.empty(NB, H // 2, W // 2, C, dtype=x.dtype, device=x.device)
+    with torch.cuda.device(x.device):
+        check(load().scda_maxpool2x2_nhwc_bf16(NB, H, W, C, x.data_ptr(), y.data_ptr(),
+                                               stream_ptr(x.device)), "scda_maxpool2x2_nhwc_bf16")
+    return y
+
+
+def maxpool2x2_bwd_nhwc(x, dy, relu_mask=True):
+    """gradient of maxpool2x2_nhwc at x; with relu_mask also through the ReLU that produced x."""
+    require_cuda(x, dy)
+    assert x.dtype == torch.bfloat16 and dy.dtype == torch.bfloat16 and x.is_contiguous() and dy.is_contiguous()
+    NB, H, W, C = x.shape
+    assert tuple(dy.shape) == (NB, H // 2, W // 2, C)
+    dx = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        check(load().scda_maxpool2x2_bwd_nhwc_bf16(NB, H, W, C, x.data_ptr(), dy.data_ptr(), dx.data_ptr(),
+                                                   1 if relu_mask else 0, stream_ptr(x.device)),
+              "scda_maxpool2x2_bwd_nhwc_bf16")
+    return dx
+
+
+def nchw_f32_to_nhwc_bf16(x, c_pad=None):
+    require_cuda(x)
+    assert x.dtype == torch.float32 and x.is_contiguous() and x.dim() == 4
+    NB, C, H, W = x.shape
+    c_pad = C if c_pad is None else c_pad
+    y = torch.empty(NB, H, W, c_pad, dtype=torch.bfloat16, device=x.device)
+    with torch.cuda.device(x.device):
+        check(load().scda_nchw_f32_to_nhwc_bf16(NB, C, H, W, c_pad, x.data_ptr(), y.data_ptr(),
+                                                stream_ptr(x.device)), "scda_nchw_f32_to_nhwc_bf16")
+    return y
+
+
+def nhwc_bf16_to_nchw_f32(x):
+    require_cuda(x)
+    assert x.dtype == torch.bfloat16 and x.is_contiguous() and x.dim() == 4
+    NB, H, W, C = x.shape
+    y = torch.empty(NB, C, H, W, dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        check(load().scda_nhwc_bf16_to_nchw_f32(NB, C, H, W, x.data_ptr(), y.data_ptr(),
+                                                stream_ptr(x.device)), "scda_nhwc_bf16_to_nchw_f32")
+    return y
+
+
+def colsum_into(x2d, out):
+    """out[N] (fp32) += column sums of x2d[M, N] (bf16, row stride any even number)."""
+    require_cuda(x2d, out)
+    assert x2d.dtype == torch.bfloat16 and x2d.dim() == 2 and x2d.stride(1) == 1
+    assert out.dtype == torch.float32 and out.is_contiguous() and out.numel() == x2d.shape[1]
+    with torch.cuda.device(x2d.device):
+        check(load().scda_colsum_bf16(x2d.shape[0], x2d.shape[1], x2d.data_ptr(), x2d.stride(0),
+                                      out.data_ptr(), stream_ptr(x2d.device)), "scda_colsum_bf16")
+    return out

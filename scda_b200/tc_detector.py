@@ -1,0 +1,388 @@
+"""bf16 NHWC tensor-core execution of the detector's dense layers.
+
+The `VGG` module of models/faster_rcnn/vgg_adver_expansion_cluster.py keeps the reference's
+modules and fp32 parameters (names, shapes, state_dict); this runtime executes them:
+
+    features   13 x [conv3x3 + bias + ReLU] (tcgen05 implicit GEMM) with 4 max-pools
+               (reference: vgg_adver_expansion_cluster.py:64-65, 101-114)
+    rpn_head   conv3x3 + ReLU, then both 1x1 convs as ONE GEMM (models/head.py:20-32)
+    rcnn       RoIPool -> fc6 -> fc7 (ReLU + dropout in the GEMM epilogue) -> cls|loc as ONE
+               GEMM (vgg_adver_expansion_cluster.py:73-80)
+
+Each stage is one torch.autograd.Function whose backward runs the layer loop by hand: the
+data gradient reads the forward weights (no transposed copies), the ReLU gradient rides in
+the dgrad epilogue (or in the max-pool backward), the weight gradients are reduced straight
+into the optimiser's flat gradient buffer when the parameter opted in
+(`p._scda_direct_grad`, set by engine.FlatAdam), otherwise they are returned to autograd.
+
+bf16 weight shadows: `shadow(p)` returns a bf16 copy in the layout the kernels want and
+re-derives it whenever `p._version` moved; engine.FlatAdam refreshes the big ones inside
+its fused optimiser kernel and stamps `p._scda_shadow_version`.
+"""
+import torch
+
+from . import tc
+from ._lib import check, load, stream_ptr
+
+
+def _is_krsc(p):
+    """physical layout [O][3][3][I] (channels_last) -> the permuted view is contiguous"""
+    return p.dim() == 4 and p.permute(0, 2, 3, 1).is_contiguous()
+
+
+class TcDetector(object):
+    def __init__(self, vgg):
+        import torch.nn as nn
+        self.convs = []                       # [conv module, pool_after]
+        for m in vgg.features.children():
+            if isinstance(m, nn.Conv2d):
+                assert m.kernel_size == (3, 3) and m.stride == (1, 1) and m.padding == (1, 1)
+                self.convs.append([m, False])
+            elif isinstance(m, nn.MaxPool2d):
+                assert m.kernel_size in (2, (2, 2)) and m.stride in (2, (2, 2)) and self.convs
+                self.convs[-1][1] = True
+            elif isinstance(m, nn.BatchNorm2d):
+                raise NotImplementedError("the tensor-core path covers the non-BN VGG variants")
+        self.convs = [tuple(c) for c in self.convs]
+        self.vgg = vgg
+        self._derived = {}
+
+    # ------------------------------------------------------------------ shadows
+    def shadow(self, p):
+        """bf16 copy of parameter p: conv weights as [O,3,3,I], everything else as stored."""
+        sh = getattr(p, "_scda_shadow", None)
+        if sh is not None and getattr(p, "_scda_shadow_version", -1) == p._version:
+            return sh
+        src = p.detach()
+        if p.dim() == 4:
+            src = src.permute(0, 2, 3, 1)
+        if sh is None or sh.shape != src.shape:
+            sh = torch.empty(src.shape, dtype=torch.bfloat16, device=p.device)
+            p._scda_shadow = sh
+        sh.copy_(src)
+        p._scda_shadow_version = p._version
+        return sh
+
+    def _derive(self, key, params, build):
+        """small shadows derived from several parameters (padded / concatenated)"""
+        stamp = tuple((p._version, getattr(p, "_scda_epoch", 0)) for p in params)
+        ent = self._derived.get(key)
+        if ent is None or ent[0] != stamp:
+            ent = (stamp, build())
+            self._derived[key] = ent
+        return ent[1]
+
+    def conv1_weight(self):
+        w = self.convs[0][0].weight
+
+        def build():
+            out = torch.zeros(w.shape[0], 3, 3, 64, dtype=torch.bfloat16, device=w.device)
+            out[..., :w.shape[1]].copy_(w.detach().permute(0, 2, 3, 1))
+            return out
+        return self._derive("conv1", (w,), build)
+
+    def rpn_cat(self):
+        h = self.vgg.rpn_head
+        ps = (h.conv_cls.weight, h.conv_cls.bias, h.conv_loc.weight, h.conv_loc.bias)
+
+        def build():
+            nc, nl, k = ps[0].shape[0], ps[2].shape[0], ps[0].shape[1]
+            n = nc + nl
+            w = torch.zeros((n + 7) // 8 * 8, k, dtype=torch.bfloat16, device=ps[0].device)
+            w[:nc].copy_(ps[0].detach().view(nc, k))
+            w[nc:n].copy_(ps[2].detach().view(nl, k))
+            b = torch.cat([ps[1].detach(), ps[3].detach()]).float().contiguous()
+            return w, b, nc, nl
+        return self._derive("rpn", ps, build)
+
+    def rcnn_cat(self):
+        v = self.vgg
+        ps = (v.fc_rcnn_cls.weight, v.fc_rcnn_cls.bias, v.fc_rcnn_loc.weight, v.fc_rcnn_loc.bias)
+
+        def build():
+            nc, nl, k = ps[0].shape[0], ps[2].shape[0], ps[0].shape[1]
+            n = nc + nl
+            w = torch.zeros((n + 7) // 8 * 8, k, dtype=torch.bfloat16, device=ps[0].device)
+            w[:nc].copy_(ps[0].detach())
+            w[nc:n].copy_(ps[2].detach())
+            b = torch.cat([ps[1].detach(), ps[3].detach()]).float().contiguous()
+            return w, b, nc, nl
+        return self._derive("rcnn", ps, build)
+
+    # ------------------------------------------------------------------ stages
+    def features(self, image):
+        params = []
+        for m, _ in self.convs:
+            params += [m.weight, m.bias]
+        return _BackboneFn.apply(image, self, *params)
+
+    def rpn(self, feat):
+        h = self.vgg.rpn_head
+        return _RpnHeadFn.apply(feat, self, h.conv3x3.weight, h.conv3x3.bias, h.conv_cls.weight,
+                                h.conv_cls.bias, h.conv_loc.weight, h.conv_loc.bias)
+
+    def rcnn(self, feat, rois):
+        v = self.vgg
+        fc6, fc7 = v.classifier[0], v.classifier[3]
+        p_drop = (v.classifier[2].p, v.classifier[5].p) if v.training else (0.0, 0.0)
+        pool = v.roipooling
+        return _RcnnHeadFn.apply(feat, rois, self, (pool.pooled_height, pool.pooled_width,
+                                                    pool.spatial_scale), p_drop,
+                                 fc6.weight, fc6.bias, fc7.weight, fc7.bias,
+                                 v.fc_rcnn_cls.weight, v.fc_rcnn_cls.bias,
+                                 v.fc_rcnn_loc.weight, v.fc_rcnn_loc.bias)
+
+
+# ---------------------------------------------------------------------- gradient sinks
+def _direct(p):
+    return getattr(p, "_scda_direct_grad", False) and p.grad is not None and p.grad.dtype == torch.float32
+
+
+def _take_fresh(p):
+    """True when p.grad is known to hold nothing yet this step (overwrite instead of add)."""
+    fresh = getattr(p, "_scda_grad_fresh", False)
+    p._scda_grad_fresh = False
+    return fresh
+
+
+def _sink_conv_wgrad(p, x, g, cin_real=None):
+    """3x3 weight gradient of parameter p ([O,I,3,3]); returns None when it went straight
+    into p.grad, else the gradient tensor for autograd."""
+    O, I = p.shape[0], p.shape[1]
+    if cin_real is None and _direct(p) and _is_krsc(p.grad):
+        tc.conv3x3_wgrad_nhwc(x, g, out=p.grad, accumulate=not _take_fresh(p))
+        return None
+    dw = tc.conv3x3_wgrad_nhwc(x, g)                       # [O,3,3,Ipad]
+    if cin_real is not None:
+        dw = dw[..., :cin_real]
+    dw = dw.permute(0, 3, 1, 2)
+    if _direct(p):
+        if _take_fresh(p):
+            p.grad.copy_(dw)
+        else:
+            p.grad.add_(dw)
+        return None
+    return dw.contiguous()
+
+
+def _sink_linear_wgrad(p, dy, x):
+    if _direct(p) and p.grad.stride(-1) == 1 and p.grad.dim() == 2:
+        tc.linear_wgrad(dy, x, out=p.grad, accumulate=not _take_fresh(p))
+        return None
+    return tc.linear_wgrad(dy, x)
+
+
+def _sink_small(p, g):
+    """small dense gradient g (fp32, shape of p)"""
+    if _direct(p):
+        if _take_fresh(p):
+            p.grad.copy_(g.view_as(p))
+        else:
+            p.grad.add_(g.view_as(p))
+        return None
+    return g.view_as(p)
+
+
+def _sink_bias(p, g2d):
+    """bias gradient = column sums of the bf16 gradient matrix g2d [rows, N]"""
+    if _direct(p) and p.grad.is_contiguous():
+        if _take_fresh(p):
+            p.grad.zero_()
+        tc.colsum_into(g2d, p.grad)
+        return None
+    out = torch.zeros(p.shape, dtype=torch.float32, device=p.device)
+    tc.colsum_into(g2d, out)
+    return out
+
+
+# ---------------------------------------------------------------------- backbone
+class _BackboneFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, image, rt, *params):
+        assert image.is_cuda and image.dtype == torch.float32 and image.dim() == 4
+        x = tc.nchw_f32_to_nhwc_bf16(image.contiguous(), 64)
+        saved = [x]
+        n = len(rt.convs)
+        for i, (m, pool) in enumerate(rt.convs):
+            w = rt.conv1_weight() if i == 0 else rt.shadow(m.weight)
+            y = tc.conv3x3_nhwc(x, w, m.bias.detach(), relu=True)
+            saved.append(y)
+            x = tc.maxpool2x2_nhwc(y) if pool else y
+            if pool:
+                saved.append(x)
+        ctx.rt = rt
+        ctx.cin = image.shape[1]
+        ctx.save_for_backward(*saved)
+        return x
+
+    @staticmethod
+    def backward(ctx, g_feat):
+        rt = ctx.rt
+        saved = list(ctx.saved_tensors)
+        # unpack: input of conv i, output of conv i
+        ins, outs = [], []
+        k = 0
+        x = saved[k]; k += 1
+        for (m, pool) in rt.convs:
+            ins.append(x)
+            y = saved[k]; k += 1
+            outs.append(y)
+            if pool:
+                x = saved[k]; k += 1
+            else:
+                x = y
+        last = len(rt.convs) - 1
+        assert not rt.convs[last][1], "the stack ends with a convolution (last pool dropped)"
+        g = g_feat.contiguous()
+        if g.dtype != torch.bfloat16:
+            g = g.to(torch.bfloat16)
+        g = torch.where(outs[last] > 0, g, torch.zeros_like(g))       # ReLU of the last conv
+        grads = [None] * (2 * len(rt.convs))
+        for i in range(last, -1, -1):
+            m, _ = rt.convs[i]
+            cout = m.weight.shape[0]
+            grads[2 * i + 1] = _sink_bias(m.bias, g.view(-1, cout))
+            if i == 0:
+                grads[0] = _sink_conv_wgrad(m.weight, ins[0], g, cin_real=ctx.cin)
+                break
+            grads[2 * i] = _sink_conv_wgrad(m.weight, ins[i], g)
+            w = rt.shadow(m.weight)
+            if rt.convs[i - 1][1]:          # the input of conv i is a pooled map
+                d_pooled = tc.conv3x3_dgrad_nhwc(g, w)
+                g = tc.maxpool2x2_bwd_nhwc(outs[i - 1], d_pooled, relu_mask=True)
+            else:
+                g = tc.conv3x3_dgrad_nhwc(g, w, mask_src=ins[i])
+        return (None, None) + tuple(grads)
+
+
+# ---------------------------------------------------------------------- RPN head
+class _RpnHeadFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, feat, rt, w3, b3, wc, bc, wl, bl):
+        NB, H, W, C = feat.shape
+        hidden = tc.conv3x3_nhwc(feat, rt.shadow(w3), b3.detach(), relu=True)
+        wcat, bcat, nc, nl = rt.rpn_cat()
+        out = tc.gemm_tn(hidden.view(-1, hidden.shape[3]), wcat[:nc + nl], bcat, out_dtype=torch.float32)
+        out = out.view(NB, H, W, nc + nl)
+        cls = out[..., :nc].permute(0, 3, 1, 2).contiguous()
+        loc = out[..., nc:].permute(0, 3, 1, 2).contiguous()
+        ctx.rt = rt
+        ctx.save_for_backward(feat, hidden)
+        return cls, loc
+
+    @staticmethod
+    def backward(ctx, g_cls, g_loc):
+        rt = ctx.rt
+        feat, hidden = ctx.saved_tensors
+        h = rt.vgg.rpn_head
+        w3, b3, wc, bc, wl, bl = (h.conv3x3.weight, h.conv3x3.bias, h.conv_cls.weight, h.conv_cls.bias,
+                                  h.conv_loc.weight, h.conv_loc.bias)
+        NB, H, W, C = hidden.shape
+        wcat, _, nc, nl = rt.rpn_cat()
+        npad = wcat.shape[0]
+        g = torch.zeros(NB, H, W, npad, dtype=torch.bfloat16, device=feat.device)
+        gb = [None, None]
+        if g_cls is not None:
+            g[..., :nc].copy_(g_cls.permute(0, 2, 3, 1))
+            gb[0] = _sink_small(bc, g_cls.sum((0, 2, 3)))
+        if g_loc is not None:
+            g[..., nc:nc + nl].copy_(g_loc.permute(0, 2, 3, 1))
+            gb[1] = _sink_small(bl, g_loc.sum((0, 2, 3)))
+        g2 = g.view(-1, npad)
+        hid2 = hidden.view(-1, C)
+        dwcat = tc.linear_wgrad(g2, hid2)                         # [npad, C] fp32
+        gwc = _sink_small(wc, dwcat[:nc])
+        gwl = _sink_small(wl, dwcat[nc:nc + nl])
+        d_hidden = tc.gemm_nn(g2, wcat, mask_src=hid2).view(NB, H, W, C)
+        gb3 = _sink_bias(b3, d_hidden.view(-1, C))
+        gw3 = _sink_conv_wgrad(w3, feat, d_hidden)
+        d_feat = tc.conv3x3_dgrad_nhwc(d_hidden, rt.shadow(w3))
+        return d_feat, None, gw3, gb3, gwc, gb[0], gwl, gb[1]
+
+
+# ---------------------------------------------------------------------- RCNN head
+def _dropout_scale(shape, p, device):
+    """keep/scale tensor of nn.Dropout(p) in training: 0 with probability p, else 1/(1-p)."""
+    if p <= 0.0:
+        return None
+    keep = torch.rand(shape, device=device) >= p
+    return keep.to(torch.bfloat16) * (1.0 / (1.0 - p))
+
+
+class _RcnnHeadFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, feat, rois, rt, pool, p_drop, w6, b6, w7, b7, wc, bc, wl, bl):
+        ph, pw, scale = pool
+        NB, H, W, C = feat.shape
+        R = rois.shape[0]
+        lib = load()
+        st = stream_ptr(feat.device)
+        feat_nchw = tc.nhwc_bf16_to_nchw_f32(feat)
+        pooled = torch.empty(R, C, ph, pw, dtype=torch.float32, device=feat.device)
+        argmax = torch.empty(R, C, ph, pw, dtype=torch.int32, device=feat.device)
+        rois = rois.contiguous().float()
+        with torch.cuda.device(feat.device):
+            check(lib.ROIPoolForwardLaucher(feat_nchw.data_ptr(), scale, R, H, W, C, ph, pw,
+                                            rois.data_ptr(), pooled.data_ptr(), argmax.data_ptr(), st),
+                  "ROIPoolForwardLaucher")
+        x = pooled.view(R, -1).to(torch.bfloat16)
+        dm6 = _dropout_scale((R, w6.shape[0]), p_drop[0], feat.device)
+        dm7 = _dropout_scale((R, w7.shape[0]), p_drop[1], feat.device)
+        h6 = tc.gemm_tn(x, rt.shadow(w6), b6.detach(), relu=True, mul_src=dm6)
+        h7 = tc.gemm_tn(h6, rt.shadow(w7), b7.detach(), relu=True, mul_src=dm7)
+        wcat, bcat, nc, nl = rt.rcnn_cat()
+        out = tc.gemm_tn(h7, wcat[:nc + nl], bcat, out_dtype=torch.float32)
+        ctx.rt, ctx.pool, ctx.geom = rt, pool, (NB, H, W, C)
+        ctx.has_drop = (dm6 is not None, dm7 is not None)
+        keep = [rois, argmax, x, h6, h7] + [t for t in (dm6, dm7) if t is not None]
+        ctx.save_for_backward(*keep)
+        ctx.set_materialize_grads(False)
+        return h7.float(), out[:, :nc].contiguous(), out[:, nc:].contiguous()
+
+    @staticmethod
+    def backward(ctx, g_fea, g_cls, g_loc):
+        rt = ctx.rt
+        saved = list(ctx.saved_tensors)
+        rois, argmax, x, h6, h7 = saved[:5]
+        rest = saved[5:]
+        dm6 = rest.pop(0) if ctx.has_drop[0] else None
+        dm7 = rest.pop(0) if ctx.has_drop[1] else None
+        v = rt.vgg
+        w6, b6, w7, b7 = v.classifier[0].weight, v.classifier[0].bias, v.classifier[3].weight, v.classifier[3].bias
+        wc, bc, wl, bl = v.fc_rcnn_cls.weight, v.fc_rcnn_cls.bias, v.fc_rcnn_loc.weight, v.fc_rcnn_loc.bias
+        ph, pw, scale = ctx.pool
+        NB, H, W, C = ctx.geom
+        R = x.shape[0]
+        wcat, _, nc, nl = rt.rcnn_cat()
+        npad = wcat.shape[0]
+        g = torch.zeros(R, npad, dtype=torch.bfloat16, device=x.device)
+        gbc = gbl = None
+        if g_cls is not None:
+            g[:, :nc].copy_(g_cls)
+            gbc = _sink_small(bc, g_cls.sum(0))
+        if g_loc is not None:
+            g[:, nc:nc + nl].copy_(g_loc)
+            gbl = _sink_small(bl, g_loc.sum(0))
+        dwcat = tc.linear_wgrad(g, h7)
+        gwc = _sink_small(wc, dwcat[:nc])
+        gwl = _sink_small(wl, dwcat[nc:nc + nl])
+        # d(pre-activation of fc7) = (g . Wcat) * dropout scale * [h7 > 0]
+        d7 = tc.gemm_nn(g, wcat, mask_src=h7, mul_src=dm7)
+        if g_fea is not None:                  # someone differentiates through the fc7 features
+            extra = g_fea.to(torch.bfloat16)
+            if dm7 is not None:
+                extra = extra * dm7
+            d7 = d7 + torch.where(h7 > 0, extra, torch.zeros_like(extra))
+        gb7 = _sink_bias(b7, d7)
+        gw7 = _sink_linear_wgrad(w7, d7, h6)
+        d6 = tc.gemm_nn(d7, rt.shadow(w7), mask_src=h6, mul_src=dm6)
+        gb6 = _sink_bias(b6, d6)
+        gw6 = _sink_linear_wgrad(w6, d6, x)
+        dx = tc.gemm_nn(d6, rt.shadow(w6), out_dtype=torch.float32)          # [R, C*ph*pw]
+        d_nchw = torch.empty(NB, C, H, W, dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            check(load().ROIPoolBackwardLaucher(dx.data_ptr(), scale, NB, R, H, W, C, ph, pw,
+                                                rois.data_ptr(), d_nchw.data_ptr(), argmax.data_ptr(),
+                                                stream_ptr(x.device)), "ROIPoolBackwardLaucher")
+        d_feat = tc.nchw_f32_to_nhwc_bf16(d_nchw)
+        return d_feat, None, None, None, None, gw6, gb6, gw7, gb7, gwc, gbc, gwl, gbl

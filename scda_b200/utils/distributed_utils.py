@@ -61,33 +61,81 @@ def broadcast_params(model):
             off += t.numel()
 
 
+def flat_layout(params, align=64):
+    """offset of each parameter in a flat buffer; every segment starts on an `align`-element
+    boundary (16-byte aligned fp32 AND bf16 views for TMA) -> (offsets, total length)"""
+    offs, off = [], 0
+    for p in params:
+        offs.append(off)
+        off += (p.numel() + align - 1) // align * align
+    return offs, off
+
+
+def flat_view(flat, off, p):
+    """view of flat[off : off + p.numel()] with p's shape; 4-D weights are laid out
+    [O][kh][kw][I] (channels_last), the order the NHWC convolution kernels read."""
+    seg = flat[off:off + p.numel()]
+    if p.dim() == 4:
+        o, i, kh, kw = p.shape
+        return seg.view(o, kh, kw, i).permute(0, 3, 1, 2)
+    return seg.view(p.shape)
+
+
 class FlatGradBucket(object):
     """All gradients of one network as views into one contiguous fp32 buffer, so the
     data-parallel exchange is a single all-reduce and the optimiser can sweep one array."""
 
-    def __init__(self, params):
+    def __init__(self, params, offsets=None, total=None, channels_last=False):
         self.params = [p for p in params if p.requires_grad]
-        n = sum(p.numel() for p in self.params)
+        if offsets is None:
+            offsets, total = flat_layout(self.params, 1)
+        self.offsets, self.channels_last = offsets, channels_last
         dev = self.params[0].device if self.params else "cpu"
-        self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
-        off = 0
-        for p in self.params:
-            p.grad = self.flat[off:off + p.numel()].view_as(p)
-            off += p.numel()
+        self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        self._views = [self._view(p, off) for p, off in zip(self.params, offsets)]
+        for p, v in zip(self.params, self._views):
+            p.grad = v
+
+    def _view(self, p, off):
+        if self.channels_last:
+            return flat_view(self.flat, off, p)
+        return self.flat[off:off + p.numel()].view_as(p)
 
     def zero(self):
-        self.flat.zero_()
+        """zero everything except gradients that a direct writer will overwrite
+        (`p._scda_direct_grad` and large): those are only marked fresh."""
+        skip = []
+        for p, off in zip(self.params, self.offsets):
+            if getattr(p, "_scda_direct_grad", False):
+                p._scda_grad_fresh = True
+                if p.numel() >= (1 << 20):
+                    skip.append((off, off + p.numel()))
+        if not skip:
+            self.flat.zero_()
+            return
+        pos = 0
+        for a, b in skip:
+            if a > pos:
+                self.flat[pos:a].zero_()
+            pos = b
+        if pos < self.flat.numel():
+            self.flat[pos:].zero_()
+
+    def settle(self):
+        """a gradient still marked fresh was never written this step: it is zero"""
+        for p, v in zip(self.params, self._views):
+            if getattr(p, "_scda_grad_fresh", False):
+                if p.numel() >= (1 << 20):
+                    v.zero_()
+                p._scda_grad_fresh = False
 
     def rebind(self):
         """Re-point p.grad at the flat buffer if something replaced it."""
-        off = 0
-        for p in self.params:
-            view = self.flat[off:off + p.numel()].view_as(p)
+        for p, view in zip(self.params, self._views):
             if p.grad is None or p.grad.data_ptr() != view.data_ptr():
                 if p.grad is not None:
                     view.copy_(p.grad)
                 p.grad = view
-            off += p.numel()
 
     def all_reduce(self, async_op=False):
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:

@@ -19,7 +19,7 @@ def test_library_is_built_and_loads():
     from scda_b200 import _lib
     assert os.path.exists(_lib.LIB_PATH), "run `python -m scda_b200.build`"
     lib = _lib.load()
-    assert lib.scda_abi_version() == 1
+    assert lib.scda_abi_version() == 2
 
 
 def test_every_declared_symbol_is_exported_and_bound():

@@ -1,0 +1,305 @@
+"""The detector's tensor-core execution (scda_b200/tc_detector.py) against the plain PyTorch
+fp32 graph of the SAME modules and weights (`model._fp32_graph = True`: torch.nn convs /
+linears in fp32 NCHW with TF32 off), plus the bf16 NHWC helper kernels against torch.
+
+Tolerances: operands are rounded to bf16 (rel 2^-8) at every layer and accumulated in fp32;
+over the 13-layer stack the feature map agrees to a few percent of its RMS, gradients of a
+scalar loss to cosine similarity > 0.99.  They are written next to each check."""
+import numpy as np
+import pytest
+
+import _inputs
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    a, b = a.float(), b.float()
+    return float((a - b).pow(2).mean().sqrt() / b.pow(2).mean().sqrt().clamp(min=1e-20))
+
+
+def _cos(a, b):
+    a, b = a.float().reshape(-1), b.float().reshape(-1)
+    return float((a * b).sum() / (a.norm() * b.norm()).clamp(min=1e-30))
+
+
+def _no_tf32():
+    import torch
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+
+
+# ------------------------------------------------------------------ helper kernels
+@pytest.mark.parametrize("NB,H,W,C", [(1, 8, 16, 64), (2, 32, 64, 128), (1, 512, 1024, 64), (1, 6, 10, 8)])
+def test_maxpool_fwd_bwd(cuda_lib, NB, H, W, C):
+    import torch
+    import torch.nn.functional as F
+    from scda_b200 import tc
+    g = torch.Generator(device="cuda").manual_seed(H + C)
+    # post-ReLU-like input with many exact ties (zeros and coarse bf16 values)
+    x = (torch.randn(NB, H, W, C, device="cuda", generator=g).clamp(min=0) * 2).round().div(2).bfloat16()
+    y = tc.maxpool2x2_nhwc(x)
+    xr = x.float().permute(0, 3, 1, 2).requires_grad_(True)
+    yr = F.max_pool2d(xr, 2, 2)
+    assert torch.equal(y.float(), yr.detach().permute(0, 2, 3, 1))
+    dy = torch.randn(NB, H // 2, W // 2, C, device="cuda", generator=g).bfloat16()
+    yr.backward(dy.float().permute(0, 3, 1, 2))
+    dx = tc.maxpool2x2_bwd_nhwc(x, dy, relu_mask=False)
+    assert torch.equal(dx.float(), xr.grad.permute(0, 2, 3, 1)), "first-maximum tie rule"
+    dxm = tc.maxpool2x2_bwd_nhwc(x, dy, relu_mask=True)
+    ref = torch.where(x.float() > 0, xr.grad.permute(0, 2, 3, 1), torch.zeros_like(dx.float()))
+    assert torch.equal(dxm.float(), ref)
+
+
+@pytest.mark.parametrize("NB,C,H,W,Cpad", [(1, 3, 512, 1024, 64), (2, 3, 17, 33, 64), (1, 512, 32, 64, 512),
+                                           (1, 70, 9, 13, 72)])
+def test_layout_kernels(cuda_lib, NB, C, H, W, Cpad):
+    import torch
+    from scda_b200 import tc
+    g = torch.Generator(device="cuda").manual_seed(C + H)
+    x = torch.randn(NB, C, H, W, device="cuda", generator=g)
+    y = tc.nchw_f32_to_nhwc_bf16(x, Cpad)
+    assert y.shape == (NB, H, W, Cpad)
+    assert torch.equal(y[..., :C], x.permute(0, 2, 3, 1).bfloat16())
+    assert float(y[..., C:].abs().sum()) == 0
+    if Cpad == C:
+        back = tc.nhwc_bf16_to_nchw_f32(y)
+        assert torch.equal(back, x.bfloat16().float())
+
+
+@pytest.mark.parametrize("M,N", [(2048, 512), (524288, 64), (512, 4096), (300, 46), (7, 2)])
+def test_colsum_and_reduce_slabs(cuda_lib, M, N):
+    import torch
+    from scda_b200 import tc
+    g = torch.Generator(device="cuda").manual_seed(M + N)
+    x = torch.randn(M, N, device="cuda", generator=g).bfloat16()
+    out = torch.ones(N, device="cuda")
+    tc.colsum_into(x, out)
+    ref = x.double().sum(0) + 1
+    assert float((out.double() - ref).abs().max()) <= 1e-5 * M ** 0.5 * 4 + 1e-4
+    part = torch.randn(5, 64, 36, device="cuda", generator=g)
+    dst = torch.full((64, 36), 2.0, device="cuda")
+    tc.reduce_slabs(part, dst, accumulate=True)
+    assert torch.allclose(dst, part.sum(0) + 2, rtol=1e-6, atol=1e-6)
+    tc.reduce_slabs(part, dst, accumulate=False)
+    assert torch.allclose(dst, part.sum(0), rtol=1e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize("NB,H,W,Cin,Cout", [(1, 8, 16, 64, 64), (1, 32, 64, 512, 512), (2, 16, 32, 128, 256),
+                                             (1, 64, 128, 256, 128), (1, 24, 40, 64, 192)])
+def test_conv_dgrad_from_forward_weights(cuda_lib, NB, H, W, Cin, Cout):
+    import torch
+    from scda_b200 import tc
+    _no_tf32()
+    g = torch.Generator(device="cuda").manual_seed(Cin + Cout + H)
+    x = torch.randn(NB, H, W, Cin, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(Cout, 3, 3, Cin, device="cuda", generator=g) / (9 * Cout) ** 0.5).bfloat16()
+    dy = torch.randn(NB, H, W, Cout, device="cuda", generator=g).bfloat16()
+    ref = torch.nn.grad.conv2d_input((NB, Cin, H, W), w.float().permute(0, 3, 1, 2),
+                                     dy.float().permute(0, 3, 1, 2), padding=1).permute(0, 2, 3, 1)
+    dx = tc.conv3x3_dgrad_nhwc(dy, w)
+    tol = 1e-2 * ref.abs() + 1e-2 * ref.pow(2).mean().sqrt()
+    assert bool(((dx.float() - ref).abs() <= tol).all())
+    dxm = tc.conv3x3_dgrad_nhwc(dy, w, mask_src=x)
+    refm = torch.where(x.float() > 0, ref, torch.zeros_like(ref))
+    assert bool(((dxm.float() - refm).abs() <= tol).all())
+
+
+def test_gemm_mul_src_epilogue(cuda_lib):
+    import torch
+    from scda_b200 import tc
+    g = torch.Generator(device="cuda").manual_seed(5)
+    a = torch.randn(512, 1024, device="cuda", generator=g).bfloat16()
+    b = (torch.randn(384, 1024, device="cuda", generator=g) / 32).bfloat16()
+    bias = torch.randn(384, device="cuda", generator=g)
+    dm = (torch.rand(512, 384, device="cuda", generator=g) >= 0.5).bfloat16() * 2
+    ref = (a.float() @ b.float().t() + bias).clamp(min=0) * dm.float()
+    out = tc.gemm_tn(a, b, bias, relu=True, mul_src=dm)
+    tol = 1e-2 * ref.abs() + 1e-2 * ref.pow(2).mean().sqrt()
+    assert bool(((out.float() - ref).abs() <= tol).all())
+    # backward form: (dY . W) * dm * [h > 0]
+    dy = torch.randn(512, 384, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(384, 640, device="cuda", generator=g) / 20).bfloat16()
+    h = torch.randn(512, 640, device="cuda", generator=g).bfloat16()
+    dm2 = (torch.rand(512, 640, device="cuda", generator=g) >= 0.5).bfloat16() * 2
+    ref2 = torch.where(h.float() > 0, dy.float() @ w.float(), torch.zeros(512, 640, device="cuda")) * dm2.float()
+    out2 = tc.gemm_nn(dy, w, mask_src=h, mul_src=dm2)
+    tol2 = 1e-2 * ref2.abs() + 1e-2 * ref2.pow(2).mean().sqrt()
+    assert bool(((out2.float() - ref2).abs() <= tol2).all())
+
+
+# ------------------------------------------------------------------ the detector stages
+def _model(seed=0):
+    import torch
+    from scda_b200.models.faster_rcnn.vgg_adver_expansion_cluster import vgg16
+    cfg = _inputs.load_cfg()
+    torch.manual_seed(seed)
+    model = vgg16(cfg=cfg["shared"]).cuda()
+    # biases are zero at init; give them values so that the bias path is exercised
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            if n.endswith("bias"):
+                p.normal_(0, 0.05)
+    return model, cfg
+
+
+def _ste_bf16(x):
+    """round to bf16 in the forward pass, identity in the backward pass"""
+    return x + (x.bfloat16().float() - x).detach()
+
+
+def _emulated_backbone_rpn(model, img):
+    """plain PyTorch fp32 graph of features + rpn_head on the SAME bf16-rounded operands the
+    kernels see: weights rounded to bf16, activations rounded after every ReLU."""
+    import torch.nn as nn
+    import torch.nn.functional as F
+    x = _ste_bf16(img)
+    for m in model.features.children():
+        if isinstance(m, nn.Conv2d):
+            x = _ste_bf16(F.relu(F.conv2d(x, _ste_bf16(m.weight), m.bias, padding=1)))
+        elif isinstance(m, nn.MaxPool2d):
+            x = F.max_pool2d(x, 2, 2)
+    h = model.rpn_head
+    hid = _ste_bf16(F.relu(F.conv2d(x, _ste_bf16(h.conv3x3.weight), h.conv3x3.bias, padding=1)))
+    cls = F.conv2d(hid, _ste_bf16(h.conv_cls.weight), h.conv_cls.bias)
+    loc = F.conv2d(hid, _ste_bf16(h.conv_loc.weight), h.conv_loc.bias)
+    return x, cls, loc
+
+
+def test_backbone_and_rpn_match_fp32_graph(cuda_lib):
+    import torch
+    _no_tf32()
+    model, cfg = _model()
+    model.train()
+    g = torch.Generator(device="cuda").manual_seed(1)
+    img = torch.randn(1, 3, 128, 256, device="cuda", generator=g)
+
+    def run(mode):
+        model.zero_grad()
+        if mode == "tc":
+            feat = model.feature_extractor(img)
+            cls, loc = model.rpn(feat)
+            feat_nchw = feat.permute(0, 3, 1, 2)
+        elif mode == "fp32":
+            model._fp32_graph = True
+            feat_nchw = model.feature_extractor(img)
+            cls, loc = model.rpn(feat_nchw)
+            model._fp32_graph = False
+        else:
+            feat_nchw, cls, loc = _emulated_backbone_rpn(model, img)
+        # a scalar loss that touches both the RPN outputs and the feature map
+        w1 = torch.linspace(-1, 1, cls.numel(), device="cuda").view_as(cls)
+        w2 = torch.linspace(1, -1, loc.numel(), device="cuda").view_as(loc)
+        loss = (cls * w1).sum() + (loc * w2).sum() + 1e-2 * (feat_nchw.float() ** 2).sum()
+        loss.backward()
+        grads = {n: p.grad.detach().clone() for n, p in model.named_parameters() if p.grad is not None}
+        return feat_nchw.detach().float(), cls.detach(), loc.detach(), grads
+
+    f_ref, c_ref, l_ref, g_ref = run("fp32")
+    f_emu, c_emu, l_emu, g_emu = run("emulated")
+    f_tc, c_tc, l_tc, g_tc = run("tc")
+    assert f_tc.shape == f_ref.shape
+    # against the true fp32 graph: 13 bf16 layers -> a few percent of the RMS
+    assert _rel(f_tc, f_ref) < 3e-2
+    assert _rel(c_tc, c_ref) < 3e-2 and _rel(l_tc, l_ref) < 3e-2
+    # against the same-operand graph: only the accumulation order and the bf16 rounding of
+    # the back-propagated gradients differ
+    assert _rel(f_tc, f_emu) < 1e-2
+    assert _rel(c_tc, c_emu) < 1e-2 and _rel(l_tc, l_emu) < 1e-2
+    names = [n for n in g_ref if n.startswith("features") or n.startswith("rpn_head")]
+    assert len(names) == 2 * 13 + 6
+    report = {}
+    for n in names:
+        assert n in g_tc, n
+        assert g_tc[n].shape == g_emu[n].shape
+        report[n] = (round(_cos(g_tc[n], g_emu[n]), 4), round(float(g_tc[n].norm() / g_emu[n].norm()), 3),
+                     round(_cos(g_tc[n], g_ref[n]), 4))
+    bad = {n: v for n, v in report.items() if not (v[0] > 0.99 and 0.95 < v[1] < 1.05 and v[2] > 0.9)}
+    assert not bad, (bad, report)
+
+
+def test_rcnn_head_matches_fp32_graph(cuda_lib):
+    import torch
+    _no_tf32()
+    model, cfg = _model(1)
+    model.eval()                                # dropout off: both graphs are deterministic
+    g = torch.Generator(device="cuda").manual_seed(2)
+    feat_nchw = torch.randn(1, 512, 32, 64, device="cuda", generator=g).clamp(min=0)
+    feat_nchw = feat_nchw.bfloat16().float()
+    rois = torch.from_numpy(_inputs.rois_uniform(96, 3, img_w=1024, img_h=512)).cuda()
+
+    def run(fp32):
+        model._fp32_graph = fp32
+        model.zero_grad()
+        if fp32:
+            f = feat_nchw.clone().requires_grad_(True)
+        else:
+            f = feat_nchw.permute(0, 2, 3, 1).contiguous().bfloat16().requires_grad_(True)
+        fea, cls, loc = model.rcnn(f, rois)
+        w1 = torch.linspace(-1, 1, cls.numel(), device="cuda").view_as(cls)
+        w2 = torch.linspace(1, -1, loc.numel(), device="cuda").view_as(loc)
+        ((cls * w1).sum() + (loc * w2).sum()).backward()
+        grads = {n: p.grad.detach().clone() for n, p in model.named_parameters() if p.grad is not None}
+        gf = f.grad.float() if fp32 else f.grad.float().permute(0, 3, 1, 2)
+        return fea.detach(), cls.detach(), loc.detach(), grads, gf
+
+    fea_r, cls_r, loc_r, g_r, gf_r = run(True)
+    fea_t, cls_t, loc_t, g_t, gf_t = run(False)
+    model._fp32_graph = False
+    assert _rel(fea_t, fea_r) < 2e-2 and _rel(cls_t, cls_r) < 2e-2 and _rel(loc_t, loc_r) < 2e-2
+    for n in ("classifier.0.weight", "classifier.0.bias", "classifier.3.weight", "classifier.3.bias",
+              "fc_rcnn_cls.weight", "fc_rcnn_cls.bias", "fc_rcnn_loc.weight", "fc_rcnn_loc.bias"):
+        assert _cos(g_t[n], g_r[n]) > 0.995, (n, _cos(g_t[n], g_r[n]))
+        assert 0.95 < float(g_t[n].norm() / g_r[n].norm()) < 1.05, n
+    assert _cos(gf_t, gf_r) > 0.995
+
+
+def test_rcnn_dropout_statistics(cuda_lib):
+    """training mode: the dropout keep/scale tensor rides in the GEMM epilogue; about half of
+    the positive fc7 activations survive and the survivors are scaled by 2."""
+    import torch
+    model, cfg = _model(2)
+    rois = torch.from_numpy(_inputs.rois_uniform(128, 4, img_w=1024, img_h=512)).cuda()
+    feat = torch.randn(1, 32, 64, 512, device="cuda").clamp(min=0).bfloat16()
+    model.eval()
+    with torch.no_grad():
+        fea_eval, _, _ = model.rcnn(feat, rois)
+    model.train()
+    torch.manual_seed(0)
+    with torch.no_grad():
+        fea_train, _, _ = model.rcnn(feat, rois)
+    frac_eval = float((fea_eval > 0).float().mean())
+    frac_train = float((fea_train > 0).float().mean())
+    assert 0.35 * frac_eval < frac_train < 0.65 * frac_eval + 0.05
+
+
+def test_flat_adam_step_matches_torch_adam_with_tc_layout(cuda_lib):
+    """FlatAdam(tensor_core=True): channels_last conv weights in the flat buffer, bf16 shadow
+    refreshed by the optimiser kernel; the update equals torch's Adam (weight decay added
+    to the gradient) on the same gradients."""
+    import copy
+    import torch
+    from scda_b200.engine import FlatAdam
+    model, cfg = _model(3)
+    ref = copy.deepcopy(model)
+    opt = FlatAdam(model, 1e-3, weight_decay=1e-4, tensor_core=True)
+    topt = torch.optim.Adam(ref.parameters(), lr=1e-3, weight_decay=1e-4)
+    g = torch.Generator(device="cuda").manual_seed(4)
+    for _ in range(2):
+        opt.zero_grad()
+        for (n, p), q in zip(model.named_parameters(), ref.parameters()):
+            gr = torch.randn(p.shape, device="cuda", generator=g) * 1e-2
+            p.grad.copy_(gr)
+            p._scda_grad_fresh = False
+            q.grad = gr.clone()
+        opt.step()
+        topt.step()
+    for (n, p), q in zip(model.named_parameters(), ref.parameters()):
+        assert torch.allclose(p.detach(), q.detach(), rtol=1e-4, atol=1e-6), n
+        sh = p._scda_shadow
+        want = p.detach().permute(0, 2, 3, 1) if p.dim() == 4 else p.detach()
+        assert torch.equal(sh, want.bfloat16()), n
+    w = model.features[2].weight
+    assert w.permute(0, 2, 3, 1).is_contiguous() and w.shape == (64, 64, 3, 3)
+    sd = model.state_dict()
+    assert sd["features.2.weight"].shape == (64, 64, 3, 3)
