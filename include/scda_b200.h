@@ -223,16 +223,39 @@ int scda_reduce_slabs_f32(const float *slabs, long long slab_stride, int n_slabs
 /* bias gradient: out[N] += column sums of x[M, ld] (bf16) */
 int scda_colsum_bf16(long long M, int N, const void *x, long long ld, float *out, cudaStream_t stream);
 
+/* --- region grouping (k-means of RoI centres) --------------------------- */
+/* replaces, inside compute_cluster_targets (functions/mask.py:193-237), the host call
+ * sklearn.cluster.KMeans(n_clusters=k, random_state=0).fit(centres) on the float32 RoI
+ * centres (:205-211) and the per-cluster member selection (:213-224).
+ * rois [n, roi_stride] fp32 rows (b, x1, y1, x2, y2, ...).  first_center_id and
+ * uniforms[(k-1) * n_local_trials] are the data-independent draws of numpy's
+ * RandomState(0) that k-means++ consumes (the caller generates them once per n, k).
+ * Outputs: labels [n] int32, centers [k, 2] fp32 (cx, cy), counts [k] int32 and, when
+ * threshold > 0, index [k * threshold] int64 = for each cluster its first `threshold`
+ * members in ascending RoI order, or — for a smaller cluster — members re-drawn with
+ * replacement using pick_uniform[k * threshold] in [0, 1).  n <= 2048, k <= 16.
+ * workspace >= scda_kmeans_workspace_bytes(n, k).  One CTA; nothing synchronises. */
+size_t scda_kmeans_workspace_bytes(int n, int k);
+int scda_kmeans_regions(const float *rois, int roi_stride, int n, int k, int first_center_id,
+                        const double *uniforms, int n_local_trials, int max_iter, float tol,
+                        const float *pick_uniform, int threshold, int *labels, float *centers,
+                        int *counts, long long *index, void *workspace, size_t workspace_bytes,
+                        cudaStream_t stream);
+
 /* --- optimiser -------------------------------------------------------- */
 /* replaces torch.optim.Adam(...).step() on each of the four networks
  * (tools/faster_rcnn_train_val.py:305-316 construct, :616,:635,:704,:750 step): one pass
  * over a network's FLAT fp32 parameter / gradient / moment buffers (torch 0.4.1 update
  * rule, weight decay added to the gradient).  grad_scale multiplies the gradient first
  * (1 when the loss was already divided by world size).  bf16_shadow, if not NULL, receives
- * the updated parameters rounded to bf16 for the tensor-core kernels.  step counts from 1. */
+ * the updated parameters rounded to bf16 for the tensor-core kernels.  step counts from 1.
+ * lr_t_dev, if not NULL, is a device float holding the bias-corrected step size
+ * lr * sqrt(1 - beta2^t) / (1 - beta1^t) for this step (then `step` and `lr` are ignored):
+ * a captured CUDA graph replays the launch while the host only refreshes that scalar. */
 int scda_adam_step(float *param, const float *grad, float *exp_avg, float *exp_avg_sq,
                    void *bf16_shadow, long long n, int step, float lr, float beta1, float beta2,
-                   float eps, float weight_decay, float grad_scale, cudaStream_t stream);
+                   float eps, float weight_decay, float grad_scale, const float *lr_t_dev,
+                   cudaStream_t stream);
 
 #ifdef __cplusplus
 }

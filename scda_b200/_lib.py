@@ -49,7 +49,9 @@ SIGNATURES = {
     "scda_gemm_bf16_nn": (_i, [_i, _i, _i, _p, C.c_longlong, _p, C.c_longlong, _p, _p, C.c_longlong, _i, _p, _p, _p]),
     "scda_linear_wgrad_bf16": (_i, [_i, _i, _i, _p, C.c_longlong, _p, C.c_longlong, _p, C.c_longlong, _i, _p]),
     "scda_conv3x3_wgrad_bf16_nhwc": (_i, [_i, _i, _i, _i, _i, _p, _p, _p, _i, _p]),
-    "scda_adam_step": (_i, [_p, _p, _p, _p, _p, C.c_longlong, _i, _f, _f, _f, _f, _f, _f, _p]),
+    "scda_kmeans_workspace_bytes": (_z, [_i, _i]),
+    "scda_kmeans_regions": (_i, [_p, _i, _i, _i, _i, _p, _i, _i, _f, _p, _i, _p, _p, _p, _p, _p, _z, _p]),
+    "scda_adam_step": (_i, [_p, _p, _p, _p, _p, C.c_longlong, _i, _f, _f, _f, _f, _f, _f, _p, _p]),
 }
 
 _LIB = None

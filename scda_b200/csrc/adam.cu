@@ -20,8 +20,9 @@ namespace {
 __global__ void __launch_bounds__(256)
 adam_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m,
             float *__restrict__ v, __nv_bfloat16 *__restrict__ shadow, long long n, float grad_scale,
-            float lr_t, float b1, float b2, float eps, float wd)
+            float lr_t, float b1, float b2, float eps, float wd, const float *__restrict__ lr_t_dev)
 {
+    if (lr_t_dev) lr_t = __ldg(lr_t_dev);     // step size kept on the device (CUDA-graph replays)
     const long long stride = (long long)gridDim.x * blockDim.x * 4;
     for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
         if (i + 4 <= n) {
@@ -65,19 +66,22 @@ adam_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restric
 SCDA_API int scda_adam_step(float *param, const float *grad, float *exp_avg, float *exp_avg_sq,
                             void *bf16_shadow, long long n, int step, float lr, float beta1,
                             float beta2, float eps, float weight_decay, float grad_scale,
-                            cudaStream_t stream)
+                            const float *lr_t_dev, cudaStream_t stream)
 {
-    if (n < 0 || step < 1) return 0;
+    if (n < 0 || (step < 1 && !lr_t_dev)) return 0;
     if (n == 0) return 1;
     if (!param || !grad || !exp_avg || !exp_avg_sq) return 0;
     if (((uintptr_t)param | (uintptr_t)grad | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq) % 16) return 0;
     if (bf16_shadow && (uintptr_t)bf16_shadow % 8) return 0;
-    const double bc1 = 1.0 - pow((double)beta1, step), bc2 = 1.0 - pow((double)beta2, step);
-    const float lr_t = (float)((double)lr * sqrt(bc2) / bc1);
+    float lr_t = 0.f;
+    if (!lr_t_dev) {
+        const double bc1 = 1.0 - pow((double)beta1, step), bc2 = 1.0 - pow((double)beta2, step);
+        lr_t = (float)((double)lr * sqrt(bc2) / bc1);
+    }
     long long want = (n / 4 + 255) / 256;
     const int grid = (int)(want < (long long)kNumSMs * 8 ? (want < 1 ? 1 : want) : (long long)kNumSMs * 8);
     adam_kernel<<<grid, 256, 0, stream>>>(param, grad, exp_avg, exp_avg_sq,
                                           (__nv_bfloat16 *)bf16_shadow, n, grad_scale, lr_t, beta1,
-                                          beta2, eps, weight_decay);
+                                          beta2, eps, weight_decay, lr_t_dev);
     return scda_launch_status();
 }

@@ -34,25 +34,30 @@ class FlatAdam(object):
     """Adam(lr, betas, eps, weight_decay) of torch 0.4.1 over one network, flat storage,
     stepped by libscda_b200's scda_adam_step.
 
-    Parameters, gradients, both moments and (tensor_core=True) a bf16 shadow of the
-    parameters live in flat buffers with one 64-element-aligned segment per parameter; 4-D
-    weights are stored [O][kh][kw][I] (the parameter keeps its [O,I,kh,kw] shape with
-    channels_last strides), so the shadow segment of a conv weight IS the KRSC operand of the
-    tcgen05 kernels and is refreshed by the optimiser kernel itself."""
+    Parameters, gradients and both moments live in flat buffers with one 64-element-aligned
+    segment per parameter.  channels_last=True stores 4-D weights [O][kh][kw][I] (the
+    parameter keeps its [O,I,kh,kw] shape with channels_last strides); tensor_core=True adds
+    a bf16 shadow of the parameters in the same layout, refreshed by the optimiser kernel
+    itself: the shadow segment of a conv weight IS the KRSC operand of the tcgen05 kernels.
 
-    def __init__(self, module, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-4, tensor_core=False):
+    The bias-corrected step size lives in a device scalar (`lr_t_dev`) that `begin_step`
+    refreshes, so `step_dev` is a pure kernel launch and can sit inside a CUDA graph."""
+
+    def __init__(self, module, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-4, tensor_core=False,
+                 channels_last=None):
         from .utils.distributed_utils import flat_layout, flat_view
+        channels_last = tensor_core if channels_last is None else channels_last
         self.params = [p for p in module.parameters() if p.requires_grad]
         assert self.params and all(p.is_cuda and p.dtype == torch.float32 for p in self.params)
         dev = self.params[0].device
         self.offsets, n = flat_layout(self.params, 64)
         self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
         for p, off in zip(self.params, self.offsets):
-            view = flat_view(self.flat, off, p) if tensor_core else self.flat[off:off + p.numel()].view_as(p)
+            view = flat_view(self.flat, off, p) if channels_last else self.flat[off:off + p.numel()].view_as(p)
             view.copy_(p.data)
             p.data = view
         self.n = n
-        self.bucket = FlatGradBucket(self.params, self.offsets, n, channels_last=tensor_core)
+        self.bucket = FlatGradBucket(self.params, self.offsets, n, channels_last=channels_last)
         module._scda_bucket = self.bucket
         self.exp_avg = torch.zeros_like(self.flat)
         self.exp_avg_sq = torch.zeros_like(self.flat)
@@ -70,6 +75,8 @@ class FlatAdam(object):
                 p._scda_direct_grad = True
         self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
         self.t = 0
+        self.lr_t_dev = torch.zeros(1, dtype=torch.float32, device=dev)
+        self._lr_t_host = torch.zeros(1, dtype=torch.float32).pin_memory()
 
     def zero_grad(self):
         self.bucket.zero()
@@ -79,18 +86,25 @@ class FlatAdam(object):
         self.bucket.settle()
         self.bucket.all_reduce()
 
-    def step(self, lr=None, grad_scale=1.0):
+    def begin_step(self, lr=None):
+        """host side of one optimiser step: count it and publish the step size"""
         self.t += 1
+        lr = float(self.lr if lr is None else lr)
+        bc1, bc2 = 1.0 - self.betas[0] ** self.t, 1.0 - self.betas[1] ** self.t
+        self._lr_t_host[0] = lr * (bc2 ** 0.5) / bc1
+        self.lr_t_dev.copy_(self._lr_t_host, non_blocking=True)
+
+    def step_dev(self, grad_scale=1.0):
+        """device side: one fused kernel over the flat buffers (graph-capturable)"""
         self.bucket.rebind()
         self.bucket.settle()
         with torch.cuda.device(self.flat.device):
             check(load().scda_adam_step(
                 self.flat.data_ptr(), self.bucket.flat.data_ptr(), self.exp_avg.data_ptr(),
                 self.exp_avg_sq.data_ptr(), self.shadow.data_ptr() if self.shadow is not None else None,
-                self.n, self.t,
-                float(self.lr if lr is None else lr), self.betas[0], self.betas[1], self.eps,
-                self.weight_decay, float(grad_scale), stream_ptr(self.flat.device)),
-                "scda_adam_step")
+                self.n, max(self.t, 1), float(self.lr), self.betas[0], self.betas[1], self.eps,
+                self.weight_decay, float(grad_scale), self.lr_t_dev.data_ptr(),
+                stream_ptr(self.flat.device)), "scda_adam_step")
         # the kernel wrote the parameters through raw pointers: stamp what is (not) in sync
         for p in self.params:
             p._scda_epoch = getattr(p, "_scda_epoch", 0) + 1
@@ -98,6 +112,10 @@ class FlatAdam(object):
                 p._scda_shadow_version = p._version
             elif hasattr(p, "_scda_shadow_version"):
                 p._scda_shadow_version = -1
+
+    def step(self, lr=None, grad_scale=1.0):
+        self.begin_step(lr)
+        self.step_dev(grad_scale)
 
 
 def get_corner_from_center(center, recon_size, new_w, new_h):
@@ -144,11 +162,17 @@ def _bce_rows(p, label_row):
 
 
 class SCDATrainer(object):
-    """The reference's four networks + optimisers for one rank."""
+    """The reference's four networks + optimisers for one rank.
+
+    The three reconstruction / discriminator updates (phases 1-3) and the forward of phase 4
+    depend only on the two cluster-feature blocks, the two crop stacks and the RNG, all of
+    fixed shape: after one eager warm-up iteration they are captured into CUDA graphs (one
+    per stretch between two gradient all-reduces) and replayed — ~1500 kernel launches per
+    iteration leave the Python/driver launch path.  use_graphs=False keeps them eager."""
 
     def __init__(self, model, dec_model, dis_model, dis_model_patch, lr, cluster_num=4,
                  threshold=128, recon_size=256, new_w=1024, new_h=512, world_size=1,
-                 weight_decay=1e-4):
+                 weight_decay=1e-4, use_graphs=True):
         self.model, self.dec_model = model, dec_model
         self.dis_model, self.dis_model_patch = dis_model, dis_model_patch
         self.opt = FlatAdam(model, lr, weight_decay=weight_decay, tensor_core=True)
@@ -157,6 +181,10 @@ class SCDATrainer(object):
         self.opt_dis_patch = FlatAdam(dis_model_patch, lr, weight_decay=weight_decay)
         self.cluster_num, self.threshold, self.recon_size = cluster_num, threshold, recon_size
         self.new_w, self.new_h, self.world_size = new_w, new_h, world_size
+        self.use_graphs = use_graphs
+        self._static, self._st = None, {}
+        self._graphs = None
+        self._by_shape = {}
 
     def nets(self):
         return (self.model, self.dec_model, self.dis_model, self.dis_model_patch)
@@ -165,80 +193,196 @@ class SCDATrainer(object):
         for n in self.nets():
             n.train()
 
-    def iteration(self, cfg, image, image_info, gts, target, lr=None):
-        """One iteration; returns a dict of 0-dim loss tensors (no host sync here)."""
-        ws = float(self.world_size)
-        x = {'cfg': cfg, 'image': image, 'image_info': image_info, 'ground_truth_bboxes': gts,
-             'ignore_regions': None, 'cluster_num': self.cluster_num, 'threshold': self.threshold}
-        outputs = self.model(x, target)
-        centers_source, centers_target = outputs['cluster_centers']
-        x_small = _crops(image, get_corner_from_center(centers_source, self.recon_size,
-                                                       self.new_w, self.new_h), self.recon_size)
-        target_small = _crops(target, get_corner_from_center(centers_target, self.recon_size,
-                                                             self.new_w, self.new_h), self.recon_size)
-        x_source_patch, x_target_patch = outputs['cluster_features']
-        x_source_recon, x_target_recon = self.dec_model(x_source_patch, x_target_patch)
-
-        # ---- (1) image discriminator
+    # ------------------------------------------------------------------ phases 1-3 (+ 4 forward)
+    def _seg_dis(self):
+        """(1) image discriminator: forward + backward (tools/faster_rcnn_train_val.py:567-611)"""
+        b, st, ws = self._static, self._st, float(self.world_size)
+        xs, xt, cs, ct = b['xs'], b['xt'], b['cs'], b['ct']
+        st['recon'] = self.dec_model(xs, xt)
+        x_source_recon, x_target_recon = st['recon']
         self.opt_dis.zero_grad()
         s_dis, t_dis = [torch.sigmoid(o) for o in self.dis_model(x_source_recon, x_target_recon)]
-        s_real, t_real = [torch.sigmoid(o) for o in self.dis_model(x_small, target_small)]
+        s_real, t_real = [torch.sigmoid(o) for o in self.dis_model(cs, ct)]
         score_1 = soft_label(1, s_real[:1])
         score_0 = soft_label(0, s_dis[:1])
         adloss_source = (_bce_rows(s_dis, score_1) + _bce_rows(s_real, score_0)).sum()
-        t_patch_pro = self.dis_model_patch(x_target_patch)
-        t_patch_mean = torch.mean(t_patch_pro, 1)
-        s_patch_pro = self.dis_model_patch(x_source_patch)
+        st['t_patch_pro'] = self.dis_model_patch(xt)
+        t_patch_mean = torch.mean(st['t_patch_pro'], 1)
+        st['s_patch_pro'] = self.dis_model_patch(xs)
         adloss_target = (t_patch_mean * _bce_rows(t_dis, score_0) + _bce_rows(t_real, score_1)).sum()
         adloss = (adloss_source + adloss_target) / ws
         adloss.backward(retain_graph=True, inputs=self.opt_dis.params)
-        self.opt_dis.all_reduce()
-        self.opt_dis.step(lr)
+        st['dis_loss'] = adloss.detach()
 
-        # ---- (2) patch discriminator
+    def _seg_dis_patch(self):
+        """(1) step; (2) patch discriminator: loss + backward (:616-630)"""
+        st, ws = self._st, float(self.world_size)
+        self.opt_dis.step_dev()
         self.opt_dis_patch.zero_grad()
-        score_0_patch = soft_label(0, t_patch_pro)
-        score_1_patch = soft_label(1, s_patch_pro)
-        dis_patch_loss = (F.binary_cross_entropy(s_patch_pro, score_1_patch)
-                          + F.binary_cross_entropy(t_patch_pro, score_0_patch)) / ws
+        score_0_patch = soft_label(0, st['t_patch_pro'])
+        score_1_patch = soft_label(1, st['s_patch_pro'])
+        dis_patch_loss = (F.binary_cross_entropy(st['s_patch_pro'], score_1_patch)
+                          + F.binary_cross_entropy(st['t_patch_pro'], score_0_patch)) / ws
         dis_patch_loss.backward(retain_graph=True, inputs=self.opt_dis_patch.params)
-        self.opt_dis_patch.all_reduce()
-        self.opt_dis_patch.step(lr)
+        st['dis_patch_loss'] = dis_patch_loss.detach()
 
-        # ---- (3) decoder
+    def _seg_dec(self):
+        """(2) step; (3) decoder: loss + backward (:635-699)"""
+        b, st, ws = self._static, self._st, float(self.world_size)
+        self.opt_dis_patch.step_dev()
         self.opt_dec.zero_grad()
+        x_source_recon, x_target_recon = st['recon']
         s_dis2, t_dis2 = self.dis_model(x_source_recon, x_target_recon)
         s_dis2, t_dis2 = torch.sigmoid(s_dis2), torch.sigmoid(t_dis2)
-        s_real2, t_real2 = [torch.sigmoid(o) for o in self.dis_model(x_small, target_small)]
-        t_patch_mean2 = torch.mean(self.dis_model_patch(x_target_patch), 1)
+        s_real2, t_real2 = [torch.sigmoid(o) for o in self.dis_model(b['cs'], b['ct'])]
+        st['t_patch_mean2'] = torch.mean(self.dis_model_patch(b['xt']), 1).detach()
+        t_patch_mean2 = st['t_patch_mean2']
         ones, zeros = torch.ones_like(t_dis2[:1]), torch.zeros_like(t_dis2[:1])
         fake_loss1_target = (t_patch_mean2 * (_bce_rows(t_dis2, ones) + _bce_rows(t_real2, zeros))).sum()
         fake_loss1_source = (_bce_rows(s_dis2, ones) + _bce_rows(s_real2, zeros)).sum()
         recon_loss = (fake_loss1_source + fake_loss1_target) / ws
-        recon_loss.backward(retain_graph=True, inputs=self.opt_dec.params)
-        self.opt_dec.all_reduce()
-        self.opt_dec.step(lr)
+        recon_loss.backward(inputs=self.opt_dec.params)
+        st['dec_loss'] = recon_loss.detach()
+        st.pop('recon'), st.pop('t_patch_pro'), st.pop('s_patch_pro')
 
-        # ---- (4) detector: decoders swapped (target features -> source reconstruction)
-        x_source_recon2, x_target_recon2 = self.dec_model(x_target_patch, x_source_patch)
-        s_dis3, t_dis3 = self.dis_model(x_source_recon2, x_target_recon2)
-        fake_dis = torch.sigmoid(t_dis3)
-        fake_loss_source = F.binary_cross_entropy(fake_dis, torch.ones_like(fake_dis))
-        fake_dis2 = torch.sigmoid(s_dis3)
-        fake_loss_target = (t_patch_mean2 * _bce_rows(fake_dis2, torch.ones_like(fake_dis2[:1]))).sum()
-        rpn_cls_loss, rpn_loc_loss, rcnn_cls_loss, rcnn_loc_loss = outputs['losses']
+    def _seg_fake(self):
+        """(3) step; forward of (4): decoders swapped, values only (:704-732).  The cluster
+        features are detached (functions/mask.py:234), so these two terms carry no gradient
+        to the detector: no autograd graph is built for them."""
+        b, st = self._static, self._st
+        self.opt_dec.step_dev()
+        with torch.no_grad():
+            x_source_recon2, x_target_recon2 = self.dec_model(b['xt'], b['xs'])
+            s_dis3, t_dis3 = self.dis_model(x_source_recon2, x_target_recon2)
+            fake_dis = torch.sigmoid(t_dis3)
+            st['fake_loss_source'] = F.binary_cross_entropy(fake_dis, torch.ones_like(fake_dis))
+            fake_dis2 = torch.sigmoid(s_dis3)
+            st['fake_loss_target'] = (st['t_patch_mean2']
+                                      * _bce_rows(fake_dis2, torch.ones_like(fake_dis2[:1]))).sum()
+
+    def _seg_forward(self):
+        """detector forward on both images, crops around the cluster centres, then (1)"""
+        b, st = self._static, self._st
+        x = {'cfg': b['cfg'], 'image': b['image'], 'image_info': b['info'], 'ground_truth_bboxes': b['gts'],
+             'ignore_regions': None, 'cluster_num': self.cluster_num, 'threshold': self.threshold,
+             'device_clusters': True}
+        outputs = self.model(x, b['target'])
+        st['det_losses'] = outputs['losses']
+        st['acc'] = outputs['accuracy']
+        centers_source, centers_target = outputs['cluster_centers']
+        b['cs'] = crops_device(b['image'], centers_source, self.recon_size, self.new_w, self.new_h)
+        b['ct'] = crops_device(b['target'], centers_target, self.recon_size, self.new_w, self.new_h)
+        b['xs'], b['xt'] = outputs['cluster_features']
+        self._seg_dis()
+
+    def _seg_detector(self):
+        """(3) step, forward of (4), then the detector backward (:736-745)"""
+        st, ws = self._st, float(self.world_size)
+        self._seg_fake()
+        rpn_cls_loss, rpn_loc_loss, rcnn_cls_loss, rcnn_loc_loss = st.pop('det_losses')
         loss = (rpn_cls_loss + rpn_loc_loss + rcnn_cls_loss + rcnn_loc_loss
-                + 0.1 * (fake_loss_source + fake_loss_target)) / ws
+                + 0.1 * (st['fake_loss_source'] + st['fake_loss_target'])) / ws
         self.opt.zero_grad()
         loss.backward(inputs=self.opt.params)
-        self.opt.all_reduce()
-        self.opt.step(lr)
-        return {'loss': loss.detach() * ws, 'rpn_cls': rpn_cls_loss.detach(),
-                'rpn_loc': rpn_loc_loss.detach(), 'rcnn_cls': rcnn_cls_loss.detach(),
-                'rcnn_loc': rcnn_loc_loss.detach(), 'fake_loss': fake_loss_target.detach(),
-                'dec_loss': recon_loss.detach(), 'dis_loss': adloss.detach(),
-                'dis_patch_loss': dis_patch_loss.detach(),
-                'rpn_acc': outputs['accuracy'][0], 'rcnn_acc': outputs['accuracy'][1]}
+        st['out'] = {'loss': loss.detach() * ws, 'rpn_cls': rpn_cls_loss.detach(),
+                     'rpn_loc': rpn_loc_loss.detach(), 'rcnn_cls': rcnn_cls_loss.detach(),
+                     'rcnn_loc': rcnn_loc_loss.detach(), 'fake_loss': st['fake_loss_target'],
+                     'dec_loss': st['dec_loss'], 'dis_loss': st['dis_loss'],
+                     'dis_patch_loss': st['dis_patch_loss'],
+                     'rpn_acc': st['acc'][0], 'rcnn_acc': st['acc'][1]}
+
+    def _seg_step(self):
+        self.opt.step_dev()
+
+    def _segments(self):
+        """the iteration cut at its four gradient all-reduces: (stretch, optimiser to reduce after)"""
+        return ((self._seg_forward, self.opt_dis), (self._seg_dis_patch, self.opt_dis_patch),
+                (self._seg_dec, self.opt_dec), (self._seg_detector, self.opt), (self._seg_step, None))
+
+    def _capture(self):
+        """one CUDA graph per stretch between two all-reduces (a single graph on one GPU);
+        all share one memory pool, so tensors handed from one stretch to the next stay put"""
+        torch.cuda.synchronize()
+        segs = self._segments()
+        if self.world_size == 1:
+            def whole():
+                for seg, _ in segs:
+                    seg()
+            plan = [whole]
+        else:
+            plan = [seg for seg, _ in segs]
+        pool = torch.cuda.graph_pool_handle()
+        graphs = []
+        for fn in plan:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, pool=pool):
+                fn()
+            graphs.append(g)
+        if self.world_size == 1:
+            graphs = graphs + [_NoGraph()] * (len(segs) - 1)
+        return graphs
+
+    def iteration(self, cfg, image, image_info, gts, target, lr=None):
+        """One iteration; returns a dict of 0-dim loss tensors (no host sync here).
+
+        image / target / gts may live on the host (pinned) or on the device: they are copied
+        into fixed device buffers, which is what lets the iteration be replayed as a graph."""
+        info_key = tuple(float(v) for v in torch.as_tensor(image_info).reshape(-1).tolist())
+        key = (tuple(image.shape), tuple(target.shape), tuple(gts.shape), info_key, id(cfg))
+        ent = self._by_shape.get(key)
+        dev = self.opt.flat.device
+        if ent is None:
+            ent = {'static': {'cfg': cfg, 'info': image_info,
+                              'image': torch.empty(image.shape, dtype=torch.float32, device=dev),
+                              'target': torch.empty(target.shape, dtype=torch.float32, device=dev),
+                              'gts': torch.empty(gts.shape, dtype=gts.dtype, device=dev)},
+                   'graphs': None, 'calls': 0, 'st': {}}
+            self._by_shape[key] = ent
+        self._static, self._st = ent['static'], ent['st']
+        b = self._static
+        b['image'].copy_(image, non_blocking=True)
+        b['target'].copy_(target, non_blocking=True)
+        b['gts'].copy_(gts, non_blocking=True)
+        for o in (self.opt_dis, self.opt_dis_patch, self.opt_dec, self.opt):
+            o.begin_step(lr)
+        multi = self.world_size > 1
+        if not self.use_graphs or ent['calls'] == 0:
+            for seg, opt in self._segments():       # eager (also the warm-up before a capture)
+                seg()
+                if opt is not None and multi:
+                    opt.all_reduce()
+        else:
+            if ent['graphs'] is None:
+                ent['graphs'] = self._capture()
+            for g, (_, opt) in zip(ent['graphs'], self._segments()):
+                g.replay()
+                if opt is not None and multi:
+                    opt.all_reduce()
+        ent['calls'] += 1
+        self._graphs = ent['graphs']
+        return {k: v.clone() for k, v in self._st['out'].items()}
+
+
+def crops_device(image, centers, recon_size, new_w, new_h):
+    """recon_size windows around the cluster centres, shifted to stay inside the image —
+    `get_corner_from_center` (tools/faster_rcnn_train_val.py:411-438) is a clamp of
+    int(c) - recon_size // 2 to [0, size - recon_size] — gathered on the device from
+    centres that never visited the host.  image [1,3,H,W], centers [K,2] -> [K,3,R,R]."""
+    if not torch.is_tensor(centers):
+        centers = torch.as_tensor(np.asarray(centers), dtype=torch.float32, device=image.device)
+    assert recon_size % 2 == 0 and image.shape[0] == 1
+    half = recon_size // 2
+    x1 = (centers[:, 0].to(torch.int64) - half).clamp(0, new_w - recon_size)
+    y1 = (centers[:, 1].to(torch.int64) - half).clamp(0, new_h - recon_size)
+    ar = torch.arange(recon_size, device=image.device)
+    ys = (y1[:, None] + ar)[:, :, None]
+    xs = (x1[:, None] + ar)[:, None, :]
+    return image[0][:, ys, xs].permute(1, 0, 2, 3).contiguous()
+
+
+class _NoGraph(object):
+    def replay(self):
+        pass
 
 
 def builder_gan(cluster_num=4, threshold=128, recon_size=256, neww=64, newh=64):
@@ -257,13 +401,14 @@ def builder_gan(cluster_num=4, threshold=128, recon_size=256, neww=64, newh=64):
 
 
 def build_trainer(cfg, lr=1.25e-5, device="cuda", cluster_num=4, threshold=128, recon_size=256,
-                  new_w=1024, new_h=512, world_size=1, seed=0):
+                  new_w=1024, new_h=512, world_size=1, seed=0, use_graphs=True):
     from .models.faster_rcnn.vgg_adver_expansion_cluster import vgg16
     torch.manual_seed(seed)
     np.random.seed(seed)
     model = vgg16(pretrained=False, cfg=cfg['shared']).to(device)
     dis_model, dec_model, dis_model_patch = builder_gan(cluster_num, threshold, recon_size)
     tr = SCDATrainer(model, dec_model.to(device), dis_model.to(device), dis_model_patch.to(device),
-                     lr, cluster_num, threshold, recon_size, new_w, new_h, world_size)
+                     lr, cluster_num, threshold, recon_size, new_w, new_h, world_size,
+                     use_graphs=use_graphs)
     tr.train_mode()
     return tr

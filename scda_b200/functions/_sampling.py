@@ -15,6 +15,28 @@ function built from the same arrays (tests/_sampling_adapter.py).
 import torch
 
 
+_CONST = {}
+
+
+def const_tensor(values, dtype, device):
+    """small constant tensor built once per (values, dtype, device): creating it from a
+    Python list on every call is an unpinned H2D copy, which a CUDA-graph capture forbids"""
+    key = (tuple(float(v) for v in values), dtype, str(device))
+    t = _CONST.get(key)
+    if t is None:
+        t = torch.tensor(list(values), dtype=dtype, device=device)
+        _CONST[key] = t
+    return t
+
+
+def scalar_i64(v, device):
+    """0-dim int64 device tensor from a Python int (a fill kernel, not an H2D copy) or from
+    a device scalar (no host read): both forms are legal inside a CUDA-graph capture"""
+    if torch.is_tensor(v):
+        return v.to(device=device, dtype=torch.int64).reshape(())
+    return torch.full((), int(v), dtype=torch.int64, device=device)
+
+
 class TorchRng(object):
     def __init__(self, generator=None):
         self.generator = generator
@@ -73,7 +95,7 @@ def choose(mask, want, rng, kmax):
     n = mask.numel()
     rank, count = ranks_of(mask)
     members = members_by_rank(mask, rank)
-    want_t = torch.as_tensor(want, dtype=torch.int64, device=dev)
+    want_t = scalar_i64(want, dev)
     keys = rng.uniform(n, dev)          # drawn unconditionally: keeps the call sequence static
     order = key_order(keys, count)
     ar = torch.arange(n, device=dev)
@@ -93,7 +115,7 @@ def drop(mask, n_keep, rng):
     dev = mask.device
     n = mask.numel()
     rank, count = ranks_of(mask)
-    n_keep_t = torch.as_tensor(n_keep, dtype=torch.int64, device=dev)
+    n_keep_t = scalar_i64(n_keep, dev)
     n_remove = (count - n_keep_t).clamp(min=0)
     keys = rng.uniform(n, dev)
     order = key_order(keys, count)

@@ -62,8 +62,8 @@ def proposal_targets_device(boxes, n_boxes, gts, cfg, image_hw, batch_ix=0, rng=
     t = torch.where(is_pos.unsqueeze(1), t, torch.zeros_like(t))              # keep log() of junk out
     t = t.double()
     if cfg['bbox_normalize_stats_precomputed']:
-        means = torch.tensor(cfg['bbox_normalize_means'], dtype=torch.float64, device=dev)
-        stds = torch.tensor(cfg['bbox_normalize_stds'], dtype=torch.float64, device=dev)
+        means = _sampling.const_tensor(cfg['bbox_normalize_means'], torch.float64, dev)
+        stds = _sampling.const_tensor(cfg['bbox_normalize_stds'], torch.float64, dev)
         t = (t - means) / stds
     onehot = torch.zeros(bs, nc, dtype=torch.bool, device=dev)
     onehot.scatter_(1, labels.clamp(min=0, max=nc - 1).unsqueeze(1), is_pos.unsqueeze(1))
@@ -92,7 +92,7 @@ def compute_proposal_targets(proposals, cfg, ground_truth_bboxes, image_info, ig
     outs = []
     for b in range(gts_all.shape[0]):
         sel = props[props[:, 0] == b][:, 1:5].contiguous()      # API path: dynamic count is known
-        n = torch.tensor(sel.shape[0], device=dev)
+        n = torch.full((), sel.shape[0], dtype=torch.int64, device=dev)
         if sel.shape[0] == 0:
             sel = torch.zeros(1, 4, device=dev)
         outs.append(proposal_targets_device(sel, n, gts_all[b], cfg,

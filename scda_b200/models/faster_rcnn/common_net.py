@@ -79,6 +79,19 @@ class ResDis_cluster(nn.Module):
         return torch.squeeze(out)
 
 
+class ConvTranspose1x1(nn.ConvTranspose2d):
+    """nn.ConvTranspose2d(n_in, n_out, kernel_size=1, stride=1, padding=0) — same parameters
+    ([n_in, n_out, 1, 1] weight, state-dict compatible) — evaluated as the equivalent 1x1
+    convolution with the weight's first two axes swapped.  cuDNN's transposed-convolution
+    weight gradient for the decoder's 32 -> 3 layer over 4 x 256 x 256 pixels takes 750 us
+    per call (profiles/r1_launches_b_*: cutlass_80 s1688gemm tn_align1); the convolution
+    form takes the regular wgrad path."""
+
+    def forward(self, x, output_size=None):
+        assert self.kernel_size == (1, 1) and self.stride == (1, 1) and self.padding == (0, 0)
+        return nn.functional.conv2d(x, self.weight.permute(1, 0, 2, 3), self.bias)
+
+
 class LeakyReLUConv2d(nn.Module):
     def __init__(self, n_in, n_out, kernel_size, stride, padding=0):
         super(LeakyReLUConv2d, self).__init__()

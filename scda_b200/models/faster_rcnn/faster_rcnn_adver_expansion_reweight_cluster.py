@@ -17,11 +17,11 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from ...functions.anchor_target import compute_anchor_targets
-from ...functions.mask import compute_cluster_targets
+from ...functions.mask import cluster_targets_device, compute_cluster_targets
 from ...functions.predict_bbox import compute_predicted_bboxes
 from ...functions.proposal_target import compute_proposal_targets, proposal_targets_device
 from ...functions.rpn_proposal import compute_rpn_proposals, rpn_proposals_device
-from .common_net import (INSResBlock, LeakyReLUConv2d, LeakyReLUConvTranspose2d_2,
+from .common_net import (ConvTranspose1x1, INSResBlock, LeakyReLUConv2d, LeakyReLUConvTranspose2d_2,
                          LinUnsRes_cluster, ResDis_cluster, gaussian_weights_init)
 
 logger = logging.getLogger('global')
@@ -131,7 +131,12 @@ class FasterRCNN_AdEx(nn.Module):
                 cfg, props, ground_truth_bboxes, image_info)
             assert rois.shape[1] == 5
             x_fea, rcnn_pred_cls, rcnn_pred_loc = self.rcnn(x, rois)
-            x_cluster_fea, x_center_cluster = compute_cluster_targets(
+            # input['device_clusters']: keep the cluster centres on the device (no host
+            # synchronisation anywhere in this forward); default = the reference's return
+            # type, centres as a host numpy array
+            on_dev = bool(input.get('device_clusters', False))
+            cluster_fn = cluster_targets_device if on_dev else compute_cluster_targets
+            x_cluster_fea, x_center_cluster = cluster_fn(
                 rois, x_fea, N_cluster=input['cluster_num'], threshold=input['threshold'])
 
             # RPN + RCNN on the target image: top-512 proposals, no ground truth (:171-189)
@@ -165,7 +170,18 @@ class FasterRCNN_AdEx(nn.Module):
             outputs['accuracy'] = [rpn_acc, rcnn_acc]
             outputs['predict'] = [props]
             # fewer than 512 surviving target proposals: reuse the source clusters (:207-215)
-            if proposals_gan.shape[0] != n_t or not bool(enough):
+            if proposals_gan.shape[0] != n_t:
+                logger.info("Different channels {} at target image".format(x_fea_gan.size(0)))
+                outputs['cluster_features'] = [x_cluster_fea, x_cluster_fea]
+                outputs['cluster_centers'] = [x_center_cluster, x_center_cluster]
+            elif on_dev:
+                # the same choice made by a device-side select on the `enough` flag
+                fea_gan, center_gan = cluster_targets_device(
+                    proposals_gan, x_fea_gan, N_cluster=input['cluster_num'], threshold=input['threshold'])
+                outputs['cluster_features'] = [x_cluster_fea, torch.where(enough, fea_gan, x_cluster_fea)]
+                outputs['cluster_centers'] = [x_center_cluster,
+                                              torch.where(enough, center_gan, x_center_cluster)]
+            elif not bool(enough):
                 logger.info("Different channels {} at target image".format(x_fea_gan.size(0)))
                 outputs['cluster_features'] = [x_cluster_fea, x_cluster_fea]
                 outputs['cluster_centers'] = [x_center_cluster, x_center_cluster]
@@ -274,7 +290,7 @@ class GAN_decoder_AE(nn.Module):
                 dec += [LeakyReLUConvTranspose2d_2(tch, tch // 2, kernel_size=3, stride=1,
                                                    padding=1, output_padding=0)]
                 tch = tch // 2
-            dec += [nn.ConvTranspose2d(tch, input_dim_b, kernel_size=1, stride=1, padding=0)]
+            dec += [ConvTranspose1x1(tch, input_dim_b, kernel_size=1, stride=1, padding=0)]
             dec += [nn.Tanh()]
             return nn.Sequential(*dec)
 

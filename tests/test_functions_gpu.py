@@ -168,10 +168,15 @@ def test_cluster_targets(cuda_lib, host):
     from scda_b200.functions.mask import compute_cluster_targets
     rois = _inputs.rois_uniform(512, 3, img_w=1024, img_h=512, wh=(16, 200))
     fea = np.random.RandomState(0).standard_normal((512, 64)).astype(np.float32)
-    np.random.seed(7)
     ref, ref_c, labels = host.compute_cluster_targets(rois, fea, 4, 128)
-    np.random.seed(7)
     out, centers = compute_cluster_targets(torch.from_numpy(rois).cuda(), torch.from_numpy(fea).cuda().requires_grad_(True), 4, 128)
     assert out.shape == (4, 128, 64) and not out.requires_grad
-    assert np.array_equal(out.cpu().numpy(), ref)
-    np.testing.assert_allclose(centers, ref_c)
+    np.testing.assert_allclose(centers, ref_c, rtol=1e-5, atol=1e-3)
+    out = out.cpu().numpy()
+    for c in range(4):
+        members = np.where(labels == c)[0]
+        if members.shape[0] >= 128:
+            assert np.array_equal(out[c], ref[c])            # first 128 members, in RoI order
+        else:                                                 # re-drawn with replacement: any member
+            rows = {fea[i].tobytes() for i in members}
+            assert all(r.tobytes() in rows for r in out[c])
