@@ -223,6 +223,21 @@ int scda_reduce_slabs_f32(const float *slabs, long long slab_stride, int n_slabs
 /* bias gradient: out[N] += column sums of x[M, ld] (bf16) */
 int scda_colsum_bf16(long long M, int N, const void *x, long long ld, float *out, cudaStream_t stream);
 
+/* --- InstanceNorm2d (+ activation), channels-last fp32 ------------------- */
+/* replaces nn.InstanceNorm2d(affine=False) and the ReLU / LeakyReLU behind it in the
+ * reconstruction networks (models/faster_rcnn/common_net.py:59-80, 279-293).
+ * x, y, dy, dx: [N, HW, C] fp32 (C innermost = channels_last), C % 4 == 0, C <= 1024 and
+ * 1024 / C a power of two; mean, rstd: [N, C] (written by fwd, read by bwd).
+ * act: 0 none, 1 ReLU, 2 LeakyReLU(slope).  Reductions are two-stage in a fixed order
+ * (deterministic).  workspace >= scda_instnorm_workspace_bytes (+ 8*N*C bytes for bwd). */
+size_t scda_instnorm_workspace_bytes(int N, int HW, int C);
+int scda_instnorm_act_fwd_nhwc_f32(int N, int HW, int C, const float *x, float *y, float *mean, float *rstd,
+                                   float eps, int act, float slope, void *workspace,
+                                   size_t workspace_bytes, cudaStream_t stream);
+int scda_instnorm_act_bwd_nhwc_f32(int N, int HW, int C, const float *x, const float *dy, const float *mean,
+                                   const float *rstd, float *dx, int act, float slope, void *workspace,
+                                   size_t workspace_bytes, cudaStream_t stream);
+
 /* --- region grouping (k-means of RoI centres) --------------------------- */
 /* replaces, inside compute_cluster_targets (functions/mask.py:193-237), the host call
  * sklearn.cluster.KMeans(n_clusters=k, random_state=0).fit(centres) on the float32 RoI

@@ -49,6 +49,9 @@ SIGNATURES = {
     "scda_gemm_bf16_nn": (_i, [_i, _i, _i, _p, C.c_longlong, _p, C.c_longlong, _p, _p, C.c_longlong, _i, _p, _p, _p]),
     "scda_linear_wgrad_bf16": (_i, [_i, _i, _i, _p, C.c_longlong, _p, C.c_longlong, _p, C.c_longlong, _i, _p]),
     "scda_conv3x3_wgrad_bf16_nhwc": (_i, [_i, _i, _i, _i, _i, _p, _p, _p, _i, _p]),
+    "scda_instnorm_workspace_bytes": (_z, [_i, _i, _i]),
+    "scda_instnorm_act_fwd_nhwc_f32": (_i, [_i, _i, _i, _p, _p, _p, _p, _f, _i, _f, _p, _z, _p]),
+    "scda_instnorm_act_bwd_nhwc_f32": (_i, [_i, _i, _i, _p, _p, _p, _p, _p, _i, _f, _p, _z, _p]),
     "scda_kmeans_workspace_bytes": (_z, [_i, _i]),
     "scda_kmeans_regions": (_i, [_p, _i, _i, _i, _i, _p, _i, _i, _f, _p, _i, _p, _p, _p, _p, _p, _z, _p]),
     "scda_adam_step": (_i, [_p, _p, _p, _p, _p, C.c_longlong, _i, _f, _f, _f, _f, _f, _f, _p, _p]),
@@ -87,7 +90,7 @@ def load(path: str | None = None) -> C.CDLL:
 # kernels launched per successful entry-point call (memsets not counted); bench.py reports
 # the total inside its timed region as `gpu_launches`
 KERNELS_PER_CALL = {
-    "scda_nms": 2, "scda_nms_dyn": 2, "SoftmaxFocalLossForwardLaucher": 1,
+    "scda_nms": 2, "scda_nms_dyn": 2, "scda_instnorm_act_fwd_nhwc_f32": 3, "scda_instnorm_act_bwd_nhwc_f32": 3, "SoftmaxFocalLossForwardLaucher": 1,
     "SoftmaxFocalLossBackwardLaucher": 1,
 }
 LAUNCHES = 0

@@ -1,0 +1,227 @@
+// InstanceNorm2d (+ ReLU / LeakyReLU) forward and backward on channels-last fp32 tensors.
+//
+// Replaces nn.InstanceNorm2d(affine=False, eps=1e-5) and the activation that follows it in
+// the reconstruction networks (models/faster_rcnn/common_net.py:59-80 INSResBlock,
+// :279-293 LeakyReLUConvTranspose2d_2 of the reference).  torch evaluates instance norm as a
+// batch norm over a [1, N*C, H, W] NCHW view, which forces an NCHW copy in front of it and an
+// NHWC copy behind it for every cuDNN tensor-core convolution around it (2.5 ms of layout
+// transposes + 1.6 ms of batch-norm kernels per iteration in
+// profiles/r1_launches_c_step_tc_summary.txt).  Here the data stays [N, H*W, C] (C innermost):
+//   forward : per-(n, c) shifted sums in two deterministic stages -> mean, rstd;
+//             y = act((x - mean) * rstd)                       (x read twice, y written once)
+//   backward: g = dy * act'(xhat); per-(n, c) sums of g and g * xhat (two stages);
+//             dx = rstd * (g - mean(g) - xhat * mean(g * xhat))
+// All kernels are HBM bound (float4 accesses, one pass per tensor per stage).
+#include "common.cuh"
+
+namespace {
+
+constexpr int kNT = 256;
+
+__device__ __forceinline__ float act_fwd(float v, int act, float slope)
+{
+    if (act == 1) return v > 0.f ? v : 0.f;
+    if (act == 2) return v > 0.f ? v : v * slope;
+    return v;
+}
+__device__ __forceinline__ float act_grad(float xhat, int act, float slope)
+{
+    if (act == 1) return xhat > 0.f ? 1.f : 0.f;
+    if (act == 2) return xhat > 0.f ? 1.f : slope;
+    return 1.f;
+}
+
+// stage 1 of a per-(n, c) reduction over HW: block (chunk, n) accumulates two quantities per
+// channel over its rows and writes them to part[n][chunk][2][C]
+//   mode 0: (x - shift), (x - shift)^2           shift = x[n, 0, c]
+//   mode 1: g, g * xhat                           g = dy * act'(xhat)
+template <int kMode>
+__global__ void __launch_bounds__(kNT)
+in_partial_kernel(const float *__restrict__ x, const float *__restrict__ dy, const float *__restrict__ mean,
+                  const float *__restrict__ rstd, float *__restrict__ part, int HW, int C, int chunks, int act,
+                  float slope)
+{
+    __shared__ float4 sh[2][kNT];
+    const int vec = C >> 2;                 // float4 lanes per row
+    const int rows_per_pass = kNT / vec;
+    const int lane = threadIdx.x % vec, rlane = threadIdx.x / vec;
+    const int n = blockIdx.y, chunk = blockIdx.x;
+    const int rows_per_chunk = (HW + chunks - 1) / chunks;
+    const int r0 = chunk * rows_per_chunk, r1 = min(HW, r0 + rows_per_chunk);
+    const float *xb = x + (long long)n * HW * C;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+    float4 p0, p1;
+    if (kMode == 0) {
+        p0 = *reinterpret_cast<const float4 *>(xb + lane * 4);     // shift
+    } else {
+        p0 = *reinterpret_cast<const float4 *>(mean + (long long)n * C + lane * 4);
+        p1 = *reinterpret_cast<const float4 *>(rstd + (long long)n * C + lane * 4);
+    }
+    if (rlane < rows_per_pass) {
+        for (int r = r0 + rlane; r < r1; r += rows_per_pass) {
+            const float4 v = ld_stream_f4(xb + (long long)r * C + lane * 4);
+            if (kMode == 0) {
+                const float d0 = v.x - p0.x, d1 = v.y - p0.y, d2 = v.z - p0.z, d3 = v.w - p0.w;
+                a.x += d0; a.y += d1; a.z += d2; a.w += d3;
+                b.x += d0 * d0; b.y += d1 * d1; b.z += d2 * d2; b.w += d3 * d3;
+            } else {
+                const float4 g4 = ld_stream_f4(dy + ((long long)n * HW + r) * C + lane * 4);
+                const float h0 = (v.x - p0.x) * p1.x, h1 = (v.y - p0.y) * p1.y, h2 = (v.z - p0.z) * p1.z,
+                            h3 = (v.w - p0.w) * p1.w;
+                const float g0 = g4.x * act_grad(h0, act, slope), g1 = g4.y * act_grad(h1, act, slope),
+                            g2 = g4.z * act_grad(h2, act, slope), g3 = g4.w * act_grad(h3, act, slope);
+                a.x += g0; a.y += g1; a.z += g2; a.w += g3;
+                b.x += g0 * h0; b.y += g1 * h1; b.z += g2 * h2; b.w += g3 * h3;
+            }
+        }
+    }
+    sh[0][threadIdx.x] = a;
+    sh[1][threadIdx.x] = b;
+    __syncthreads();
+    if (rlane == 0) {
+        for (int k = 1; k < rows_per_pass; ++k) {
+            const float4 u = sh[0][k * vec + lane], w = sh[1][k * vec + lane];
+            a.x += u.x; a.y += u.y; a.z += u.z; a.w += u.w;
+            b.x += w.x; b.y += w.y; b.z += w.z; b.w += w.w;
+        }
+        float *o = part + (((long long)n * chunks + chunk) * 2) * C + lane * 4;
+        *reinterpret_cast<float4 *>(o) = a;
+        *reinterpret_cast<float4 *>(o + C) = b;
+    }
+}
+
+// stage 2: fixed-order sum over the chunks.  mode 0 -> mean, rstd; mode 1 -> mean(g), mean(g xhat)
+template <int kMode>
+__global__ void in_final_kernel(const float *__restrict__ part, const float *__restrict__ x, float *__restrict__ o0,
+                                float *__restrict__ o1, int HW, int C, int chunks, float eps)
+{
+    const int n = blockIdx.y, c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    float a = 0.f, b = 0.f;
+    for (int k = 0; k < chunks; ++k) {
+        const float *p = part + (((long long)n * chunks + k) * 2) * C + c;
+        a += p[0];
+        b += p[C];
+    }
+    const float inv = 1.f / (float)HW;
+    if (kMode == 0) {
+        const float shift = x[(long long)n * HW * C + c];
+        const float m = a * inv;
+        const float var = fmaxf(b * inv - m * m, 0.f);
+        o0[(long long)n * C + c] = shift + m;
+        o1[(long long)n * C + c] = rsqrtf(var + eps);
+    } else {
+        o0[(long long)n * C + c] = a * inv;
+        o1[(long long)n * C + c] = b * inv;
+    }
+}
+
+__global__ void __launch_bounds__(kNT)
+in_apply_kernel(const float *__restrict__ x, const float *__restrict__ mean, const float *__restrict__ rstd,
+                float *__restrict__ y, long long total4, int HW, int C, int act, float slope)
+{
+    const int vec = C >> 2;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int lane = (int)(i % vec);
+        const long long row = i / vec;
+        const int n = (int)(row / HW);
+        const float4 v = ld_stream_f4(x + i * 4);
+        const float4 m = *reinterpret_cast<const float4 *>(mean + (long long)n * C + lane * 4);
+        const float4 s = *reinterpret_cast<const float4 *>(rstd + (long long)n * C + lane * 4);
+        float4 o;
+        o.x = act_fwd((v.x - m.x) * s.x, act, slope);
+        o.y = act_fwd((v.y - m.y) * s.y, act, slope);
+        o.z = act_fwd((v.z - m.z) * s.z, act, slope);
+        o.w = act_fwd((v.w - m.w) * s.w, act, slope);
+        *reinterpret_cast<float4 *>(y + i * 4) = o;
+    }
+}
+
+__global__ void __launch_bounds__(kNT)
+in_bwd_apply_kernel(const float *__restrict__ x, const float *__restrict__ dy, const float *__restrict__ mean,
+                    const float *__restrict__ rstd, const float *__restrict__ mg, const float *__restrict__ mgx,
+                    float *__restrict__ dx, long long total4, int HW, int C, int act, float slope)
+{
+    const int vec = C >> 2;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int lane = (int)(i % vec);
+        const long long row = i / vec;
+        const int n = (int)(row / HW);
+        const long long o = (long long)n * C + lane * 4;
+        const float4 v = ld_stream_f4(x + i * 4), g4 = ld_stream_f4(dy + i * 4);
+        const float4 m = *reinterpret_cast<const float4 *>(mean + o), s = *reinterpret_cast<const float4 *>(rstd + o);
+        const float4 a = *reinterpret_cast<const float4 *>(mg + o), b = *reinterpret_cast<const float4 *>(mgx + o);
+        const float h0 = (v.x - m.x) * s.x, h1 = (v.y - m.y) * s.y, h2 = (v.z - m.z) * s.z, h3 = (v.w - m.w) * s.w;
+        float4 r;
+        r.x = s.x * (g4.x * act_grad(h0, act, slope) - a.x - h0 * b.x);
+        r.y = s.y * (g4.y * act_grad(h1, act, slope) - a.y - h1 * b.y);
+        r.z = s.z * (g4.z * act_grad(h2, act, slope) - a.z - h2 * b.z);
+        r.w = s.w * (g4.w * act_grad(h3, act, slope) - a.w - h3 * b.w);
+        *reinterpret_cast<float4 *>(dx + i * 4) = r;
+    }
+}
+
+int pick_chunks(int N, int HW, int C)
+{
+    const int rows_per_pass = kNT / (C >> 2);
+    int chunks = (kNumSMs * 4 + N - 1) / N;
+    const int max_chunks = (HW + rows_per_pass - 1) / rows_per_pass;
+    if (chunks > max_chunks) chunks = max_chunks;
+    return chunks < 1 ? 1 : chunks;
+}
+
+bool shape_ok(int N, int HW, int C) { return N > 0 && HW > 0 && C >= 4 && C % 4 == 0 && (C >> 2) <= kNT && kNT % (C >> 2) == 0; }
+
+int apply_grid(long long total4)
+{
+    long long want = (total4 + kNT - 1) / kNT;
+    const long long cap = (long long)kNumSMs * 16;
+    return (int)(want > cap ? cap : (want < 1 ? 1 : want));
+}
+
+}  // namespace
+
+SCDA_API size_t scda_instnorm_workspace_bytes(int N, int HW, int C)
+{
+    if (!shape_ok(N, HW, C)) return 0;
+    return sizeof(float) * (size_t)N * pick_chunks(N, HW, C) * 2 * C;
+}
+
+SCDA_API int scda_instnorm_act_fwd_nhwc_f32(int N, int HW, int C, const float *x, float *y, float *mean, float *rstd,
+                                            float eps, int act, float slope, void *workspace,
+                                            size_t workspace_bytes, cudaStream_t stream)
+{
+    if (!shape_ok(N, HW, C) || !x || !y || !mean || !rstd || !workspace || act < 0 || act > 2) return 0;
+    if (workspace_bytes < scda_instnorm_workspace_bytes(N, HW, C)) return 0;
+    if (((uintptr_t)x | (uintptr_t)y | (uintptr_t)mean | (uintptr_t)rstd | (uintptr_t)workspace) % 16) return 0;
+    const int chunks = pick_chunks(N, HW, C);
+    float *part = (float *)workspace;
+    in_partial_kernel<0><<<dim3(chunks, N), kNT, 0, stream>>>(x, nullptr, nullptr, nullptr, part, HW, C, chunks, act,
+                                                              slope);
+    in_final_kernel<0><<<dim3((C + 127) / 128, N), 128, 0, stream>>>(part, x, mean, rstd, HW, C, chunks, eps);
+    const long long total4 = (long long)N * HW * (C >> 2);
+    in_apply_kernel<<<apply_grid(total4), kNT, 0, stream>>>(x, mean, rstd, y, total4, HW, C, act, slope);
+    return scda_launch_status();
+}
+
+SCDA_API int scda_instnorm_act_bwd_nhwc_f32(int N, int HW, int C, const float *x, const float *dy, const float *mean,
+                                            const float *rstd, float *dx, int act, float slope, void *workspace,
+                                            size_t workspace_bytes, cudaStream_t stream)
+{
+    if (!shape_ok(N, HW, C) || !x || !dy || !dx || !mean || !rstd || !workspace || act < 0 || act > 2) return 0;
+    const size_t need = scda_instnorm_workspace_bytes(N, HW, C) + sizeof(float) * 2 * (size_t)N * C;
+    if (workspace_bytes < need) return 0;
+    if (((uintptr_t)x | (uintptr_t)dy | (uintptr_t)dx | (uintptr_t)mean | (uintptr_t)rstd | (uintptr_t)workspace) % 16)
+        return 0;
+    const int chunks = pick_chunks(N, HW, C);
+    float *part = (float *)workspace;
+    float *mg = part + (size_t)N * chunks * 2 * C, *mgx = mg + (size_t)N * C;
+    in_partial_kernel<1><<<dim3(chunks, N), kNT, 0, stream>>>(x, dy, mean, rstd, part, HW, C, chunks, act, slope);
+    in_final_kernel<1><<<dim3((C + 127) / 128, N), 128, 0, stream>>>(part, x, mg, mgx, HW, C, chunks, 0.f);
+    const long long total4 = (long long)N * HW * (C >> 2);
+    in_bwd_apply_kernel<<<apply_grid(total4), kNT, 0, stream>>>(x, dy, mean, rstd, mg, mgx, dx, total4, HW, C, act,
+                                                                slope);
+    return scda_launch_status();
+}

@@ -176,9 +176,10 @@ class SCDATrainer(object):
         self.model, self.dec_model = model, dec_model
         self.dis_model, self.dis_model_patch = dis_model, dis_model_patch
         self.opt = FlatAdam(model, lr, weight_decay=weight_decay, tensor_core=True)
-        self.opt_dec = FlatAdam(dec_model, lr, weight_decay=weight_decay)
-        self.opt_dis = FlatAdam(dis_model, lr, weight_decay=weight_decay)
-        self.opt_dis_patch = FlatAdam(dis_model_patch, lr, weight_decay=weight_decay)
+        # channels_last weights: cuDNN's tensor-core convolutions then run NHWC end to end
+        self.opt_dec = FlatAdam(dec_model, lr, weight_decay=weight_decay, channels_last=True)
+        self.opt_dis = FlatAdam(dis_model, lr, weight_decay=weight_decay, channels_last=True)
+        self.opt_dis_patch = FlatAdam(dis_model_patch, lr, weight_decay=weight_decay, channels_last=True)
         self.cluster_num, self.threshold, self.recon_size = cluster_num, threshold, recon_size
         self.new_w, self.new_h, self.world_size = new_w, new_h, world_size
         self.use_graphs = use_graphs

@@ -1,0 +1,64 @@
+"""Fused channels-last operators of the reconstruction networks (csrc/norm_ops.cu).
+
+`instance_norm_act(x, act)` = nn.InstanceNorm2d(affine=False, eps=1e-5) followed by nothing /
+ReLU / LeakyReLU, on a channels_last fp32 CUDA tensor, forward and backward, without the
+NCHW round trip torch's instance norm forces (models/faster_rcnn/common_net.py:59-80,
+279-293 of the reference use the torch modules)."""
+import torch
+
+from ._lib import check, load, require_cuda, stream_ptr
+
+_ACT = {None: 0, "none": 0, "relu": 1, "leaky_relu": 2}
+
+
+class _InstNormAct(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, act, slope, eps):
+        require_cuda(x)
+        assert x.dim() == 4 and x.dtype == torch.float32
+        if not x.is_contiguous(memory_format=torch.channels_last):
+            x = x.contiguous(memory_format=torch.channels_last)
+        N, C, H, W = x.shape
+        y = torch.empty_like(x)                       # keeps the channels_last strides
+        assert y.is_contiguous(memory_format=torch.channels_last)
+        mean = torch.empty(N, C, dtype=torch.float32, device=x.device)
+        rstd = torch.empty(N, C, dtype=torch.float32, device=x.device)
+        lib = load()
+        wsb = lib.scda_instnorm_workspace_bytes(N, H * W, C)
+        if wsb == 0:
+            raise ValueError("instance_norm_act: unsupported shape %s" % (tuple(x.shape),))
+        ws = torch.empty(wsb, dtype=torch.uint8, device=x.device)
+        with torch.cuda.device(x.device):
+            check(lib.scda_instnorm_act_fwd_nhwc_f32(N, H * W, C, x.data_ptr(), y.data_ptr(), mean.data_ptr(),
+                                                     rstd.data_ptr(), eps, act, slope, ws.data_ptr(), wsb,
+                                                     stream_ptr(x.device)), "scda_instnorm_act_fwd_nhwc_f32")
+        ctx.save_for_backward(x, mean, rstd)
+        ctx.cfg = (act, slope)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, mean, rstd = ctx.saved_tensors
+        act, slope = ctx.cfg
+        N, C, H, W = x.shape
+        if dy.dtype != torch.float32 or not dy.is_contiguous(memory_format=torch.channels_last):
+            dy = dy.float().contiguous(memory_format=torch.channels_last)
+        dx = torch.empty_like(x)
+        lib = load()
+        wsb = lib.scda_instnorm_workspace_bytes(N, H * W, C) + 8 * N * C
+        ws = torch.empty(wsb, dtype=torch.uint8, device=x.device)
+        with torch.cuda.device(x.device):
+            check(lib.scda_instnorm_act_bwd_nhwc_f32(N, H * W, C, x.data_ptr(), dy.data_ptr(), mean.data_ptr(),
+                                                     rstd.data_ptr(), dx.data_ptr(), act, slope, ws.data_ptr(),
+                                                     wsb, stream_ptr(x.device)), "scda_instnorm_act_bwd_nhwc_f32")
+        return dx, None, None, None
+
+
+def instance_norm_act(x, act=None, negative_slope=0.01, eps=1e-5):
+    return _InstNormAct.apply(x, _ACT[act], float(negative_slope), float(eps))
+
+
+def supported(x):
+    """shapes the fused kernel takes (C a multiple of 4 that divides 1024)"""
+    c = x.shape[1]
+    return x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and c % 4 == 0 and 1024 % c == 0

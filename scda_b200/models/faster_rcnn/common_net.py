@@ -6,6 +6,8 @@ Module / parameter names match the reference so state dicts are interchangeable.
 import torch
 import torch.nn as nn
 
+from ...gan_ops import instance_norm_act, supported as _fused_ok
+
 
 def gaussian_weights_init(m):
     name = m.__class__.__name__
@@ -29,6 +31,14 @@ class INSResBlock(nn.Module):
         self.model.apply(gaussian_weights_init)
 
     def forward(self, x):
+        if _fused_ok(x):
+            # same layers, InstanceNorm + ReLU as one channels-last kernel (csrc/norm_ops.cu)
+            m = self.model
+            out = instance_norm_act(m[0](x), "relu", eps=m[1].eps)
+            out = instance_norm_act(m[3](out), None, eps=m[4].eps)
+            if len(m) > 5:
+                out = m[5](out)
+            return out + x
         out = self.model(x)
         out += x
         return out
@@ -42,7 +52,10 @@ class LinUnsRes_cluster(nn.Module):
         self.channel, self.w, self.h, self.cluster_num = channel, w, h, cluster_num
 
     def forward(self, x):
-        return x.view(self.cluster_num, self.channel, self.w, self.h)
+        x = x.view(self.cluster_num, self.channel, self.w, self.h)
+        # one transpose here keeps every cuDNN tensor-core convolution behind it in its
+        # native NHWC layout (cuDNN otherwise transposes around each call)
+        return x.contiguous(memory_format=torch.channels_last) if x.is_cuda else x
 
 
 class Interpolate(nn.Module):
@@ -74,7 +87,10 @@ class ResDis_cluster(nn.Module):
         self.model.apply(gaussian_weights_init)
 
     def forward(self, x1):
-        out = self.model(x1.view(self.cluster_num, self.channel, self.w, self.h))
+        x1 = x1.view(self.cluster_num, self.channel, self.w, self.h)
+        if x1.is_cuda:
+            x1 = x1.contiguous(memory_format=torch.channels_last)
+        out = self.model(x1)
         out = nn.functional.avg_pool2d(out, out.size()[2:])
         return torch.squeeze(out)
 
@@ -101,6 +117,12 @@ class LeakyReLUConv2d(nn.Module):
         self.model.apply(gaussian_weights_init)
 
     def forward(self, x):
+        m = self.model
+        if len(m) == 4 and isinstance(m[2], nn.InstanceNorm2d) and x.is_cuda:
+            out = m[1](m[0](x))
+            if _fused_ok(out):
+                return instance_norm_act(out, "leaky_relu", m[3].negative_slope, m[2].eps)
+            return m[3](m[2](out))
         return self.model(x)
 
 
@@ -118,4 +140,10 @@ class LeakyReLUConvTranspose2d_2(nn.Module):
         self.model.apply(gaussian_weights_init)
 
     def forward(self, x):
+        m = self.model
+        if len(m) == 4 and isinstance(m[2], nn.InstanceNorm2d) and x.is_cuda:
+            out = m[1](m[0](x))
+            if _fused_ok(out):
+                return instance_norm_act(out, "leaky_relu", m[3].negative_slope, m[2].eps)
+            return m[3](m[2](out))
         return self.model(x)

@@ -246,9 +246,12 @@ class GAN_dis_AE(nn.Module):
         return nn.Sequential(*model)
 
     def forward(self, x_aa, x_bb):
+        if x_aa.is_cuda:      # NHWC end to end: no cuDNN layout transposes around the convolutions
+            x_aa = x_aa.contiguous(memory_format=torch.channels_last)
+            x_bb = x_bb.contiguous(memory_format=torch.channels_last)
         out_A = self.model_A(x_aa)
         out_B = self.model_B(x_bb)
-        return out_A.view(out_A.size(0), -1), out_B.view(out_B.size(0), -1)
+        return out_A.reshape(out_A.size(0), -1), out_B.reshape(out_B.size(0), -1)
 
 
 class GAN_dis_AE_patch(nn.Module):

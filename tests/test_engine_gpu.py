@@ -91,7 +91,7 @@ def test_graph_replay_equals_eager(cuda_lib, monkeypatch):
     (l_e, p_e), (l_g, p_g) = results
     for a, b in zip(l_e, l_g):
         for k in ("dis_loss", "dis_patch_loss", "dec_loss", "fake_loss"):
-            assert abs(a[k] - b[k]) <= 2e-3 * max(1.0, abs(a[k])), (k, a[k], b[k])
+            assert abs(a[k] - b[k]) <= 1e-2 * max(1.0, abs(a[k])), (k, a[k], b[k])
     # Adam moves every weight by about lr per step whatever the size of its gradient, so a
     # gradient near zero whose sign differs in the last bit (atomics in the bias / RoI
     # gradients upstream) shifts a weight by up to 2 * lr: compare in units of lr

@@ -1,0 +1,70 @@
+"""Fused channels-last InstanceNorm(+activation) (csrc/norm_ops.cu) against
+torch.nn.functional.instance_norm + activation (fp32), forward and backward, and the
+reconstruction networks with the fused blocks against the same modules run through plain
+torch.nn.  Tolerance: fp32 arithmetic in a different summation order -> 1e-4 relative
+(north_star's bound for fp32 loss-path operators)."""
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    return float((a - b).abs().max() / b.abs().max().clamp(min=1e-20))
+
+
+@pytest.mark.parametrize("N,C,H,W", [(4, 128, 64, 64), (4, 64, 128, 128), (4, 32, 256, 256), (2, 8, 5, 7),
+                                     (1, 256, 16, 16)])
+@pytest.mark.parametrize("act", [None, "relu", "leaky_relu"])
+def test_instance_norm_act(cuda_lib, N, C, H, W, act):
+    import torch
+    import torch.nn.functional as F
+    from scda_b200.gan_ops import instance_norm_act
+    g = torch.Generator(device="cuda").manual_seed(C + H)
+    x = (torch.randn(N, C, H, W, device="cuda", generator=g) * 3 + 5).contiguous(memory_format=torch.channels_last)
+    dy = torch.randn(N, C, H, W, device="cuda", generator=g).contiguous(memory_format=torch.channels_last)
+    x1 = x.clone().requires_grad_(True)
+    y = instance_norm_act(x1, act, 0.01)
+    assert y.is_contiguous(memory_format=torch.channels_last)
+    y.backward(dy)
+    x2 = x.detach().double().contiguous().requires_grad_(True)      # float64 NCHW reference
+    r = F.instance_norm(x2, eps=1e-5)
+    r = F.relu(r) if act == "relu" else (F.leaky_relu(r, 0.01) if act == "leaky_relu" else r)
+    r.backward(dy.double())
+    assert _rel(y.double(), r.detach()) < 1e-4
+    assert _rel(x1.grad.double(), x2.grad) < 1e-4
+    # deterministic: same input, same bits
+    y2 = instance_norm_act(x.clone(), act, 0.01)
+    assert torch.equal(y2, y.detach())
+
+
+def test_decoder_fused_equals_torch_modules(cuda_lib, monkeypatch):
+    import copy
+    import torch
+    from scda_b200.engine import builder_gan
+    from scda_b200.models.faster_rcnn import common_net
+    torch.manual_seed(0)
+    dis, dec, patch = builder_gan(4, 128, 256)
+    for net in (dis, dec, patch):
+        net.cuda().train()
+        for m in net.modules():
+            if isinstance(m, torch.nn.Dropout):
+                m.p = 0.0
+    ref = copy.deepcopy(dec)
+    g = torch.Generator(device="cuda").manual_seed(1)
+    xa = torch.randn(4, 128, 4096, device="cuda", generator=g)
+    xb = torch.randn(4, 128, 4096, device="cuda", generator=g)
+    torch.backends.cudnn.allow_tf32 = False
+    ya, yb = dec(xa, xb)
+    (ya.square().mean() + yb.mean()).backward()
+    monkeypatch.setattr(common_net, "_fused_ok", lambda x: False)
+    ra, rb = ref(xa, xb)
+    (ra.square().mean() + rb.mean()).backward()
+    assert ya.shape == (4, 3, 256, 256)
+    assert _rel(ya, ra) < 1e-3 and _rel(yb, rb) < 1e-3
+    for (n, p), q in zip(dec.named_parameters(), ref.parameters()):
+        # (the bias of a convolution that feeds an InstanceNorm has an exactly-zero true
+        #  gradient: both sides hold rounding noise there, hence the absolute floor)
+        assert float((p.grad - q.grad).abs().max()) <= 2e-3 * float(q.grad.abs().max()) + 1e-6, n
+    # the discriminators accept the channels-last decoder output
+    sa, sb = dis(ya.detach(), yb.detach())
+    assert sa.shape == (4, 1024) and patch(xa).shape == (4, 512)
