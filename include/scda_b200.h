@@ -238,6 +238,14 @@ int scda_instnorm_act_bwd_nhwc_f32(int N, int HW, int C, const float *x, const f
                                    const float *rstd, float *dx, int act, float slope, void *workspace,
                                    size_t workspace_bytes, cudaStream_t stream);
 
+/* bilinear x2 up-sampling, align_corners=True (common_net.py:160-169 `Interpolate`), on
+ * channels-last fp32: x [N,H,W,C] -> y [N,2H,2W,C]; the backward is its transpose written as
+ * a gather (deterministic).  C % 4 == 0. */
+int scda_upsample_bilinear2x_nhwc_f32(int N, int H, int W, int C, const float *x, float *y,
+                                      cudaStream_t stream);
+int scda_upsample_bilinear2x_bwd_nhwc_f32(int N, int H, int W, int C, const float *dy, float *dx,
+                                          cudaStream_t stream);
+
 /* --- region grouping (k-means of RoI centres) --------------------------- */
 /* replaces, inside compute_cluster_targets (functions/mask.py:193-237), the host call
  * sklearn.cluster.KMeans(n_clusters=k, random_state=0).fit(centres) on the float32 RoI
@@ -256,6 +264,21 @@ int scda_kmeans_regions(const float *rois, int roi_stride, int n, int k, int fir
                         const float *pick_uniform, int threshold, int *labels, float *centers,
                         int *counts, long long *index, void *workspace, size_t workspace_bytes,
                         cudaStream_t stream);
+
+/* --- RoI max pooling on the NHWC bf16 feature map ------------------------ */
+/* the operator of ROIPoolForwardLaucher / ROIPoolBackwardLaucher above (same RoI rounding,
+ * bin windows and first-maximum rule, roi_pooling_kernel.cu:24-93,128-203) in the layout of
+ * the tensor-core stages: feat [batch,H,W,C] bf16 -> out [num_rois, C, PH, PW] bf16 (the
+ * reference's channel-major order = fc6's input) and argmax [num_rois, C, PH, PW] uint16 =
+ * h * W + w inside the RoI's image, 0xFFFF for an empty bin.  C % 8 == 0, H * W < 65535.
+ * Backward: dfeat [batch,H,W,C] fp32 is zeroed, then every dout element is added at its
+ * argmax (fp32 red.add: sums are order-independent up to fp32 rounding). */
+int scda_roi_pool_nhwc_bf16_fwd(const void *feat, float spatial_scale, int num_rois, int batch, int H,
+                                int W, int C, int PH, int PW, const float *rois, void *out,
+                                unsigned short *argmax, cudaStream_t stream);
+int scda_roi_pool_nhwc_bf16_bwd(const void *dout, const unsigned short *argmax, const float *rois,
+                                int num_rois, int batch, int H, int W, int C, int PH, int PW,
+                                float *dfeat, cudaStream_t stream);
 
 /* --- optimiser -------------------------------------------------------- */
 /* replaces torch.optim.Adam(...).step() on each of the four networks

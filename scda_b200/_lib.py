@@ -52,6 +52,10 @@ SIGNATURES = {
     "scda_instnorm_workspace_bytes": (_z, [_i, _i, _i]),
     "scda_instnorm_act_fwd_nhwc_f32": (_i, [_i, _i, _i, _p, _p, _p, _p, _f, _i, _f, _p, _z, _p]),
     "scda_instnorm_act_bwd_nhwc_f32": (_i, [_i, _i, _i, _p, _p, _p, _p, _p, _i, _f, _p, _z, _p]),
+    "scda_upsample_bilinear2x_nhwc_f32": (_i, [_i, _i, _i, _i, _p, _p, _p]),
+    "scda_upsample_bilinear2x_bwd_nhwc_f32": (_i, [_i, _i, _i, _i, _p, _p, _p]),
+    "scda_roi_pool_nhwc_bf16_fwd": (_i, [_p, _f, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p]),
+    "scda_roi_pool_nhwc_bf16_bwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p]),
     "scda_kmeans_workspace_bytes": (_z, [_i, _i]),
     "scda_kmeans_regions": (_i, [_p, _i, _i, _i, _i, _p, _i, _i, _f, _p, _i, _p, _p, _p, _p, _p, _z, _p]),
     "scda_adam_step": (_i, [_p, _p, _p, _p, _p, C.c_longlong, _i, _f, _f, _f, _f, _f, _f, _p, _p]),

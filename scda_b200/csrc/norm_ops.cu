@@ -90,18 +90,33 @@ in_partial_kernel(const float *__restrict__ x, const float *__restrict__ dy, con
     }
 }
 
-// stage 2: fixed-order sum over the chunks.  mode 0 -> mean, rstd; mode 1 -> mean(g), mean(g xhat)
+// stage 2: sum over the chunks in a fixed order.  Block = 32 channels x 8 chunk lanes: lane k
+// adds chunks k, k+8, ... (independent loads in flight), the 8 partial sums are then added in
+// lane order.  mode 0 -> mean, rstd; mode 1 -> mean(g), mean(g xhat)
 template <int kMode>
-__global__ void in_final_kernel(const float *__restrict__ part, const float *__restrict__ x, float *__restrict__ o0,
-                                float *__restrict__ o1, int HW, int C, int chunks, float eps)
+__global__ void __launch_bounds__(256)
+in_final_kernel(const float *__restrict__ part, const float *__restrict__ x, float *__restrict__ o0,
+                float *__restrict__ o1, int HW, int C, int chunks, float eps)
 {
-    const int n = blockIdx.y, c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
+    __shared__ float sa[8][32], sb[8][32];
+    const int n = blockIdx.y, cl = threadIdx.x & 31, kl = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + cl;
     float a = 0.f, b = 0.f;
-    for (int k = 0; k < chunks; ++k) {
-        const float *p = part + (((long long)n * chunks + k) * 2) * C + c;
-        a += p[0];
-        b += p[C];
+    if (c < C) {
+        for (int k = kl; k < chunks; k += 8) {
+            const float *p = part + (((long long)n * chunks + k) * 2) * C + c;
+            a += p[0];
+            b += p[C];
+        }
+    }
+    sa[kl][cl] = a;
+    sb[kl][cl] = b;
+    __syncthreads();
+    if (kl != 0 || c >= C) return;
+#pragma unroll
+    for (int k = 1; k < 8; ++k) {
+        a += sa[k][cl];
+        b += sb[k][cl];
     }
     const float inv = 1.f / (float)HW;
     if (kMode == 0) {
@@ -200,7 +215,7 @@ SCDA_API int scda_instnorm_act_fwd_nhwc_f32(int N, int HW, int C, const float *x
     float *part = (float *)workspace;
     in_partial_kernel<0><<<dim3(chunks, N), kNT, 0, stream>>>(x, nullptr, nullptr, nullptr, part, HW, C, chunks, act,
                                                               slope);
-    in_final_kernel<0><<<dim3((C + 127) / 128, N), 128, 0, stream>>>(part, x, mean, rstd, HW, C, chunks, eps);
+    in_final_kernel<0><<<dim3((C + 31) / 32, N), 256, 0, stream>>>(part, x, mean, rstd, HW, C, chunks, eps);
     const long long total4 = (long long)N * HW * (C >> 2);
     in_apply_kernel<<<apply_grid(total4), kNT, 0, stream>>>(x, mean, rstd, y, total4, HW, C, act, slope);
     return scda_launch_status();
@@ -219,9 +234,130 @@ SCDA_API int scda_instnorm_act_bwd_nhwc_f32(int N, int HW, int C, const float *x
     float *part = (float *)workspace;
     float *mg = part + (size_t)N * chunks * 2 * C, *mgx = mg + (size_t)N * C;
     in_partial_kernel<1><<<dim3(chunks, N), kNT, 0, stream>>>(x, dy, mean, rstd, part, HW, C, chunks, act, slope);
-    in_final_kernel<1><<<dim3((C + 127) / 128, N), 128, 0, stream>>>(part, x, mg, mgx, HW, C, chunks, 0.f);
+    in_final_kernel<1><<<dim3((C + 31) / 32, N), 256, 0, stream>>>(part, x, mg, mgx, HW, C, chunks, 0.f);
     const long long total4 = (long long)N * HW * (C >> 2);
     in_bwd_apply_kernel<<<apply_grid(total4), kNT, 0, stream>>>(x, dy, mean, rstd, mg, mgx, dx, total4, HW, C, act,
                                                                 slope);
+    return scda_launch_status();
+}
+
+// ------------------------------------------------------------------------------------------
+// Bilinear x2 up-sampling, align_corners=True, channels-last fp32 (the `Interpolate` in front
+// of the two decoder convolutions, models/faster_rcnn/common_net.py:160-169, 279-293).
+// Index arithmetic = PyTorch's upsample_bilinear2d: r = (in-1)/(out-1) in fp32, src = r * dst,
+// i0 = (int)src, i1 = i0 + (i0 < in-1), l1 = src - i0, l0 = 1 - l1.
+// Forward: thread = (output pixel, float4 of channels).  Backward is the transpose written as
+// a GATHER (thread = input pixel x float4; it enumerates the few output rows / columns whose
+// taps land on it with the same fp32 index arithmetic) — no atomics, deterministic.
+namespace {
+
+__device__ __forceinline__ void bil_coord(float r, int dst, int in, int &i0, int &i1, float &l0, float &l1)
+{
+    const float src = r * (float)dst;
+    i0 = (int)src;
+    i1 = i0 + (i0 < in - 1 ? 1 : 0);
+    l1 = src - (float)i0;
+    l0 = 1.f - l1;
+}
+
+__global__ void __launch_bounds__(256)
+upsample2x_fwd_kernel(const float *__restrict__ x, float *__restrict__ y, int N, int H, int W, int C, float rh,
+                      float rw)
+{
+    const int Ho = H * 2, Wo = W * 2, vec = C >> 2;
+    const long long total = (long long)N * Ho * Wo * vec;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int lane = (int)(i % vec);
+        long long t = i / vec;
+        const int wo = (int)(t % Wo);
+        t /= Wo;
+        const int ho = (int)(t % Ho);
+        const int n = (int)(t / Ho);
+        int h0, h1, w0, w1;
+        float a0, a1, b0, b1;
+        bil_coord(rh, ho, H, h0, h1, a0, a1);
+        bil_coord(rw, wo, W, w0, w1, b0, b1);
+        const float *base = x + (long long)n * H * W * C + lane * 4;
+        const float4 p00 = __ldg(reinterpret_cast<const float4 *>(base + ((long long)h0 * W + w0) * C));
+        const float4 p01 = __ldg(reinterpret_cast<const float4 *>(base + ((long long)h0 * W + w1) * C));
+        const float4 p10 = __ldg(reinterpret_cast<const float4 *>(base + ((long long)h1 * W + w0) * C));
+        const float4 p11 = __ldg(reinterpret_cast<const float4 *>(base + ((long long)h1 * W + w1) * C));
+        float4 o;
+        o.x = a0 * (b0 * p00.x + b1 * p01.x) + a1 * (b0 * p10.x + b1 * p11.x);
+        o.y = a0 * (b0 * p00.y + b1 * p01.y) + a1 * (b0 * p10.y + b1 * p11.y);
+        o.z = a0 * (b0 * p00.z + b1 * p01.z) + a1 * (b0 * p10.z + b1 * p11.z);
+        o.w = a0 * (b0 * p00.w + b1 * p01.w) + a1 * (b0 * p10.w + b1 * p11.w);
+        st_stream_f4(y + i * 4, o);
+    }
+}
+
+// weight with which output index `dst` taps input index `i` along one dimension
+__device__ __forceinline__ float bil_weight(float r, int dst, int in, int i)
+{
+    int i0, i1;
+    float l0, l1;
+    bil_coord(r, dst, in, i0, i1, l0, l1);
+    float w = 0.f;
+    if (i0 == i) w += l0;
+    if (i1 == i) w += l1;
+    return w;
+}
+
+__global__ void __launch_bounds__(256)
+upsample2x_bwd_kernel(const float *__restrict__ dy, float *__restrict__ dx, int N, int H, int W, int C, float rh,
+                      float rw)
+{
+    const int Ho = H * 2, Wo = W * 2, vec = C >> 2;
+    const long long total = (long long)N * H * W * vec;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int lane = (int)(i % vec);
+        long long t = i / vec;
+        const int w = (int)(t % W);
+        t /= W;
+        const int h = (int)(t % H);
+        const int n = (int)(t / H);
+        // outputs whose source index lies in (h-1, h+1): dst in ((h-1)/r, (h+1)/r)
+        const int hlo = max(0, (int)floorf((float)(h - 1) / rh) - 1), hhi = min(Ho - 1, (int)ceilf((float)(h + 1) / rh) + 1);
+        const int wlo = max(0, (int)floorf((float)(w - 1) / rw) - 1), whi = min(Wo - 1, (int)ceilf((float)(w + 1) / rw) + 1);
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float *base = dy + (long long)n * Ho * Wo * C + lane * 4;
+        for (int ho = hlo; ho <= hhi; ++ho) {
+            const float wh = bil_weight(rh, ho, H, h);
+            if (wh == 0.f) continue;
+            for (int wo = wlo; wo <= whi; ++wo) {
+                const float ww = bil_weight(rw, wo, W, w);
+                if (ww == 0.f) continue;
+                const float4 g = __ldg(reinterpret_cast<const float4 *>(base + ((long long)ho * Wo + wo) * C));
+                const float k = wh * ww;
+                acc.x += k * g.x; acc.y += k * g.y; acc.z += k * g.z; acc.w += k * g.w;
+            }
+        }
+        *reinterpret_cast<float4 *>(dx + i * 4) = acc;
+    }
+}
+
+}  // namespace
+
+SCDA_API int scda_upsample_bilinear2x_nhwc_f32(int N, int H, int W, int C, const float *x, float *y,
+                                               cudaStream_t stream)
+{
+    if (N <= 0 || H < 2 || W < 2 || C < 4 || C % 4 || !x || !y) return 0;
+    if (((uintptr_t)x | (uintptr_t)y) % 16) return 0;
+    const float rh = (float)(H - 1) / (float)(2 * H - 1), rw = (float)(W - 1) / (float)(2 * W - 1);
+    const long long total = (long long)N * H * 2 * W * 2 * (C >> 2);
+    upsample2x_fwd_kernel<<<apply_grid(total), 256, 0, stream>>>(x, y, N, H, W, C, rh, rw);
+    return scda_launch_status();
+}
+
+SCDA_API int scda_upsample_bilinear2x_bwd_nhwc_f32(int N, int H, int W, int C, const float *dy, float *dx,
+                                                   cudaStream_t stream)
+{
+    if (N <= 0 || H < 2 || W < 2 || C < 4 || C % 4 || !dy || !dx) return 0;
+    if (((uintptr_t)dy | (uintptr_t)dx) % 16) return 0;
+    const float rh = (float)(H - 1) / (float)(2 * H - 1), rw = (float)(W - 1) / (float)(2 * W - 1);
+    const long long total = (long long)N * H * W * (C >> 2);
+    upsample2x_bwd_kernel<<<apply_grid(total), 256, 0, stream>>>(dy, dx, N, H, W, C, rh, rw);
     return scda_launch_status();
 }

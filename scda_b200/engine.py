@@ -76,7 +76,6 @@ class FlatAdam(object):
         self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
         self.t = 0
         self.lr_t_dev = torch.zeros(1, dtype=torch.float32, device=dev)
-        self._lr_t_host = torch.zeros(1, dtype=torch.float32).pin_memory()
 
     def zero_grad(self):
         self.bucket.zero()
@@ -91,8 +90,9 @@ class FlatAdam(object):
         self.t += 1
         lr = float(self.lr if lr is None else lr)
         bc1, bc2 = 1.0 - self.betas[0] ** self.t, 1.0 - self.betas[1] ** self.t
-        self._lr_t_host[0] = lr * (bc2 ** 0.5) / bc1
-        self.lr_t_dev.copy_(self._lr_t_host, non_blocking=True)
+        # a fill kernel carries the value in its launch arguments; an async copy from a reused
+        # pinned scalar could be overtaken by the next step's value (the host runs ahead)
+        self.lr_t_dev.fill_(lr * (bc2 ** 0.5) / bc1)
 
     def step_dev(self, grad_scale=1.0):
         """device side: one fused kernel over the flat buffers (graph-capturable)"""

@@ -62,3 +62,43 @@ def supported(x):
     """shapes the fused kernel takes (C a multiple of 4 that divides 1024)"""
     c = x.shape[1]
     return x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and c % 4 == 0 and 1024 % c == 0
+
+
+class _Upsample2x(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        require_cuda(x)
+        if not x.is_contiguous(memory_format=torch.channels_last):
+            x = x.contiguous(memory_format=torch.channels_last)
+        N, C, H, W = x.shape
+        y = torch.empty((N, C, 2 * H, 2 * W), dtype=x.dtype, device=x.device,
+                        memory_format=torch.channels_last)
+        with torch.cuda.device(x.device):
+            check(load().scda_upsample_bilinear2x_nhwc_f32(N, H, W, C, x.data_ptr(), y.data_ptr(),
+                                                           stream_ptr(x.device)),
+                  "scda_upsample_bilinear2x_nhwc_f32")
+        ctx.shape = (N, C, H, W)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        N, C, H, W = ctx.shape
+        if dy.dtype != torch.float32 or not dy.is_contiguous(memory_format=torch.channels_last):
+            dy = dy.float().contiguous(memory_format=torch.channels_last)
+        dx = torch.empty((N, C, H, W), dtype=torch.float32, device=dy.device, memory_format=torch.channels_last)
+        with torch.cuda.device(dy.device):
+            check(load().scda_upsample_bilinear2x_bwd_nhwc_f32(N, H, W, C, dy.data_ptr(), dx.data_ptr(),
+                                                               stream_ptr(dy.device)),
+                  "scda_upsample_bilinear2x_bwd_nhwc_f32")
+        return dx
+
+
+def upsample_bilinear2x(x):
+    """F.interpolate(x, scale_factor=2, mode='bilinear', align_corners=True) on a channels_last
+    fp32 CUDA tensor (C % 4 == 0, H, W >= 2)."""
+    return _Upsample2x.apply(x)
+
+
+def upsample_supported(x, scale_factor, mode):
+    return (x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and scale_factor == 2
+            and mode == 'bilinear' and x.shape[1] % 4 == 0 and x.shape[2] >= 2 and x.shape[3] >= 2)

@@ -6,7 +6,7 @@ Module / parameter names match the reference so state dicts are interchangeable.
 import torch
 import torch.nn as nn
 
-from ...gan_ops import instance_norm_act, supported as _fused_ok
+from ...gan_ops import instance_norm_act, supported as _fused_ok, upsample_bilinear2x, upsample_supported
 
 
 def gaussian_weights_init(m):
@@ -64,6 +64,8 @@ class Interpolate(nn.Module):
         self.scale_factor, self.mode = scale_factor, mode
 
     def forward(self, x):
+        if upsample_supported(x, self.scale_factor, self.mode):
+            return upsample_bilinear2x(x)          # channels-last kernel, csrc/norm_ops.cu
         return nn.functional.interpolate(x, scale_factor=self.scale_factor, mode=self.mode,
                                          align_corners=True)
 

@@ -232,3 +232,36 @@ def colsum_into(x2d, out):
         check(load().scda_colsum_bf16(x2d.shape[0], x2d.shape[1], x2d.data_ptr(), x2d.stride(0),
                                       out.data_ptr(), stream_ptr(x2d.device)), "scda_colsum_bf16")
     return out
+
+
+def roi_pool_nhwc(feat, rois, pooled_height, pooled_width, spatial_scale):
+    """feat [NB,H,W,C] bf16, rois [R,5] fp32 -> (out [R, C*PH*PW] bf16 in channel-major order,
+    argmax uint16 view as int16 tensor of the same shape)."""
+    require_cuda(feat, rois)
+    assert feat.dtype == torch.bfloat16 and feat.is_contiguous() and feat.dim() == 4
+    assert rois.dtype == torch.float32 and rois.is_contiguous() and rois.dim() == 2 and rois.shape[1] == 5
+    NB, H, W, C = feat.shape
+    R = rois.shape[0]
+    n = C * pooled_height * pooled_width
+    out = torch.empty(R, n, dtype=torch.bfloat16, device=feat.device)
+    argmax = torch.empty(R, n, dtype=torch.int16, device=feat.device)      # bits of a uint16
+    with torch.cuda.device(feat.device):
+        check(load().scda_roi_pool_nhwc_bf16_fwd(feat.data_ptr(), spatial_scale, R, NB, H, W, C, pooled_height,
+                                                 pooled_width, rois.data_ptr(), out.data_ptr(),
+                                                 argmax.data_ptr(), stream_ptr(feat.device)),
+              "scda_roi_pool_nhwc_bf16_fwd")
+    return out, argmax
+
+
+def roi_pool_nhwc_bwd(dout, argmax, rois, geom, pooled_height, pooled_width):
+    """dout [R, C*PH*PW] bf16 -> dfeat [NB,H,W,C] fp32"""
+    require_cuda(dout, argmax, rois)
+    NB, H, W, C = geom
+    assert dout.dtype == torch.bfloat16 and dout.is_contiguous() and argmax.is_contiguous()
+    dfeat = torch.empty(NB, H, W, C, dtype=torch.float32, device=dout.device)
+    with torch.cuda.device(dout.device):
+        check(load().scda_roi_pool_nhwc_bf16_bwd(dout.data_ptr(), argmax.data_ptr(), rois.data_ptr(),
+                                                 rois.shape[0], NB, H, W, C, pooled_height, pooled_width,
+                                                 dfeat.data_ptr(), stream_ptr(dout.device)),
+              "scda_roi_pool_nhwc_bf16_bwd")
+    return dfeat

@@ -22,7 +22,6 @@ its fused optimiser kernel and stamps `p._scda_shadow_version`.
 import torch
 
 from . import tc
-from ._lib import check, load, stream_ptr
 
 
 def _is_krsc(p):
@@ -315,17 +314,8 @@ class _RcnnHeadFn(torch.autograd.Function):
         ph, pw, scale = pool
         NB, H, W, C = feat.shape
         R = rois.shape[0]
-        lib = load()
-        st = stream_ptr(feat.device)
-        feat_nchw = tc.nhwc_bf16_to_nchw_f32(feat)
-        pooled = torch.empty(R, C, ph, pw, dtype=torch.float32, device=feat.device)
-        argmax = torch.empty(R, C, ph, pw, dtype=torch.int32, device=feat.device)
         rois = rois.contiguous().float()
-        with torch.cuda.device(feat.device):
-            check(lib.ROIPoolForwardLaucher(feat_nchw.data_ptr(), scale, R, H, W, C, ph, pw,
-                                            rois.data_ptr(), pooled.data_ptr(), argmax.data_ptr(), st),
-                  "ROIPoolForwardLaucher")
-        x = pooled.view(R, -1).to(torch.bfloat16)
+        x, argmax = tc.roi_pool_nhwc(feat, rois, ph, pw, scale)      # [R, C*ph*pw] bf16, fc6's order
         dm6 = _dropout_scale((R, w6.shape[0]), p_drop[0], feat.device)
         dm7 = _dropout_scale((R, w7.shape[0]), p_drop[1], feat.device)
         h6 = tc.gemm_tn(x, rt.shadow(w6), b6.detach(), relu=True, mul_src=dm6)
@@ -378,11 +368,6 @@ class _RcnnHeadFn(torch.autograd.Function):
         d6 = tc.gemm_nn(d7, rt.shadow(w7), mask_src=h6, mul_src=dm6)
         gb6 = _sink_bias(b6, d6)
         gw6 = _sink_linear_wgrad(w6, d6, x)
-        dx = tc.gemm_nn(d6, rt.shadow(w6), out_dtype=torch.float32)          # [R, C*ph*pw]
-        d_nchw = torch.empty(NB, C, H, W, dtype=torch.float32, device=x.device)
-        with torch.cuda.device(x.device):
-            check(load().ROIPoolBackwardLaucher(dx.data_ptr(), scale, NB, R, H, W, C, ph, pw,
-                                                rois.data_ptr(), d_nchw.data_ptr(), argmax.data_ptr(),
-                                                stream_ptr(x.device)), "ROIPoolBackwardLaucher")
-        d_feat = tc.nchw_f32_to_nhwc_bf16(d_nchw)
+        dx = tc.gemm_nn(d6, rt.shadow(w6))                                    # [R, C*ph*pw] bf16
+        d_feat = tc.roi_pool_nhwc_bwd(dx, argmax, rois, (NB, H, W, C), ph, pw).to(torch.bfloat16)
         return d_feat, None, None, None, None, gw6, gb6, gw7, gb7, gwc, gbc, gwl, gbl

@@ -37,6 +37,25 @@ def test_instance_norm_act(cuda_lib, N, C, H, W, act):
     assert torch.equal(y2, y.detach())
 
 
+@pytest.mark.parametrize("N,C,H,W", [(4, 128, 64, 64), (4, 64, 128, 128), (2, 8, 5, 7), (1, 4, 2, 3)])
+def test_upsample_bilinear2x(cuda_lib, N, C, H, W):
+    import torch
+    import torch.nn.functional as F
+    from scda_b200.gan_ops import upsample_bilinear2x
+    g = torch.Generator(device="cuda").manual_seed(C + W)
+    x = torch.randn(N, C, H, W, device="cuda", generator=g).contiguous(memory_format=torch.channels_last)
+    dy = torch.randn(N, C, 2 * H, 2 * W, device="cuda", generator=g).contiguous(memory_format=torch.channels_last)
+    x1 = x.clone().requires_grad_(True)
+    y = upsample_bilinear2x(x1)
+    y.backward(dy)
+    x2 = x.detach().contiguous().requires_grad_(True)
+    r = F.interpolate(x2, scale_factor=2, mode='bilinear', align_corners=True)
+    r.backward(dy.contiguous())
+    assert y.shape == r.shape and y.is_contiguous(memory_format=torch.channels_last)
+    assert float((y - r).abs().max()) <= 1e-5 * float(r.abs().max())
+    assert float((x1.grad - x2.grad).abs().max()) <= 1e-5 * float(x2.grad.abs().max())
+
+
 def test_decoder_fused_equals_torch_modules(cuda_lib, monkeypatch):
     import copy
     import torch
@@ -57,6 +76,7 @@ def test_decoder_fused_equals_torch_modules(cuda_lib, monkeypatch):
     ya, yb = dec(xa, xb)
     (ya.square().mean() + yb.mean()).backward()
     monkeypatch.setattr(common_net, "_fused_ok", lambda x: False)
+    monkeypatch.setattr(common_net, "upsample_supported", lambda x, s, m: False)
     ra, rb = ref(xa, xb)
     (ra.square().mean() + rb.mean()).backward()
     assert ya.shape == (4, 3, 256, 256)
