@@ -277,29 +277,36 @@ def test_rcnn_dropout_statistics(cuda_lib):
     assert 0.35 * frac_eval < frac_train < 0.65 * frac_eval + 0.05
 
 
-def test_flat_adam_step_matches_torch_adam_with_tc_layout(cuda_lib):
+def test_flat_adam_step_matches_torch041_rule_with_tc_layout(cuda_lib):
     """FlatAdam(tensor_core=True): channels_last conv weights in the flat buffer, bf16 shadow
-    refreshed by the optimiser kernel; the update equals torch's Adam (weight decay added
-    to the gradient) on the same gradients."""
+    refreshed by the optimiser kernel; the update is torch 0.4.1's Adam (the version the
+    reference pins, README.md:16): weight decay added to the gradient, eps added to sqrt(v)
+    BEFORE the bias correction — p -= lr * sqrt(1-b2^t)/(1-b1^t) * m / (sqrt(v) + eps) —
+    restated here with torch ops.  (Modern torch.optim.Adam divides sqrt(v) by sqrt(1-b2^t)
+    first, which moves weights with a near-zero gradient differently.)"""
     import copy
     import torch
     from scda_b200.engine import FlatAdam
     model, cfg = _model(3)
-    ref = copy.deepcopy(model)
-    opt = FlatAdam(model, 1e-3, weight_decay=1e-4, tensor_core=True)
-    topt = torch.optim.Adam(ref.parameters(), lr=1e-3, weight_decay=1e-4)
+    ref = [p.detach().clone() for p in model.parameters()]
+    m = [torch.zeros_like(p) for p in ref]
+    v = [torch.zeros_like(p) for p in ref]
+    lr, wd, b1, b2, eps = 1e-3, 1e-4, 0.9, 0.999, 1e-8
+    opt = FlatAdam(model, lr, weight_decay=wd, tensor_core=True)
     g = torch.Generator(device="cuda").manual_seed(4)
-    for _ in range(2):
+    for t in range(1, 3):
         opt.zero_grad()
-        for (n, p), q in zip(model.named_parameters(), ref.parameters()):
+        for i, (n, p) in enumerate(model.named_parameters()):
             gr = torch.randn(p.shape, device="cuda", generator=g) * 1e-2
             p.grad.copy_(gr)
             p._scda_grad_fresh = False
-            q.grad = gr.clone()
+            gk = gr + wd * ref[i]
+            m[i] = b1 * m[i] + (1 - b1) * gk
+            v[i] = b2 * v[i] + (1 - b2) * gk * gk
+            ref[i] = ref[i] - lr * (1 - b2 ** t) ** 0.5 / (1 - b1 ** t) * m[i] / (v[i].sqrt() + eps)
         opt.step()
-        topt.step()
-    for (n, p), q in zip(model.named_parameters(), ref.parameters()):
-        assert torch.allclose(p.detach(), q.detach(), rtol=1e-4, atol=1e-6), n
+    for (n, p), q in zip(model.named_parameters(), ref):
+        assert torch.allclose(p.detach(), q, rtol=1e-5, atol=2e-7), n
         sh = p._scda_shadow
         want = p.detach().permute(0, 2, 3, 1) if p.dim() == 4 else p.detach()
         assert torch.equal(sh, want.bfloat16()), n
