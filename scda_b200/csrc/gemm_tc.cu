@@ -23,6 +23,7 @@
 //   warps 4-7: epilogue: tcgen05.ld 32 lanes x 32 columns at a time -> bias, ReLU or the
 //              ReLU-gradient mask of the layer input, bf16/fp32 pack -> global
 #include <cuda.h>
+#include <stdlib.h>
 #include <cuda_bf16.h>
 
 #include "common.cuh"
@@ -101,6 +102,67 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap *map
         ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
         : "memory");
 }
+// CTA-pair (cta_group::2) forms.  The TMA box lands in the issuing CTA's own shared memory but
+// completes its bytes on the LEADER CTA's mbarrier (`bar` is a shared::cluster address).
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_pair(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1,
+                                                 int c2, int c3)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+// one MMA over both SMs of the pair: D rows 0-127 in the leader's TMEM, 128-255 in the peer's;
+// A from each CTA's own shared memory, B = the two CTAs' halves side by side
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                               uint32_t accumulate)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrives (when the pair's MMAs retire) on the mbarrier at this offset in BOTH CTAs
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar)
+{
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"((uint16_t)3)
+                 : "memory");
+}
+// shared::cluster address of `addr` (a shared::cta address of this CTA) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t addr, uint32_t rank)
+{
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr)
+{
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                           uint32_t accumulate)
 {
@@ -166,10 +228,10 @@ __host__ __device__ constexpr uint32_t make_idesc(int m, int n, int a_mn = 0, in
            ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
-template <int kBlockN, int kStages>
+template <int kBlockN, int kStages, int kCluster = 1>
 struct SmemLayout {
     static constexpr int kABytes = kBlockM * kBlockK * 2;   // 16 KB
-    static constexpr int kBBytes = kBlockN * kBlockK * 2;
+    static constexpr int kBBytes = kBlockN / kCluster * kBlockK * 2;   // a CTA pair holds half of B each
     static constexpr int kStageBytes = kABytes + kBBytes;
     static constexpr int kTileBytes = kStages * kStageBytes;
     static constexpr int kBarOffset = kTileBytes;           // full[kStages], empty[kStages], tmem_full[2], tmem_empty[2]
@@ -182,11 +244,13 @@ struct TileCoord {
     int img, h0, w0;
 };
 
-__device__ __forceinline__ TileCoord tile_coord(const TcParams &p, int tile, int n_tiles, int block_n)
+__device__ __forceinline__ TileCoord tile_coord(const TcParams &p, int tile, int n_tiles, int block_n,
+                                                int cluster, int rank)
 {
     TileCoord t;
-    t.m_tile = tile / n_tiles;
-    t.n0 = (tile - t.m_tile * n_tiles) * block_n;
+    const int m_group = tile / n_tiles;
+    t.m_tile = m_group * cluster + rank;
+    t.n0 = (tile - m_group * n_tiles) * block_n;
     t.img = 0; t.h0 = 0; t.w0 = 0;
     if (p.conv) {
         const int per_img = p.tiles_h * p.tiles_w;
@@ -198,16 +262,28 @@ __device__ __forceinline__ TileCoord tile_coord(const TcParams &p, int tile, int
     return t;
 }
 
-// Persistent kernel: grid = min(#tiles, #SMs); every CTA walks tiles blockIdx.x, +gridDim.x, ...
-// (n tile fastest, so CTAs running side by side share the A tile in L2).  The accumulator is
-// double-buffered in TMEM (2 x kBlockN columns): the epilogue warps drain tile i while the MMA
-// warp is already accumulating tile i+1 and the TMA warp is loading ahead of both.
-template <int kBlockN, int kStages, bool kBMn>
+// Persistent kernel: grid = min(#tile groups, #SMs / kCluster) clusters; cluster i walks tile
+// groups i, i + #clusters, ... (n tile fastest).  The accumulator is double-buffered in TMEM
+// (2 x kBlockN columns): the epilogue warps drain tile i while the MMA warp is already
+// accumulating tile i+1 and the TMA warp is loading ahead of both.
+//
+// kCluster == 2 is the CTA-PAIR form (tcgen05 cta_group::2): the two CTAs of a cluster (same
+// TPC) own two consecutive m tiles of the same n tile and execute ONE 256 x kBlockN MMA per
+// k-step.  Each CTA stages its own A tile and only HALF of the B tile; the tensor core of each
+// SM reads the other half straight out of the peer's shared memory.  The kernel is bound by
+// the bytes an SM can pull through the L2 fabric (~42 B/clk/SM with all SMs loading,
+// profiles/r1_ncu_conv_*): per 128 x 256 x 64 block of work a lone CTA stages 48 KB, a paired
+// CTA 32 KB.  Protocol: both producers complete their bytes on the LEADER's `full` barrier;
+// only the leader's MMA lane issues; its commits arrive on the `empty` / `tmem_full` barriers of
+// BOTH CTAs; the epilogue warps of both CTAs arrive on the leader's `tmem_empty`.
+template <int kBlockN, int kStages, bool kBMn, int kCluster>
 __global__ void __launch_bounds__(kThreads, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const TcParams p, const int m_tiles, const int n_tiles)
 {
-    using L = SmemLayout<kBlockN, kStages>;
+    static_assert(kCluster == 1 || kCluster == 2, "one CTA or a CTA pair");
+    constexpr bool kPair = kCluster == 2;
+    using L = SmemLayout<kBlockN, kStages, kCluster>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B needs 1024 B alignment
     uint8_t *gen = smem_raw + (base - smem_u32(smem_raw));
@@ -218,7 +294,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(gen + L::kBarOffset + L::kNumBars * 8);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int total_tiles = m_tiles * n_tiles;
+    const int rank = kPair ? (int)cluster_ctarank() : 0;
+    const bool leader = rank == 0;
+    const int m_groups = (m_tiles + kCluster - 1) / kCluster;
+    const int total_tiles = m_groups * n_tiles;              // tile groups
+    const int first_tile = blockIdx.x / kCluster, tile_step = gridDim.x / kCluster;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
@@ -231,72 +311,83 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(bar_tfull + a * 8, 1);
-            mbar_init(bar_tempty + a * 8, 4);    // one arrival per epilogue warp
+            mbar_init(bar_tempty + a * 8, 4 * kCluster);   // one arrival per epilogue warp (of the pair)
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
         const uint32_t ncols = 2 * kBlockN;
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
-                         smem_u32((const void *)tmem_slot)),
-                     "r"(ncols)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (kPair) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                             smem_u32((const void *)tmem_slot)), "r"(ncols) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                             smem_u32((const void *)tmem_slot)), "r"(ncols) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (kPair) cluster_sync_all();       // both CTAs' barriers exist before any remote traffic
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
         if (lane == 0) {
             const int cblocks = p.conv ? p.Cin / kBlockK : 0;
+            // the barrier the loads complete on: this CTA's, or (pair) the leader's
+            const uint32_t full_remote = kPair ? map_to_cta(bar_full, 0) : bar_full;
+            constexpr int kHalfN = kBlockN / kCluster;           // B columns staged by this CTA
             uint32_t it = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const TileCoord t = tile_coord(p, tile, n_tiles, kBlockN);
+            for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
+                const TileCoord t = tile_coord(p, tile, n_tiles, kBlockN, kCluster, rank);
+                const int nb = t.n0 + rank * kHalfN;
                 for (int kb = 0; kb < p.num_k_blocks; ++kb, ++it) {
                     const int s = it % kStages;
                     const uint32_t ph = (it / kStages) & 1;
                     mbar_wait(bar_empty + s * 8, ph ^ 1);
                     const uint32_t a_dst = base + s * L::kStageBytes;
                     const uint32_t b_dst = a_dst + L::kABytes;
-                    mbar_expect_tx(bar_full + s * 8, L::kStageBytes);
+                    const uint32_t fb = full_remote + s * 8;
+                    if (leader) mbar_expect_tx(bar_full + s * 8, L::kStageBytes * kCluster);
+                    int b_k = kb * kBlockK, b_col = 0;
                     if (p.conv) {
                         const int tap = kb / cblocks, cb = kb - tap * cblocks;
                         const int r = tap / 3, sx = tap - r * 3;
-                        tma_load_4d(a_dst, &map_a, bar_full + s * 8, cb * kBlockK, t.w0 + sx - 1, t.h0 + r - 1,
-                                    t.img);
-                        if (kBMn) {
-                            // data gradient straight from the forward weights W[co][tap][ci] seen as
-                            // [co rows][9*N cols]: reduction index = co (rows), output channel = ci
-                            // (contiguous), tap mirrored (r, s) -> (2 - r, 2 - s)
+                        if (kPair)
+                            tma_load_4d_pair(a_dst, &map_a, fb, cb * kBlockK, t.w0 + sx - 1, t.h0 + r - 1, t.img);
+                        else
+                            tma_load_4d(a_dst, &map_a, fb, cb * kBlockK, t.w0 + sx - 1, t.h0 + r - 1, t.img);
+                        // K-major weights [n][tap, ci]: column = tap * Cin + ci.  MN-major (data
+                        // gradient straight from the forward weights W[co][tap][ci] seen as
+                        // [co rows][9*N cols]): reduction index = co (rows), output channel = ci
+                        // (contiguous), tap mirrored (r, s) -> (2 - r, 2 - s)
+                        b_k = kBMn ? cb * kBlockK : tap * p.Cin + cb * kBlockK;
+                        b_col = kBMn ? (8 - tap) * p.N : 0;
+                    } else {
+                        if (kPair) tma_load_2d_pair(a_dst, &map_a, fb, kb * kBlockK, t.m_tile * kBlockM);
+                        else tma_load_2d(a_dst, &map_a, fb, kb * kBlockK, t.m_tile * kBlockM);
+                    }
+                    if (kBMn) {
+                        // B given as [K rows][N contiguous]: one {64 n, 64 k} box per 64-wide n chunk
 #pragma unroll
-                            for (int c = 0; c < kBlockN / 64; ++c)
-                                tma_load_2d(b_dst + c * (kBlockK * 128), &map_b, bar_full + s * 8,
-                                            (8 - tap) * p.N + t.n0 + c * 64, cb * kBlockK);
-                        } else {
-                            tma_load_2d(b_dst, &map_b, bar_full + s * 8, tap * p.Cin + cb * kBlockK, t.n0);
+                        for (int c = 0; c < kHalfN / 64; ++c) {
+                            if (kPair) tma_load_2d_pair(b_dst + c * (kBlockK * 128), &map_b, fb, b_col + nb + c * 64, b_k);
+                            else tma_load_2d(b_dst + c * (kBlockK * 128), &map_b, fb, b_col + nb + c * 64, b_k);
                         }
                     } else {
-                        tma_load_2d(a_dst, &map_a, bar_full + s * 8, kb * kBlockK, t.m_tile * kBlockM);
-                        if (kBMn) {
-                            // B given as [K rows][N contiguous]: one {64 n, 64 k} box per 64-wide n chunk
-#pragma unroll
-                            for (int c = 0; c < kBlockN / 64; ++c)
-                                tma_load_2d(b_dst + c * (kBlockK * 128), &map_b, bar_full + s * 8,
-                                            t.n0 + c * 64, kb * kBlockK);
-                        } else {
-                            tma_load_2d(b_dst, &map_b, bar_full + s * 8, kb * kBlockK, t.n0);
-                        }
+                        if (kPair) tma_load_2d_pair(b_dst, &map_b, fb, b_k, nb);
+                        else tma_load_2d(b_dst, &map_b, fb, b_k, nb);
                     }
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc(kBlockM, kBlockN, 0, kBMn ? 1 : 0);
+        if (lane == 0 && leader) {
+            constexpr uint32_t idesc = make_idesc(kBlockM * kCluster, kBlockN, 0, kBMn ? 1 : 0);
             uint32_t it = 0, ti = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
+            for (int tile = first_tile; tile < total_tiles; tile += tile_step, ++ti) {
                 const uint32_t acc = ti & 1, acc_ph = (ti >> 1) & 1;
                 mbar_wait(bar_tempty + acc * 8, acc_ph ^ 1);     // epilogue has drained this buffer
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -313,19 +404,24 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         const uint64_t ad = make_kmajor_desc(a_src + k * kUmmaK * 2);
                         const uint64_t bd = kBMn ? make_mnmajor_desc(b_src + k * kUmmaK * 128, kBlockK * 128)
                                                  : make_kmajor_desc(b_src + k * kUmmaK * 2);
-                        umma_bf16(tmem_d, ad, bd, idesc, (kb | k) != 0);
+                        if (kPair) umma_bf16_pair(tmem_d, ad, bd, idesc, (kb | k) != 0);
+                        else umma_bf16(tmem_d, ad, bd, idesc, (kb | k) != 0);
                     }
-                    umma_commit(bar_empty + s * 8);   // frees the stage when these MMAs retire
+                    // frees the stage (in both CTAs of a pair) when these MMAs retire
+                    if (kPair) umma_commit_pair(bar_empty + s * 8);
+                    else umma_commit(bar_empty + s * 8);
                 }
-                umma_commit(bar_tfull + acc * 8);     // accumulator complete
+                if (kPair) umma_commit_pair(bar_tfull + acc * 8);     // accumulator complete
+                else umma_commit(bar_tfull + acc * 8);
             }
         }
     } else if (warp >= 4) {
         const int ew = warp - 4;                  // TMEM lane quarter this warp may read
         const bool f32 = p.flags & kFlagOutF32;
+        const uint32_t tempty_remote = kPair ? map_to_cta(bar_tempty, 0) : bar_tempty;
         uint32_t ti = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
-            const TileCoord t = tile_coord(p, tile, n_tiles, kBlockN);
+        for (int tile = first_tile; tile < total_tiles; tile += tile_step, ++ti) {
+            const TileCoord t = tile_coord(p, tile, n_tiles, kBlockN, kCluster, rank);
             const uint32_t acc = ti & 1, acc_ph = (ti >> 1) & 1;
             const int n0 = t.n0;
             mbar_wait(bar_tfull + acc * 8, acc_ph);
@@ -336,7 +432,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             if (p.conv) {
                 const int th = row / p.TW, tw = row - th * p.TW;
                 const int h = t.h0 + th, w = t.w0 + tw;
-                row_ok = h < p.H && w < p.W;
+                row_ok = h < p.H && w < p.W && t.m_tile < m_tiles;   // (phantom tile of an odd group)
                 out_row = ((long long)t.img * p.H + h) * p.W + w;
             } else {
                 out_row = (long long)t.m_tile * kBlockM + row;
@@ -351,7 +447,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     // the whole accumulator of this warp's lanes is in registers: hand the buffer back
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(bar_tempty + acc * 8);
+                    if (lane == 0) {
+                        if (kPair) mbar_arrive_cluster(tempty_remote + acc * 8);
+                        else mbar_arrive(bar_tempty + acc * 8);
+                    }
                 }
                 if (!row_ok) continue;
                 const int ncol = min(32, p.N - (n0 + c0));
@@ -441,11 +540,16 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (kPair) cluster_sync_all();       // no CTA leaves while its peer may still signal or read it
     if (warp == 2) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t ncols = 2 * kBlockN;
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ncols)
-                     : "memory");
+        if (kPair)
+            asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ncols)
+                         : "memory");
+        else
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ncols)
+                         : "memory");
     }
 }
 
@@ -493,35 +597,61 @@ bool make_map(CUtensorMap *map, const void *ptr, int rank, const cuuint64_t *dim
     return r == CUDA_SUCCESS;
 }
 
-template <int kBlockN, int kStages, bool kBMn>
-int launch_tc(const CUtensorMap &ma, const CUtensorMap &mb, const TcParams &p, int m_tiles, cudaStream_t stream)
+template <int kBlockN, int kStages, bool kBMn, int kCluster>
+int launch_tc_c(const CUtensorMap &ma, const CUtensorMap &mb, const TcParams &p, int m_tiles, cudaStream_t stream)
 {
-    using L = SmemLayout<kBlockN, kStages>;
+    using L = SmemLayout<kBlockN, kStages, kCluster>;
+    static_assert(L::kTotal <= 227 * 1024, "shared memory budget");
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<kBlockN, kStages, kBMn>,
+        cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<kBlockN, kStages, kBMn, kCluster>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
         if (e != cudaSuccess) return -(int)e;
         attr_done = true;
     }
     const int n_tiles = ceil_div(p.N, kBlockN);
-    const long long total = (long long)m_tiles * n_tiles;
-    const int grid = (int)(total < num_sms() ? total : num_sms());
-    tc_gemm_kernel<kBlockN, kStages, kBMn><<<grid, kThreads, L::kTotal, stream>>>(ma, mb, p, m_tiles, n_tiles);
+    const long long groups = (long long)ceil_div(m_tiles, kCluster) * n_tiles;
+    const int max_clusters = num_sms() / kCluster;
+    const int clusters = (int)(groups < max_clusters ? groups : max_clusters);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(clusters * kCluster);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = L::kTotal;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = kCluster;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, tc_gemm_kernel<kBlockN, kStages, kBMn, kCluster>, ma, mb, p, m_tiles,
+                                       n_tiles);
+    if (e != cudaSuccess) return -(int)e;
     return scda_launch_status();
 }
 
 int dispatch_tc(const CUtensorMap &ma, const CUtensorMap &mb, const TcParams &p, int m_tiles, int block_n,
-                cudaStream_t stream, bool b_mn = false)
+                int cluster, cudaStream_t stream, bool b_mn = false)
 {
-    if (b_mn) {
-        if (block_n == 64) return launch_tc<64, 8, true>(ma, mb, p, m_tiles, stream);
-        if (block_n == 128) return launch_tc<128, 6, true>(ma, mb, p, m_tiles, stream);
-        return launch_tc<256, 4, true>(ma, mb, p, m_tiles, stream);
+    // stages: as many as fit in ~200 KB (stage = 16 KB of A + this CTA's share of B)
+    if (cluster == 2) {
+        if (b_mn) {
+            if (block_n == 128) return launch_tc_c<128, 8, true, 2>(ma, mb, p, m_tiles, stream);
+            return launch_tc_c<256, 6, true, 2>(ma, mb, p, m_tiles, stream);
+        }
+        if (block_n == 64) return launch_tc_c<64, 9, false, 2>(ma, mb, p, m_tiles, stream);
+        if (block_n == 128) return launch_tc_c<128, 8, false, 2>(ma, mb, p, m_tiles, stream);
+        return launch_tc_c<256, 6, false, 2>(ma, mb, p, m_tiles, stream);
     }
-    if (block_n == 64) return launch_tc<64, 8, false>(ma, mb, p, m_tiles, stream);
-    if (block_n == 128) return launch_tc<128, 6, false>(ma, mb, p, m_tiles, stream);
-    return launch_tc<256, 4, false>(ma, mb, p, m_tiles, stream);
+    if (b_mn) {
+        if (block_n == 64) return launch_tc_c<64, 8, true, 1>(ma, mb, p, m_tiles, stream);
+        if (block_n == 128) return launch_tc_c<128, 6, true, 1>(ma, mb, p, m_tiles, stream);
+        return launch_tc_c<256, 4, true, 1>(ma, mb, p, m_tiles, stream);
+    }
+    if (block_n == 64) return launch_tc_c<64, 8, false, 1>(ma, mb, p, m_tiles, stream);
+    if (block_n == 128) return launch_tc_c<128, 6, false, 1>(ma, mb, p, m_tiles, stream);
+    return launch_tc_c<256, 4, false, 1>(ma, mb, p, m_tiles, stream);
 }
 
 // N tile: 64 for narrow outputs; 256 when that still leaves every SM a tile (fewer bytes
@@ -531,6 +661,38 @@ int pick_block_n(int N, long long m_tiles = 1 << 30)
     if (N <= 64) return 64;
     if (N % 256 == 0 && m_tiles * (N / 256) >= num_sms()) return 256;
     return 128;
+}
+
+// Tile plan: N tile width and one CTA (cl = 1) or a CTA pair (cl = 2) per tile group.  The pair
+// halves the B bytes each SM stages.  Measured on B200 (profiles/r1_convbench_c_pairs.txt): the
+// 256-wide pair wins where the reduction is long (K >= 4096: conv4_2/4_3 58 -> 52 us, fc6 data
+// gradient 128 -> 99 us = 1.06 PFLOP/s) and there are enough tile groups for ~all 74 SM pairs;
+// it ties at K = 2304 and the 64/128-wide pairs LOSE 5-10 % (cluster launch + cross-CTA barrier
+// latency is not amortised), so those keep the one-CTA form.
+// SCDA_TC_CLUSTER=1 forces one CTA, =2 forces pairs wherever they are legal (tests, experiments).
+struct TilePlan {
+    int bn, cl;
+};
+
+TilePlan plan_tiles(int N, int K, long long m_tiles, bool b_mn)
+{
+    static int forced = -1;
+    if (forced < 0) {
+        const char *e = getenv("SCDA_TC_CLUSTER");
+        forced = e ? atoi(e) : 0;
+        if (forced != 1 && forced != 2) forced = 0;
+    }
+    if (forced != 1 && m_tiles >= 2) {
+        const long long pairs = (m_tiles + 1) / 2;
+        if (forced == 2) {
+            if (N % 256 == 0) return {256, 2};
+            if (N > 64) return {128, 2};
+            if (!b_mn) return {64, 2};
+        } else if (N % 256 == 0 && K >= 4096 && pairs * (N / 256) >= (long long)(num_sms() / 2) * 4 / 5) {
+            return {256, 2};
+        }
+    }
+    return {pick_block_n(N, m_tiles), 1};
 }
 
 // ---------------------------------------------------------------------------------------
@@ -726,12 +888,13 @@ SCDA_API int scda_gemm_bf16_tn(int M, int N, int K, const void *A, long long lda
     if ((flags & kFlagMaskPos) && !mask_src) return 0;
     if ((flags & kFlagMulSrc) && !mul_src) return 0;
     if ((flags & kFlagAccumulate) && !(flags & kFlagOutF32)) return 0;
-    const int bn = pick_block_n(N, ceil_div(M, kBlockM));
+    const TilePlan tp = plan_tiles(N, K, ceil_div(M, kBlockM), false);
+    const int bn = tp.bn, cl = tp.cl;
     CUtensorMap ma, mb;
     cuuint64_t da[2] = {(cuuint64_t)K, (cuuint64_t)M}, sa[1] = {(cuuint64_t)lda * 2};
     cuuint32_t ba[2] = {kBlockK, kBlockM};
     cuuint64_t db[2] = {(cuuint64_t)K, (cuuint64_t)N}, sb[1] = {(cuuint64_t)ldb * 2};
-    cuuint32_t bb[2] = {kBlockK, (cuuint32_t)bn};
+    cuuint32_t bb[2] = {kBlockK, (cuuint32_t)(bn / cl)};
     if (!make_map(&ma, A, 2, da, sa, ba) || !make_map(&mb, B, 2, db, sb, bb)) return 0;
     TcParams p = {};
     p.M = M; p.N = N; p.K = K;
@@ -741,7 +904,7 @@ SCDA_API int scda_gemm_bf16_tn(int M, int N, int K, const void *A, long long lda
     p.mask_src = (const __nv_bfloat16 *)mask_src;
     p.mul_src = (const __nv_bfloat16 *)mul_src;
     p.flags = flags;
-    return dispatch_tc(ma, mb, p, ceil_div(M, kBlockM), bn, stream);
+    return dispatch_tc(ma, mb, p, ceil_div(M, kBlockM), bn, cl, stream);
 }
 
 SCDA_API int scda_conv3x3_bf16_nhwc(int NB, int H, int W, int Cin, int Cout, const void *x, const void *w_krsc,
@@ -757,13 +920,14 @@ SCDA_API int scda_conv3x3_bf16_nhwc(int NB, int H, int W, int Cin, int Cout, con
         if (W % 8 == 0) { TW = 8; TH = 16; } else return 0;
     }
     const int tiles_w = W / TW, tiles_h = ceil_div(H, TH);
-    const int bn = pick_block_n(Cout, (long long)NB * tiles_h * tiles_w);
+    const TilePlan tp = plan_tiles(Cout, 9 * Cin, (long long)NB * tiles_h * tiles_w, false);
+    const int bn = tp.bn, cl = tp.cl;
     CUtensorMap ma, mb;
     cuuint64_t da[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)NB};
     cuuint64_t sa[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)W * Cin * 2, (cuuint64_t)H * W * Cin * 2};
     cuuint32_t ba[4] = {kBlockK, (cuuint32_t)TW, (cuuint32_t)TH, 1};
     cuuint64_t db[2] = {(cuuint64_t)9 * Cin, (cuuint64_t)Cout}, sb[1] = {(cuuint64_t)9 * Cin * 2};
-    cuuint32_t bb[2] = {kBlockK, (cuuint32_t)bn};
+    cuuint32_t bb[2] = {kBlockK, (cuuint32_t)(bn / cl)};
     if (!make_map(&ma, x, 4, da, sa, ba) || !make_map(&mb, w_krsc, 2, db, sb, bb)) return 0;
     TcParams p = {};
     p.M = NB * H * W; p.N = Cout; p.K = 9 * Cin;
@@ -773,7 +937,7 @@ SCDA_API int scda_conv3x3_bf16_nhwc(int NB, int H, int W, int Cin, int Cout, con
     p.bias = bias; p.out = y; p.ldc = Cout;
     p.mask_src = (const __nv_bfloat16 *)mask_src;
     p.flags = flags;
-    return dispatch_tc(ma, mb, p, NB * tiles_h * tiles_w, bn, stream);
+    return dispatch_tc(ma, mb, p, NB * tiles_h * tiles_w, bn, cl, stream);
 }
 
 SCDA_API int scda_conv3x3_dgrad_bf16_nhwc(int NB, int H, int W, int Cin, int Cout, const void *dy,
@@ -791,7 +955,8 @@ SCDA_API int scda_conv3x3_dgrad_bf16_nhwc(int NB, int H, int W, int Cin, int Cou
         if (W % 8 == 0) { TW = 8; TH = 16; } else return 0;
     }
     const int tiles_w = W / TW, tiles_h = ceil_div(H, TH);
-    const int bn = pick_block_n(Cin, (long long)NB * tiles_h * tiles_w);
+    const TilePlan tp = plan_tiles(Cin, 9 * Cout, (long long)NB * tiles_h * tiles_w, true);
+    const int bn = tp.bn, cl = tp.cl;
     CUtensorMap ma, mb;
     cuuint64_t da[4] = {(cuuint64_t)Cout, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)NB};
     cuuint64_t sa[3] = {(cuuint64_t)Cout * 2, (cuuint64_t)W * Cout * 2, (cuuint64_t)H * W * Cout * 2};
@@ -807,7 +972,7 @@ SCDA_API int scda_conv3x3_dgrad_bf16_nhwc(int NB, int H, int W, int Cin, int Cou
     p.bias = nullptr; p.out = dx; p.ldc = Cin;
     p.mask_src = (const __nv_bfloat16 *)mask_src;
     p.flags = flags;
-    return dispatch_tc(ma, mb, p, NB * tiles_h * tiles_w, bn, stream, true);
+    return dispatch_tc(ma, mb, p, NB * tiles_h * tiles_w, bn, cl, stream, true);
 }
 
 SCDA_API int scda_gemm_bf16_nn(int M, int N, int K, const void *A, long long lda, const void *B, long long ldb,
@@ -820,7 +985,8 @@ SCDA_API int scda_gemm_bf16_nn(int M, int N, int K, const void *A, long long lda
     if ((flags & kFlagMaskPos) && !mask_src) return 0;
     if ((flags & kFlagMulSrc) && !mul_src) return 0;
     if ((flags & kFlagAccumulate) && !(flags & kFlagOutF32)) return 0;
-    const int bn = pick_block_n(N, ceil_div(M, kBlockM));
+    const TilePlan tp = plan_tiles(N, K, ceil_div(M, kBlockM), true);
+    const int bn = tp.bn, cl = tp.cl;
     CUtensorMap ma, mb;
     cuuint64_t da[2] = {(cuuint64_t)K, (cuuint64_t)M}, sa[1] = {(cuuint64_t)lda * 2};
     cuuint32_t ba[2] = {kBlockK, kBlockM};
@@ -834,7 +1000,7 @@ SCDA_API int scda_gemm_bf16_nn(int M, int N, int K, const void *A, long long lda
     p.mask_src = (const __nv_bfloat16 *)mask_src;
     p.mul_src = (const __nv_bfloat16 *)mul_src;
     p.flags = flags;
-    return dispatch_tc(ma, mb, p, ceil_div(M, kBlockM), bn, stream, true);
+    return dispatch_tc(ma, mb, p, ceil_div(M, kBlockM), bn, cl, stream, true);
 }
 
 SCDA_API int scda_linear_wgrad_bf16(int rows, int Nout, int Kin, const void *dY, long long lddy, const void *X,
