@@ -188,6 +188,13 @@ int scda_conv3x3_dgrad_bf16_nhwc(int NB, int H, int W, int Cin, int Cout, const 
                                  const void *w_krsc, void *dx, int flags, const void *mask_src,
                                  cudaStream_t stream);
 
+/* Tuning / test hook for the two 3x3 entry points above: halo = 1 stages the input tile once for
+ * all nine taps (csrc/conv_halo.cu, the default), 0 = one TMA box per tap (csrc/gemm_tc.cu);
+ * block_n (0 auto | 64 | 128) and sub_tiles (0 auto | 1 | 2) force the halo kernel's tile plan.
+ * A negative argument leaves that setting unchanged.  Results are identical up to fp32
+ * summation order.  Process-wide, not synchronised with concurrent launches. */
+int scda_conv3x3_set_plan(int halo, int block_n, int sub_tiles);
+
 /* C[M,N] = A[M,K] . B[K,N] + bias: B row-major with N contiguous (the data gradient of
  * nn.Linear, dX = dY . W, reads W[out,in] this way; no transposed weight copy is kept). */
 int scda_gemm_bf16_nn(int M, int N, int K, const void *A, long long lda, const void *B, long long ldb,

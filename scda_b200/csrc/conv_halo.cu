@@ -1,0 +1,439 @@
+// 3x3 convolution (stride 1, zero padding 1, bf16 NHWC, fp32 accumulate in TMEM) with the im2col
+// folded into the SHARED-MEMORY STAGING: the input halo of a pixel tile is loaded ONCE per
+// 64-channel block and all nine taps are MMA operands read out of that one copy.
+//
+// Replaces cuDNN behind the reference's nn.Conv2d(k=3, p=1) layers on the hot path (13 VGG convs:
+// models/faster_rcnn/vgg_adver_expansion_cluster.py:101-114; RPN 3x3: models/head.py:13-18; the
+// decoder's 3x3 convs: models/faster_rcnn/common_net.py:59-80,279-293) and their data gradients.
+//
+// Why: the per-tap form (gemm_tc.cu, one TMA box per tap) pulls every input pixel through the
+// L2->SM fabric nine times and every weight once per 128 pixels; ncu shows it bound there
+// (profiles/r1_ncu_conv_f_full.txt: 7-8 TB/s L2->SM, tensor pipe 15-47 %).  Here a CTA owns a
+// (8*kSub) x 16 pixel region:
+//   A  one 4-D TMA box {64 ch, 8*kSub+2, 18, 1} at {c0, w0-1, h0-1, n}: the halo, rows of 128 B
+//      (one pixel x 64 channels), 128B-swizzled, zero-filled outside the image (= the padding).
+//      Tap (r,s) of sub-tile j is the SAME bytes seen through a K-major UMMA descriptor whose
+//      start address is shifted by (r*HW + s + 8j) rows and whose 8-row-group stride (SBO) is one
+//      halo row (HW*128 B): 8 consecutive pixels of an image row are 8 consecutive 128 B rows.
+//      The 128B swizzle is a function of the absolute shared-memory address on both the TMA and
+//      the MMA side, so a start that is not 1024 B aligned un-swizzles correctly with the
+//      descriptor's base_offset field left 0 (measured: scripts/probe_desc.cu,
+//      profiles/r1_probe_umma_desc_row_shift.txt — every row shift 0..19 x SBO 1024/1280/2048/2304).
+//   B  one weight tile per (tap, channel block), used by the kSub sub-tiles back to back.
+// Bytes staged per 128 px x 128 ch x 64 k x 9 taps of work: 295 KB (per-tap form) ->
+// 170 KB (kSub=1) -> 94 KB (kSub=2).
+//
+// Warp roles (128 + 128*kSub threads, one CTA per SM, persistent over tiles):
+//   warp 0: B producer   warp 3: A (halo) producer   warp 1: MMA issuer   warp 2: TMEM alloc
+//   warps 4..: epilogue, 4 warps per sub-tile (TMEM lane quarters), double-buffered accumulators
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "conv_halo.h"
+#include "tc_ptx.cuh"
+
+namespace {
+
+using namespace tcptx;
+
+constexpr int kTileH = 16;          // sub-tile = 8 wide x 16 tall = 128 pixels = the MMA's M
+constexpr int kSubW = 8;
+constexpr int kHaloH = kTileH + 2;
+constexpr int kAStages = 2;
+
+enum : int { kFlagRelu = 1, kFlagOutF32 = 2, kFlagMaskPos = 4, kFlagAccumulate = 8 };
+
+struct HaloParams {
+    int H, W, Cred, N;           // Cred: channels of the A tensor (the reduction); N: output channels
+    int cblocks;                 // Cred / 64
+    int tiles_w, tiles_h, m_tiles, n_tiles;
+    const float *bias;
+    void *out;                   // [NB*H*W, ldc]
+    long long ldc;
+    const __nv_bfloat16 *mask_src;
+    int flags;
+};
+
+template <int kBlockN, int kSub, int kBStages>
+struct HaloSmem {
+    static constexpr int kHaloW = kSubW * kSub + 2;
+    static constexpr int kABox = kHaloW * kHaloH * 128;                 // bytes one halo box delivers
+    static constexpr int kABytes = (kABox + 1023) / 1024 * 1024;
+    static constexpr int kBBytes = kBlockN * 128;
+    static constexpr int kBOffset = kAStages * kABytes;
+    static constexpr int kBarOffset = kBOffset + kBStages * kBBytes;
+    static constexpr int kNumBars = 2 * kAStages + 2 * kBStages + 4;
+    static constexpr int kTotal = kBarOffset + kNumBars * 8 + 16 + 1024;
+};
+
+struct HaloTile {
+    int n0, img, h0, w0;
+};
+
+template <int kBlockN, int kSub>
+__device__ __forceinline__ HaloTile halo_tile(const HaloParams &p, int tile)
+{
+    HaloTile t;
+    const int m_tile = tile / p.n_tiles;
+    t.n0 = (tile - m_tile * p.n_tiles) * kBlockN;
+    const int per_img = p.tiles_h * p.tiles_w;
+    t.img = m_tile / per_img;
+    const int r = m_tile - t.img * per_img;
+    t.h0 = (r / p.tiles_w) * kTileH;
+    t.w0 = (r % p.tiles_w) * (kSubW * kSub);
+    return t;
+}
+
+template <int kBlockN, int kSub, bool kBMn, int kBStages>
+__global__ void __launch_bounds__(128 + 128 * kSub, 1)
+conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                 const HaloParams p)
+{
+    using L = HaloSmem<kBlockN, kSub, kBStages>;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t *gen = smem_raw + (base - smem_u32(smem_raw));
+    const uint32_t bar_afull = base + L::kBarOffset;
+    const uint32_t bar_aempty = bar_afull + kAStages * 8;
+    const uint32_t bar_bfull = bar_aempty + kAStages * 8;
+    const uint32_t bar_bempty = bar_bfull + kBStages * 8;
+    const uint32_t bar_tfull = bar_bempty + kBStages * 8;
+    const uint32_t bar_tempty = bar_tfull + 2 * 8;
+    volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(gen + L::kBarOffset + L::kNumBars * 8);
+    constexpr uint32_t kAccCols = kSub * kBlockN;        // TMEM columns of one accumulator set
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int total_tiles = p.m_tiles * p.n_tiles;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < kAStages; ++s) {
+            mbar_init(bar_afull + s * 8, 1);
+            mbar_init(bar_aempty + s * 8, 1);
+        }
+        for (int s = 0; s < kBStages; ++s) {
+            mbar_init(bar_bfull + s * 8, 1);
+            mbar_init(bar_bempty + s * 8, 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(bar_tfull + a * 8, 1);
+            mbar_init(bar_tempty + a * 8, 4 * kSub);     // one arrival per epilogue warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                         smem_u32((const void *)tmem_slot)), "r"(2u * kAccCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 3) {
+        // ---- A producer: one halo box per (tile, channel block)
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const HaloTile t = halo_tile<kBlockN, kSub>(p, tile);
+                for (int cb = 0; cb < p.cblocks; ++cb, ++it) {
+                    const int s = it % kAStages;
+                    mbar_wait(bar_aempty + s * 8, ((it / kAStages) & 1) ^ 1);
+                    mbar_expect_tx(bar_afull + s * 8, L::kABox);
+                    tma_load_4d(base + s * L::kABytes, &map_a, bar_afull + s * 8, cb * 64, t.w0 - 1, t.h0 - 1,
+                                t.img);
+                }
+            }
+        }
+    } else if (warp == 0) {
+        // ---- B producer: one weight tile per (tile, channel block, tap)
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const HaloTile t = halo_tile<kBlockN, kSub>(p, tile);
+                for (int cb = 0; cb < p.cblocks; ++cb) {
+                    for (int tap = 0; tap < 9; ++tap, ++it) {
+                        const int s = it % kBStages;
+                        mbar_wait(bar_bempty + s * 8, ((it / kBStages) & 1) ^ 1);
+                        mbar_expect_tx(bar_bfull + s * 8, L::kBBytes);
+                        const uint32_t b_dst = base + L::kBOffset + s * L::kBBytes;
+                        if (kBMn) {
+                            // data gradient: B straight from the forward weights W[co][tap][ci] seen
+                            // as [co rows][9 * N cols]; reduction index = co (rows), output channel
+                            // = ci (contiguous), tap mirrored
+#pragma unroll
+                            for (int c = 0; c < kBlockN / 64; ++c)
+                                tma_load_2d(b_dst + c * (64 * 128), &map_b, bar_bfull + s * 8,
+                                            (8 - tap) * p.N + t.n0 + c * 64, cb * 64);
+                        } else {
+                            tma_load_2d(b_dst, &map_b, bar_bfull + s * 8, tap * p.Cred + cb * 64, t.n0);
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ---- MMA issuer
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(128, kBlockN, 0, kBMn ? 1 : 0);
+            constexpr uint32_t kSbo = L::kHaloW * 128;
+            uint32_t ait = 0, bit = 0, ti = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
+                const uint32_t acc = ti & 1;
+                mbar_wait(bar_tempty + acc * 8, ((ti >> 1) & 1) ^ 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t tmem_d = tmem_base + acc * kAccCols;
+                for (int cb = 0; cb < p.cblocks; ++cb, ++ait) {
+                    const int as = ait % kAStages;
+                    mbar_wait(bar_afull + as * 8, (ait / kAStages) & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t a_src = base + as * L::kABytes;
+                    for (int tap = 0; tap < 9; ++tap, ++bit) {
+                        const int bs = bit % kBStages;
+                        mbar_wait(bar_bfull + bs * 8, (bit / kBStages) & 1);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        const uint32_t b_src = base + L::kBOffset + bs * L::kBBytes;
+                        const int r = tap / 3, sx = tap - 3 * r;
+#pragma unroll
+                        for (int sub = 0; sub < kSub; ++sub) {
+                            const uint32_t a0 = a_src + (uint32_t)(r * L::kHaloW + sx + kSubW * sub) * 128u;
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const uint64_t ad = make_kmajor_desc_ex(a0 + k * 32, kSbo, 0);
+                                const uint64_t bd = kBMn ? make_mnmajor_desc(b_src + k * 16 * 128, 64 * 128)
+                                                         : make_kmajor_desc(b_src + k * 32);
+                                umma_bf16(tmem_d + sub * kBlockN, ad, bd, idesc, (cb | tap | k) != 0);
+                            }
+                        }
+                        umma_commit(bar_bempty + bs * 8);
+                    }
+                    umma_commit(bar_aempty + as * 8);
+                }
+                umma_commit(bar_tfull + acc * 8);
+            }
+        }
+    } else if (warp >= 4) {
+        // ---- epilogue
+        const int ew = warp - 4;
+        const int q = ew & 3;                 // TMEM lane quarter this warp may read
+        const int sub = ew >> 2;
+        const bool f32 = p.flags & kFlagOutF32;
+        const bool vec_ok = (p.ldc % 8 == 0);
+        uint32_t ti = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
+            const HaloTile t = halo_tile<kBlockN, kSub>(p, tile);
+            const uint32_t acc = ti & 1;
+            mbar_wait(bar_tfull + acc * 8, (ti >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const int row = q * 32 + lane;
+            const int h = t.h0 + (row >> 3), w = t.w0 + (row & 7) + kSubW * sub;
+            const bool row_ok = h < p.H && w < p.W;
+            const long long out_row = ((long long)t.img * p.H + h) * p.W + w;
+#pragma unroll 1
+            for (int c0 = 0; c0 < kBlockN; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * kAccCols + sub * kBlockN + c0, v);
+                if (c0 + 32 >= kBlockN) {
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_tempty + acc * 8);
+                }
+                if (!row_ok) continue;
+                const int ncol = min(32, p.N - (t.n0 + c0));
+                if (ncol <= 0) continue;
+                const bool full = ncol == 32 && vec_ok;
+                float f[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    float x = __uint_as_float(v[j]);
+                    if (p.bias && j < ncol) x += __ldg(p.bias + t.n0 + c0 + j);
+                    if (p.flags & kFlagRelu) x = fmaxf(x, 0.f);
+                    f[j] = x;
+                }
+                const long long o = out_row * p.ldc + t.n0 + c0;
+                if (p.flags & kFlagMaskPos) {
+                    const __nv_bfloat16 *ms = p.mask_src + o;
+                    if (full) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 8) {
+                            const uint4 qv = __ldg(reinterpret_cast<const uint4 *>(ms + j));
+                            const __nv_bfloat16 *qb = reinterpret_cast<const __nv_bfloat16 *>(&qv);
+#pragma unroll
+                            for (int e = 0; e < 8; ++e)
+                                if (!(__bfloat162float(qb[e]) > 0.f)) f[j + e] = 0.f;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (j < ncol && !(__bfloat162float(ms[j]) > 0.f)) f[j] = 0.f;
+                    }
+                }
+                if (f32) {
+                    float *dst = reinterpret_cast<float *>(p.out) + o;
+                    if (p.flags & kFlagAccumulate) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (j < ncol) dst[j] += f[j];
+                    } else if (full) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4)
+                            *reinterpret_cast<float4 *>(dst + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (j < ncol) dst[j] = f[j];
+                    }
+                } else {
+                    __nv_bfloat16 *dst = reinterpret_cast<__nv_bfloat16 *>(p.out) + o;
+                    if (full) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 8) {
+                            uint4 pk;
+                            __nv_bfloat162 b0 = __floats2bfloat162_rn(f[j], f[j + 1]);
+                            __nv_bfloat162 b1 = __floats2bfloat162_rn(f[j + 2], f[j + 3]);
+                            __nv_bfloat162 b2 = __floats2bfloat162_rn(f[j + 4], f[j + 5]);
+                            __nv_bfloat162 b3 = __floats2bfloat162_rn(f[j + 6], f[j + 7]);
+                            pk.x = *reinterpret_cast<uint32_t *>(&b0);
+                            pk.y = *reinterpret_cast<uint32_t *>(&b1);
+                            pk.z = *reinterpret_cast<uint32_t *>(&b2);
+                            pk.w = *reinterpret_cast<uint32_t *>(&b3);
+                            *reinterpret_cast<uint4 *>(dst + j) = pk;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (j < ncol) dst[j] = __float2bfloat16_rn(f[j]);
+                    }
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 2) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2u * kAccCols)
+                     : "memory");
+    }
+}
+
+template <int kBlockN, int kSub, bool kBMn, int kBStages>
+int launch_halo(const CUtensorMap &ma, const CUtensorMap &mb, const HaloParams &p, cudaStream_t stream)
+{
+    using L = HaloSmem<kBlockN, kSub, kBStages>;
+    static_assert(L::kTotal <= 227 * 1024, "shared memory budget");
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<kBlockN, kSub, kBMn, kBStages>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
+        if (e != cudaSuccess) return -(int)e;
+        attr_done = true;
+    }
+    const long long tiles = (long long)p.m_tiles * p.n_tiles;
+    const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
+    conv_halo_kernel<kBlockN, kSub, kBMn, kBStages><<<grid, 128 + 128 * kSub, L::kTotal, stream>>>(ma, mb, p);
+    return scda_launch_status();
+}
+
+int env_int(const char *name, int dflt)
+{
+    const char *e = getenv(name);
+    return e && *e ? atoi(e) : dflt;
+}
+
+}  // namespace
+
+// Tile plan of the halo kernel for a layer: bn = N tile (64 | 128), sub = sub-tiles per CTA
+// (1 | 2); returns false where the per-tap kernel of gemm_tc.cu should be used instead.
+// scda_conv3x3_set_plan (or SCDA_CONV_HALO / SCDA_HALO_BN / SCDA_HALO_SUB at load) overrides it.
+static int g_enabled = -1, g_force_bn = 0, g_force_sub = 0;
+
+static void plan_init()
+{
+    if (g_enabled >= 0) return;
+    g_enabled = env_int("SCDA_CONV_HALO", 1) ? 1 : 0;
+    g_force_bn = env_int("SCDA_HALO_BN", 0);
+    g_force_sub = env_int("SCDA_HALO_SUB", 0);
+}
+
+SCDA_API int scda_conv3x3_set_plan(int halo, int block_n, int sub_tiles)
+{
+    plan_init();
+    if (halo >= 0) g_enabled = halo ? 1 : 0;
+    if (block_n >= 0) {
+        if (block_n != 0 && block_n != 64 && block_n != 128) return 0;
+        g_force_bn = block_n;
+    }
+    if (sub_tiles >= 0) {
+        if (sub_tiles > 2) return 0;
+        g_force_sub = sub_tiles;
+    }
+    return 1;
+}
+
+bool scda_conv_halo_plan(int NB, int H, int W, int Cred, int Nout, bool dgrad, int *bn, int *sub)
+{
+    plan_init();
+    if (!g_enabled || Cred % 64 || Nout % 64) return false;
+    (void)dgrad;
+    int b = (Nout % 128 == 0) ? 128 : 64;
+    const long long th = ceil_div(H, kTileH);
+    // two sub-tiles per CTA (half the weight bytes per pixel) while that still gives ~every SM a tile
+    int s = 2;
+    long long tiles = (long long)NB * th * ceil_div(W, 16) * (Nout / b);
+    if (tiles < (long long)num_sms() * 3 / 4) {
+        s = 1;
+        tiles = (long long)NB * th * ceil_div(W, 8) * (Nout / b);
+        if (tiles < (long long)num_sms() * 3 / 4 && b == 128) b = 64;
+    }
+    if (g_force_bn == 64 || (g_force_bn == 128 && Nout % 128 == 0)) b = g_force_bn;
+    if (g_force_sub == 1 || g_force_sub == 2) s = g_force_sub;
+    *bn = b;
+    *sub = s;
+    return true;
+}
+
+int scda_conv_halo_launch(int NB, int H, int W, int Cred, int Nout, const void *a, const void *w_krsc,
+                          const float *bias, void *out, int flags, const void *mask_src, bool dgrad, int bn,
+                          int sub, cudaStream_t stream)
+{
+    const int region_w = kSubW * sub;
+    HaloParams p = {};
+    p.H = H; p.W = W; p.Cred = Cred; p.N = Nout;
+    p.cblocks = Cred / 64;
+    p.tiles_w = ceil_div(W, region_w);
+    p.tiles_h = ceil_div(H, kTileH);
+    p.m_tiles = NB * p.tiles_h * p.tiles_w;
+    p.n_tiles = ceil_div(Nout, bn);
+    p.bias = bias; p.out = out; p.ldc = Nout;
+    p.mask_src = (const __nv_bfloat16 *)mask_src;
+    p.flags = flags;
+    CUtensorMap ma, mb;
+    cuuint64_t da[4] = {(cuuint64_t)Cred, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)NB};
+    cuuint64_t sa[3] = {(cuuint64_t)Cred * 2, (cuuint64_t)W * Cred * 2, (cuuint64_t)H * W * Cred * 2};
+    cuuint32_t ba[4] = {64, (cuuint32_t)(region_w + 2), (cuuint32_t)kHaloH, 1};
+    if (!make_map(&ma, a, 4, da, sa, ba)) return 0;
+    if (dgrad) {
+        // forward weights [Cred = Cout_fwd rows][9 * Nout cols]
+        cuuint64_t db[2] = {(cuuint64_t)9 * Nout, (cuuint64_t)Cred}, sb[1] = {(cuuint64_t)9 * Nout * 2};
+        cuuint32_t bb[2] = {64, 64};
+        if (!make_map(&mb, w_krsc, 2, db, sb, bb)) return 0;
+        if (bn == 64) return sub == 1 ? launch_halo<64, 1, true, 8>(ma, mb, p, stream)
+                                      : launch_halo<64, 2, true, 8>(ma, mb, p, stream);
+        return sub == 1 ? launch_halo<128, 1, true, 8>(ma, mb, p, stream)
+                        : launch_halo<128, 2, true, 8>(ma, mb, p, stream);
+    }
+    cuuint64_t db[2] = {(cuuint64_t)9 * Cred, (cuuint64_t)Nout}, sb[1] = {(cuuint64_t)9 * Cred * 2};
+    cuuint32_t bb[2] = {64, (cuuint32_t)bn};
+    if (!make_map(&mb, w_krsc, 2, db, sb, bb)) return 0;
+    if (bn == 64) return sub == 1 ? launch_halo<64, 1, false, 8>(ma, mb, p, stream)
+                                  : launch_halo<64, 2, false, 8>(ma, mb, p, stream);
+    return sub == 1 ? launch_halo<128, 1, false, 8>(ma, mb, p, stream)
+                    : launch_halo<128, 2, false, 8>(ma, mb, p, stream);
+}

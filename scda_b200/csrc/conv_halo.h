@@ -1,0 +1,10 @@
+// Internal (not exported) interface of csrc/conv_halo.cu, used by the conv entry points in gemm_tc.cu.
+#pragma once
+#include <cuda_runtime.h>
+
+bool scda_conv_halo_plan(int NB, int H, int W, int Cred, int Nout, bool dgrad, int *bn, int *sub);
+// a: [NB,H,W,Cred] bf16; forward: w_krsc = [Nout][3][3][Cred]; dgrad: the FORWARD weights
+// [Cred][3][3][Nout] (read as an MN-major operand with the tap mirrored).  flags as in gemm_tc.cu.
+int scda_conv_halo_launch(int NB, int H, int W, int Cred, int Nout, const void *a, const void *w_krsc,
+                          const float *bias, void *out, int flags, const void *mask_src, bool dgrad, int bn,
+                          int sub, cudaStream_t stream);

@@ -27,6 +27,8 @@
 #include <cuda_bf16.h>
 
 #include "common.cuh"
+#include "conv_halo.h"
+#include "tc_ptx.cuh"
 
 namespace {
 
@@ -57,176 +59,8 @@ struct TcParams {
     int flags;
 };
 
-// ----------------------------------------------------------------------------- PTX
-__device__ __forceinline__ uint32_t smem_u32(const void *p)
-{
-    return (uint32_t)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar)
-{
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
-{
-    asm volatile(
-        "{\n"
-        ".reg .pred P1;\n"
-        "LAB_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-        "@P1 bra DONE;\n"
-        "bra LAB_WAIT;\n"
-        "DONE:\n"
-        "}\n" ::"r"(bar), "r"(parity)
-        : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1)
-{
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
-        : "memory");
-}
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1,
-                                            int c2, int c3)
-{
-    asm volatile(
-        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-        : "memory");
-}
-// CTA-pair (cta_group::2) forms.  The TMA box lands in the issuing CTA's own shared memory but
-// completes its bytes on the LEADER CTA's mbarrier (`bar` is a shared::cluster address).
-__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1)
-{
-    asm volatile(
-        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
-        " [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
-        : "memory");
-}
-__device__ __forceinline__ void tma_load_4d_pair(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1,
-                                                 int c2, int c3)
-{
-    asm volatile(
-        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
-        " [%0], [%1, {%3, %4, %5, %6}], [%2];"
-        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-        : "memory");
-}
-// one MMA over both SMs of the pair: D rows 0-127 in the leader's TMEM, 128-255 in the peer's;
-// A from each CTA's own shared memory, B = the two CTAs' halves side by side
-__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                               uint32_t accumulate)
-{
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
-        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-// arrives (when the pair's MMAs retire) on the mbarrier at this offset in BOTH CTAs
-__device__ __forceinline__ void umma_commit_pair(uint32_t bar)
-{
-    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-                 ::"r"(bar), "h"((uint16_t)3)
-                 : "memory");
-}
-// shared::cluster address of `addr` (a shared::cta address of this CTA) in CTA `rank` of the cluster
-__device__ __forceinline__ uint32_t map_to_cta(uint32_t addr, uint32_t rank)
-{
-    uint32_t r;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
-    return r;
-}
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr)
-{
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-__device__ __forceinline__ uint32_t cluster_ctarank()
-{
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
-}
-__device__ __forceinline__ void cluster_sync_all()
-{
-    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                          uint32_t accumulate)
-{
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar)
-{
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
-                 : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32])
-{
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
+using namespace tcptx;
 
-// K-major, 128B-swizzled operand tile: rows of 128 B, 8-row groups 1024 B apart
-// (cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46),
-//  version=1 [46,48), layout SWIZZLE_128B=2 [61,64)).
-__device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t saddr)
-{
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-    d |= (uint64_t)1 << 16;                  // LBO (unused for swizzled K-major)
-    d |= (uint64_t)(1024 >> 4) << 32;        // SBO
-    d |= (uint64_t)1 << 46;                  // descriptor version (Blackwell)
-    d |= (uint64_t)2 << 61;                  // SWIZZLE_128B
-    return d;
-}
-// MN-major, 128B-swizzled operand: the tile is stored [k rows][64 mn] (128 B per k row, the
-// image a TMA box {64 mn, rows} leaves in shared memory); 8-k-row groups are 1024 B apart
-// (SBO) and successive 64-wide mn chunks are `chunk_bytes` apart (LBO).
-// Canonical form ((T,8,m),(8,k)):((1,T,LBO),(8T,SBO)), cute mma_traits_sm100.hpp.
-__device__ __forceinline__ uint64_t make_mnmajor_desc(uint32_t saddr, uint32_t chunk_bytes)
-{
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-    d |= (uint64_t)((chunk_bytes >> 4) & 0x3FFF) << 16;   // LBO
-    d |= (uint64_t)(1024 >> 4) << 32;                     // SBO
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
-    return d;
-}
-// cute::UMMA::InstrDescriptor, kind::f16: D=F32 [4,6)=1, A=BF16 [7,10)=1, B=BF16 [10,13)=1,
-// A major [15], B major [16] (0 = K, 1 = MN), N>>3 at [17,23), M>>4 at [24,29)
-__host__ __device__ constexpr uint32_t make_idesc(int m, int n, int a_mn = 0, int b_mn = 0)
-{
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
-           ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
-}
 
 template <int kBlockN, int kStages, int kCluster = 1>
 struct SmemLayout {
@@ -554,49 +388,6 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 }
 
 // ------------------------------------------------------------------- host side
-typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
-                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
-                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
-                                  CUtensorMapFloatOOBfill);
-
-EncodeTiledFn encode_fn()
-{
-    static EncodeTiledFn fn = nullptr;
-    if (!fn) {
-        void *ptr = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
-            q == cudaDriverEntryPointSuccess)
-            fn = (EncodeTiledFn)ptr;
-    }
-    return fn;
-}
-
-int num_sms()
-{
-    static int n = 0;
-    if (!n) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess ||
-            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
-            n = kNumSMs;
-    }
-    return n;
-}
-
-// bf16 tensor, dims/strides innermost first; box innermost = 64 elements (128 B), 128B swizzle
-bool make_map(CUtensorMap *map, const void *ptr, int rank, const cuuint64_t *dims, const cuuint64_t *strides_bytes,
-              const cuuint32_t *box)
-{
-    EncodeTiledFn fn = encode_fn();
-    if (!fn) return false;
-    cuuint32_t ones[5] = {1, 1, 1, 1, 1};
-    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void *>(ptr), dims,
-                    strides_bytes, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    return r == CUDA_SUCCESS;
-}
-
 template <int kBlockN, int kStages, bool kBMn, int kCluster>
 int launch_tc_c(const CUtensorMap &ma, const CUtensorMap &mb, const TcParams &p, int m_tiles, cudaStream_t stream)
 {
@@ -915,6 +706,12 @@ SCDA_API int scda_conv3x3_bf16_nhwc(int NB, int H, int W, int Cin, int Cout, con
     if (Cin % kBlockK) return 0;               // channel blocks of 64 (conv1_1 has its own kernel)
     if ((flags & kFlagMaskPos) && !mask_src) return 0;
     if ((flags & kFlagAccumulate) && !(flags & kFlagOutF32)) return 0;
+    {
+        int hbn, hsub;       // halo form (conv_halo.cu): the input tile is staged once for all 9 taps
+        if (!(flags & kFlagMulSrc) && scda_conv_halo_plan(NB, H, W, Cin, Cout, false, &hbn, &hsub))
+            return scda_conv_halo_launch(NB, H, W, Cin, Cout, x, w_krsc, bias, y, flags, mask_src, false, hbn,
+                                         hsub, stream);
+    }
     int TW = 16, TH = 8;
     if (W % 16) {                                 // narrow maps: 8 x 16 tile turned around
         if (W % 8 == 0) { TW = 8; TH = 16; } else return 0;
@@ -950,6 +747,12 @@ SCDA_API int scda_conv3x3_dgrad_bf16_nhwc(int NB, int H, int W, int Cin, int Cou
     if (Cin % 64 || Cout % kBlockK) return 0;
     if ((flags & kFlagMaskPos) && !mask_src) return 0;
     if (flags & (kFlagAccumulate | kFlagMulSrc | kFlagRelu)) return 0;
+    {
+        int hbn, hsub;
+        if (scda_conv_halo_plan(NB, H, W, Cout, Cin, true, &hbn, &hsub))
+            return scda_conv_halo_launch(NB, H, W, Cout, Cin, dy, w_krsc, nullptr, dx, flags, mask_src, true, hbn,
+                                         hsub, stream);
+    }
     int TW = 16, TH = 8;
     if (W % 16) {
         if (W % 8 == 0) { TW = 8; TH = 16; } else return 0;

@@ -96,6 +96,12 @@ def conv3x3_nhwc(x, w_krsc, bias=None, relu=False, out_dtype=torch.bfloat16, mas
     return y
 
 
+def set_conv_plan(halo=-1, block_n=-1, sub_tiles=-1):
+    """tuning / test hook (scda_conv3x3_set_plan): halo 1|0, block_n 0|64|128, sub_tiles 0|1|2"""
+    if load().scda_conv3x3_set_plan(int(halo), int(block_n), int(sub_tiles)) != 1:
+        raise ValueError("scda_conv3x3_set_plan: bad arguments")
+
+
 def conv3x3_dgrad_nhwc(dy, w_krsc, mask_src=None, out_dtype=torch.bfloat16):
     """dx[N,H,W,Cin] from dy[N,H,W,Cout] and the FORWARD weights w[Cout,3,3,Cin]; with
     mask_src (= the layer input, a ReLU output) the ReLU gradient is applied as well."""

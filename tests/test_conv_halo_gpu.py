@@ -1,0 +1,95 @@
+"""The halo form of the 3x3 convolution (csrc/conv_halo.cu: input tile staged once, nine taps read
+through shifted UMMA descriptors) under every tile plan, forward and data gradient, against a
+plain PyTorch fp32 convolution of the same bf16-rounded operands and against the per-tap kernel.
+Tolerance as in test_tc_gpu.py: fp32 accumulation, bf16 output rounding."""
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+PLANS = [(1, 64, 1), (1, 64, 2), (1, 128, 1), (1, 128, 2), (1, 0, 0), (0, 0, 0)]
+SHAPES = [(1, 16, 16, 64, 64), (1, 32, 64, 128, 128), (2, 32, 64, 64, 256), (1, 24, 40, 64, 192),
+          (1, 20, 24, 192, 128), (3, 16, 8, 128, 64), (1, 64, 128, 256, 512), (1, 48, 72, 64, 64)]
+
+
+def _close(out, ref, rtol=1e-2):
+    out, ref = out.float(), ref.float()
+    tol = rtol * ref.abs() + rtol * ref.pow(2).mean().sqrt()
+    bad = (out - ref).abs() > tol
+    assert not bool(bad.any()), "mismatch: %d / %d, max abs err %g (ref rms %g)" % (
+        int(bad.sum()), bad.numel(), float((out - ref).abs().max()), float(ref.pow(2).mean().sqrt()))
+
+
+@pytest.fixture
+def plan_reset(cuda_lib):
+    from scda_b200 import tc
+    yield tc
+    tc.set_conv_plan(1, 0, 0)
+
+
+@pytest.mark.parametrize("NB,H,W,Cin,Cout", SHAPES)
+def test_forward_all_plans(plan_reset, NB, H, W, Cin, Cout):
+    import torch
+    import torch.nn.functional as F
+    tc = plan_reset
+    g = torch.Generator(device="cuda").manual_seed(H * W + Cin + Cout)
+    x = torch.randn(NB, H, W, Cin, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(Cout, 3, 3, Cin, device="cuda", generator=g) / (9 * Cin) ** 0.5).bfloat16()
+    bias = torch.randn(Cout, device="cuda", generator=g)
+    torch.backends.cudnn.allow_tf32 = False
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float().permute(0, 3, 1, 2), bias, padding=1)
+    ref = ref.permute(0, 2, 3, 1)
+    for halo, bn, sub in PLANS:
+        tc.set_conv_plan(halo, bn, sub)
+        _close(tc.conv3x3_nhwc(x, w, bias), ref)
+        _close(tc.conv3x3_nhwc(x, w, bias, relu=True, out_dtype=torch.float32), ref.clamp(min=0), rtol=2e-3)
+
+
+@pytest.mark.parametrize("NB,H,W,Cin,Cout", SHAPES)
+def test_dgrad_all_plans(plan_reset, NB, H, W, Cin, Cout):
+    import torch
+    tc = plan_reset
+    g = torch.Generator(device="cuda").manual_seed(H + W + Cin * Cout)
+    x = torch.randn(NB, H, W, Cin, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(Cout, 3, 3, Cin, device="cuda", generator=g) / (9 * Cout) ** 0.5).bfloat16()
+    dy = torch.randn(NB, H, W, Cout, device="cuda", generator=g).bfloat16()
+    torch.backends.cudnn.allow_tf32 = False
+    ref = torch.nn.grad.conv2d_input((NB, Cin, H, W), w.float().permute(0, 3, 1, 2),
+                                     dy.float().permute(0, 3, 1, 2), padding=1).permute(0, 2, 3, 1)
+    refm = torch.where(x.float() > 0, ref, torch.zeros_like(ref))
+    for halo, bn, sub in PLANS:
+        tc.set_conv_plan(halo, bn, sub)
+        _close(tc.conv3x3_dgrad_nhwc(dy, w), ref)
+        _close(tc.conv3x3_dgrad_nhwc(dy, w, mask_src=x), refm)
+
+
+def test_halo_equals_per_tap_on_integers(plan_reset):
+    """Small-integer operands make every product and partial sum exact in fp32, so the two kernels
+    (different summation orders) must agree BIT FOR BIT."""
+    import torch
+    tc = plan_reset
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.randint(-3, 4, (1, 32, 48, 128), device="cuda", generator=g).bfloat16()
+    w = torch.randint(-2, 3, (128, 3, 3, 128), device="cuda", generator=g).bfloat16()
+    tc.set_conv_plan(0, 0, 0)
+    y0 = tc.conv3x3_nhwc(x, w, out_dtype=torch.float32)
+    d0 = tc.conv3x3_dgrad_nhwc(x, w, out_dtype=torch.float32)
+    for bn, sub in ((64, 1), (64, 2), (128, 1), (128, 2)):
+        tc.set_conv_plan(1, bn, sub)
+        assert torch.equal(tc.conv3x3_nhwc(x, w, out_dtype=torch.float32), y0)
+        assert torch.equal(tc.conv3x3_dgrad_nhwc(x, w, out_dtype=torch.float32), d0)
+
+
+def test_backbone_full_size_persistent_tiles(plan_reset):
+    """conv2_2 at the benchmark resolution (128 -> 128 @ 256 x 512): many tiles per CTA, both
+    accumulator buffers and every pipeline slot wrap; exact-integer comparison with the per-tap
+    kernel."""
+    import torch
+    tc = plan_reset
+    g = torch.Generator(device="cuda").manual_seed(9)
+    x = torch.randint(-2, 3, (1, 256, 512, 128), device="cuda", generator=g).bfloat16()
+    w = torch.randint(-1, 2, (128, 3, 3, 128), device="cuda", generator=g).bfloat16()
+    tc.set_conv_plan(0, 0, 0)
+    y0 = tc.conv3x3_nhwc(x, w, out_dtype=torch.float32)
+    for bn, sub in ((128, 2), (64, 1)):
+        tc.set_conv_plan(1, bn, sub)
+        assert torch.equal(tc.conv3x3_nhwc(x, w, out_dtype=torch.float32), y0)
