@@ -32,6 +32,7 @@
 
 #include "common.cuh"
 #include "conv_halo.h"
+#include "tc_epilogue.cuh"
 #include "tc_ptx.cuh"
 
 namespace {
@@ -42,8 +43,6 @@ constexpr int kTileH = 16;          // sub-tile = 8 wide x 16 tall = 128 pixels 
 constexpr int kSubW = 8;
 constexpr int kHaloH = kTileH + 2;
 constexpr int kAStages = 2;
-
-enum : int { kFlagRelu = 1, kFlagOutF32 = 2, kFlagMaskPos = 4, kFlagAccumulate = 8 };
 
 struct HaloParams {
     int H, W, Cred, N;           // Cred: channels of the A tensor (the reduction); N: output channels
@@ -84,6 +83,42 @@ __device__ __forceinline__ HaloTile halo_tile(const HaloParams &p, int tile)
     t.h0 = (r / p.tiles_w) * kTileH;
     t.w0 = (r % p.tiles_w) * (kSubW * kSub);
     return t;
+}
+
+template <int kBlockN, int kSub, int kSpec>
+__device__ __forceinline__ void halo_epilogue(const HaloParams &p, const EpiParams &e, uint32_t tmem_base,
+                                              uint32_t bar_tfull, uint32_t bar_tempty, int ew, int lane)
+{
+    constexpr uint32_t kAccCols = kSub * kBlockN;
+    const int q = ew & 3;                 // TMEM lane quarter this warp may read
+    const int sub = ew >> 2;
+    const int total_tiles = p.m_tiles * p.n_tiles;
+    const bool aligned = ((reinterpret_cast<uintptr_t>(e.out) | reinterpret_cast<uintptr_t>(e.bias) |
+                           reinterpret_cast<uintptr_t>(e.mask_src)) & 15) == 0;
+    const bool vec_ok = (e.ldc % 8 == 0) && aligned;
+    uint32_t ti = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
+        const HaloTile t = halo_tile<kBlockN, kSub>(p, tile);
+        const uint32_t acc = ti & 1;
+        mbar_wait(bar_tfull + acc * 8, (ti >> 1) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int row = q * 32 + lane;
+        const int h = t.h0 + (row >> 3), w = t.w0 + (row & 7) + kSubW * sub;
+        const bool row_ok = h < p.H && w < p.W;
+        const long long out_row = ((long long)t.img * p.H + h) * p.W + w;
+#pragma unroll 1
+        for (int c0 = 0; c0 < kBlockN; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * kAccCols + sub * kBlockN + c0, v);
+            if (c0 + 32 >= kBlockN) {
+                // this warp's share of the accumulator is in registers: hand the buffer back
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_tempty + acc * 8);
+            }
+            if (row_ok) epilogue_chunk<kSpec>(v, e, out_row, t.n0 + c0, vec_ok);
+        }
+    }
 }
 
 template <int kBlockN, int kSub, bool kBMn, int kBStages>
@@ -183,6 +218,14 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         if (lane == 0) {
             constexpr uint32_t idesc = make_idesc(128, kBlockN, 0, kBMn ? 1 : 0);
             constexpr uint32_t kSbo = L::kHaloW * 128;
+            // descriptors as (lo, hi) words: hi is constant, lo = start >> 4 (+ LBO field) and only
+            // ever gets a compile-time offset added (tap / sub-tile row shift, K advance)
+            const uint64_t a_proto = make_kmajor_desc_ex(0, kSbo, 0);
+            const uint64_t b_proto = kBMn ? make_mnmajor_desc(0, 64 * 128) : make_kmajor_desc(0);
+            const uint32_t a_hi = (uint32_t)(a_proto >> 32), b_hi = (uint32_t)(b_proto >> 32);
+            const uint32_t a_lo0 = (uint32_t)a_proto + (base >> 4);
+            const uint32_t b_lo0 = (uint32_t)b_proto + ((base + L::kBOffset) >> 4);
+            constexpr uint32_t kBk = kBMn ? (16 * 128) >> 4 : 32 >> 4;      // K advance of B per MMA
             uint32_t ait = 0, bit = 0, ti = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
                 const uint32_t acc = ti & 1;
@@ -190,26 +233,24 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t tmem_d = tmem_base + acc * kAccCols;
                 for (int cb = 0; cb < p.cblocks; ++cb, ++ait) {
-                    const int as = ait % kAStages;
+                    const uint32_t as = ait % kAStages;
                     mbar_wait(bar_afull + as * 8, (ait / kAStages) & 1);
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint32_t a_src = base + as * L::kABytes;
+                    const uint32_t a_lo = a_lo0 + as * (L::kABytes >> 4);
+#pragma unroll
                     for (int tap = 0; tap < 9; ++tap, ++bit) {
-                        const int bs = bit % kBStages;
+                        const uint32_t bs = bit % kBStages;
                         mbar_wait(bar_bfull + bs * 8, (bit / kBStages) & 1);
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                        const uint32_t b_src = base + L::kBOffset + bs * L::kBBytes;
-                        const int r = tap / 3, sx = tap - 3 * r;
+                        const uint32_t b_lo = b_lo0 + bs * (L::kBBytes >> 4);
+                        const uint32_t first = (uint32_t)(cb | tap);
 #pragma unroll
                         for (int sub = 0; sub < kSub; ++sub) {
-                            const uint32_t a0 = a_src + (uint32_t)(r * L::kHaloW + sx + kSubW * sub) * 128u;
+                            // rows (tap/3) * HW + tap%3 + 8*sub of 128 B each = 8 units of 16 B per row
+                            const uint32_t a_off = (uint32_t)((tap / 3) * L::kHaloW + (tap % 3) + kSubW * sub) * 8u;
 #pragma unroll
-                            for (int k = 0; k < 4; ++k) {
-                                const uint64_t ad = make_kmajor_desc_ex(a0 + k * 32, kSbo, 0);
-                                const uint64_t bd = kBMn ? make_mnmajor_desc(b_src + k * 16 * 128, 64 * 128)
-                                                         : make_kmajor_desc(b_src + k * 32);
-                                umma_bf16(tmem_d + sub * kBlockN, ad, bd, idesc, (cb | tap | k) != 0);
-                            }
+                            for (int k = 0; k < 4; ++k)
+                                umma_bf16_lohi(tmem_d + sub * kBlockN, a_lo + a_off + k * 2, a_hi, b_lo + k * kBk, b_hi,
+                                               idesc, first | (uint32_t)k);
                         }
                         umma_commit(bar_bempty + bs * 8);
                     }
@@ -219,100 +260,19 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             }
         }
     } else if (warp >= 4) {
-        // ---- epilogue
-        const int ew = warp - 4;
-        const int q = ew & 3;                 // TMEM lane quarter this warp may read
-        const int sub = ew >> 2;
-        const bool f32 = p.flags & kFlagOutF32;
-        const bool vec_ok = (p.ldc % 8 == 0);
-        uint32_t ti = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
-            const HaloTile t = halo_tile<kBlockN, kSub>(p, tile);
-            const uint32_t acc = ti & 1;
-            mbar_wait(bar_tfull + acc * 8, (ti >> 1) & 1);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const int row = q * 32 + lane;
-            const int h = t.h0 + (row >> 3), w = t.w0 + (row & 7) + kSubW * sub;
-            const bool row_ok = h < p.H && w < p.W;
-            const long long out_row = ((long long)t.img * p.H + h) * p.W + w;
-#pragma unroll 1
-            for (int c0 = 0; c0 < kBlockN; c0 += 32) {
-                uint32_t v[32];
-                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * kAccCols + sub * kBlockN + c0, v);
-                if (c0 + 32 >= kBlockN) {
-                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(bar_tempty + acc * 8);
-                }
-                if (!row_ok) continue;
-                const int ncol = min(32, p.N - (t.n0 + c0));
-                if (ncol <= 0) continue;
-                const bool full = ncol == 32 && vec_ok;
-                float f[32];
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    float x = __uint_as_float(v[j]);
-                    if (p.bias && j < ncol) x += __ldg(p.bias + t.n0 + c0 + j);
-                    if (p.flags & kFlagRelu) x = fmaxf(x, 0.f);
-                    f[j] = x;
-                }
-                const long long o = out_row * p.ldc + t.n0 + c0;
-                if (p.flags & kFlagMaskPos) {
-                    const __nv_bfloat16 *ms = p.mask_src + o;
-                    if (full) {
-#pragma unroll
-                        for (int j = 0; j < 32; j += 8) {
-                            const uint4 qv = __ldg(reinterpret_cast<const uint4 *>(ms + j));
-                            const __nv_bfloat16 *qb = reinterpret_cast<const __nv_bfloat16 *>(&qv);
-#pragma unroll
-                            for (int e = 0; e < 8; ++e)
-                                if (!(__bfloat162float(qb[e]) > 0.f)) f[j + e] = 0.f;
-                        }
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (j < ncol && !(__bfloat162float(ms[j]) > 0.f)) f[j] = 0.f;
-                    }
-                }
-                if (f32) {
-                    float *dst = reinterpret_cast<float *>(p.out) + o;
-                    if (p.flags & kFlagAccumulate) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (j < ncol) dst[j] += f[j];
-                    } else if (full) {
-#pragma unroll
-                        for (int j = 0; j < 32; j += 4)
-                            *reinterpret_cast<float4 *>(dst + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (j < ncol) dst[j] = f[j];
-                    }
-                } else {
-                    __nv_bfloat16 *dst = reinterpret_cast<__nv_bfloat16 *>(p.out) + o;
-                    if (full) {
-#pragma unroll
-                        for (int j = 0; j < 32; j += 8) {
-                            uint4 pk;
-                            __nv_bfloat162 b0 = __floats2bfloat162_rn(f[j], f[j + 1]);
-                            __nv_bfloat162 b1 = __floats2bfloat162_rn(f[j + 2], f[j + 3]);
-                            __nv_bfloat162 b2 = __floats2bfloat162_rn(f[j + 4], f[j + 5]);
-                            __nv_bfloat162 b3 = __floats2bfloat162_rn(f[j + 6], f[j + 7]);
-                            pk.x = *reinterpret_cast<uint32_t *>(&b0);
-                            pk.y = *reinterpret_cast<uint32_t *>(&b1);
-                            pk.z = *reinterpret_cast<uint32_t *>(&b2);
-                            pk.w = *reinterpret_cast<uint32_t *>(&b3);
-                            *reinterpret_cast<uint4 *>(dst + j) = pk;
-                        }
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (j < ncol) dst[j] = __float2bfloat16_rn(f[j]);
-                    }
-                }
-            }
-        }
+        // ---- epilogue (flag set resolved at compile time for the combinations the detector uses)
+        EpiParams e;
+        e.bias = p.bias; e.out = p.out; e.ldc = p.ldc; e.mask_src = p.mask_src; e.mul_src = nullptr;
+        e.flags = p.flags | (p.bias ? kFlagBias : 0);
+        e.N = p.N;
+        if (e.flags == (kFlagRelu | kFlagBias))
+            halo_epilogue<kBlockN, kSub, kFlagRelu | kFlagBias>(p, e, tmem_base, bar_tfull, bar_tempty, warp - 4, lane);
+        else if (e.flags == kFlagMaskPos)
+            halo_epilogue<kBlockN, kSub, kFlagMaskPos>(p, e, tmem_base, bar_tfull, bar_tempty, warp - 4, lane);
+        else if (e.flags == 0)
+            halo_epilogue<kBlockN, kSub, 0>(p, e, tmem_base, bar_tfull, bar_tempty, warp - 4, lane);
+        else
+            halo_epilogue<kBlockN, kSub, -1>(p, e, tmem_base, bar_tfull, bar_tempty, warp - 4, lane);
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();

@@ -28,6 +28,7 @@
 
 #include "common.cuh"
 #include "conv_halo.h"
+#include "tc_epilogue.cuh"
 #include "tc_ptx.cuh"
 
 namespace {
@@ -37,13 +38,6 @@ constexpr int kBlockK = 64;        // 64 bf16 = 128 B = one swizzle row
 constexpr int kUmmaK = 16;
 constexpr int kThreads = 256;
 
-enum : int {
-    kFlagRelu = 1,        // y = max(y, 0)
-    kFlagOutF32 = 2,      // write fp32 instead of bf16
-    kFlagMaskPos = 4,     // y = (mask_src > 0) ? y : 0     (ReLU backward fused into dgrad)
-    kFlagAccumulate = 8,  // y += previous contents (fp32 output only)
-    kFlagMulSrc = 16,     // y *= mul_src            (dropout keep/scale tensor, bf16)
-};
 
 struct TcParams {
     int M, N, K;                 // GEMM view (CONV: M = NB*H*W, K = 9*Cin)
@@ -94,6 +88,52 @@ __device__ __forceinline__ TileCoord tile_coord(const TcParams &p, int tile, int
         t.w0 = (r % p.tiles_w) * p.TW;
     }
     return t;
+}
+
+template <int kBlockN, int kCluster, int kSpec>
+__device__ __forceinline__ void gemm_epilogue(const TcParams &p, const EpiParams &e, uint32_t tmem_base,
+                                              uint32_t bar_tfull, uint32_t bar_tempty, uint32_t tempty_remote,
+                                              int ew, int lane, int rank, int m_tiles, int n_tiles,
+                                              int first_tile, int tile_step, int total_tiles)
+{
+    constexpr bool kPair = kCluster == 2;
+    const bool aligned = ((reinterpret_cast<uintptr_t>(e.out) | reinterpret_cast<uintptr_t>(e.bias) |
+                           reinterpret_cast<uintptr_t>(e.mask_src) | reinterpret_cast<uintptr_t>(e.mul_src)) & 15) == 0;
+    const bool vec_ok = (e.ldc % 8 == 0) && aligned;
+    uint32_t ti = 0;
+    for (int tile = first_tile; tile < total_tiles; tile += tile_step, ++ti) {
+        const TileCoord t = tile_coord(p, tile, n_tiles, kBlockN, kCluster, rank);
+        const uint32_t acc = ti & 1, acc_ph = (ti >> 1) & 1;
+        mbar_wait(bar_tfull + acc * 8, acc_ph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int row = ew * 32 + lane;           // accumulator row = TMEM lane
+        long long out_row;
+        bool row_ok;
+        if (p.conv) {
+            const int th = row / p.TW, tw = row - th * p.TW;
+            const int h = t.h0 + th, w = t.w0 + tw;
+            row_ok = h < p.H && w < p.W && t.m_tile < m_tiles;   // (phantom tile of an odd group)
+            out_row = ((long long)t.img * p.H + h) * p.W + w;
+        } else {
+            out_row = (long long)t.m_tile * kBlockM + row;
+            row_ok = out_row < p.M;
+        }
+#pragma unroll 1
+        for (int c0 = 0; c0 < kBlockN; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * kBlockN + c0), v);
+            if (c0 + 32 >= kBlockN) {
+                // the whole accumulator of this warp's lanes is in registers: hand the buffer back
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) {
+                    if (kPair) mbar_arrive_cluster(tempty_remote + acc * 8);
+                    else mbar_arrive(bar_tempty + acc * 8);
+                }
+            }
+            if (row_ok) epilogue_chunk<kSpec>(v, e, out_row, t.n0 + c0, vec_ok && (t.n0 % 8 == 0));
+        }
+    }
 }
 
 // Persistent kernel: grid = min(#tile groups, #SMs / kCluster) clusters; cluster i walks tile
@@ -220,6 +260,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     } else if (warp == 1) {
         if (lane == 0 && leader) {
             constexpr uint32_t idesc = make_idesc(kBlockM * kCluster, kBlockN, 0, kBMn ? 1 : 0);
+            // descriptors as (lo, hi) words: hi constant, lo = (start >> 4) | LBO field; between MMAs
+            // only a constant is added to lo (conv_halo.cu has the measurement behind this)
+            const uint64_t a_proto = make_kmajor_desc(0);
+            const uint64_t b_proto = kBMn ? make_mnmajor_desc(0, kBlockK * 128) : make_kmajor_desc(0);
+            const uint32_t a_hi = (uint32_t)(a_proto >> 32), b_hi = (uint32_t)(b_proto >> 32);
+            const uint32_t a_lo0 = (uint32_t)a_proto + (base >> 4);
+            const uint32_t b_lo0 = (uint32_t)b_proto + ((base + L::kABytes) >> 4);
+            constexpr uint32_t kBk = kBMn ? (kUmmaK * 128) >> 4 : (kUmmaK * 2) >> 4;
             uint32_t it = 0, ti = 0;
             for (int tile = first_tile; tile < total_tiles; tile += tile_step, ++ti) {
                 const uint32_t acc = ti & 1, acc_ph = (ti >> 1) & 1;
@@ -227,19 +275,18 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t tmem_d = tmem_base + acc * kBlockN;
                 for (int kb = 0; kb < p.num_k_blocks; ++kb, ++it) {
-                    const int s = it % kStages;
+                    const uint32_t s = it % kStages;
                     const uint32_t ph = (it / kStages) & 1;
                     mbar_wait(bar_full + s * 8, ph);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint32_t a_src = base + s * L::kStageBytes;
-                    const uint32_t b_src = a_src + L::kABytes;
+                    const uint32_t a_lo = a_lo0 + s * (L::kStageBytes >> 4);
+                    const uint32_t b_lo = b_lo0 + s * (L::kStageBytes >> 4);
 #pragma unroll
                     for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-                        const uint64_t ad = make_kmajor_desc(a_src + k * kUmmaK * 2);
-                        const uint64_t bd = kBMn ? make_mnmajor_desc(b_src + k * kUmmaK * 128, kBlockK * 128)
-                                                 : make_kmajor_desc(b_src + k * kUmmaK * 2);
-                        if (kPair) umma_bf16_pair(tmem_d, ad, bd, idesc, (kb | k) != 0);
-                        else umma_bf16(tmem_d, ad, bd, idesc, (kb | k) != 0);
+                        if (kPair) umma_bf16_pair_lohi(tmem_d, a_lo + k * 2, a_hi, b_lo + k * kBk, b_hi, idesc,
+                                                       (uint32_t)(kb | k));
+                        else umma_bf16_lohi(tmem_d, a_lo + k * 2, a_hi, b_lo + k * kBk, b_hi, idesc,
+                                            (uint32_t)(kb | k));
                     }
                     // frees the stage (in both CTAs of a pair) when these MMAs retire
                     if (kPair) umma_commit_pair(bar_empty + s * 8);
@@ -250,127 +297,22 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             }
         }
     } else if (warp >= 4) {
-        const int ew = warp - 4;                  // TMEM lane quarter this warp may read
-        const bool f32 = p.flags & kFlagOutF32;
+        // epilogue, flag set resolved at compile time for the combinations the detector uses
+        EpiParams e;
+        e.bias = p.bias; e.out = p.out; e.ldc = p.ldc; e.mask_src = p.mask_src; e.mul_src = p.mul_src;
+        e.flags = p.flags | (p.bias ? kFlagBias : 0);
+        e.N = p.N;
         const uint32_t tempty_remote = kPair ? map_to_cta(bar_tempty, 0) : bar_tempty;
-        uint32_t ti = 0;
-        for (int tile = first_tile; tile < total_tiles; tile += tile_step, ++ti) {
-            const TileCoord t = tile_coord(p, tile, n_tiles, kBlockN, kCluster, rank);
-            const uint32_t acc = ti & 1, acc_ph = (ti >> 1) & 1;
-            const int n0 = t.n0;
-            mbar_wait(bar_tfull + acc * 8, acc_ph);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const int row = ew * 32 + lane;           // accumulator row = TMEM lane
-            long long out_row;
-            bool row_ok;
-            if (p.conv) {
-                const int th = row / p.TW, tw = row - th * p.TW;
-                const int h = t.h0 + th, w = t.w0 + tw;
-                row_ok = h < p.H && w < p.W && t.m_tile < m_tiles;   // (phantom tile of an odd group)
-                out_row = ((long long)t.img * p.H + h) * p.W + w;
-            } else {
-                out_row = (long long)t.m_tile * kBlockM + row;
-                row_ok = out_row < p.M;
-            }
-            const bool vec_ok = (p.ldc % 8 == 0) && (n0 % 8 == 0);
-#pragma unroll 1
-            for (int c0 = 0; c0 < kBlockN; c0 += 32) {
-                uint32_t v[32];
-                tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * kBlockN + c0), v);
-                if (c0 + 32 >= kBlockN) {
-                    // the whole accumulator of this warp's lanes is in registers: hand the buffer back
-                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                    __syncwarp();
-                    if (lane == 0) {
-                        if (kPair) mbar_arrive_cluster(tempty_remote + acc * 8);
-                        else mbar_arrive(bar_tempty + acc * 8);
-                    }
-                }
-                if (!row_ok) continue;
-                const int ncol = min(32, p.N - (n0 + c0));
-                if (ncol <= 0) continue;
-                const bool full = ncol == 32 && vec_ok;
-                float f[32];
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    float x = __uint_as_float(v[j]);
-                    if (p.bias && j < ncol) x += __ldg(p.bias + n0 + c0 + j);
-                    if (p.flags & kFlagRelu) x = fmaxf(x, 0.f);
-                    f[j] = x;
-                }
-                const long long o = out_row * p.ldc + n0 + c0;
-                if (p.flags & kFlagMaskPos) {
-                    const __nv_bfloat16 *ms = p.mask_src + o;
-                    if (full) {
-#pragma unroll
-                        for (int j = 0; j < 32; j += 8) {
-                            const uint4 q = __ldg(reinterpret_cast<const uint4 *>(ms + j));
-                            const __nv_bfloat16 *qb = reinterpret_cast<const __nv_bfloat16 *>(&q);
-#pragma unroll
-                            for (int e = 0; e < 8; ++e)
-                                if (!(__bfloat162float(qb[e]) > 0.f)) f[j + e] = 0.f;
-                        }
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (j < ncol && !(__bfloat162float(ms[j]) > 0.f)) f[j] = 0.f;
-                    }
-                }
-                if (p.flags & kFlagMulSrc) {
-                    const __nv_bfloat16 *ms = p.mul_src + o;
-                    if (full) {
-#pragma unroll
-                        for (int j = 0; j < 32; j += 8) {
-                            const uint4 q = __ldg(reinterpret_cast<const uint4 *>(ms + j));
-                            const __nv_bfloat16 *qb = reinterpret_cast<const __nv_bfloat16 *>(&q);
-#pragma unroll
-                            for (int e = 0; e < 8; ++e) f[j + e] *= __bfloat162float(qb[e]);
-                        }
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (j < ncol) f[j] *= __bfloat162float(ms[j]);
-                    }
-                }
-                if (f32) {
-                    float *dst = reinterpret_cast<float *>(p.out) + o;
-                    if (p.flags & kFlagAccumulate) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (j < ncol) dst[j] += f[j];
-                    } else if (full) {
-#pragma unroll
-                        for (int j = 0; j < 32; j += 4)
-                            *reinterpret_cast<float4 *>(dst + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (j < ncol) dst[j] = f[j];
-                    }
-                } else {
-                    __nv_bfloat16 *dst = reinterpret_cast<__nv_bfloat16 *>(p.out) + o;
-                    if (full) {
-#pragma unroll
-                        for (int j = 0; j < 32; j += 8) {
-                            uint4 pk;
-                            __nv_bfloat162 b0 = __floats2bfloat162_rn(f[j], f[j + 1]);
-                            __nv_bfloat162 b1 = __floats2bfloat162_rn(f[j + 2], f[j + 3]);
-                            __nv_bfloat162 b2 = __floats2bfloat162_rn(f[j + 4], f[j + 5]);
-                            __nv_bfloat162 b3 = __floats2bfloat162_rn(f[j + 6], f[j + 7]);
-                            pk.x = *reinterpret_cast<uint32_t *>(&b0);
-                            pk.y = *reinterpret_cast<uint32_t *>(&b1);
-                            pk.z = *reinterpret_cast<uint32_t *>(&b2);
-                            pk.w = *reinterpret_cast<uint32_t *>(&b3);
-                            *reinterpret_cast<uint4 *>(dst + j) = pk;
-                        }
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (j < ncol) dst[j] = __float2bfloat16_rn(f[j]);
-                    }
-                }
-            }
-        }
+#define SCDA_EPI(SPEC)                                                                                         \
+    gemm_epilogue<kBlockN, kCluster, SPEC>(p, e, tmem_base, bar_tfull, bar_tempty, tempty_remote, warp - 4,   \
+                                           lane, rank, m_tiles, n_tiles, first_tile, tile_step, total_tiles)
+        if (e.flags == (kFlagRelu | kFlagBias)) SCDA_EPI(kFlagRelu | kFlagBias);
+        else if (e.flags == (kFlagRelu | kFlagBias | kFlagMulSrc)) SCDA_EPI(kFlagRelu | kFlagBias | kFlagMulSrc);
+        else if (e.flags == kFlagMaskPos) SCDA_EPI(kFlagMaskPos);
+        else if (e.flags == (kFlagMaskPos | kFlagMulSrc)) SCDA_EPI(kFlagMaskPos | kFlagMulSrc);
+        else if (e.flags == 0) SCDA_EPI(0);
+        else SCDA_EPI(-1);
+#undef SCDA_EPI
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -592,19 +534,19 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     } else if (warp == 1) {
         if (lane == 0) {
             constexpr uint32_t idesc = make_idesc(kBlockM, kBlockN, 1, 1);
+            const uint64_t proto = make_mnmajor_desc(0, L::kChunk);
+            const uint32_t proto_lo = (uint32_t)proto, proto_hi = (uint32_t)(proto >> 32);
             for (int kb = kb0; kb < kb1; ++kb) {
                 const int it = kb - kb0, s = it % kStages;
                 const uint32_t ph = (it / kStages) & 1;
                 mbar_wait(bar_full + s * 8, ph);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t a_src = base + s * L::kStageBytes;
-                const uint32_t b_src = a_src + L::kABytes;
+                const uint32_t a_lo = proto_lo + ((base + s * L::kStageBytes) >> 4);
+                const uint32_t b_lo = a_lo + (L::kABytes >> 4);
 #pragma unroll
-                for (int k = 0; k < 128 / kUmmaK; ++k) {
-                    const uint64_t ad = make_mnmajor_desc(a_src + k * kUmmaK * 128, L::kChunk);
-                    const uint64_t bd = make_mnmajor_desc(b_src + k * kUmmaK * 128, L::kChunk);
-                    umma_bf16(tmem_base, ad, bd, idesc, (it | k) != 0);
-                }
+                for (int k = 0; k < 128 / kUmmaK; ++k)
+                    umma_bf16_lohi(tmem_base, a_lo + k * ((kUmmaK * 128) >> 4), proto_hi, b_lo + k * ((kUmmaK * 128) >> 4),
+                                   proto_hi, idesc, (uint32_t)(it | k));
                 umma_commit(bar_empty + s * 8);
             }
             umma_commit(bar_tmem);

@@ -194,6 +194,40 @@ __device__ __forceinline__ uint64_t make_kmajor_desc_ex(uint32_t saddr, uint32_t
     return d;
 }
 
+// MMA with the two 64-bit shared-memory descriptors passed as (lo, hi) 32-bit halves: the issuing
+// lane keeps the constant high words in registers and only ADDS to the low word (the 14-bit
+// start-address field, addr >> 4) between MMAs — one integer add per operand instead of
+// rebuilding the descriptor.  The single issuing thread is on the critical path: a
+// 128x64x16 MMA retires in ~32 clocks.
+__device__ __forceinline__ void umma_bf16_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
+                                               uint32_t b_hi, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        ".reg .b64 ad, bd;\n"
+        "mov.b64 ad, {%1, %2};\n"
+        "mov.b64 bd, {%3, %4};\n"
+        "setp.ne.b32 p, %6, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], ad, bd, %5, p;\n"
+        "}\n" ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
+                                                    uint32_t b_hi, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        ".reg .b64 ad, bd;\n"
+        "mov.b64 ad, {%1, %2};\n"
+        "mov.b64 bd, {%3, %4};\n"
+        "setp.ne.b32 p, %6, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], ad, bd, %5, p;\n"
+        "}\n" ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
 // ------------------------------------------------------------------- host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
