@@ -84,7 +84,7 @@ class ClockSampler(threading.Thread):
                     self.samples.append([s.strip() for s in out.split(",")])
             except Exception:
                 pass
-            time.sleep(0.2)
+            time.sleep(0.05)
 
     def summary(self):
         self.stop_flag = True
@@ -202,7 +202,9 @@ def our_arm(args):
         dist.init_process_group("nccl", device_id=dev)
     _lib.load()
     cfg = load_cfg()
-    tr = build_trainer(cfg, world_size=world, seed=0, use_graphs=not args.no_graphs)
+    tr = build_trainer(cfg, world_size=world, seed=0, use_graphs=not args.no_graphs,
+                       overlap=not args.no_overlap,
+                       graph_collectives=False if args.no_graph_collectives else None)
     if world > 1:
         from scda_b200.utils.distributed_utils import broadcast_params
         for net in tr.nets():
@@ -265,8 +267,13 @@ def our_arm(args):
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
                 "config": {"workload": WORKLOAD, "parallelism": "dp%d" % world,
-                           "execution": "eager" if args.no_graphs else "one CUDA graph per iteration"
-                           if world == 1 else "five CUDA graphs per iteration, cut at the gradient all-reduces",
+                           "execution": ("eager" if args.no_graphs else
+                                         "one CUDA graph per iteration" + (", NCCL all-reduces captured" if world > 1 else "")
+                                         if tr._whole_graph() else
+                                         "five CUDA graphs per iteration, cut at the gradient all-reduces")
+                           + (", detector backward + Adam overlapped with the reconstruction/discriminator "
+                              "updates on a second stream" if tr.overlap and (args.no_graphs or tr._whole_graph())
+                              else ""),
                            "l2": "per-step working set (547 MB of fp32 weights + activations) exceeds the "
                                  "126 MB L2; no explicit flush"},
                 "clocks": clocks,
@@ -285,13 +292,16 @@ def our_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-budget", type=int, default=150, help="seconds for the --impl reference arm")
     ap.add_argument("--cpu-budget-inline", type=int, default=45)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graphs", action="store_true", help="eager execution (for kernel profilers)")
+    ap.add_argument("--no-overlap", action="store_true", help="single stream (no detector/GAN overlap)")
+    ap.add_argument("--no-graph-collectives", action="store_true",
+                    help="world > 1: cut the graph at the all-reduces instead of capturing NCCL")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)

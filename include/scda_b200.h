@@ -229,6 +229,10 @@ int scda_reduce_slabs_f32(const float *slabs, long long slab_stride, int n_slabs
                           long long n, int accumulate, cudaStream_t stream);
 /* bias gradient: out[N] += column sums of x[M, ld] (bf16) */
 int scda_colsum_bf16(long long M, int N, const void *x, long long ld, float *out, cudaStream_t stream);
+/* the same for a contiguous fp32 matrix x[M, N] (N % 4 == 0, N / 4 a power of two <= 256): bias
+ * gradient of the channels-last convolutions of the reconstruction networks
+ * (models/faster_rcnn/common_net.py:59-80, 251-293: nn.Conv2d(bias=True)) */
+int scda_colsum_f32(long long M, int N, const float *x, float *out, cudaStream_t stream);
 
 /* --- InstanceNorm2d (+ activation), channels-last fp32 ------------------- */
 /* replaces nn.InstanceNorm2d(affine=False) and the ReLU / LeakyReLU behind it in the

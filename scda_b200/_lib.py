@@ -45,6 +45,7 @@ SIGNATURES = {
     "scda_nhwc_bf16_to_nchw_f32": (_i, [_i, _i, _i, _i, _p, _p, _p]),
     "scda_reduce_slabs_f32": (_i, [_p, C.c_longlong, _i, _p, C.c_longlong, _i, _p]),
     "scda_colsum_bf16": (_i, [C.c_longlong, _i, _p, C.c_longlong, _p, _p]),
+    "scda_colsum_f32": (_i, [C.c_longlong, _i, _p, _p, _p]),
     "scda_conv3x3_bf16_nhwc": (_i, [_i, _i, _i, _i, _i, _p, _p, _p, _p, _i, _p, _p]),
     "scda_gemm_bf16_nn": (_i, [_i, _i, _i, _p, C.c_longlong, _p, C.c_longlong, _p, _p, C.c_longlong, _i, _p, _p, _p]),
     "scda_linear_wgrad_bf16": (_i, [_i, _i, _i, _p, C.c_longlong, _p, C.c_longlong, _p, C.c_longlong, _i, _p]),

@@ -164,15 +164,15 @@ def _bce_rows(p, label_row):
 class SCDATrainer(object):
     """The reference's four networks + optimisers for one rank.
 
-    The three reconstruction / discriminator updates (phases 1-3) and the forward of phase 4
-    depend only on the two cluster-feature blocks, the two crop stacks and the RNG, all of
-    fixed shape: after one eager warm-up iteration they are captured into CUDA graphs (one
-    per stretch between two gradient all-reduces) and replayed — ~1500 kernel launches per
-    iteration leave the Python/driver launch path.  use_graphs=False keeps them eager."""
+    Nothing in the iteration synchronises with the host and every shape is fixed: after one
+    eager warm-up iteration it is captured into ONE CUDA graph (two streams inside: detector
+    backward + Adam beside the reconstruction / discriminator updates; with world > 1 the four
+    NCCL all-reduces are captured too) and replayed — ~2800 kernel launches per iteration
+    leave the Python/driver launch path.  use_graphs=False keeps it eager."""
 
     def __init__(self, model, dec_model, dis_model, dis_model_patch, lr, cluster_num=4,
                  threshold=128, recon_size=256, new_w=1024, new_h=512, world_size=1,
-                 weight_decay=1e-4, use_graphs=True):
+                 weight_decay=1e-4, use_graphs=True, overlap=True, graph_collectives=None):
         self.model, self.dec_model = model, dec_model
         self.dis_model, self.dis_model_patch = dis_model, dis_model_patch
         self.opt = FlatAdam(model, lr, weight_decay=weight_decay, tensor_core=True)
@@ -183,6 +183,18 @@ class SCDATrainer(object):
         self.cluster_num, self.threshold, self.recon_size = cluster_num, threshold, recon_size
         self.new_w, self.new_h, self.world_size = new_w, new_h, world_size
         self.use_graphs = use_graphs
+        # overlap: the three reconstruction / discriminator updates run on a second stream
+        # beside the detector's backward and optimiser step (nothing flows between them: the
+        # cluster features are detached, functions/mask.py:234 of the reference).
+        # graph_collectives (world > 1): capture the NCCL all-reduces inside the one graph;
+        # None = the SCDA_GRAPH_COLLECTIVES environment variable, default on.
+        self.overlap = overlap
+        if graph_collectives is None:
+            import os
+            graph_collectives = os.environ.get("SCDA_GRAPH_COLLECTIVES", "1") != "0"
+        self.graph_collectives = graph_collectives
+        self._side = None
+        self._tside = None
         self._static, self._st = None, {}
         self._graphs = None
         self._by_shape = {}
@@ -262,11 +274,13 @@ class SCDATrainer(object):
                                       * _bce_rows(fake_dis2, torch.ones_like(fake_dis2[:1]))).sum()
 
     def _seg_forward(self):
-        """detector forward on both images, crops around the cluster centres, then (1)"""
+        """detector forward on both images, crops around the cluster centres"""
         b, st = self._static, self._st
         x = {'cfg': b['cfg'], 'image': b['image'], 'image_info': b['info'], 'ground_truth_bboxes': b['gts'],
              'ignore_regions': None, 'cluster_num': self.cluster_num, 'threshold': self.threshold,
              'device_clusters': True}
+        if self.overlap:
+            x['target_stream'] = self._target_stream()
         outputs = self.model(x, b['target'])
         st['det_losses'] = outputs['losses']
         st['acc'] = outputs['accuracy']
@@ -274,53 +288,122 @@ class SCDATrainer(object):
         b['cs'] = crops_device(b['image'], centers_source, self.recon_size, self.new_w, self.new_h)
         b['ct'] = crops_device(b['target'], centers_target, self.recon_size, self.new_w, self.new_h)
         b['xs'], b['xt'] = outputs['cluster_features']
-        self._seg_dis()
 
-    def _seg_detector(self):
-        """(3) step, forward of (4), then the detector backward (:736-745)"""
+    def _seg_det_backward(self):
+        """(4) detector backward (:736-745).  The two "fake" terms of the reference's loss carry
+        no gradient to the detector (quirk above), so the backward runs on the four detection
+        losses and does not wait for the reconstruction networks."""
         st, ws = self._st, float(self.world_size)
-        self._seg_fake()
-        rpn_cls_loss, rpn_loc_loss, rcnn_cls_loss, rcnn_loc_loss = st.pop('det_losses')
-        loss = (rpn_cls_loss + rpn_loc_loss + rcnn_cls_loss + rcnn_loc_loss
-                + 0.1 * (st['fake_loss_source'] + st['fake_loss_target'])) / ws
+        rpn_cls_loss, rpn_loc_loss, rcnn_cls_loss, rcnn_loc_loss = st['det_losses']
+        st['det_loss_sum'] = rpn_cls_loss + rpn_loc_loss + rcnn_cls_loss + rcnn_loc_loss
         self.opt.zero_grad()
-        loss.backward(inputs=self.opt.params)
-        st['out'] = {'loss': loss.detach() * ws, 'rpn_cls': rpn_cls_loss.detach(),
+        (st['det_loss_sum'] / ws).backward(inputs=self.opt.params)
+
+    def _seg_step(self):
+        self.opt.step_dev()
+
+    def _seg_outputs(self):
+        st = self._st
+        rpn_cls_loss, rpn_loc_loss, rcnn_cls_loss, rcnn_loc_loss = st.pop('det_losses')
+        loss = st.pop('det_loss_sum').detach() + 0.1 * (st['fake_loss_source'] + st['fake_loss_target'])
+        st['out'] = {'loss': loss, 'rpn_cls': rpn_cls_loss.detach(),
                      'rpn_loc': rpn_loc_loss.detach(), 'rcnn_cls': rcnn_cls_loss.detach(),
                      'rcnn_loc': rcnn_loc_loss.detach(), 'fake_loss': st['fake_loss_target'],
                      'dec_loss': st['dec_loss'], 'dis_loss': st['dis_loss'],
                      'dis_patch_loss': st['dis_patch_loss'],
                      'rpn_acc': st['acc'][0], 'rcnn_acc': st['acc'][1]}
 
-    def _seg_step(self):
-        self.opt.step_dev()
+    # ------------------------------------------------------------------ the iteration
+    def _gan_chain(self, reduce):
+        self._seg_dis()
+        reduce(self.opt_dis)
+        self._seg_dis_patch()
+        reduce(self.opt_dis_patch)
+        self._seg_dec()
+        reduce(self.opt_dec)
+        self._seg_fake()
+
+    def _det_chain(self, reduce):
+        self._seg_det_backward()
+        reduce(self.opt)
+        self._seg_step()
+
+    def _side_stream(self):
+        """stream of the reconstruction / discriminator chain: the longer of the two chains,
+        so it gets the higher priority when both have blocks waiting for an SM"""
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.opt.flat.device, priority=-1)
+        return self._side
+
+    def _target_stream(self):
+        if self._tside is None:
+            self._tside = torch.cuda.Stream(device=self.opt.flat.device)
+        return self._tside
+
+    def _body(self, reduce):
+        """One iteration on the current stream (eager, or inside a capture).  With `overlap`
+        the current stream forks after the detector forward: the side stream runs phases 1-3
+        and the forward of phase 4 (hundreds of small cuDNN / elementwise kernels, latency
+        bound), the current stream runs the detector backward and Adam (tensor-core / HBM
+        bound), and they join before the losses are assembled."""
+        self._seg_forward()
+        if self.overlap:
+            main = torch.cuda.current_stream()
+            side = self._side_stream()
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                self._gan_chain(reduce)
+            self._det_chain(reduce)
+            main.wait_stream(side)
+        else:
+            self._gan_chain(reduce)
+            self._det_chain(reduce)
+        self._seg_outputs()
+
+    def _reduce_fn(self):
+        if self.world_size > 1:
+            return lambda opt: opt.all_reduce()
+        return lambda opt: None
 
     def _segments(self):
-        """the iteration cut at its four gradient all-reduces: (stretch, optimiser to reduce after)"""
-        return ((self._seg_forward, self.opt_dis), (self._seg_dis_patch, self.opt_dis_patch),
-                (self._seg_dec, self.opt_dec), (self._seg_detector, self.opt), (self._seg_step, None))
+        """fallback plan for world > 1 when the collectives are not captured: the iteration cut
+        at its four gradient all-reduces, one stream: (stretch, optimiser to reduce after)"""
+        def first():
+            self._seg_forward()
+            self._seg_dis()
+
+        def fourth():
+            self._seg_fake()
+            self._seg_det_backward()
+
+        def last():
+            self._seg_step()
+            self._seg_outputs()
+        return ((first, self.opt_dis), (self._seg_dis_patch, self.opt_dis_patch),
+                (self._seg_dec, self.opt_dec), (fourth, self.opt), (last, None))
+
+    def _whole_graph(self):
+        """world 1, or world > 1 with the all-reduces captured: ONE graph holds the iteration"""
+        return self.world_size == 1 or self.graph_collectives
 
     def _capture(self):
-        """one CUDA graph per stretch between two all-reduces (a single graph on one GPU);
-        all share one memory pool, so tensors handed from one stretch to the next stay put"""
+        """Capture the iteration.  One graph (two streams inside, forked and joined within the
+        capture) when `_whole_graph()`; otherwise one graph per stretch between two all-reduces,
+        all sharing one memory pool so tensors handed from one stretch to the next stay put."""
         torch.cuda.synchronize()
-        segs = self._segments()
-        if self.world_size == 1:
-            def whole():
-                for seg, _ in segs:
-                    seg()
-            plan = [whole]
-        else:
-            plan = [seg for seg, _ in segs]
         pool = torch.cuda.graph_pool_handle()
+        if self._whole_graph():
+            reduce = self._reduce_fn()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, pool=pool):
+                self._body(reduce)
+            return [g]
         graphs = []
-        for fn in plan:
+        for fn, _ in self._segments():
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g, pool=pool):
                 fn()
             graphs.append(g)
-        if self.world_size == 1:
-            graphs = graphs + [_NoGraph()] * (len(segs) - 1)
         return graphs
 
     def iteration(self, cfg, image, image_info, gts, target, lr=None):
@@ -346,19 +429,18 @@ class SCDATrainer(object):
         b['gts'].copy_(gts, non_blocking=True)
         for o in (self.opt_dis, self.opt_dis_patch, self.opt_dec, self.opt):
             o.begin_step(lr)
-        multi = self.world_size > 1
         if not self.use_graphs or ent['calls'] == 0:
-            for seg, opt in self._segments():       # eager (also the warm-up before a capture)
-                seg()
-                if opt is not None and multi:
-                    opt.all_reduce()
+            self._body(self._reduce_fn())           # eager (also the warm-up before a capture)
         else:
             if ent['graphs'] is None:
                 ent['graphs'] = self._capture()
-            for g, (_, opt) in zip(ent['graphs'], self._segments()):
-                g.replay()
-                if opt is not None and multi:
-                    opt.all_reduce()
+            if self._whole_graph():
+                ent['graphs'][0].replay()
+            else:
+                for g, (_, opt) in zip(ent['graphs'], self._segments()):
+                    g.replay()
+                    if opt is not None:
+                        opt.all_reduce()
         ent['calls'] += 1
         self._graphs = ent['graphs']
         return {k: v.clone() for k, v in self._st['out'].items()}
@@ -381,11 +463,6 @@ def crops_device(image, centers, recon_size, new_w, new_h):
     return image[0][:, ys, xs].permute(1, 0, 2, 3).contiguous()
 
 
-class _NoGraph(object):
-    def replay(self):
-        pass
-
-
 def builder_gan(cluster_num=4, threshold=128, recon_size=256, neww=64, newh=64):
     """The three GAN networks with the hyper-parameters of the reference's builder_gan
     (tools/faster_rcnn_train_val.py:255-273)."""
@@ -402,7 +479,8 @@ def builder_gan(cluster_num=4, threshold=128, recon_size=256, neww=64, newh=64):
 
 
 def build_trainer(cfg, lr=1.25e-5, device="cuda", cluster_num=4, threshold=128, recon_size=256,
-                  new_w=1024, new_h=512, world_size=1, seed=0, use_graphs=True):
+                  new_w=1024, new_h=512, world_size=1, seed=0, use_graphs=True, overlap=True,
+                  graph_collectives=None):
     from .models.faster_rcnn.vgg_adver_expansion_cluster import vgg16
     torch.manual_seed(seed)
     np.random.seed(seed)
@@ -410,6 +488,6 @@ def build_trainer(cfg, lr=1.25e-5, device="cuda", cluster_num=4, threshold=128, 
     dis_model, dec_model, dis_model_patch = builder_gan(cluster_num, threshold, recon_size)
     tr = SCDATrainer(model, dec_model.to(device), dis_model.to(device), dis_model_patch.to(device),
                      lr, cluster_num, threshold, recon_size, new_w, new_h, world_size,
-                     use_graphs=use_graphs)
+                     use_graphs=use_graphs, overlap=overlap, graph_collectives=graph_collectives)
     tr.train_mode()
     return tr

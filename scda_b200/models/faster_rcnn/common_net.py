@@ -6,7 +6,18 @@ Module / parameter names match the reference so state dicts are interchangeable.
 import torch
 import torch.nn as nn
 
-from ...gan_ops import instance_norm_act, supported as _fused_ok, upsample_bilinear2x, upsample_supported
+from ...gan_ops import (conv2d_bias_cl, conv_bias_supported, instance_norm_act, supported as _fused_ok,
+                        upsample_bilinear2x, upsample_supported)
+
+
+class Conv2dCL(nn.Conv2d):
+    """nn.Conv2d (same parameters, same state dict); on CUDA the bias gradient is computed by
+    the library's channels-last column-sum kernel instead of torch's strided reduction."""
+
+    def forward(self, x):
+        if conv_bias_supported(x, self):
+            return conv2d_bias_cl(x, self)
+        return super(Conv2dCL, self).forward(x)
 
 
 def gaussian_weights_init(m):
@@ -20,10 +31,10 @@ class INSResBlock(nn.Module):
 
     def __init__(self, inplanes, planes, stride=1, dropout=0.0):
         super(INSResBlock, self).__init__()
-        model = [nn.Conv2d(inplanes, planes, kernel_size=3, stride=stride, padding=1),
+        model = [Conv2dCL(inplanes, planes, kernel_size=3, stride=stride, padding=1),
                  nn.InstanceNorm2d(planes),
                  nn.ReLU(inplace=True),
-                 nn.Conv2d(planes, planes, kernel_size=3, stride=1, padding=1),
+                 Conv2dCL(planes, planes, kernel_size=3, stride=1, padding=1),
                  nn.InstanceNorm2d(planes)]
         if dropout > 0:
             model += [nn.Dropout(p=dropout)]
@@ -114,7 +125,7 @@ class LeakyReLUConv2d(nn.Module):
     def __init__(self, n_in, n_out, kernel_size, stride, padding=0):
         super(LeakyReLUConv2d, self).__init__()
         self.model = nn.Sequential(
-            nn.Conv2d(n_in, n_out, kernel_size=kernel_size, stride=stride, padding=padding, bias=True),
+            Conv2dCL(n_in, n_out, kernel_size=kernel_size, stride=stride, padding=padding, bias=True),
             nn.LeakyReLU(inplace=True))
         self.model.apply(gaussian_weights_init)
 
@@ -135,7 +146,7 @@ class LeakyReLUConvTranspose2d_2(nn.Module):
         super(LeakyReLUConvTranspose2d_2, self).__init__()
         self.model = nn.Sequential(
             Interpolate(scale_factor=2, mode='bilinear'),
-            nn.Conv2d(in_channels=n_in, out_channels=n_out, kernel_size=kernel_size,
+            Conv2dCL(in_channels=n_in, out_channels=n_out, kernel_size=kernel_size,
                       padding=padding, stride=1, bias=True),
             nn.InstanceNorm2d(num_features=n_out),
             nn.LeakyReLU(inplace=True))

@@ -122,46 +122,69 @@ class FasterRCNN_AdEx(nn.Module):
         rpn_pred_cls, rpn_pred_loc = self.rpn(x)
 
         if self.training:
+            pcfg = cfg['train_rpn_proposal_cfg']
+            n_t = cfg['train_proposal_target_cfg']['batch_size']
+            # input['device_clusters']: keep the cluster centres on the device (no host
+            # synchronisation anywhere in this forward); default = the reference's return
+            # type, centres as a host numpy array
+            on_dev = bool(input.get('device_clusters', False))
+            cluster_fn = cluster_targets_device if on_dev else compute_cluster_targets
+
+            def run_target():
+                """RPN + RCNN on the target image: top-512 proposals, no ground truth (:171-189)
+                (nothing downstream differentiates through this branch: its only product, the
+                cluster features, is detached by compute_cluster_targets — functions/mask.py:234)"""
+                with torch.no_grad():
+                    x_gan = self.feature_extractor(target)
+                    rpn_pred_cls_gan, rpn_pred_loc_gan = self.rpn(x_gan)
+                props_gan = rpn_proposals_device(self._rpn_scores(rpn_pred_cls_gan).data,
+                                                 rpn_pred_loc_gan.data, pcfg, image_info)
+                gan_rows = []
+                for b, (boxes, n_keep) in enumerate(props_gan):
+                    gan_rows.append((torch.cat([torch.full((boxes.shape[0], 1), float(b),
+                                                           device=boxes.device), boxes[:, :4]], 1),
+                                     n_keep))
+                if len(gan_rows) == 1 and gan_rows[0][0].shape[0] >= n_t:
+                    proposals_gan = gan_rows[0][0][:n_t].contiguous()
+                    enough = gan_rows[0][1] >= n_t           # 0-dim device flag, read by the caller
+                else:
+                    ks = [int(n.item()) for _, n in gan_rows]
+                    proposals_gan = torch.cat([r[:k] for (r, _), k in zip(gan_rows, ks)], 0)[:n_t].contiguous()
+                    enough = torch.tensor(proposals_gan.shape[0] == n_t, device=x_gan.device)
+                with torch.no_grad():
+                    x_fea_gan, _, _ = self.rcnn(x_gan, proposals_gan)
+                clusters = None
+                if on_dev and proposals_gan.shape[0] == n_t:
+                    clusters = cluster_targets_device(proposals_gan, x_fea_gan, N_cluster=input['cluster_num'],
+                                                      threshold=input['threshold'])
+                return x_gan, proposals_gan, enough, x_fea_gan, clusters
+
+            # input['target_stream']: run the target branch on that stream, beside the source
+            # branch (its dense backbone fills the SMs the source's latency-bound proposal /
+            # target plumbing leaves idle); forked from and joined back into the current stream
+            tstream = input.get('target_stream') if on_dev else None
+            if tstream is not None:
+                cur_stream = torch.cuda.current_stream()
+                tstream.wait_stream(cur_stream)
+                with torch.cuda.stream(tstream):
+                    tgt = run_target()
+
             rpn_loss_cls, rpn_loss_loc, rpn_acc = self._add_rpn_loss(
                 partial_fn['anchor_target_fn'], rpn_pred_cls, rpn_pred_loc)
-            pcfg = cfg['train_rpn_proposal_cfg']
             props = rpn_proposals_device(self._rpn_scores(rpn_pred_cls).data, rpn_pred_loc.data,
                                          pcfg, image_info)
             rois, cls_targets, loc_targets, loc_weights = self._train_rois(
                 cfg, props, ground_truth_bboxes, image_info)
             assert rois.shape[1] == 5
             x_fea, rcnn_pred_cls, rcnn_pred_loc = self.rcnn(x, rois)
-            # input['device_clusters']: keep the cluster centres on the device (no host
-            # synchronisation anywhere in this forward); default = the reference's return
-            # type, centres as a host numpy array
-            on_dev = bool(input.get('device_clusters', False))
-            cluster_fn = cluster_targets_device if on_dev else compute_cluster_targets
             x_cluster_fea, x_center_cluster = cluster_fn(
                 rois, x_fea, N_cluster=input['cluster_num'], threshold=input['threshold'])
 
-            # RPN + RCNN on the target image: top-512 proposals, no ground truth (:171-189)
-            # (nothing downstream differentiates through this branch: its only product, the
-            #  cluster features, is detached by compute_cluster_targets — functions/mask.py:234)
-            with torch.no_grad():
-                x_gan = self.feature_extractor(target)
-                rpn_pred_cls_gan, rpn_pred_loc_gan = self.rpn(x_gan)
-            props_gan = rpn_proposals_device(self._rpn_scores(rpn_pred_cls_gan).data,
-                                             rpn_pred_loc_gan.data, pcfg, image_info)
-            n_t = cfg['train_proposal_target_cfg']['batch_size']
-            gan_rows = []
-            for b, (boxes, n_keep) in enumerate(props_gan):
-                gan_rows.append((torch.cat([torch.full((boxes.shape[0], 1), float(b),
-                                                       device=boxes.device), boxes[:, :4]], 1),
-                                 n_keep))
-            if len(gan_rows) == 1 and gan_rows[0][0].shape[0] >= n_t:
-                proposals_gan = gan_rows[0][0][:n_t].contiguous()
-                enough = gan_rows[0][1] >= n_t           # 0-dim device flag, read by the caller
+            if tstream is not None:
+                cur_stream.wait_stream(tstream)
             else:
-                ks = [int(n.item()) for _, n in gan_rows]
-                proposals_gan = torch.cat([r[:k] for (r, _), k in zip(gan_rows, ks)], 0)[:n_t].contiguous()
-                enough = torch.tensor(proposals_gan.shape[0] == n_t, device=x.device)
-            with torch.no_grad():
-                x_fea_gan, _, _ = self.rcnn(x_gan, proposals_gan)
+                tgt = run_target()
+            x_gan, proposals_gan, enough, x_fea_gan, clusters_gan = tgt
             assert x_gan.size() == x.size(), "gan_features does not match the backbone"
 
             rcnn_loss_cls, rcnn_loss_loc, rcnn_acc = self._add_rcnn_loss(
@@ -176,8 +199,7 @@ class FasterRCNN_AdEx(nn.Module):
                 outputs['cluster_centers'] = [x_center_cluster, x_center_cluster]
             elif on_dev:
                 # the same choice made by a device-side select on the `enough` flag
-                fea_gan, center_gan = cluster_targets_device(
-                    proposals_gan, x_fea_gan, N_cluster=input['cluster_num'], threshold=input['threshold'])
+                fea_gan, center_gan = clusters_gan
                 outputs['cluster_features'] = [x_cluster_fea, torch.where(enough, fea_gan, x_cluster_fea)]
                 outputs['cluster_centers'] = [x_center_cluster,
                                               torch.where(enough, center_gan, x_center_cluster)]

@@ -38,7 +38,7 @@ def main():
     from scda_b200.models.faster_rcnn import faster_rcnn_adver_expansion_reweight_cluster as M
     torch.cuda.set_device(0)
     cfg = bench.load_cfg()
-    tr = engine.build_trainer(cfg, world_size=1, seed=0, use_graphs=False)
+    tr = engine.build_trainer(cfg, world_size=1, seed=0, use_graphs=False, overlap=False)
     image, target, gts, info = bench.synth_batch(0, pinned=False)
     image, target, gts = image.cuda(), target.cuda(), gts.cuda()
     for _ in range(4):

@@ -60,8 +60,13 @@ def test_iteration_updates_all_four_networks(cuda_lib):
 
 
 def test_graph_replay_equals_eager(cuda_lib, monkeypatch):
-    """dropout off, fixed soft labels and sampling keys: the captured iteration and the eager
-    iteration produce the same losses and the same parameters after three iterations."""
+    """dropout off, fixed soft labels and sampling keys, a learning rate small enough that the
+    weights stay put: the captured (two-stream) iteration and the eager single-stream iteration
+    compute the same losses and the same gradients on every one of three iterations.
+    (Comparing Adam UPDATES at a real learning rate is ill-conditioned: Adam moves each weight by
+    ~lr whatever the size of its gradient, so gradients at the fp32 / TF32 noise floor — e.g.
+    the biases in front of an InstanceNorm, whose true gradient is zero — flip sign between two
+    runs of cuDNN and the difference compounds.)"""
     import torch
     from scda_b200 import engine
     monkeypatch.setattr(engine, "soft_label",
@@ -77,31 +82,39 @@ def test_graph_replay_equals_eager(cuda_lib, monkeypatch):
     monkeypatch.setattr(torch, "rand", fake_rand)
     img, tgt, gts, info = _batch(1)
     results = []
-    for use_graphs in (False, True):
-        tr, cfg = _trainer(use_graphs, deterministic=True)
-        start = [torch.cat([p.detach().reshape(-1) for p in net.parameters()]).clone() for net in tr.nets()]
-        losses = []
+    for use_graphs, overlap in ((False, False), (True, True)):
+        from scda_b200.engine import build_trainer
+        cfg = _inputs.load_cfg()
+        tr = build_trainer(cfg, lr=1e-9, new_w=W, new_h=H, world_size=1, seed=0, use_graphs=use_graphs,
+                           overlap=overlap)
+        for net in tr.nets():
+            for m in net.modules():
+                if isinstance(m, torch.nn.Dropout):
+                    m.p = 0.0
+        losses, grads = [], []
         for it in range(3):
             torch.manual_seed(100 + it)
             np.random.seed(100 + it)
             out = tr.iteration(cfg, img, info, gts, tgt)
             losses.append({k: float(v) for k, v in out.items()})
+            grads.append([o.bucket.flat.clone() for o in (tr.opt, tr.opt_dec, tr.opt_dis, tr.opt_dis_patch)])
         torch.cuda.synchronize()
-        moved = [torch.cat([p.detach().reshape(-1) for p in net.parameters()]) - s0
-                 for net, s0 in zip(tr.nets(), start)]
-        results.append((losses, moved))
-    (l_e, m_e), (l_g, m_g) = results
+        if use_graphs:
+            assert tr._graphs is not None and len(tr._graphs) == 1
+        results.append((losses, grads))
+    (l_e, g_e), (l_g, g_g) = results
     for a, b in zip(l_e, l_g):
-        for k in ("loss", "dis_loss", "dis_patch_loss", "dec_loss", "fake_loss"):
-            assert abs(a[k] - b[k]) <= 1e-2 * max(1.0, abs(a[k])), (k, a[k], b[k])
-    # Adam moves every weight by about lr per step whatever the size of its gradient, so
-    # weights whose gradient is at the noise floor (TF32 convolutions whose cuDNN algorithm
-    # may differ under capture, atomics in the RoI / bias gradients) move differently: the
-    # parameter UPDATE of each network is compared as a whole, by direction and by size
-    for a, b in zip(m_e, m_g):
-        cos = float((a * b).sum() / (a.norm() * b.norm()))
-        assert cos > 0.97, cos
-        assert 0.95 < float(a.norm() / b.norm()) < 1.05
+        for k in ("loss", "rpn_cls", "rpn_loc", "rcnn_cls", "rcnn_loc", "dis_loss", "dis_patch_loss", "dec_loss",
+                  "fake_loss"):
+            assert abs(a[k] - b[k]) <= 2e-3 * max(1.0, abs(a[k])), (k, a[k], b[k])
+    # gradients: bf16 tensor-core detector (deterministic kernels, atomics only in the RoI / bias
+    # sums), TF32 cuDNN reconstruction networks (the algorithm may differ under capture)
+    for it in range(3):
+        for name, a, b, lim in zip(("detector", "decoder", "dis", "dis_patch"), g_e[it], g_g[it],
+                                   (0.9999, 0.999, 0.999, 0.999)):
+            cos = float((a * b).sum() / (a.norm() * b.norm()))
+            assert cos > lim, (it, name, cos)
+            assert 0.99 < float(a.norm() / b.norm()) < 1.01, (it, name, float(a.norm() / b.norm()))
 
 
 def test_direct_gradient_sink_equals_autograd_gradients(cuda_lib):

@@ -88,3 +88,28 @@ def test_decoder_fused_equals_torch_modules(cuda_lib, monkeypatch):
     # the discriminators accept the channels-last decoder output
     sa, sb = dis(ya.detach(), yb.detach())
     assert sa.shape == (4, 1024) and patch(xa).shape == (4, 512)
+
+
+@pytest.mark.parametrize("cin,cout,stride,hw", [(128, 128, 1, 64), (3, 32, 2, 256), (64, 32, 1, 128), (32, 64, 2, 40)])
+def test_conv2d_cl_matches_nn_conv2d(cuda_lib, cin, cout, stride, hw):
+    """Conv2dCL = nn.Conv2d; only the bias gradient takes another route (scda_colsum_f32)."""
+    import torch
+    from scda_b200.models.faster_rcnn.common_net import Conv2dCL
+    torch.backends.cudnn.allow_tf32 = False
+    torch.manual_seed(cin + cout)
+    ours = Conv2dCL(cin, cout, 3, stride, 1).cuda()
+    ref = torch.nn.Conv2d(cin, cout, 3, stride, 1).cuda()
+    ref.load_state_dict(ours.state_dict())
+    x = torch.randn(4, cin, hw, hw, device="cuda").contiguous(memory_format=torch.channels_last)
+    xa, xb = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    ya, yb = ours(xa), ref(xb)
+    assert torch.allclose(ya, yb, rtol=1e-4, atol=1e-5)
+    g = torch.randn_like(ya)
+    ya.backward(g)
+    yb.backward(g)
+    assert torch.allclose(xa.grad, xb.grad, rtol=1e-3, atol=1e-4)
+    assert torch.allclose(ours.weight.grad, ref.weight.grad, rtol=1e-3, atol=1e-2)
+    # bias gradient = sum of g over (N, H, W): fp32 sums of ~1e5 terms in a different order
+    assert torch.allclose(ours.bias.grad, ref.bias.grad, rtol=1e-3, atol=2e-2)
+    exact = g.double().sum((0, 2, 3))
+    assert float((ours.bias.grad.double() - exact).abs().max()) <= float((ref.bias.grad.double() - exact).abs().max()) + 1e-2
