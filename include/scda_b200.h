@@ -257,6 +257,22 @@ int scda_upsample_bilinear2x_nhwc_f32(int N, int H, int W, int C, const float *x
 int scda_upsample_bilinear2x_bwd_nhwc_f32(int N, int H, int W, int C, const float *dy, float *dx,
                                           cudaStream_t stream);
 
+/* the same kernels with the output (fwd: y; bwd: dx) and the incoming gradient (bwd: dy) in fp32
+ * (dtype code 0) or bf16 (1): the bf16 forms feed / are fed by the tensor-core convolutions of
+ * the decoder without a separate cast pass.  x, mean, rstd stay fp32. */
+int scda_instnorm_act_fwd_nhwc(int N, int HW, int C, const float *x, void *y, int y_dtype, float *mean,
+                               float *rstd, float eps, int act, float slope, void *workspace,
+                               size_t workspace_bytes, cudaStream_t stream);
+int scda_instnorm_act_bwd_nhwc(int N, int HW, int C, const float *x, const void *dy, int dy_dtype,
+                               const float *mean, const float *rstd, void *dx, int dx_dtype, int act,
+                               float slope, void *workspace, size_t workspace_bytes, cudaStream_t stream);
+/* bilinear x2 up-sampling (align_corners) of a channels-last fp32 tensor into fp32 (0) or bf16 (1) */
+int scda_upsample_bilinear2x_nhwc(int N, int H, int W, int C, const float *x, void *y, int y_dtype,
+                                  cudaStream_t stream);
+/* its transpose: dy [N, 2H, 2W, C] fp32 (0) or bf16 (1) -> dx [N, H, W, C] fp32 */
+int scda_upsample_bilinear2x_bwd_nhwc(int N, int H, int W, int C, const void *dy, int dy_dtype, float *dx,
+                                      cudaStream_t stream);
+
 /* --- region grouping (k-means of RoI centres) --------------------------- */
 /* replaces, inside compute_cluster_targets (functions/mask.py:193-237), the host call
  * sklearn.cluster.KMeans(n_clusters=k, random_state=0).fit(centres) on the float32 RoI

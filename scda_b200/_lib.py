@@ -54,6 +54,10 @@ SIGNATURES = {
     "scda_instnorm_act_fwd_nhwc_f32": (_i, [_i, _i, _i, _p, _p, _p, _p, _f, _i, _f, _p, _z, _p]),
     "scda_instnorm_act_bwd_nhwc_f32": (_i, [_i, _i, _i, _p, _p, _p, _p, _p, _i, _f, _p, _z, _p]),
     "scda_upsample_bilinear2x_nhwc_f32": (_i, [_i, _i, _i, _i, _p, _p, _p]),
+    "scda_instnorm_act_fwd_nhwc": (_i, [_i, _i, _i, _p, _p, _i, _p, _p, _f, _i, _f, _p, _z, _p]),
+    "scda_instnorm_act_bwd_nhwc": (_i, [_i, _i, _i, _p, _p, _i, _p, _p, _p, _i, _i, _f, _p, _z, _p]),
+    "scda_upsample_bilinear2x_nhwc": (_i, [_i, _i, _i, _i, _p, _p, _i, _p]),
+    "scda_upsample_bilinear2x_bwd_nhwc": (_i, [_i, _i, _i, _i, _p, _i, _p, _p]),
     "scda_upsample_bilinear2x_bwd_nhwc_f32": (_i, [_i, _i, _i, _i, _p, _p, _p]),
     "scda_roi_pool_nhwc_bf16_fwd": (_i, [_p, _f, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p]),
     "scda_roi_pool_nhwc_bf16_bwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p]),
@@ -96,7 +100,8 @@ def load(path: str | None = None) -> C.CDLL:
 # kernels launched per successful entry-point call (memsets not counted); bench.py reports
 # the total inside its timed region as `gpu_launches`
 KERNELS_PER_CALL = {
-    "scda_nms": 2, "scda_nms_dyn": 2, "scda_instnorm_act_fwd_nhwc_f32": 3, "scda_instnorm_act_bwd_nhwc_f32": 3, "SoftmaxFocalLossForwardLaucher": 1,
+    "scda_nms": 2, "scda_nms_dyn": 2, "scda_instnorm_act_fwd_nhwc_f32": 3, "scda_instnorm_act_bwd_nhwc_f32": 3,
+    "scda_instnorm_act_fwd_nhwc": 3, "scda_instnorm_act_bwd_nhwc": 3, "SoftmaxFocalLossForwardLaucher": 1,
     "SoftmaxFocalLossBackwardLaucher": 1,
 }
 LAUNCHES = 0

@@ -26,7 +26,9 @@ import numpy as np
 import torch
 import torch.nn.functional as F
 
+from . import gan_ops
 from ._lib import check, load, stream_ptr
+from .gan_ops import run_pair
 from .utils.distributed_utils import FlatGradBucket
 
 
@@ -177,7 +179,9 @@ class SCDATrainer(object):
         self.dis_model, self.dis_model_patch = dis_model, dis_model_patch
         self.opt = FlatAdam(model, lr, weight_decay=weight_decay, tensor_core=True)
         # channels_last weights: cuDNN's tensor-core convolutions then run NHWC end to end
-        self.opt_dec = FlatAdam(dec_model, lr, weight_decay=weight_decay, channels_last=True)
+        # (the decoder's 64-multiple 3x3 convolutions run on the tensor-core kernels: bf16 shadows)
+        self.opt_dec = FlatAdam(dec_model, lr, weight_decay=weight_decay, tensor_core=gan_ops.TC_GAN,
+                                channels_last=True)
         self.opt_dis = FlatAdam(dis_model, lr, weight_decay=weight_decay, channels_last=True)
         self.opt_dis_patch = FlatAdam(dis_model_patch, lr, weight_decay=weight_decay, channels_last=True)
         self.cluster_num, self.threshold, self.recon_size = cluster_num, threshold, recon_size
@@ -187,14 +191,22 @@ class SCDATrainer(object):
         # beside the detector's backward and optimiser step (nothing flows between them: the
         # cluster features are detached, functions/mask.py:234 of the reference).
         # graph_collectives (world > 1): capture the NCCL all-reduces inside the one graph;
-        # None = the SCDA_GRAPH_COLLECTIVES environment variable, default on.
+        # None = the SCDA_GRAPH_COLLECTIVES environment variable, default OFF: on 2 x B200 the
+        # captured form hung (NCCL 2.28.9 / torch 2.11, profiles/r1_ddp2_check.txt), the cut form is
+        # what the multi-GPU numbers are measured with.
         self.overlap = overlap
+        import os
+        self.pair_streams = os.environ.get("SCDA_PAIR_STREAMS", "1") != "0"
         if graph_collectives is None:
             import os
-            graph_collectives = os.environ.get("SCDA_GRAPH_COLLECTIVES", "1") != "0"
+            graph_collectives = os.environ.get("SCDA_GRAPH_COLLECTIVES", "0") != "0"
         self.graph_collectives = graph_collectives
         self._side = None
         self._tside = None
+        if overlap and hasattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch"):
+            # gradients are produced on whichever stream ran the forward of their branch and are
+            # accumulated into the flat buffers there; the mismatch torch warns about is intended
+            torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
         self._static, self._st = None, {}
         self._graphs = None
         self._by_shape = {}
@@ -214,8 +226,10 @@ class SCDATrainer(object):
         st['recon'] = self.dec_model(xs, xt)
         x_source_recon, x_target_recon = st['recon']
         self.opt_dis.zero_grad()
-        s_dis, t_dis = [torch.sigmoid(o) for o in self.dis_model(x_source_recon, x_target_recon)]
-        s_real, t_real = [torch.sigmoid(o) for o in self.dis_model(cs, ct)]
+        on_recon, on_real = run_pair(lambda: self.dis_model(x_source_recon, x_target_recon),
+                                     lambda: self.dis_model(cs, ct))
+        s_dis, t_dis = [torch.sigmoid(o) for o in on_recon]
+        s_real, t_real = [torch.sigmoid(o) for o in on_real]
         score_1 = soft_label(1, s_real[:1])
         score_0 = soft_label(0, s_dis[:1])
         adloss_source = (_bce_rows(s_dis, score_1) + _bce_rows(s_real, score_0)).sum()
@@ -245,9 +259,10 @@ class SCDATrainer(object):
         self.opt_dis_patch.step_dev()
         self.opt_dec.zero_grad()
         x_source_recon, x_target_recon = st['recon']
-        s_dis2, t_dis2 = self.dis_model(x_source_recon, x_target_recon)
+        (s_dis2, t_dis2), on_real = run_pair(lambda: self.dis_model(x_source_recon, x_target_recon),
+                                             lambda: self.dis_model(b['cs'], b['ct']))
         s_dis2, t_dis2 = torch.sigmoid(s_dis2), torch.sigmoid(t_dis2)
-        s_real2, t_real2 = [torch.sigmoid(o) for o in self.dis_model(b['cs'], b['ct'])]
+        s_real2, t_real2 = [torch.sigmoid(o) for o in on_real]
         st['t_patch_mean2'] = torch.mean(self.dis_model_patch(b['xt']), 1).detach()
         t_patch_mean2 = st['t_patch_mean2']
         ones, zeros = torch.ones_like(t_dis2[:1]), torch.zeros_like(t_dis2[:1])
@@ -346,6 +361,7 @@ class SCDATrainer(object):
         and the forward of phase 4 (hundreds of small cuDNN / elementwise kernels, latency
         bound), the current stream runs the detector backward and Adam (tensor-core / HBM
         bound), and they join before the losses are assembled."""
+        gan_ops.PAIR_STREAMS = bool(self.overlap and self.pair_streams)
         self._seg_forward()
         if self.overlap:
             main = torch.cuda.current_stream()

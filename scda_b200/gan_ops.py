@@ -4,6 +4,8 @@
 ReLU / LeakyReLU, on a channels_last fp32 CUDA tensor, forward and backward, without the
 NCHW round trip torch's instance norm forces (models/faster_rcnn/common_net.py:59-80,
 279-293 of the reference use the torch modules)."""
+import os
+
 import torch
 
 from ._lib import check, load, require_cuda, stream_ptr
@@ -66,37 +68,41 @@ def supported(x):
 
 class _Upsample2x(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x):
+    def forward(ctx, x, out_bf16):
         require_cuda(x)
         if not x.is_contiguous(memory_format=torch.channels_last):
             x = x.contiguous(memory_format=torch.channels_last)
         N, C, H, W = x.shape
-        y = torch.empty((N, C, 2 * H, 2 * W), dtype=x.dtype, device=x.device,
+        y = torch.empty((N, C, 2 * H, 2 * W), dtype=torch.bfloat16 if out_bf16 else x.dtype, device=x.device,
                         memory_format=torch.channels_last)
         with torch.cuda.device(x.device):
-            check(load().scda_upsample_bilinear2x_nhwc_f32(N, H, W, C, x.data_ptr(), y.data_ptr(),
-                                                           stream_ptr(x.device)),
-                  "scda_upsample_bilinear2x_nhwc_f32")
+            check(load().scda_upsample_bilinear2x_nhwc(N, H, W, C, x.data_ptr(), y.data_ptr(),
+                                                       1 if out_bf16 else 0, stream_ptr(x.device)),
+                  "scda_upsample_bilinear2x_nhwc")
         ctx.shape = (N, C, H, W)
         return y
 
     @staticmethod
     def backward(ctx, dy):
         N, C, H, W = ctx.shape
-        if dy.dtype != torch.float32 or not dy.is_contiguous(memory_format=torch.channels_last):
-            dy = dy.float().contiguous(memory_format=torch.channels_last)
+        if dy.dtype not in (torch.float32, torch.bfloat16):
+            dy = dy.float()
+        if not dy.is_contiguous(memory_format=torch.channels_last):
+            dy = dy.contiguous(memory_format=torch.channels_last)
         dx = torch.empty((N, C, H, W), dtype=torch.float32, device=dy.device, memory_format=torch.channels_last)
         with torch.cuda.device(dy.device):
-            check(load().scda_upsample_bilinear2x_bwd_nhwc_f32(N, H, W, C, dy.data_ptr(), dx.data_ptr(),
-                                                               stream_ptr(dy.device)),
-                  "scda_upsample_bilinear2x_bwd_nhwc_f32")
-        return dx
+            check(load().scda_upsample_bilinear2x_bwd_nhwc(N, H, W, C, dy.data_ptr(),
+                                                           1 if dy.dtype == torch.bfloat16 else 0, dx.data_ptr(),
+                                                           stream_ptr(dy.device)),
+                  "scda_upsample_bilinear2x_bwd_nhwc")
+        return dx, None
 
 
-def upsample_bilinear2x(x):
+def upsample_bilinear2x(x, out_bf16=False):
     """F.interpolate(x, scale_factor=2, mode='bilinear', align_corners=True) on a channels_last
-    fp32 CUDA tensor (C % 4 == 0, H, W >= 2)."""
-    return _Upsample2x.apply(x)
+    fp32 CUDA tensor (C % 4 == 0, H, W >= 2); out_bf16 writes the result as bf16 (the operand
+    dtype of the tensor-core convolution behind it)."""
+    return _Upsample2x.apply(x, bool(out_bf16))
 
 
 def upsample_supported(x, scale_factor, mode):
@@ -151,3 +157,136 @@ def conv2d_bias_cl(x, conv):
     if not x.is_contiguous(memory_format=torch.channels_last):
         x = x.contiguous(memory_format=torch.channels_last)
     return _ConvBiasCL.apply(x, conv.weight, conv.bias, conv.stride, conv.padding)
+
+
+# ---------------------------------------------------------------------------------------
+# Two independent sub-networks side by side (decode_A | decode_B, model_A | model_B, the
+# discriminator on reconstructions | on real crops): each is a chain of small kernels that
+# fills a fraction of the 148 SMs, so the second one runs on a helper stream forked from and
+# joined back into the current one.  Off unless the engine turns it on (PAIR_STREAMS).
+PAIR_STREAMS = False
+_HELPERS = {}
+
+
+def _helper_stream(cur):
+    key = (cur.device.index, cur.cuda_stream)
+    st = _HELPERS.get(key)
+    if st is None:
+        st = torch.cuda.Stream(device=cur.device, priority=cur.priority)
+        _HELPERS[key] = st
+    return st
+
+
+def _tensors(obj):
+    if torch.is_tensor(obj):
+        yield obj
+    elif isinstance(obj, (tuple, list)):
+        for o in obj:
+            for t in _tensors(o):
+                yield t
+
+
+def run_pair(fa, fb):
+    """(fa(), fb()); on CUDA with PAIR_STREAMS fb runs on a helper stream beside fa."""
+    if not (PAIR_STREAMS and torch.cuda.is_available()):
+        return fa(), fb()
+    cur = torch.cuda.current_stream()
+    side = _helper_stream(cur)
+    side.wait_stream(cur)
+    with torch.cuda.stream(side):
+        b = fb()
+    a = fa()
+    cur.wait_stream(side)
+    for t in _tensors(b):
+        if t.is_cuda:
+            t.record_stream(cur)        # allocated on the helper, consumed (and freed) on `cur`
+    return a, b
+
+
+# ---------------------------------------------------------------------------------------
+# conv3x3 (+ bias) -> InstanceNorm -> activation as ONE autograd node on the tensor cores.
+# The decoder's stride-1 3x3 convolutions with 64-multiple channel counts (6 residual-block
+# convolutions + the first up-sampling convolution per decoder, ~80 % of the decoder's flops;
+# models/faster_rcnn/common_net.py:59-80, 279-293 of the reference, cuDNN fp32 there) run on
+# the same tcgen05 halo kernel as the backbone (csrc/conv_halo.cu): bf16 operands, fp32
+# accumulation, fp32 convolution output (the InstanceNorm statistics are taken in fp32).
+# Fusing the three layers into one node lets every tensor cross a kernel boundary in the dtype
+# its consumer wants (IN output / IN input-gradient in bf16 for the next MMA) with no cast pass.
+TC_GAN = os.environ.get("SCDA_GAN_TC", "1") != "0"
+
+
+class _ConvINActTC(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, act, slope, eps, out_bf16):
+        from . import tc
+        from .tc_detector import shadow_of
+        require_cuda(x)
+        if not x.is_contiguous(memory_format=torch.channels_last):
+            x = x.contiguous(memory_format=torch.channels_last)
+        xb = x if x.dtype == torch.bfloat16 else x.to(torch.bfloat16)       # keeps channels_last
+        xn = xb.permute(0, 2, 3, 1)                                         # [N,H,W,C] contiguous view
+        N, H, W, _ = xn.shape
+        w = shadow_of(weight)                                               # bf16 [O,3,3,I]
+        O = w.shape[0]
+        c = tc.conv3x3_nhwc(xn, w, bias.detach() if bias is not None else None, out_dtype=torch.float32)
+        y = torch.empty(N, H, W, O, dtype=torch.bfloat16 if out_bf16 else torch.float32, device=x.device)
+        mean = torch.empty(N, O, dtype=torch.float32, device=x.device)
+        rstd = torch.empty(N, O, dtype=torch.float32, device=x.device)
+        lib = load()
+        wsb = lib.scda_instnorm_workspace_bytes(N, H * W, O)
+        if wsb == 0:
+            raise ValueError("conv_in_act_tc: unsupported shape %s" % (tuple(c.shape),))
+        ws = torch.empty(wsb, dtype=torch.uint8, device=x.device)
+        with torch.cuda.device(x.device):
+            check(lib.scda_instnorm_act_fwd_nhwc(N, H * W, O, c.data_ptr(), y.data_ptr(), 1 if out_bf16 else 0,
+                                                 mean.data_ptr(), rstd.data_ptr(), eps, act, slope, ws.data_ptr(),
+                                                 wsb, stream_ptr(x.device)), "scda_instnorm_act_fwd_nhwc")
+        ctx.save_for_backward(xb, c, mean, rstd)
+        ctx.params = (weight, bias)
+        ctx.cfg = (act, slope, x.dtype)
+        return y.permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, dy):
+        from . import tc
+        from .tc_detector import _sink_bias, _sink_conv_wgrad, shadow_of
+        xb, c, mean, rstd = ctx.saved_tensors
+        weight, bias = ctx.params
+        act, slope, x_dtype = ctx.cfg
+        N, H, W, O = c.shape
+        if dy.dtype not in (torch.float32, torch.bfloat16):
+            dy = dy.float()
+        if not dy.is_contiguous(memory_format=torch.channels_last):
+            dy = dy.contiguous(memory_format=torch.channels_last)
+        dc = torch.empty(N, H, W, O, dtype=torch.bfloat16, device=c.device)
+        lib = load()
+        wsb = lib.scda_instnorm_workspace_bytes(N, H * W, O) + 8 * N * O
+        ws = torch.empty(wsb, dtype=torch.uint8, device=c.device)
+        with torch.cuda.device(c.device):
+            check(lib.scda_instnorm_act_bwd_nhwc(N, H * W, O, c.data_ptr(), dy.data_ptr(),
+                                                 1 if dy.dtype == torch.bfloat16 else 0, mean.data_ptr(),
+                                                 rstd.data_ptr(), dc.data_ptr(), 1, act, slope, ws.data_ptr(), wsb,
+                                                 stream_ptr(c.device)), "scda_instnorm_act_bwd_nhwc")
+        xn = xb.permute(0, 2, 3, 1)
+        gb = _sink_bias(bias, dc.view(-1, O)) if bias is not None and ctx.needs_input_grad[2] else None
+        gw = _sink_conv_wgrad(weight, xn, dc) if ctx.needs_input_grad[1] else None
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = tc.conv3x3_dgrad_nhwc(dc, shadow_of(weight), out_dtype=x_dtype).permute(0, 3, 1, 2)
+        return dx, gw, gb, None, None, None, None
+
+
+def conv_in_act_tc_supported(x, conv):
+    return (TC_GAN and x.is_cuda and x.dim() == 4 and x.dtype in (torch.float32, torch.bfloat16)
+            and conv.kernel_size == (3, 3) and conv.stride == (1, 1) and conv.padding == (1, 1)
+            and conv.dilation == (1, 1) and conv.groups == 1 and conv.padding_mode == 'zeros'
+            and conv.in_channels % 64 == 0 and conv.out_channels % 64 == 0 and conv.out_channels <= 1024
+            and 1024 % conv.out_channels == 0 and x.shape[3] % 8 == 0
+            and conv.weight.dtype == torch.float32)
+
+
+def conv_in_act_tc(x, conv, act=None, negative_slope=0.01, eps=1e-5, out_bf16=False):
+    """act(InstanceNorm(conv(x))) for an nn.Conv2d(k=3, s=1, p=1); returns a channels_last tensor
+    (fp32, or bf16 with out_bf16)."""
+    return _ConvINActTC.apply(x, conv.weight, conv.bias, _ACT[act], float(negative_slope), float(eps),
+                              bool(out_bf16))

@@ -6,8 +6,8 @@ Module / parameter names match the reference so state dicts are interchangeable.
 import torch
 import torch.nn as nn
 
-from ...gan_ops import (conv2d_bias_cl, conv_bias_supported, instance_norm_act, supported as _fused_ok,
-                        upsample_bilinear2x, upsample_supported)
+from ...gan_ops import (conv2d_bias_cl, conv_bias_supported, conv_in_act_tc, conv_in_act_tc_supported,
+                        instance_norm_act, supported as _fused_ok, upsample_bilinear2x, upsample_supported)
 
 
 class Conv2dCL(nn.Conv2d):
@@ -42,9 +42,17 @@ class INSResBlock(nn.Module):
         self.model.apply(gaussian_weights_init)
 
     def forward(self, x):
+        m = self.model
+        if conv_in_act_tc_supported(x, m[0]) and conv_in_act_tc_supported(x, m[3]):
+            # conv + InstanceNorm (+ ReLU) as one node on the tensor cores; the block-internal
+            # activation travels as bf16 (gan_ops._ConvINActTC)
+            out = conv_in_act_tc(x, m[0], "relu", eps=m[1].eps, out_bf16=True)
+            out = conv_in_act_tc(out, m[3], None, eps=m[4].eps)
+            if len(m) > 5:
+                out = m[5](out)
+            return out + x
         if _fused_ok(x):
             # same layers, InstanceNorm + ReLU as one channels-last kernel (csrc/norm_ops.cu)
-            m = self.model
             out = instance_norm_act(m[0](x), "relu", eps=m[1].eps)
             out = instance_norm_act(m[3](out), None, eps=m[4].eps)
             if len(m) > 5:
@@ -155,6 +163,9 @@ class LeakyReLUConvTranspose2d_2(nn.Module):
     def forward(self, x):
         m = self.model
         if len(m) == 4 and isinstance(m[2], nn.InstanceNorm2d) and x.is_cuda:
+            if conv_in_act_tc_supported(x, m[1]) and upsample_supported(x, m[0].scale_factor, m[0].mode):
+                up = upsample_bilinear2x(x, out_bf16=True)        # written as the MMA operand dtype
+                return conv_in_act_tc(up, m[1], "leaky_relu", m[3].negative_slope, m[2].eps)
             out = m[1](m[0](x))
             if _fused_ok(out):
                 return instance_norm_act(out, "leaky_relu", m[3].negative_slope, m[2].eps)

@@ -21,6 +21,7 @@ from ...functions.mask import cluster_targets_device, compute_cluster_targets
 from ...functions.predict_bbox import compute_predicted_bboxes
 from ...functions.proposal_target import compute_proposal_targets, proposal_targets_device
 from ...functions.rpn_proposal import compute_rpn_proposals, rpn_proposals_device
+from ...gan_ops import run_pair
 from .common_net import (ConvTranspose1x1, INSResBlock, LeakyReLUConv2d, LeakyReLUConvTranspose2d_2,
                          LinUnsRes_cluster, ResDis_cluster, gaussian_weights_init)
 
@@ -271,8 +272,7 @@ class GAN_dis_AE(nn.Module):
         if x_aa.is_cuda:      # NHWC end to end: no cuDNN layout transposes around the convolutions
             x_aa = x_aa.contiguous(memory_format=torch.channels_last)
             x_bb = x_bb.contiguous(memory_format=torch.channels_last)
-        out_A = self.model_A(x_aa)
-        out_B = self.model_B(x_bb)
+        out_A, out_B = run_pair(lambda: self.model_A(x_aa), lambda: self.model_B(x_bb))
         return out_A.reshape(out_A.size(0), -1), out_B.reshape(out_B.size(0), -1)
 
 
@@ -326,4 +326,4 @@ class GAN_decoder_AE(nn.Module):
         self.decode_A.apply(gaussian_weights_init)
 
     def forward(self, x_aa, x_bb):
-        return self.decode_A(x_aa), self.decode_B(x_bb)
+        return run_pair(lambda: self.decode_A(x_aa), lambda: self.decode_B(x_bb))

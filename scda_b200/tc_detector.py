@@ -29,6 +29,24 @@ def _is_krsc(p):
     return p.dim() == 4 and p.permute(0, 2, 3, 1).is_contiguous()
 
 
+def shadow_of(p):
+    """bf16 copy of parameter p: conv weights as [O,3,3,I], everything else as stored.  Kept on
+    the parameter (`_scda_shadow`) and re-derived only when `p._version` moved; engine.FlatAdam
+    refreshes it inside the optimiser kernel and stamps `_scda_shadow_version` itself."""
+    sh = getattr(p, "_scda_shadow", None)
+    if sh is not None and getattr(p, "_scda_shadow_version", -1) == p._version:
+        return sh
+    src = p.detach()
+    if p.dim() == 4:
+        src = src.permute(0, 2, 3, 1)
+    if sh is None or sh.shape != src.shape:
+        sh = torch.empty(src.shape, dtype=torch.bfloat16, device=p.device)
+        p._scda_shadow = sh
+    sh.copy_(src)
+    p._scda_shadow_version = p._version
+    return sh
+
+
 class TcDetector(object):
     def __init__(self, vgg):
         import torch.nn as nn
@@ -48,19 +66,7 @@ class TcDetector(object):
 
     # ------------------------------------------------------------------ shadows
     def shadow(self, p):
-        """bf16 copy of parameter p: conv weights as [O,3,3,I], everything else as stored."""
-        sh = getattr(p, "_scda_shadow", None)
-        if sh is not None and getattr(p, "_scda_shadow_version", -1) == p._version:
-            return sh
-        src = p.detach()
-        if p.dim() == 4:
-            src = src.permute(0, 2, 3, 1)
-        if sh is None or sh.shape != src.shape:
-            sh = torch.empty(src.shape, dtype=torch.bfloat16, device=p.device)
-            p._scda_shadow = sh
-        sh.copy_(src)
-        p._scda_shadow_version = p._version
-        return sh
+        return shadow_of(p)
 
     def _derive(self, key, params, build):
         """small shadows derived from several parameters (padded / concatenated)"""

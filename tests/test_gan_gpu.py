@@ -73,6 +73,9 @@ def test_decoder_fused_equals_torch_modules(cuda_lib, monkeypatch):
     xa = torch.randn(4, 128, 4096, device="cuda", generator=g)
     xb = torch.randn(4, 128, 4096, device="cuda", generator=g)
     torch.backends.cudnn.allow_tf32 = False
+    # fp32 path (cuDNN convolutions + the fused fp32 InstanceNorm kernels); the tensor-core
+    # path has its own test below
+    monkeypatch.setattr(common_net, "conv_in_act_tc_supported", lambda x, conv: False)
     ya, yb = dec(xa, xb)
     (ya.square().mean() + yb.mean()).backward()
     monkeypatch.setattr(common_net, "_fused_ok", lambda x: False)
@@ -113,3 +116,85 @@ def test_conv2d_cl_matches_nn_conv2d(cuda_lib, cin, cout, stride, hw):
     assert torch.allclose(ours.bias.grad, ref.bias.grad, rtol=1e-3, atol=2e-2)
     exact = g.double().sum((0, 2, 3))
     assert float((ours.bias.grad.double() - exact).abs().max()) <= float((ref.bias.grad.double() - exact).abs().max()) + 1e-2
+
+
+def test_decoder_tensor_core_path(cuda_lib, monkeypatch):
+    """The decoder with its 64-multiple 3x3 convolutions on the tcgen05 halo kernel (bf16
+    operands, fp32 accumulate, conv + InstanceNorm + activation as one autograd node) against the
+    same modules in plain fp32 torch.  Tolerance: bf16 operand rounding (2^-9 relative per
+    operand) through 8 convolutions, each re-normalised by its InstanceNorm -> a few 1e-2 of the
+    output range; gradients by direction and size."""
+    import copy
+    import torch
+    from scda_b200 import gan_ops
+    from scda_b200.engine import builder_gan
+    from scda_b200.models.faster_rcnn import common_net
+    assert gan_ops.TC_GAN
+    torch.manual_seed(0)
+    _, dec, _ = builder_gan(4, 128, 256)
+    dec.cuda().train()
+    for m in dec.modules():
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+    ref = copy.deepcopy(dec)
+    g = torch.Generator(device="cuda").manual_seed(1)
+    xa = torch.randn(4, 128, 4096, device="cuda", generator=g).requires_grad_(True)
+    xb = torch.randn(4, 128, 4096, device="cuda", generator=g)
+    xr = xa.detach().clone().requires_grad_(True)
+    torch.backends.cudnn.allow_tf32 = False
+    calls = []
+    real = common_net.conv_in_act_tc
+
+    def spy(*a, **k):
+        calls.append(1)
+        return real(*a, **k)
+    monkeypatch.setattr(common_net, "conv_in_act_tc", spy)
+    ya, yb = dec(xa, xb)
+    assert len(calls) == 14, "6 residual convolutions + 1 up-sampling convolution per decoder"
+    (ya.square().mean() + yb.mean()).backward()
+    monkeypatch.setattr(common_net, "conv_in_act_tc_supported", lambda x, conv: False)
+    monkeypatch.setattr(common_net, "_fused_ok", lambda x: False)
+    monkeypatch.setattr(common_net, "upsample_supported", lambda x, s, m: False)
+    ra, rb = ref(xr, xb)
+    (ra.square().mean() + rb.mean()).backward()
+    assert _rel(ya, ra) < 5e-2 and _rel(yb, rb) < 5e-2
+    assert float((ya - ra).pow(2).mean().sqrt() / ra.pow(2).mean().sqrt()) < 2e-2
+
+    def cos(a, b):
+        return float((a * b).sum() / (a.norm() * b.norm()).clamp(min=1e-30))
+    assert cos(xa.grad, xr.grad) > 0.99 and 0.9 < float(xa.grad.norm() / xr.grad.norm()) < 1.1
+    for (n, p), q in zip(dec.named_parameters(), ref.parameters()):
+        if n.endswith("weight"):
+            assert cos(p.grad, q.grad) > 0.98, (n, cos(p.grad, q.grad))
+            assert 0.9 < float(p.grad.norm() / q.grad.norm()) < 1.1, n
+
+
+@pytest.mark.parametrize("dy_bf16,dx_bf16", [(False, True), (True, True), (True, False)])
+def test_instance_norm_bf16_io(cuda_lib, dy_bf16, dx_bf16):
+    """scda_instnorm_act_{fwd,bwd}_nhwc with bf16 outputs / incoming gradients = the fp32 kernels
+    followed / preceded by a round to bf16."""
+    import torch
+    from scda_b200._lib import check, load, stream_ptr
+    N, H, W, C = 4, 32, 32, 128
+    g = torch.Generator(device="cuda").manual_seed(3)
+    x = torch.randn(N, H, W, C, device="cuda", generator=g) * 2 + 1
+    dy = torch.randn(N, H, W, C, device="cuda", generator=g)
+    lib = load()
+    wsb = lib.scda_instnorm_workspace_bytes(N, H * W, C) + 8 * N * C
+    ws = torch.empty(wsb, dtype=torch.uint8, device="cuda")
+    mean, rstd = torch.empty(N, C, device="cuda"), torch.empty(N, C, device="cuda")
+    y32, y16 = torch.empty_like(x), torch.empty(N, H, W, C, dtype=torch.bfloat16, device="cuda")
+    for y, code in ((y32, 0), (y16, 1)):
+        check(lib.scda_instnorm_act_fwd_nhwc(N, H * W, C, x.data_ptr(), y.data_ptr(), code, mean.data_ptr(),
+                                             rstd.data_ptr(), 1e-5, 2, 0.01, ws.data_ptr(), wsb, stream_ptr()), "fwd")
+    assert torch.equal(y16, y32.bfloat16())
+    dyi = dy.bfloat16() if dy_bf16 else dy
+    dx_ref = torch.empty_like(x)
+    check(lib.scda_instnorm_act_bwd_nhwc(N, H * W, C, x.data_ptr(), dyi.float().data_ptr(), 0, mean.data_ptr(),
+                                         rstd.data_ptr(), dx_ref.data_ptr(), 0, 2, 0.01, ws.data_ptr(), wsb,
+                                         stream_ptr()), "bwd ref")
+    dx = torch.empty(N, H, W, C, dtype=torch.bfloat16 if dx_bf16 else torch.float32, device="cuda")
+    check(lib.scda_instnorm_act_bwd_nhwc(N, H * W, C, x.data_ptr(), dyi.data_ptr(), 1 if dy_bf16 else 0,
+                                         mean.data_ptr(), rstd.data_ptr(), dx.data_ptr(), 1 if dx_bf16 else 0, 2, 0.01,
+                                         ws.data_ptr(), wsb, stream_ptr()), "bwd")
+    assert torch.equal(dx, dx_ref.bfloat16() if dx_bf16 else dx_ref)
