@@ -204,7 +204,8 @@ def our_arm(args):
     cfg = load_cfg()
     tr = build_trainer(cfg, world_size=world, seed=0, use_graphs=not args.no_graphs,
                        overlap=not args.no_overlap,
-                       graph_collectives=False if args.no_graph_collectives else None)
+                       graph_collectives=False if args.no_graph_collectives else None,
+                       force_cut=args.force_cut)
     if world > 1:
         from scda_b200.utils.distributed_utils import broadcast_params
         for net in tr.nets():
@@ -270,10 +271,11 @@ def our_arm(args):
                            "execution": ("eager" if args.no_graphs else
                                          "one CUDA graph per iteration" + (", NCCL all-reduces captured" if world > 1 else "")
                                          if tr._whole_graph() else
-                                         "five CUDA graphs per iteration, cut at the gradient all-reduces")
+                                         "eight CUDA graphs per iteration, cut at the gradient all-reduces "
+                                         "(NCCL issued between them)")
                            + (", detector backward + Adam overlapped with the reconstruction/discriminator "
-                              "updates on a second stream" if tr.overlap and (args.no_graphs or tr._whole_graph())
-                              else ""),
+                              "updates on a second stream, target-image branch beside the source branch"
+                              if tr.overlap else ""),
                            "l2": "per-step working set (547 MB of fp32 weights + activations) exceeds the "
                                  "126 MB L2; no explicit flush"},
                 "clocks": clocks,
@@ -300,6 +302,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graphs", action="store_true", help="eager execution (for kernel profilers)")
     ap.add_argument("--no-overlap", action="store_true", help="single stream (no detector/GAN overlap)")
+    ap.add_argument("--force-cut", action="store_true", help="1 GPU: replay the cut (world > 1) graph plan")
     ap.add_argument("--no-graph-collectives", action="store_true",
                     help="world > 1: cut the graph at the all-reduces instead of capturing NCCL")
     args = ap.parse_args()

@@ -174,7 +174,7 @@ class SCDATrainer(object):
 
     def __init__(self, model, dec_model, dis_model, dis_model_patch, lr, cluster_num=4,
                  threshold=128, recon_size=256, new_w=1024, new_h=512, world_size=1,
-                 weight_decay=1e-4, use_graphs=True, overlap=True, graph_collectives=None):
+                 weight_decay=1e-4, use_graphs=True, overlap=True, graph_collectives=None, force_cut=False):
         self.model, self.dec_model = model, dec_model
         self.dis_model, self.dis_model_patch = dis_model, dis_model_patch
         self.opt = FlatAdam(model, lr, weight_decay=weight_decay, tensor_core=True)
@@ -201,6 +201,7 @@ class SCDATrainer(object):
             import os
             graph_collectives = os.environ.get("SCDA_GRAPH_COLLECTIVES", "0") != "0"
         self.graph_collectives = graph_collectives
+        self.force_cut = force_cut          # tests: the cut (world > 1) replay plan on one GPU
         self._side = None
         self._tside = None
         if overlap and hasattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch"):
@@ -382,45 +383,73 @@ class SCDATrainer(object):
         return lambda opt: None
 
     def _segments(self):
-        """fallback plan for world > 1 when the collectives are not captured: the iteration cut
-        at its four gradient all-reduces, one stream: (stretch, optimiser to reduce after)"""
-        def first():
-            self._seg_forward()
-            self._seg_dis()
-
-        def fourth():
-            self._seg_fake()
-            self._seg_det_backward()
-
-        def last():
-            self._seg_step()
-            self._seg_outputs()
-        return ((first, self.opt_dis), (self._seg_dis_patch, self.opt_dis_patch),
-                (self._seg_dec, self.opt_dec), (fourth, self.opt), (last, None))
+        """world > 1 with the collectives NOT captured: the iteration cut at its four gradient
+        all-reduces -> (stretch, stream it runs on, optimiser whose gradients are all-reduced
+        after it).  With `overlap` the reconstruction / discriminator stretches replay on the side
+        stream beside the detector's backward; the collectives are issued from the host in one
+        fixed order on every rank (dis, patch, dec, detector)."""
+        side = 'side' if self.overlap else 'main'
+        return (('fwd', self._seg_forward, 'main', None),
+                ('dis', self._seg_dis, side, self.opt_dis),
+                ('dis_patch', self._seg_dis_patch, side, self.opt_dis_patch),
+                ('dec', self._seg_dec, side, self.opt_dec),
+                ('fake', self._seg_fake, side, None),
+                ('det_bwd', self._seg_det_backward, 'main', self.opt),
+                ('step', self._seg_step, 'main', None),
+                ('out', self._seg_outputs, 'main', None))
 
     def _whole_graph(self):
         """world 1, or world > 1 with the all-reduces captured: ONE graph holds the iteration"""
-        return self.world_size == 1 or self.graph_collectives
+        return (self.world_size == 1 or self.graph_collectives) and not self.force_cut
 
     def _capture(self):
-        """Capture the iteration.  One graph (two streams inside, forked and joined within the
-        capture) when `_whole_graph()`; otherwise one graph per stretch between two all-reduces,
-        all sharing one memory pool so tensors handed from one stretch to the next stay put."""
+        """Capture the iteration.  One graph (several streams inside, forked and joined within
+        the capture) when `_whole_graph()`; otherwise one graph per stretch between two
+        all-reduces.  Graphs that replay on the same stream share a memory pool (tensors handed
+        from one stretch to the next stay put); the two streams' graphs replay concurrently and
+        therefore allocate from different pools."""
         torch.cuda.synchronize()
-        pool = torch.cuda.graph_pool_handle()
+        gan_ops.PAIR_STREAMS = bool(self.overlap and self.pair_streams)
         if self._whole_graph():
             reduce = self._reduce_fn()
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, pool=pool):
+            with torch.cuda.graph(g, pool=torch.cuda.graph_pool_handle()):
                 self._body(reduce)
             return [g]
+        pools = {'main': torch.cuda.graph_pool_handle(), 'side': torch.cuda.graph_pool_handle()}
         graphs = []
-        for fn, _ in self._segments():
+        for _, fn, where, _ in self._segments():
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, pool=pool):
+            with torch.cuda.graph(g, pool=pools[where]):
                 fn()
             graphs.append(g)
         return graphs
+
+    def _replay_cut(self, graphs):
+        """replay of the cut form: main-stream stretches on the current stream, side-stream
+        stretches (and their all-reduces) on the side stream, forked after the forward and
+        joined before the losses are assembled"""
+        main = torch.cuda.current_stream()
+        side = self._side_stream() if self.overlap else main
+        segs = self._segments()
+        by_name = {name: (g, opt) for g, (name, _, _, opt) in zip(graphs, segs)}
+
+        def run(names):
+            for n in names:
+                g, opt = by_name[n]
+                g.replay()
+                if opt is not None:
+                    opt.all_reduce()
+        run(['fwd'])
+        if self.overlap:
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                run(['dis', 'dis_patch', 'dec', 'fake'])
+            run(['det_bwd', 'step'])
+            main.wait_stream(side)
+        else:
+            run(['dis', 'dis_patch', 'dec', 'fake', 'det_bwd', 'step'])
+        run(['out'])
 
     def iteration(self, cfg, image, image_info, gts, target, lr=None):
         """One iteration; returns a dict of 0-dim loss tensors (no host sync here).
@@ -453,10 +482,7 @@ class SCDATrainer(object):
             if self._whole_graph():
                 ent['graphs'][0].replay()
             else:
-                for g, (_, opt) in zip(ent['graphs'], self._segments()):
-                    g.replay()
-                    if opt is not None:
-                        opt.all_reduce()
+                self._replay_cut(ent['graphs'])
         ent['calls'] += 1
         self._graphs = ent['graphs']
         return {k: v.clone() for k, v in self._st['out'].items()}
@@ -496,7 +522,7 @@ def builder_gan(cluster_num=4, threshold=128, recon_size=256, neww=64, newh=64):
 
 def build_trainer(cfg, lr=1.25e-5, device="cuda", cluster_num=4, threshold=128, recon_size=256,
                   new_w=1024, new_h=512, world_size=1, seed=0, use_graphs=True, overlap=True,
-                  graph_collectives=None):
+                  graph_collectives=None, force_cut=False):
     from .models.faster_rcnn.vgg_adver_expansion_cluster import vgg16
     torch.manual_seed(seed)
     np.random.seed(seed)
@@ -504,6 +530,7 @@ def build_trainer(cfg, lr=1.25e-5, device="cuda", cluster_num=4, threshold=128, 
     dis_model, dec_model, dis_model_patch = builder_gan(cluster_num, threshold, recon_size)
     tr = SCDATrainer(model, dec_model.to(device), dis_model.to(device), dis_model_patch.to(device),
                      lr, cluster_num, threshold, recon_size, new_w, new_h, world_size,
-                     use_graphs=use_graphs, overlap=overlap, graph_collectives=graph_collectives)
+                     use_graphs=use_graphs, overlap=overlap, graph_collectives=graph_collectives,
+                     force_cut=force_cut)
     tr.train_mode()
     return tr

@@ -57,8 +57,7 @@ def main():
 
     def whole():
         tr._static, tr._st = tr._by_shape[list(tr._by_shape)[0]]['static'], {}
-        for seg, _ in tr._segments():
-            seg()
+        tr._body(tr._reduce_fn())
 
     fn = {'backbone': backbone, 'rpn': rpn, 'anchor': anchor, 'props': props, 'forward': forward,
           'fwd_bwd': fwd_bwd, 'whole': whole}[stage]
