@@ -212,6 +212,11 @@ int scda_linear_wgrad_bf16(int rows, int Nout, int Kin, const void *dY, long lon
 int scda_conv3x3_wgrad_bf16_nhwc(int NB, int H, int W, int Cin, int Cout, const void *x, const void *dy,
                                  float *dw_partials, int splits, cudaStream_t stream);
 
+/* Tuning / test hook: form of scda_conv3x3_wgrad_bf16_nhwc.  0 (default) = one tap per CTA; 1 = one kernel
+ * column (three taps) per CTA, the shifted input rows staged once for the three (faster in isolation, but it
+ * occupies up to all 512 TMEM columns of the SM).  Same results up to fp32 summation order.  Process-wide. */
+int scda_conv3x3_wgrad_set_form(int three_taps);
+
 /* --- bf16 NHWC companions of the tensor-core kernels (HBM bound) --------- */
 /* nn.MaxPool2d(2, 2) of the VGG stack (vgg_adver_expansion_cluster.py:105-106) on NHWC bf16 */
 int scda_maxpool2x2_nhwc_bf16(int NB, int H, int W, int C, const void *x, void *y, cudaStream_t stream);

@@ -64,6 +64,7 @@ SIGNATURES = {
     "scda_kmeans_workspace_bytes": (_z, [_i, _i]),
     "scda_kmeans_regions": (_i, [_p, _i, _i, _i, _i, _p, _i, _i, _f, _p, _i, _p, _p, _p, _p, _p, _z, _p]),
     "scda_conv3x3_set_plan": (_i, [_i, _i, _i]),
+    "scda_conv3x3_wgrad_set_form": (_i, [_i]),
     "scda_adam_step": (_i, [_p, _p, _p, _p, _p, C.c_longlong, _i, _f, _f, _f, _f, _f, _f, _p, _p]),
 }
 

@@ -11,6 +11,7 @@ forward is the 512 x 5 RoI table for the k-means of compute_cluster_targets.
 """
 import functools
 import logging
+import os
 
 import torch
 import torch.nn as nn
@@ -119,8 +120,9 @@ class FasterRCNN_AdEx(nn.Module):
         partial_fn = self._pin_args_to_fn(cfg, ground_truth_bboxes, image_info, ignore_regions)
 
         outputs = {'losses': [], 'predict': [], 'accuracy': []}
-        x = self.feature_extractor(x_input)
-        rpn_pred_cls, rpn_pred_loc = self.rpn(x)
+        if not self.training:
+            x = self.feature_extractor(x_input)
+            rpn_pred_cls, rpn_pred_loc = self.rpn(x)
 
         if self.training:
             pcfg = cfg['train_rpn_proposal_cfg']
@@ -164,12 +166,21 @@ class FasterRCNN_AdEx(nn.Module):
             # branch (its dense backbone fills the SMs the source's latency-bound proposal /
             # target plumbing leaves idle); forked from and joined back into the current stream
             tstream = input.get('target_stream') if on_dev else None
-            if tstream is not None:
+            # (measured on B200: forking after the source backbone was issued schedules better than before it)
+            early = os.environ.get("SCDA_EARLY_FORK", "0") == "1"
+            if tstream is not None and early:
                 cur_stream = torch.cuda.current_stream()
                 tstream.wait_stream(cur_stream)
                 with torch.cuda.stream(tstream):
                     tgt = run_target()
 
+            x = self.feature_extractor(x_input)
+            rpn_pred_cls, rpn_pred_loc = self.rpn(x)
+            if tstream is not None and not early:
+                cur_stream = torch.cuda.current_stream()
+                tstream.wait_stream(cur_stream)
+                with torch.cuda.stream(tstream):
+                    tgt = run_target()
             rpn_loss_cls, rpn_loss_loc, rpn_acc = self._add_rpn_loss(
                 partial_fn['anchor_target_fn'], rpn_pred_cls, rpn_pred_loc)
             props = rpn_proposals_device(self._rpn_scores(rpn_pred_cls).data, rpn_pred_loc.data,

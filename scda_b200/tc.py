@@ -4,6 +4,8 @@ their bf16 NHWC companions (csrc/nhwc_ops.cu).
 Tensors are bf16 CUDA tensors; activations are NHWC ([N, H, W, C] contiguous), conv
 weights [Cout, 3, 3, Cin] ("KRSC").  Outputs are allocated here, the kernels only borrow
 pointers (include/scda_b200.h)."""
+import os
+
 import torch
 
 from ._lib import check, load, require_cuda, stream_ptr
@@ -141,15 +143,28 @@ def linear_wgrad(dy, x, out=None, accumulate=False):
     return out
 
 
+WGRAD3 = os.environ.get("SCDA_WGRAD3", "0") == "1"      # three taps per CTA (csrc/gemm_tc.cu: tc_wgrad3_kernel)
+
+
 def _wgrad_splits(NB, H, W, Cin, Cout, target_ctas):
+    """how many ranges the pixel reduction is cut into: enough CTAs for `target_ctas`, every
+    range non-empty.  CTAs per range = (taps or kernel columns) x Cout tiles x Cin tiles."""
     tiles = NB * H * W // 128
-    base = 9 * ((Cout + 127) // 128) * ((Cin + (63 if Cin <= 64 else 127)) // (64 if Cin <= 64 else 128))
+    base = (3 if WGRAD3 else 9) * ((Cout + 127) // 128) * ((Cin + (63 if Cin <= 64 else 127)) // (64 if Cin <= 64 else 128))
     splits = max(1, min(tiles, target_ctas // max(base, 1)))
     per = -(-tiles // splits)
     return -(-tiles // per)
 
 
-def conv3x3_wgrad_nhwc(x, dy, target_ctas=296, out=None, accumulate=False):
+def set_wgrad_form(three_taps):
+    """tuning / test hook (scda_conv3x3_wgrad_set_form): one tap (False) or one kernel column (True) per CTA"""
+    global WGRAD3
+    if load().scda_conv3x3_wgrad_set_form(1 if three_taps else 0) != 1:
+        raise ValueError("scda_conv3x3_wgrad_set_form: bad arguments")
+    WGRAD3 = bool(three_taps)
+
+
+def conv3x3_wgrad_nhwc(x, dy, target_ctas=None, out=None, accumulate=False):
     """dW[Cout, 3, 3, Cin] fp32 from x[N,H,W,Cin], dy[N,H,W,Cout] (both bf16 NHWC).  With
     `out` (a contiguous fp32 [Cout,3,3,Cin] buffer) the split-K slabs are reduced straight
     into it (overwriting, or adding when accumulate)."""
@@ -158,6 +173,8 @@ def conv3x3_wgrad_nhwc(x, dy, target_ctas=296, out=None, accumulate=False):
     assert x.is_contiguous() and dy.is_contiguous() and x.shape[:3] == dy.shape[:3]
     NB, H, W, Cin = x.shape
     Cout = dy.shape[3]
+    if target_ctas is None:
+        target_ctas = 148 if WGRAD3 else 296          # one wave of one-CTA-per-SM blocks / two waves
     splits = _wgrad_splits(NB, H, W, Cin, Cout, target_ctas)
     part = torch.empty(splits, Cout, 3, 3, Cin, dtype=torch.float32, device=x.device)
     with torch.cuda.device(x.device):

@@ -135,8 +135,13 @@ def test_conv3x3_wgrad(cuda_lib, NB, H, W, Cin, Cout):
     torch.backends.cudnn.allow_tf32 = False
     ref = torch.nn.grad.conv2d_weight(x.float().permute(0, 3, 1, 2), (Cout, Cin, 3, 3),
                                       dy.float().permute(0, 3, 1, 2), padding=1).permute(0, 2, 3, 1)
-    _close(tc.conv3x3_wgrad_nhwc(x, dy), ref, rtol=3e-3)
-    _close(tc.conv3x3_wgrad_nhwc(x, dy, target_ctas=9), ref, rtol=3e-3)       # no split
+    try:
+        for three in (False, True):        # one tap per CTA / one kernel column (three taps) per CTA
+            tc.set_wgrad_form(three)
+            _close(tc.conv3x3_wgrad_nhwc(x, dy), ref, rtol=3e-3)
+            _close(tc.conv3x3_wgrad_nhwc(x, dy, target_ctas=9), ref, rtol=3e-3)       # no split
+    finally:
+        tc.set_wgrad_form(False)
 
 
 def test_conv3x3_dgrad_via_flipped_weights(cuda_lib):
