@@ -145,6 +145,11 @@ def reference_arm(args):
     print(json.dumps(line), flush=True)
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch, averaged over the 13 backbone launches, from the
+# committed `ncu --set full` capture of the same kernels (scripts/prof_conv.py)
+NCU_DRAM_BYTES_PER_LAUNCH = None
+NCU_TRAFFIC_SOURCE = None
+
 VGG_CONVS = [(3, 64, 512, 1024), (64, 64, 512, 1024), (64, 128, 256, 512), (128, 128, 256, 512),
              (128, 256, 128, 256), (256, 256, 128, 256), (256, 256, 128, 256), (256, 512, 64, 128),
              (512, 512, 64, 128), (512, 512, 64, 128), (512, 512, 32, 64), (512, 512, 32, 64),
@@ -152,7 +157,7 @@ VGG_CONVS = [(3, 64, 512, 1024), (64, 64, 512, 1024), (64, 128, 256, 512), (128,
 
 
 def roofline_probe(dev):
-    """Dominant hand-written kernel = the tcgen05 implicit-GEMM convolution (tc_gemm_kernel):
+    """Dominant hand-written kernel = the tcgen05 halo convolution (conv_halo_kernel):
     the 13 backbone launches of one image timed back to back with CUDA events on the launch
     stream (L2 flushed before each pass).  Algorithmic work = 2 * H * W * Cin * Cout * 9 per
     layer (conv1_1 counted with its 3 real input channels) = 320.71 GFLOP per image
@@ -180,11 +185,58 @@ def roofline_probe(dev):
             ts.append(a.elapsed_time(b) * 1e-3)
     t = float(np.mean(ts))
     return {"bound": "tensor", "achieved": flops / t / 1e12, "peak": tf, "unit": "TFLOP/s",
-            "frac": flops / t / 1e12 / tf, "traffic": None,
-            "kernel": "tc_gemm_kernel (tcgen05 implicit-GEMM conv3x3 + bias + ReLU), 13 backbone launches",
+            "frac": flops / t / 1e12 / tf, "traffic": NCU_DRAM_BYTES_PER_LAUNCH,
+            "traffic_source": NCU_TRAFFIC_SOURCE,
+            "kernel": "conv_halo_kernel (tcgen05 + TMA 3x3 convolution, input halo staged once for the nine taps, "
+                      "+ bias + ReLU), 13 backbone launches",
             "peak_source": src + " (MEASURED_PEAKS.json bf16_tflops, burst: kernels timed alone)",
             "algorithmic_flops_per_launch": flops / len(VGG_CONVS),
             "avg_launch_us": t / len(VGG_CONVS) * 1e6}
+
+
+def aux_ops(dev):
+    """BASELINE.json's second metric, "RoIAlign+NMS us/image": the reference's RoIAlign forward at config 1
+    (1x256x64x64 features, 128 RoIs, 7x7), the RoI max-pool the model really uses (NHWC bf16, 512 RoIs on the
+    1x512x32x64 map) and NMS(0.7) over 12 000 score-sorted synthetic proposals (config 5 generator), each through
+    the C ABI, CUDA events on the launch stream, L2 flushed, median of 10."""
+    import _inputs
+    from scda_b200 import _lib, tc
+    lib = _lib.load()
+    st = torch.cuda.current_stream().cuda_stream
+    flush = torch.zeros(64 * 1024 * 1024, device=dev)
+
+    def timeit(fn):
+        ts = []
+        for i in range(13):
+            flush.add_(1.0)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            b.synchronize()
+            if i >= 3:
+                ts.append(a.elapsed_time(b) * 1e3)
+        return float(np.median(ts))
+    feat1 = torch.from_numpy(_inputs.features((1, 256, 64, 64), 0)).to(dev)
+    rois1 = torch.from_numpy(_inputs.rois_uniform(128, 1)).to(dev)
+    out1 = torch.empty(128, 256, 7, 7, device=dev)
+    t_align = timeit(lambda: lib.ROIAlignForwardLaucher(feat1.data_ptr(), 1 / 16., 128, 64, 64, 256, 7, 7,
+                                                        rois1.data_ptr(), out1.data_ptr(), st))
+    featn = torch.randn(1, 32, 64, 512, device=dev).bfloat16()
+    rois = torch.from_numpy(_inputs.rois_uniform(512, 1, img_w=IMG_W, img_h=IMG_H)).to(dev)
+    t_pool = timeit(lambda: tc.roi_pool_nhwc(featn, rois, 7, 7, 1 / 16.))
+    n = 12000
+    boxes = torch.from_numpy(_inputs.nms_boxes(n, n)).to(dev)
+    keep = torch.empty(n, dtype=torch.int64, device=dev)
+    num = torch.zeros(1, dtype=torch.int64, device=dev)
+    wsb = lib.scda_nms_workspace_bytes(n)
+    ws = torch.empty(wsb // 8 + 1, dtype=torch.int64, device=dev)
+    t_nms = timeit(lambda: lib.scda_nms(n, boxes.data_ptr(), 0.7, 0, keep.data_ptr(), num.data_ptr(), ws.data_ptr(),
+                                        wsb, st))
+    return {"roi_align_fwd_us": round(t_align, 1), "roi_pool_nhwc_fwd_us": round(t_pool, 1),
+            "nms_12k_us": round(t_nms, 1), "nms_12k_kept": int(num.item()),
+            "roi_align_plus_nms_us_per_image": round(t_align + t_nms, 1),
+            "what": "RoIAlign fwd 1x256x64x64/128 RoIs + NMS(0.7) of 12000 sorted boxes, on-device scan included"}
 
 
 def our_arm(args):
@@ -283,6 +335,8 @@ def our_arm(args):
                         "h2d_bytes_per_step": int(h_image.numel() * 4 + h_target.numel() * 4 + h_gts.numel() * 4),
                         "d2h_bytes_per_step": 4, "last_loss": last},
                 "gpu_launches": launches, "roofline": roof}
+        if world == 1:
+            line["aux"] = aux_ops(dev)
         if world == 1 and not args.no_cpu_baseline:
             r = cpu_reference_run(2, 1, budget_s=args.cpu_budget_inline)
             line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
