@@ -204,6 +204,7 @@ class SCDATrainer(object):
         self.force_cut = force_cut          # tests: the cut (world > 1) replay plan on one GPU
         self._side = None
         self._tside = None
+        self._aside = None
         if overlap and hasattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch"):
             # gradients are produced on whichever stream ran the forward of their branch and are
             # accumulated into the flat buffers there; the mismatch torch warns about is intended
@@ -297,6 +298,7 @@ class SCDATrainer(object):
              'device_clusters': True}
         if self.overlap:
             x['target_stream'] = self._target_stream()
+            x['aux_stream'] = self._aux_stream()
         outputs = self.model(x, b['target'])
         st['det_losses'] = outputs['losses']
         st['acc'] = outputs['accuracy']
@@ -350,6 +352,11 @@ class SCDATrainer(object):
         if self._side is None:
             self._side = torch.cuda.Stream(device=self.opt.flat.device, priority=-1)
         return self._side
+
+    def _aux_stream(self):
+        if self._aside is None:
+            self._aside = torch.cuda.Stream(device=self.opt.flat.device)
+        return self._aside
 
     def _target_stream(self):
         if self._tside is None:

@@ -174,8 +174,27 @@ class FasterRCNN_AdEx(nn.Module):
                 with torch.cuda.stream(tstream):
                     tgt = run_target()
 
+            # input['aux_stream']: the anchor targets depend on the ground truth and the feature-map
+            # SIZE only, not on the network: computed on that stream beside the backbone
+            astream = input.get('aux_stream') if on_dev else None
+            conv_loc = getattr(getattr(self, 'rpn_head', None), 'conv_loc', None)
+            anchor_pre = None
+            if astream is not None and conv_loc is not None:
+                stride = int(cfg['train_anchor_target_cfg']['anchor_stride'])
+                size_pre = (x_input.shape[0], conv_loc.out_channels, x_input.shape[2] // stride,
+                            x_input.shape[3] // stride)
+                main_stream = torch.cuda.current_stream()
+                astream.wait_stream(main_stream)
+                with torch.cuda.stream(astream):
+                    anchor_pre = (size_pre, partial_fn['anchor_target_fn'](size_pre))
+
             x = self.feature_extractor(x_input)
             rpn_pred_cls, rpn_pred_loc = self.rpn(x)
+            if anchor_pre is not None:
+                main_stream.wait_stream(astream)
+                if tuple(rpn_pred_loc.size()) == tuple(anchor_pre[0]):
+                    pre = anchor_pre[1]
+                    partial_fn['anchor_target_fn'] = lambda size: pre
             if tstream is not None and not early:
                 cur_stream = torch.cuda.current_stream()
                 tstream.wait_stream(cur_stream)

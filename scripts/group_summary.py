@@ -15,7 +15,8 @@ for j in range(3,len(idx),4):
     iters.append(rows[start:idx[j]+1]); start=idx[j]+1
 last=iters[-2]
 def grp(k):
-    if 'tc_gemm' in k: return 'ours: tc_gemm (fwd/dgrad)'
+    if 'conv_halo' in k: return 'ours: conv_halo (3x3 fwd/dgrad)'
+    if 'tc_gemm' in k: return 'ours: tc_gemm (fc / 1x1 fwd/dgrad)'
     if 'tc_wgrad' in k or 'reduce_slabs' in k: return 'ours: tc_wgrad + slabs'
     if 'adam' in k: return 'ours: adam'
     if 'nms' in k: return 'ours: nms'

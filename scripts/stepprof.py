@@ -17,7 +17,7 @@ def main():
     from scda_b200.engine import build_trainer
     torch.cuda.set_device(0)
     cfg = bench.load_cfg()
-    tr = build_trainer(cfg, world_size=1, seed=0)
+    tr = build_trainer(cfg, world_size=1, seed=0, use_graphs=False, overlap=False)
     image, target, gts, info = bench.synth_batch(0, pinned=False)
     image, target, gts = image.cuda(), target.cuda(), gts.cuda()
     for _ in range(3):
@@ -26,7 +26,7 @@ def main():
     with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA], record_shapes=True) as prof:
         tr.iteration(cfg, image, info, gts, target)
         torch.cuda.synchronize()
-    print(prof.key_averages(group_by_input_shape=True).table(sort_by="self_cuda_time_total", row_limit=60,
+    print(prof.key_averages(group_by_input_shape=True).table(sort_by="self_cuda_time_total", row_limit=90,
                                                              max_name_column_width=60, max_shapes_column_width=70))
     print(prof.key_averages().table(sort_by="self_cpu_time_total", row_limit=25, max_name_column_width=60))
 
