@@ -154,6 +154,26 @@ int scda_softmax_focal_loss_sum(const int N, const float *logits, const int *tar
                                 const int num_classes, float *losses, float *priors,
                                 float *loss_sum, cudaStream_t stream);
 
+/* --- fused detector / adversarial losses -------------------------------- */
+/* smooth_l1_loss_with_sigma(pred * mask, target) of the reference
+ * (models/faster_rcnn/faster_rcnn_adver_expansion_reweight_cluster.py:238-246; RPN :54-55, RCNN :64-66):
+ * loss_sum[0] = sum_i f(pred[i] * mask[i] - target[i]),  f(d) = 0.5 sigma^2 d^2 if |d| < 1/sigma^2 else
+ * |d| - 0.5/sigma^2.  mask may be NULL (= 1).  One block, fixed summation order (deterministic). */
+int scda_smooth_l1_sigma_sum_fwd(long long n, const float *pred, const float *mask, const float *target,
+                                 float sigma, float *loss_sum, cudaStream_t stream);
+/* grad_pred[i] = grad_loss[0] * f'(d_i) * mask[i] */
+int scda_smooth_l1_sigma_sum_bwd(long long n, const float *pred, const float *mask, const float *target,
+                                 float sigma, const float *grad_loss, float *grad_pred, cudaStream_t stream);
+/* the adversarial terms of the four-phase update (tools/faster_rcnn_train_val.py:577-600, 655-680, 716-732):
+ * row_mean[k] = mean_m F.binary_cross_entropy(sigmoid(logits[k, m]), labels[m * label_stride]) for K cluster
+ * rows against ONE label row (label_stride 1) or one constant (label_stride 0); logs clamped at -100 as
+ * torch does.  One block per row, fixed summation order. */
+int scda_bce_sigmoid_rows_fwd(int K, int M, const float *logits, const float *labels, int label_stride,
+                              float *row_mean, cudaStream_t stream);
+/* grad_logits[k, m] = grad_rows[k] / M * (p - y) / max(p (1 - p), 1e-12) * p (1 - p),  p = sigmoid(logit) */
+int scda_bce_sigmoid_rows_bwd(int K, int M, const float *logits, const float *labels, int label_stride,
+                              const float *grad_rows, float *grad_logits, cudaStream_t stream);
+
 /* --- tensor-core GEMM / 3x3 convolution (tcgen05 + TMA) ----------------- */
 /* flags for both entry points */
 #define SCDA_TC_RELU        1   /* y = max(y, 0)                                        */

@@ -63,6 +63,10 @@ SIGNATURES = {
     "scda_roi_pool_nhwc_bf16_bwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p]),
     "scda_kmeans_workspace_bytes": (_z, [_i, _i]),
     "scda_kmeans_regions": (_i, [_p, _i, _i, _i, _i, _p, _i, _i, _f, _p, _i, _p, _p, _p, _p, _p, _z, _p]),
+    "scda_smooth_l1_sigma_sum_fwd": (_i, [C.c_longlong, _p, _p, _p, _f, _p, _p]),
+    "scda_smooth_l1_sigma_sum_bwd": (_i, [C.c_longlong, _p, _p, _p, _f, _p, _p, _p]),
+    "scda_bce_sigmoid_rows_fwd": (_i, [_i, _i, _p, _p, _i, _p, _p]),
+    "scda_bce_sigmoid_rows_bwd": (_i, [_i, _i, _p, _p, _i, _p, _p, _p]),
     "scda_conv3x3_set_plan": (_i, [_i, _i, _i]),
     "scda_conv3x3_wgrad_set_form": (_i, [_i]),
     "scda_adam_step": (_i, [_p, _p, _p, _p, _p, C.c_longlong, _i, _f, _f, _f, _f, _f, _f, _p, _p]),

@@ -1,0 +1,148 @@
+// Fused loss kernels of the detector and the adversarial phases (HBM / latency bound, tiny):
+//
+//  * smooth-L1 with sigma on masked predictions, summed —
+//    `smooth_l1_loss_with_sigma(pred * mask, target)` of the reference
+//    (models/faster_rcnn/faster_rcnn_adver_expansion_reweight_cluster.py:238-246, called at :54-55 and
+//    :64-66): d = pred*mask - target; loss = sum(0.5 s^2 d^2 if |d| < 1/s^2 else |d| - 0.5/s^2).
+//    The reference spends ~10 elementwise launches and a reduction on it, forward alone.
+//  * sigmoid + per-row binary cross entropy — the adversarial terms of the four-phase update
+//    (tools/faster_rcnn_train_val.py:577-600, 655-680, 716-732): `F.binary_cross_entropy(sigmoid(x[k]), y)`
+//    for every cluster row k against ONE label row y (soft labels U(0.8,1)/U(0,0.3) or a constant),
+//    with torch's clamp of the logs at -100 (aten/native/Loss.cpp) and its backward
+//    (p - y) / max(p (1 - p), 1e-12) chained through the sigmoid.
+//
+// Reductions are block-local trees in a fixed order (one block per output): deterministic.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kLT = 1024;
+
+__device__ __forceinline__ float block_sum(float v, float *sh)
+{
+    v = warp_sum(v);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) sh[w] = v;
+    __syncthreads();
+    if (w == 0) {
+        float t = lane < (blockDim.x >> 5) ? sh[lane] : 0.f;
+        t = warp_sum(t);
+        if (lane == 0) sh[0] = t;
+    }
+    __syncthreads();
+    const float r = sh[0];
+    __syncthreads();
+    return r;
+}
+
+__global__ void __launch_bounds__(kLT)
+smooth_l1_fwd_kernel(const float *__restrict__ pred, const float *__restrict__ mask,
+                     const float *__restrict__ target, long long n, float sigma2, float *__restrict__ out)
+{
+    __shared__ float sh[32];
+    const float thr = 1.f / sigma2, half = 0.5f / sigma2;
+    float acc = 0.f;
+    for (long long i = threadIdx.x; i < n; i += kLT) {
+        const float p = mask ? pred[i] * mask[i] : pred[i];
+        const float d = p - target[i];
+        const float a = fabsf(d);
+        acc += a < thr ? d * d * sigma2 * 0.5f : a - half;
+    }
+    const float s = block_sum(acc, sh);
+    if (threadIdx.x == 0) out[0] = s;
+}
+
+__global__ void __launch_bounds__(256)
+smooth_l1_bwd_kernel(const float *__restrict__ pred, const float *__restrict__ mask,
+                     const float *__restrict__ target, const float *__restrict__ gout, long long n, float sigma2,
+                     float *__restrict__ gpred)
+{
+    const float thr = 1.f / sigma2;
+    const float g = gout[0];
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x) {
+        const float m = mask ? mask[i] : 1.f;
+        const float d = pred[i] * m - target[i];
+        const float a = fabsf(d);
+        const float dl = a < thr ? sigma2 * d : (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f));
+        gpred[i] = g * dl * m;
+    }
+}
+
+// one block per row k: out[k] = mean_m BCE(sigmoid(x[k, m]), y[m * ystride])
+__global__ void __launch_bounds__(kLT)
+bce_rows_fwd_kernel(const float *__restrict__ x, const float *__restrict__ y, int ystride, int M,
+                    float *__restrict__ out)
+{
+    __shared__ float sh[32];
+    const int k = blockIdx.x;
+    float acc = 0.f;
+    for (int m = threadIdx.x; m < M; m += kLT) {
+        const float p = 1.f / (1.f + expf(-x[(long long)k * M + m]));
+        const float t = y[(long long)m * ystride];
+        const float lp = fmaxf(logf(p), -100.f), lq = fmaxf(log1pf(-p), -100.f);     // Loss.cu of torch 2.x
+        acc += (t - 1.f) * lq - t * lp;
+    }
+    const float s = block_sum(acc, sh);
+    if (threadIdx.x == 0) out[k] = s / (float)M;
+}
+
+__global__ void __launch_bounds__(256)
+bce_rows_bwd_kernel(const float *__restrict__ x, const float *__restrict__ y, int ystride, int K, int M,
+                    const float *__restrict__ gout, float *__restrict__ gx)
+{
+    const long long n = (long long)K * M;
+    const float inv = 1.f / (float)M;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int k = (int)(i / M), m = (int)(i - (long long)k * M);
+        const float p = 1.f / (1.f + expf(-x[i]));
+        const float t = y[(long long)m * ystride];
+        const float q = (1.f - p) * p;
+        // binary_cross_entropy_backward then sigmoid_backward, as torch chains them
+        const float gp = gout[k] * inv * (p - t) / fmaxf(q, 1e-12f);
+        gx[i] = gp * q;
+    }
+}
+
+int ew_grid(long long n)
+{
+    long long b = (n + 255) / 256;
+    const long long cap = (long long)kNumSMs * 8;
+    return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+}  // namespace
+
+SCDA_API int scda_smooth_l1_sigma_sum_fwd(long long n, const float *pred, const float *mask, const float *target,
+                                          float sigma, float *loss_sum, cudaStream_t stream)
+{
+    if (n <= 0 || !pred || !target || !loss_sum || !(sigma > 0.f)) return 0;
+    smooth_l1_fwd_kernel<<<1, kLT, 0, stream>>>(pred, mask, target, n, sigma * sigma, loss_sum);
+    return scda_launch_status();
+}
+
+SCDA_API int scda_smooth_l1_sigma_sum_bwd(long long n, const float *pred, const float *mask, const float *target,
+                                          float sigma, const float *grad_loss, float *grad_pred, cudaStream_t stream)
+{
+    if (n <= 0 || !pred || !target || !grad_loss || !grad_pred || !(sigma > 0.f)) return 0;
+    smooth_l1_bwd_kernel<<<ew_grid(n), 256, 0, stream>>>(pred, mask, target, grad_loss, n, sigma * sigma, grad_pred);
+    return scda_launch_status();
+}
+
+SCDA_API int scda_bce_sigmoid_rows_fwd(int K, int M, const float *logits, const float *labels, int label_stride,
+                                       float *row_mean, cudaStream_t stream)
+{
+    if (K <= 0 || M <= 0 || !logits || !labels || !row_mean || label_stride < 0) return 0;
+    bce_rows_fwd_kernel<<<K, kLT, 0, stream>>>(logits, labels, label_stride, M, row_mean);
+    return scda_launch_status();
+}
+
+SCDA_API int scda_bce_sigmoid_rows_bwd(int K, int M, const float *logits, const float *labels, int label_stride,
+                                       const float *grad_rows, float *grad_logits, cudaStream_t stream)
+{
+    if (K <= 0 || M <= 0 || !logits || !labels || !grad_rows || !grad_logits || label_stride < 0) return 0;
+    bce_rows_bwd_kernel<<<ew_grid((long long)K * M), 256, 0, stream>>>(logits, labels, label_stride, K, M, grad_rows,
+                                                                       grad_logits);
+    return scda_launch_status();
+}

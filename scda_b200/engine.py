@@ -29,6 +29,7 @@ import torch.nn.functional as F
 from . import gan_ops
 from ._lib import check, load, stream_ptr
 from .gan_ops import run_pair
+from .loss_ops import bce_sigmoid_rows
 from .utils.distributed_utils import FlatGradBucket
 
 
@@ -158,8 +159,12 @@ def soft_label(flag, like, generator=None):
     return 0.8 + 0.2 * u if flag == 1 else 0.3 * u
 
 
-def _bce_rows(p, label_row):
-    """sum over clusters of F.binary_cross_entropy(p[c:c+1], label_row) -> per-cluster vector."""
+def _bce_rows(logits, label_row):
+    """per-cluster vector of F.binary_cross_entropy(sigmoid(logits[c:c+1]), label_row)
+    (tools/faster_rcnn_train_val.py:577-600): one fused kernel each way (csrc/loss_ops.cu)."""
+    if logits.is_cuda:
+        return bce_sigmoid_rows(logits, label_row)
+    p = torch.sigmoid(logits)
     return F.binary_cross_entropy(p, label_row.expand_as(p), reduction='none').mean(dim=1)
 
 
@@ -230,8 +235,7 @@ class SCDATrainer(object):
         self.opt_dis.zero_grad()
         on_recon, on_real = run_pair(lambda: self.dis_model(x_source_recon, x_target_recon),
                                      lambda: self.dis_model(cs, ct))
-        s_dis, t_dis = [torch.sigmoid(o) for o in on_recon]
-        s_real, t_real = [torch.sigmoid(o) for o in on_real]
+        (s_dis, t_dis), (s_real, t_real) = on_recon, on_real        # logits: the sigmoid lives in _bce_rows
         score_1 = soft_label(1, s_real[:1])
         score_0 = soft_label(0, s_dis[:1])
         adloss_source = (_bce_rows(s_dis, score_1) + _bce_rows(s_real, score_0)).sum()
@@ -263,8 +267,7 @@ class SCDATrainer(object):
         x_source_recon, x_target_recon = st['recon']
         (s_dis2, t_dis2), on_real = run_pair(lambda: self.dis_model(x_source_recon, x_target_recon),
                                              lambda: self.dis_model(b['cs'], b['ct']))
-        s_dis2, t_dis2 = torch.sigmoid(s_dis2), torch.sigmoid(t_dis2)
-        s_real2, t_real2 = [torch.sigmoid(o) for o in on_real]
+        s_real2, t_real2 = on_real                                  # logits, as above
         st['t_patch_mean2'] = torch.mean(self.dis_model_patch(b['xt']), 1).detach()
         t_patch_mean2 = st['t_patch_mean2']
         ones, zeros = torch.ones_like(t_dis2[:1]), torch.zeros_like(t_dis2[:1])
@@ -284,11 +287,10 @@ class SCDATrainer(object):
         with torch.no_grad():
             x_source_recon2, x_target_recon2 = self.dec_model(b['xt'], b['xs'])
             s_dis3, t_dis3 = self.dis_model(x_source_recon2, x_target_recon2)
-            fake_dis = torch.sigmoid(t_dis3)
-            st['fake_loss_source'] = F.binary_cross_entropy(fake_dis, torch.ones_like(fake_dis))
-            fake_dis2 = torch.sigmoid(s_dis3)
+            # F.binary_cross_entropy over the whole [K, M] block = the mean of the K row means
+            st['fake_loss_source'] = _bce_rows(t_dis3, torch.ones_like(t_dis3[:1])).mean()
             st['fake_loss_target'] = (st['t_patch_mean2']
-                                      * _bce_rows(fake_dis2, torch.ones_like(fake_dis2[:1]))).sum()
+                                      * _bce_rows(s_dis3, torch.ones_like(s_dis3[:1]))).sum()
 
     def _seg_forward(self):
         """detector forward on both images, crops around the cluster centres"""

@@ -23,6 +23,7 @@ from ...functions.predict_bbox import compute_predicted_bboxes
 from ...functions.proposal_target import compute_proposal_targets, proposal_targets_device
 from ...functions.rpn_proposal import compute_rpn_proposals, rpn_proposals_device
 from ...gan_ops import run_pair
+from ...loss_ops import smooth_l1_masked_sum
 from .common_net import (ConvTranspose1x1, INSResBlock, LeakyReLUConv2d, LeakyReLUConvTranspose2d_2,
                          LinUnsRes_cluster, ResDis_cluster, gaussian_weights_init)
 
@@ -54,14 +55,14 @@ class FasterRCNN_AdEx(nn.Module):
         rpn_pred_cls = rpn_pred_cls.permute(0, 2, 3, 1).contiguous().view(-1, 2)
         cls_targets = cls_targets.permute(0, 2, 3, 1).contiguous().view(-1)
         rpn_loss_cls = F.cross_entropy(rpn_pred_cls, cls_targets, ignore_index=-1)
-        rpn_loss_loc = smooth_l1_loss_with_sigma(rpn_pred_loc * loc_masks, loc_targets) / loc_normalizer
+        rpn_loss_loc = _smooth_l1_masked(rpn_pred_loc, loc_masks, loc_targets) / loc_normalizer
         acc = accuracy(rpn_pred_cls.data, cls_targets.data)[0]
         return rpn_loss_cls, rpn_loss_loc, acc
 
     def _add_rcnn_loss(self, rcnn_pred_cls, rcnn_pred_loc, cls_targets, loc_targets, loc_weights):
         rcnn_loss_cls = F.cross_entropy(rcnn_pred_cls, cls_targets)
         loc_normalizer = cls_targets.shape[0]
-        rcnn_loss_loc = smooth_l1_loss_with_sigma(rcnn_pred_loc * loc_weights, loc_targets) / loc_normalizer
+        rcnn_loss_loc = _smooth_l1_masked(rcnn_pred_loc, loc_weights, loc_targets) / loc_normalizer
         acc = accuracy(rcnn_pred_cls, cls_targets)[0]
         return rcnn_loss_cls, rcnn_loss_loc, acc
 
@@ -254,6 +255,14 @@ class FasterRCNN_AdEx(nn.Module):
             bboxes = partial_fn['predict_bbox_fn'](proposals, rcnn_pred_cls, rcnn_pred_loc)
             outputs['predict'] = [proposals, bboxes]
         return outputs
+
+
+def _smooth_l1_masked(pred, mask, targets, sigma=3.0):
+    """smooth_l1_loss_with_sigma(pred * mask, targets): one fused kernel each way on CUDA
+    (csrc/loss_ops.cu), the reference's chain of tensor ops elsewhere"""
+    if pred.is_cuda and pred.dtype == torch.float32 and mask.dtype == torch.float32 and mask.shape == pred.shape:
+        return smooth_l1_masked_sum(pred, mask, targets.float(), sigma)
+    return smooth_l1_loss_with_sigma(pred * mask, targets, sigma)
 
 
 def smooth_l1_loss_with_sigma(pred, targets, sigma=3.0):

@@ -1,0 +1,71 @@
+"""Fused loss kernels (csrc/loss_ops.cu) through the C ABI against the oracle's restatement of the
+reference formula (oracle/host.py: smooth_l1_loss_with_sigma, reference
+models/faster_rcnn/faster_rcnn_adver_expansion_reweight_cluster.py:238-246) and against the tensor-op
+chain the reference executes for the adversarial terms (torch.sigmoid + F.binary_cross_entropy,
+tools/faster_rcnn_train_val.py:577-600).  fp32 sums in a different order: 1e-5 relative (north_star: 1e-4)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("shape", [(1, 60, 32, 64), (512, 36), (7,), (3, 1025)])
+@pytest.mark.parametrize("with_mask", [True, False])
+def test_smooth_l1_masked_sum(cuda_lib, shape, with_mask):
+    import torch
+    from oracle import host
+    from scda_b200.loss_ops import smooth_l1_masked_sum
+    from scda_b200.models.faster_rcnn.faster_rcnn_adver_expansion_reweight_cluster import smooth_l1_loss_with_sigma
+    g = torch.Generator().manual_seed(len(shape) * 17 + shape[-1])
+    pred = (torch.randn(shape, generator=g) * 0.3)
+    target = (torch.randn(shape, generator=g) * 0.3)
+    mask = (torch.rand(shape, generator=g) > 0.6).float() if with_mask else None
+    p = pred.cuda().requires_grad_(True)
+    loss = smooth_l1_masked_sum(p, mask.cuda() if with_mask else None, target.cuda(), 3.0)
+    (loss * 0.37).backward()
+    eff = pred * mask if with_mask else pred
+    want = host.smooth_l1_loss_with_sigma(eff.numpy().astype(np.float64), target.numpy().astype(np.float64), 3.0)
+    assert abs(float(loss) - float(want)) <= 1e-5 * max(1.0, abs(float(want)))
+    # gradient against autograd through the reference's own chain of tensor ops
+    q = pred.clone().double().requires_grad_(True)
+    ref = smooth_l1_loss_with_sigma(q * mask.double() if with_mask else q, target.double(), 3.0)
+    (ref * 0.37).backward()
+    assert torch.allclose(p.grad.cpu().double(), q.grad, rtol=1e-5, atol=1e-7)
+    # elements sitting exactly on the |d| = 1/sigma^2 switch take the linear branch on both sides
+    d = torch.tensor([1.0 / 9.0, -1.0 / 9.0, 0.0, 0.05])
+    z = torch.zeros(4)
+    got = float(smooth_l1_masked_sum(d.cuda(), None, z.cuda(), 3.0))
+    assert abs(got - float(smooth_l1_loss_with_sigma(d, z, 3.0))) < 1e-6
+
+
+@pytest.mark.parametrize("K,M", [(4, 1024), (4, 512), (1, 1), (3, 1500)])
+@pytest.mark.parametrize("label", ["row", "one", "zero", "const"])
+def test_bce_sigmoid_rows(cuda_lib, K, M, label):
+    import torch
+    import torch.nn.functional as F
+    from scda_b200.loss_ops import bce_sigmoid_rows
+    g = torch.Generator().manual_seed(K * 131 + M)
+    x = torch.randn(K, M, generator=g) * 4          # saturating logits included
+    x[0, 0] = 40.0                                  # p == 1 in fp32: the -100 clamp and the 1e-12 floor
+    if M > 1:
+        x[-1, -1] = -120.0                          # p == 0
+    if label == "row":
+        y = 0.8 + 0.2 * torch.rand(1, M, generator=g)
+    elif label == "const":
+        y = torch.full((1,), 0.15)
+    else:
+        y = torch.ones(1, M) if label == "one" else torch.zeros(1, M)
+    w = torch.rand(K, generator=g)
+    xa = x.cuda().requires_grad_(True)
+    out = bce_sigmoid_rows(xa, y.cuda())
+    (out * w.cuda()).sum().backward()
+    xr = x.clone().cuda().requires_grad_(True)       # the reference's chain, on the same device
+    p = torch.sigmoid(xr)
+    ref = F.binary_cross_entropy(p, y.cuda().expand_as(p) if y.numel() > 1 else y.cuda().expand(K, M),
+                                 reduction='none').mean(dim=1)
+    (ref * w.cuda()).sum().backward()
+    assert out.shape == (K,)
+    assert torch.allclose(out, ref.detach(), rtol=1e-5, atol=1e-6)
+    assert torch.allclose(xa.grad, xr.grad, rtol=1e-4, atol=1e-8)
+    # deterministic
+    assert torch.equal(bce_sigmoid_rows(x.cuda(), y.cuda()), out.detach())
