@@ -210,6 +210,7 @@ class SCDATrainer(object):
         self._side = None
         self._tside = None
         self._aside = None
+        self._pside = None
         if overlap and hasattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch"):
             # gradients are produced on whichever stream ran the forward of their branch and are
             # accumulated into the flat buffers there; the mismatch torch warns about is intended
@@ -226,10 +227,25 @@ class SCDATrainer(object):
             n.train()
 
     # ------------------------------------------------------------------ phases 1-3 (+ 4 forward)
-    def _seg_dis(self):
-        """(1) image discriminator: forward + backward (tools/faster_rcnn_train_val.py:567-611)"""
+    def _seg_dis(self, patch_stream=None, reduce=None):
+        """(1) image discriminator: forward + backward (tools/faster_rcnn_train_val.py:567-611).
+        With `patch_stream` the patch discriminator's two forwards AND its whole update (phase 2:
+        loss, backward, all-reduce, Adam) run on that stream beside this phase: phase 2 needs
+        nothing from phase 1, and phase 1 needs only the VALUE mean(patch(x_target)) from it."""
         b, st, ws = self._static, self._st, float(self.world_size)
         xs, xt, cs, ct = b['xs'], b['xt'], b['cs'], b['ct']
+        cur = torch.cuda.current_stream()
+        if patch_stream is not None:
+            patch_stream.wait_stream(cur)
+            with torch.cuda.stream(patch_stream):
+                st['t_patch_pro'] = self.dis_model_patch(xt)
+                t_patch_mean = torch.mean(st['t_patch_pro'], 1)
+                st['s_patch_pro'] = self.dis_model_patch(xs)
+                have_mean = torch.cuda.Event()
+                have_mean.record(patch_stream)
+                self._patch_update()
+                reduce(self.opt_dis_patch)
+                self.opt_dis_patch.step_dev()
         st['recon'] = self.dec_model(xs, xt)
         x_source_recon, x_target_recon = st['recon']
         self.opt_dis.zero_grad()
@@ -239,18 +255,21 @@ class SCDATrainer(object):
         score_1 = soft_label(1, s_real[:1])
         score_0 = soft_label(0, s_dis[:1])
         adloss_source = (_bce_rows(s_dis, score_1) + _bce_rows(s_real, score_0)).sum()
-        st['t_patch_pro'] = self.dis_model_patch(xt)
-        t_patch_mean = torch.mean(st['t_patch_pro'], 1)
-        st['s_patch_pro'] = self.dis_model_patch(xs)
+        if patch_stream is None:
+            st['t_patch_pro'] = self.dis_model_patch(xt)
+            t_patch_mean = torch.mean(st['t_patch_pro'], 1)
+            st['s_patch_pro'] = self.dis_model_patch(xs)
+        else:
+            cur.wait_event(have_mean)
+            t_patch_mean.record_stream(cur)
         adloss_target = (t_patch_mean * _bce_rows(t_dis, score_0) + _bce_rows(t_real, score_1)).sum()
         adloss = (adloss_source + adloss_target) / ws
         adloss.backward(retain_graph=True, inputs=self.opt_dis.params)
         st['dis_loss'] = adloss.detach()
 
-    def _seg_dis_patch(self):
-        """(1) step; (2) patch discriminator: loss + backward (:616-630)"""
+    def _patch_update(self):
+        """(2) patch discriminator: loss + backward (:616-630)"""
         st, ws = self._st, float(self.world_size)
-        self.opt_dis.step_dev()
         self.opt_dis_patch.zero_grad()
         score_0_patch = soft_label(0, st['t_patch_pro'])
         score_1_patch = soft_label(1, st['s_patch_pro'])
@@ -259,10 +278,18 @@ class SCDATrainer(object):
         dis_patch_loss.backward(retain_graph=True, inputs=self.opt_dis_patch.params)
         st['dis_patch_loss'] = dis_patch_loss.detach()
 
+    def _seg_dis_patch(self):
+        """(1) step; (2) patch discriminator update, in the reference's order"""
+        self.opt_dis.step_dev()
+        self._patch_update()
+
     def _seg_dec(self):
         """(2) step; (3) decoder: loss + backward (:635-699)"""
-        b, st, ws = self._static, self._st, float(self.world_size)
         self.opt_dis_patch.step_dev()
+        self._dec_update()
+
+    def _dec_update(self):
+        b, st, ws = self._static, self._st, float(self.world_size)
         self.opt_dec.zero_grad()
         x_source_recon, x_target_recon = st['recon']
         (s_dis2, t_dis2), on_real = run_pair(lambda: self.dis_model(x_source_recon, x_target_recon),
@@ -335,13 +362,29 @@ class SCDATrainer(object):
 
     # ------------------------------------------------------------------ the iteration
     def _gan_chain(self, reduce):
-        self._seg_dis()
-        reduce(self.opt_dis)
-        self._seg_dis_patch()
-        reduce(self.opt_dis_patch)
-        self._seg_dec()
+        if self.overlap and self.pair_streams and self._whole_graph():
+            # phase 2 beside phase 1 (see _seg_dis); the cut plan of world > 1 keeps the phases in
+            # the reference's order, one stretch each
+            cur = torch.cuda.current_stream()
+            helper = self._patch_stream()
+            self._seg_dis(patch_stream=helper, reduce=reduce)
+            reduce(self.opt_dis)
+            self.opt_dis.step_dev()
+            cur.wait_stream(helper)
+            self._dec_update()
+        else:
+            self._seg_dis()
+            reduce(self.opt_dis)
+            self._seg_dis_patch()
+            reduce(self.opt_dis_patch)
+            self._seg_dec()
         reduce(self.opt_dec)
         self._seg_fake()
+
+    def _patch_stream(self):
+        if self._pside is None:
+            self._pside = torch.cuda.Stream(device=self.opt.flat.device, priority=-1)
+        return self._pside
 
     def _det_chain(self, reduce):
         self._seg_det_backward()
