@@ -42,7 +42,6 @@ using namespace tcptx;
 constexpr int kTileH = 16;          // sub-tile = 8 wide x 16 tall = 128 pixels = the MMA's M
 constexpr int kSubW = 8;
 constexpr int kHaloH = kTileH + 2;
-constexpr int kAStages = 2;
 
 struct HaloParams {
     int H, W, Cred, N;           // Cred: channels of the A tensor (the reduction); N: output channels
@@ -55,8 +54,18 @@ struct HaloParams {
     int flags;
 };
 
+// Halo stages: with 64 output channels a tile retires its nine taps in ~2.3 k clocks, about the
+// latency of the next tile's 41 KB halo box (324 strided 128 B rows, streamed from HBM at the
+// conv1_x resolution), so two stages leave the MMA lane waiting; the narrow B ring of N = 64
+// leaves room for a third.
+template <int kBlockN>
+struct HaloAStages {
+    static constexpr int value = kBlockN == 64 ? 3 : 2;
+};
+
 template <int kBlockN, int kSub, int kBStages>
 struct HaloSmem {
+    static constexpr int kAStages = HaloAStages<kBlockN>::value;
     static constexpr int kHaloW = kSubW * kSub + 2;
     static constexpr int kABox = kHaloW * kHaloH * 128;                 // bytes one halo box delivers
     static constexpr int kABytes = (kABox + 1023) / 1024 * 1024;
@@ -127,6 +136,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                  const HaloParams p)
 {
     using L = HaloSmem<kBlockN, kSub, kBStages>;
+    constexpr int kAStages = L::kAStages;
+    constexpr bool kBRes = kBStages == 9;        // nine slots = the resident-weights form
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t *gen = smem_raw + (base - smem_u32(smem_raw));
@@ -173,7 +184,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 
     if (warp == 3) {
         // ---- A producer: one halo box per (tile, channel block)
-        if (lane == 0) {
+        if (elect_one()) {
             uint32_t it = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const HaloTile t = halo_tile<kBlockN, kSub>(p, tile);
@@ -188,14 +199,17 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         }
     } else if (warp == 0) {
         // ---- B producer: one weight tile per (tile, channel block, tap)
-        if (lane == 0) {
+        if (elect_one()) {
             uint32_t it = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            // kBRes: one channel block, one N tile -> the nine weight tiles are loaded ONCE and stay
+            // in their nine slots for every pixel tile this CTA walks
+            for (int tile = blockIdx.x; tile < (kBRes ? min(total_tiles, (int)blockIdx.x + 1) : total_tiles);
+                 tile += gridDim.x) {
                 const HaloTile t = halo_tile<kBlockN, kSub>(p, tile);
                 for (int cb = 0; cb < p.cblocks; ++cb) {
                     for (int tap = 0; tap < 9; ++tap, ++it) {
                         const int s = it % kBStages;
-                        mbar_wait(bar_bempty + s * 8, ((it / kBStages) & 1) ^ 1);
+                        if (!kBRes) mbar_wait(bar_bempty + s * 8, ((it / kBStages) & 1) ^ 1);
                         mbar_expect_tx(bar_bfull + s * 8, L::kBBytes);
                         const uint32_t b_dst = base + L::kBOffset + s * L::kBBytes;
                         if (kBMn) {
@@ -215,7 +229,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         }
     } else if (warp == 1) {
         // ---- MMA issuer
-        if (lane == 0) {
+        if (elect_one()) {
             constexpr uint32_t idesc = make_idesc(128, kBlockN, 0, kBMn ? 1 : 0);
             constexpr uint32_t kSbo = L::kHaloW * 128;
             // descriptors as (lo, hi) words: hi is constant, lo = start >> 4 (+ LBO field) and only
@@ -238,8 +252,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                     const uint32_t a_lo = a_lo0 + as * (L::kABytes >> 4);
 #pragma unroll
                     for (int tap = 0; tap < 9; ++tap, ++bit) {
-                        const uint32_t bs = bit % kBStages;
-                        mbar_wait(bar_bfull + bs * 8, (bit / kBStages) & 1);
+                        const uint32_t bs = kBRes ? (uint32_t)tap : bit % kBStages;
+                        // (resident: the slot's first and only phase; later waits return at once)
+                        mbar_wait(bar_bfull + bs * 8, kBRes ? 0u : (bit / kBStages) & 1);
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                         const uint32_t b_lo = b_lo0 + bs * (L::kBBytes >> 4);
                         const uint32_t first = (uint32_t)(cb | tap);
@@ -252,7 +267,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                                 umma_bf16_lohi(tmem_d + sub * kBlockN, a_lo + a_off + k * 2, a_hi, b_lo + k * kBk, b_hi,
                                                idesc, first | (uint32_t)k);
                         }
-                        umma_commit(bar_bempty + bs * 8);
+                        if (!kBRes) umma_commit(bar_bempty + bs * 8);
                     }
                     umma_commit(bar_aempty + as * 8);
                 }
@@ -312,7 +327,7 @@ int env_int(const char *name, int dflt)
 // Tile plan of the halo kernel for a layer: bn = N tile (64 | 128), sub = sub-tiles per CTA
 // (1 | 2); returns false where the per-tap kernel of gemm_tc.cu should be used instead.
 // scda_conv3x3_set_plan (or SCDA_CONV_HALO / SCDA_HALO_BN / SCDA_HALO_SUB at load) overrides it.
-static int g_enabled = -1, g_force_bn = 0, g_force_sub = 0;
+static int g_enabled = -1, g_force_bn = 0, g_force_sub = 0, g_resident = 1;
 
 static void plan_init()
 {
@@ -320,6 +335,7 @@ static void plan_init()
     g_enabled = env_int("SCDA_CONV_HALO", 1) ? 1 : 0;
     g_force_bn = env_int("SCDA_HALO_BN", 0);
     g_force_sub = env_int("SCDA_HALO_SUB", 0);
+    g_resident = env_int("SCDA_HALO_RESIDENT", 1);
 }
 
 SCDA_API int scda_conv3x3_set_plan(int halo, int block_n, int sub_tiles)
@@ -342,15 +358,17 @@ bool scda_conv_halo_plan(int NB, int H, int W, int Cred, int Nout, bool dgrad, i
     plan_init();
     if (!g_enabled || Cred % 64 || Nout % 64) return false;
     (void)dgrad;
+    // measured on B200 (profiles/r1_halobench_d_elect.jsonl): with the MMA lane issuing back to back,
+    // one sub-tile per CTA (twice the tiles, 256 TMEM columns) beats two for 128-wide N tiles; 64-channel
+    // outputs keep two sub-tiles (the weight tile is small, the halo overlap is what is left to save);
+    // layers with few pixels fall back to 64-wide N tiles to give ~every SM a tile
     int b = (Nout % 128 == 0) ? 128 : 64;
     const long long th = ceil_div(H, kTileH);
-    // two sub-tiles per CTA (half the weight bytes per pixel) while that still gives ~every SM a tile
-    int s = 2;
-    long long tiles = (long long)NB * th * ceil_div(W, 16) * (Nout / b);
+    int s = b == 64 ? 2 : 1;
+    long long tiles = (long long)NB * th * ceil_div(W, kSubW * s) * (Nout / b);
     if (tiles < (long long)num_sms() * 3 / 4) {
         s = 1;
-        tiles = (long long)NB * th * ceil_div(W, 8) * (Nout / b);
-        if (tiles < (long long)num_sms() * 3 / 4 && b == 128) b = 64;
+        if (b == 128) b = 64;
     }
     if (g_force_bn == 64 || (g_force_bn == 128 && Nout % 128 == 0)) b = g_force_bn;
     if (g_force_sub == 1 || g_force_sub == 2) s = g_force_sub;
@@ -374,6 +392,9 @@ int scda_conv_halo_launch(int NB, int H, int W, int Cred, int Nout, const void *
     p.bias = bias; p.out = out; p.ldc = Nout;
     p.mask_src = (const __nv_bfloat16 *)mask_src;
     p.flags = flags;
+    // 64 -> 64 channels (conv1_x and its data gradient): the whole 72 KB of weights stays in shared
+    // memory (a B ring of 8 KB tiles is latency bound there: 31 B/clk needed, ~1 us per TMA round trip)
+    const bool resident = p.cblocks == 1 && p.n_tiles == 1 && bn == 64 && g_resident != 0;
     CUtensorMap ma, mb;
     cuuint64_t da[4] = {(cuuint64_t)Cred, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)NB};
     cuuint64_t sa[3] = {(cuuint64_t)Cred * 2, (cuuint64_t)W * Cred * 2, (cuuint64_t)H * W * Cred * 2};
@@ -384,6 +405,8 @@ int scda_conv_halo_launch(int NB, int H, int W, int Cred, int Nout, const void *
         cuuint64_t db[2] = {(cuuint64_t)9 * Nout, (cuuint64_t)Cred}, sb[1] = {(cuuint64_t)9 * Nout * 2};
         cuuint32_t bb[2] = {64, 64};
         if (!make_map(&mb, w_krsc, 2, db, sb, bb)) return 0;
+        if (bn == 64 && resident) return sub == 1 ? launch_halo<64, 1, true, 9>(ma, mb, p, stream)
+                                                  : launch_halo<64, 2, true, 9>(ma, mb, p, stream);
         if (bn == 64) return sub == 1 ? launch_halo<64, 1, true, 8>(ma, mb, p, stream)
                                       : launch_halo<64, 2, true, 8>(ma, mb, p, stream);
         return sub == 1 ? launch_halo<128, 1, true, 8>(ma, mb, p, stream)
@@ -392,6 +415,8 @@ int scda_conv_halo_launch(int NB, int H, int W, int Cred, int Nout, const void *
     cuuint64_t db[2] = {(cuuint64_t)9 * Cred, (cuuint64_t)Nout}, sb[1] = {(cuuint64_t)9 * Cred * 2};
     cuuint32_t bb[2] = {64, (cuuint32_t)bn};
     if (!make_map(&mb, w_krsc, 2, db, sb, bb)) return 0;
+    if (bn == 64 && resident) return sub == 1 ? launch_halo<64, 1, false, 9>(ma, mb, p, stream)
+                                              : launch_halo<64, 2, false, 9>(ma, mb, p, stream);
     if (bn == 64) return sub == 1 ? launch_halo<64, 1, false, 8>(ma, mb, p, stream)
                                   : launch_halo<64, 2, false, 8>(ma, mb, p, stream);
     return sub == 1 ? launch_halo<128, 1, false, 8>(ma, mb, p, stream)

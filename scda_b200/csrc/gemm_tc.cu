@@ -208,7 +208,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (elect_one()) {
             const int cblocks = p.conv ? p.Cin / kBlockK : 0;
             // the barrier the loads complete on: this CTA's, or (pair) the leader's
             const uint32_t full_remote = kPair ? map_to_cta(bar_full, 0) : bar_full;
@@ -258,7 +258,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             }
         }
     } else if (warp == 1) {
-        if (lane == 0 && leader) {
+        if (elect_one() && leader) {
             constexpr uint32_t idesc = make_idesc(kBlockM * kCluster, kBlockN, 0, kBMn ? 1 : 0);
             // descriptors as (lo, hi) words: hi constant, lo = (start >> 4) | LBO field; between MMAs
             // only a constant is added to lo (conv_halo.cu has the measurement behind this)
@@ -502,7 +502,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (elect_one()) {
             for (int kb = kb0; kb < kb1; ++kb) {
                 const int it = kb - kb0, s = it % kStages;
                 const uint32_t ph = (it / kStages) & 1;
@@ -532,7 +532,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        if (elect_one()) {
             constexpr uint32_t idesc = make_idesc(kBlockM, kBlockN, 1, 1);
             const uint64_t proto = make_mnmajor_desc(0, L::kChunk);
             const uint32_t proto_lo = (uint32_t)proto, proto_hi = (uint32_t)(proto >> 32);
@@ -658,7 +658,7 @@ tc_wgrad3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (elect_one()) {
             for (int kb = kb0; kb < kb1; ++kb) {
                 const int it = kb - kb0, s = it % kStages;
                 const uint32_t ph = (it / kStages) & 1;
@@ -679,7 +679,7 @@ tc_wgrad3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        if (elect_one()) {
             constexpr uint32_t idesc = make_idesc(kBlockM, kBlockN, 1, 1);
             const uint64_t a_proto = make_mnmajor_desc(0, L::kAChunk), b_proto = make_mnmajor_desc(0, L::kBChunk);
             const uint32_t a_hi = (uint32_t)(a_proto >> 32), b_hi = (uint32_t)(b_proto >> 32);

@@ -194,6 +194,21 @@ __device__ __forceinline__ uint64_t make_kmajor_desc_ex(uint32_t saddr, uint32_t
     return d;
 }
 
+// one lane of a fully active warp (elect.sync): a branch on this predicate tells ptxas that exactly
+// one thread runs the tcgen05 / TMA instructions behind it, so it emits them without the
+// per-instruction ELECT / vote loop it wraps around `if (lane == 0)` code
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "elect.sync _|p, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n" : "=r"(pred));
+    return pred != 0;
+}
+
 // MMA with the two 64-bit shared-memory descriptors passed as (lo, hi) 32-bit halves: the issuing
 // lane keeps the constant high words in registers and only ADDS to the low word (the 14-bit
 // start-address field, addr >> 4) between MMAs — one integer add per operand instead of
