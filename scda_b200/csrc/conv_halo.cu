@@ -327,7 +327,7 @@ int env_int(const char *name, int dflt)
 // Tile plan of the halo kernel for a layer: bn = N tile (64 | 128), sub = sub-tiles per CTA
 // (1 | 2); returns false where the per-tap kernel of gemm_tc.cu should be used instead.
 // scda_conv3x3_set_plan (or SCDA_CONV_HALO / SCDA_HALO_BN / SCDA_HALO_SUB at load) overrides it.
-static int g_enabled = -1, g_force_bn = 0, g_force_sub = 0, g_resident = 1;
+static int g_enabled = -1, g_force_bn = 0, g_force_sub = 0, g_resident = 1, g_sub128 = 1;
 
 static void plan_init()
 {
@@ -336,6 +336,7 @@ static void plan_init()
     g_force_bn = env_int("SCDA_HALO_BN", 0);
     g_force_sub = env_int("SCDA_HALO_SUB", 0);
     g_resident = env_int("SCDA_HALO_RESIDENT", 1);
+    g_sub128 = env_int("SCDA_HALO_SUB128", 1) == 2 ? 2 : 1;
 }
 
 SCDA_API int scda_conv3x3_set_plan(int halo, int block_n, int sub_tiles)
@@ -364,7 +365,7 @@ bool scda_conv_halo_plan(int NB, int H, int W, int Cred, int Nout, bool dgrad, i
     // layers with few pixels fall back to 64-wide N tiles to give ~every SM a tile
     int b = (Nout % 128 == 0) ? 128 : 64;
     const long long th = ceil_div(H, kTileH);
-    int s = b == 64 ? 2 : 1;
+    int s = b == 64 ? 2 : g_sub128;
     long long tiles = (long long)NB * th * ceil_div(W, kSubW * s) * (Nout / b);
     if (tiles < (long long)num_sms() * 3 / 4) {
         s = 1;
