@@ -4,6 +4,7 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -262,6 +263,8 @@ inline EncodeTiledFn encode_fn()
     return fn;
 }
 
+// CTAs of a persistent tensor-core kernel = SMs of the device, or fewer with SCDA_TC_SM_LIMIT (experiment
+// knob: leave some SMs to the kernels of the other streams of the overlapped iteration)
 inline int num_sms()
 {
     static int n = 0;
@@ -270,6 +273,9 @@ inline int num_sms()
         if (cudaGetDevice(&dev) != cudaSuccess ||
             cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
             n = kNumSMs;
+        const char *e = getenv("SCDA_TC_SM_LIMIT");
+        const int lim = e && *e ? atoi(e) : 0;
+        if (lim > 0 && lim < n) n = lim;
     }
     return n;
 }
