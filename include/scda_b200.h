@@ -192,7 +192,8 @@ int scda_gemm_bf16_tn(int M, int N, int K, const void *A, long long lda, const v
 /* replaces the cuDNN convolution behind nn.Conv2d(k=3, s=1, p=1) (VGG backbone,
  * vgg_adver_expansion_cluster.py:101-114; RPN conv3x3, models/head.py:13):
  * x NHWC bf16 [NB,H,W,Cin], w bf16 [Cout][3][3][Cin], y NHWC [NB,H,W,Cout] bf16 or fp32.
- * Cin % 64 == 0, W % 8 == 0.  With the weights flipped and transposed by the caller the same
+ * Cin % 64 == 0, Cout % 32 == 0 (32 output channels ride in a 64-wide tile whose upper weight rows are TMA
+ * out-of-bounds zeros), W % 8 == 0.  With the weights flipped and transposed by the caller the same
  * entry point computes the data gradient; SCDA_TC_MASK_POS then applies the ReLU gradient of
  * the layer input (mask_src = that input, same shape as y). */
 int scda_conv3x3_bf16_nhwc(int NB, int H, int W, int Cin, int Cout, const void *x, const void *w_krsc,
@@ -203,7 +204,8 @@ int scda_conv3x3_bf16_nhwc(int NB, int H, int W, int Cin, int Cout, const void *
  * transposed copy is kept): dy NHWC bf16 [NB,H,W,Cout], w bf16 [Cout][3][3][Cin] ->
  * dx NHWC [NB,H,W,Cin] (bf16, or fp32 with SCDA_TC_OUT_F32).  The weights enter the MMA as an
  * MN-major operand with the tap mirrored.  SCDA_TC_MASK_POS applies the ReLU gradient of the
- * layer input (mask_src = that input).  Cin, Cout % 64 == 0, W % 8 == 0. */
+ * layer input (mask_src = that input).  Cin % 64 == 0, Cout % 32 == 0 (halo form; the per-tap form needs
+ * Cout % 64 == 0), W % 8 == 0. */
 int scda_conv3x3_dgrad_bf16_nhwc(int NB, int H, int W, int Cin, int Cout, const void *dy,
                                  const void *w_krsc, void *dx, int flags, const void *mask_src,
                                  cudaStream_t stream);
@@ -228,7 +230,7 @@ int scda_linear_wgrad_bf16(int rows, int Nout, int Kin, const void *dY, long lon
 /* weight gradient of the 3x3 convolution: x NHWC bf16 [NB,H,W,Cin], dy NHWC bf16
  * [NB,H,W,Cout] -> dw_partials fp32 [splits][Cout][3][3][Cin]; the pixel reduction is cut
  * into `splits` equal ranges of 128-pixel tiles (every slab is written; the caller sums
- * them, so the result does not depend on scheduling).  Cin, Cout % 64 == 0. */
+ * them, so the result does not depend on scheduling).  Cin % 64 == 0, Cout % 32 == 0. */
 int scda_conv3x3_wgrad_bf16_nhwc(int NB, int H, int W, int Cin, int Cout, const void *x, const void *dy,
                                  float *dw_partials, int splits, cudaStream_t stream);
 

@@ -357,8 +357,12 @@ SCDA_API int scda_conv3x3_set_plan(int halo, int block_n, int sub_tiles)
 bool scda_conv_halo_plan(int NB, int H, int W, int Cred, int Nout, bool dgrad, int *bn, int *sub)
 {
     plan_init();
-    if (!g_enabled || Cred % 64 || Nout % 64) return false;
-    (void)dgrad;
+    // forward: the reduction walks whole 64-channel blocks of a K-major weight row (tap, ci), so Cred
+    // must be a multiple of 64; 32 output channels ride in a 64-wide N tile whose upper weight rows are
+    // TMA out-of-bounds zeros.  Data gradient: 32 reduction channels (Cout_fwd = 32) are a 64-channel
+    // block whose upper half is zero-filled on BOTH operands (activation box and MN-major weight rows).
+    if (!g_enabled) return false;
+    if (dgrad ? (Cred % 32 || Nout % 64) : (Cred % 64 || Nout % 32)) return false;
     // measured on B200 (profiles/r1_halobench_d_elect.jsonl): with the MMA lane issuing back to back,
     // one sub-tile per CTA (twice the tiles, 256 TMEM columns) beats two for 128-wide N tiles; 64-channel
     // outputs keep two sub-tiles (the weight tile is small, the halo overlap is what is left to save);
@@ -366,7 +370,7 @@ bool scda_conv_halo_plan(int NB, int H, int W, int Cred, int Nout, bool dgrad, i
     int b = (Nout % 128 == 0) ? 128 : 64;
     const long long th = ceil_div(H, kTileH);
     int s = b == 64 ? 2 : g_sub128;
-    long long tiles = (long long)NB * th * ceil_div(W, kSubW * s) * (Nout / b);
+    long long tiles = (long long)NB * th * ceil_div(W, kSubW * s) * ceil_div(Nout, b);
     if (tiles < (long long)num_sms() * 3 / 4) {
         s = 1;
         if (b == 128) b = 64;
@@ -385,7 +389,7 @@ int scda_conv_halo_launch(int NB, int H, int W, int Cred, int Nout, const void *
     const int region_w = kSubW * sub;
     HaloParams p = {};
     p.H = H; p.W = W; p.Cred = Cred; p.N = Nout;
-    p.cblocks = Cred / 64;
+    p.cblocks = ceil_div(Cred, 64);
     p.tiles_w = ceil_div(W, region_w);
     p.tiles_h = ceil_div(H, kTileH);
     p.m_tiles = NB * p.tiles_h * p.tiles_w;

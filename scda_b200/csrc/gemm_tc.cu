@@ -854,7 +854,7 @@ SCDA_API int scda_conv3x3_dgrad_bf16_nhwc(int NB, int H, int W, int Cin, int Cou
     // dx[n,h,w,ci] = sum_{r,s,co} dy[n,h-(r-1),w-(s-1),co] W[co][r][s][ci]: the forward kernel with
     // A = dy, reduction over (tap, co), and B read from the FORWARD weights as an MN-major operand.
     if (NB <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0 || !dy || !w_krsc || !dx) return 0;
-    if (Cin % 64 || Cout % kBlockK) return 0;
+    if (Cin % 64 || Cout % 32) return 0;
     if ((flags & kFlagMaskPos) && !mask_src) return 0;
     if (flags & (kFlagAccumulate | kFlagMulSrc | kFlagRelu)) return 0;
     {
@@ -863,6 +863,7 @@ SCDA_API int scda_conv3x3_dgrad_bf16_nhwc(int NB, int H, int W, int Cin, int Cou
             return scda_conv_halo_launch(NB, H, W, Cout, Cin, dy, w_krsc, nullptr, dx, flags, mask_src, true, hbn,
                                          hsub, stream);
     }
+    if (Cout % kBlockK) return 0;              // (the per-tap form needs whole 64-channel blocks)
     int TW = 16, TH = 8;
     if (W % 16) {
         if (W % 8 == 0) { TW = 8; TH = 16; } else return 0;
@@ -965,7 +966,7 @@ SCDA_API int scda_conv3x3_wgrad_bf16_nhwc(int NB, int H, int W, int Cin, int Cou
 {
     // dw_partials: [splits][Cout][3][3][Cin] fp32; the caller sums the slabs
     if (NB <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0 || !x || !dy || !dw_partials || splits < 1) return 0;
-    if (Cin % 64 || Cout % 64) return 0;
+    if (Cin % 64 || Cout % 32) return 0;      // Cout = 32: the upper half of the 64-wide dY box is TMA zero fill
     int TW = 16, TH = 8;
     if (W % 16) {
         if (W % 8 == 0) { TW = 8; TH = 16; } else return 0;

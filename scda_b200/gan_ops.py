@@ -213,6 +213,9 @@ def run_pair(fa, fb):
 # Fusing the three layers into one node lets every tensor cross a kernel boundary in the dtype
 # its consumer wants (IN output / IN input-gradient in bf16 for the next MMA) with no cast pass.
 TC_GAN = os.environ.get("SCDA_GAN_TC", "1") != "0"
+# 32 output channels (the decoder's last 3x3 layer) ride in a 64-wide tile with TMA zero fill; "0" leaves that
+# layer on cuDNN (A/B knob)
+_TC_MIN_OUT = 64 if os.environ.get("SCDA_GAN_TC32", "1") == "0" else 32
 
 
 class _ConvINActTC(torch.autograd.Function):
@@ -280,7 +283,7 @@ def conv_in_act_tc_supported(x, conv):
     return (TC_GAN and x.is_cuda and x.dim() == 4 and x.dtype in (torch.float32, torch.bfloat16)
             and conv.kernel_size == (3, 3) and conv.stride == (1, 1) and conv.padding == (1, 1)
             and conv.dilation == (1, 1) and conv.groups == 1 and conv.padding_mode == 'zeros'
-            and conv.in_channels % 64 == 0 and conv.out_channels % 64 == 0 and conv.out_channels <= 1024
+            and conv.in_channels % 64 == 0 and conv.out_channels % _TC_MIN_OUT == 0 and conv.out_channels <= 1024
             and 1024 % conv.out_channels == 0 and x.shape[3] % 8 == 0
             and conv.weight.dtype == torch.float32)
 

@@ -8,7 +8,8 @@ pytestmark = pytest.mark.gpu
 
 PLANS = [(1, 64, 1), (1, 64, 2), (1, 128, 1), (1, 128, 2), (1, 0, 0), (0, 0, 0)]
 SHAPES = [(1, 16, 16, 64, 64), (1, 32, 64, 128, 128), (2, 32, 64, 64, 256), (1, 24, 40, 64, 192),
-          (1, 20, 24, 192, 128), (3, 16, 8, 128, 64), (1, 64, 128, 256, 512), (1, 48, 72, 64, 64)]
+          (1, 20, 24, 192, 128), (3, 16, 8, 128, 64), (1, 64, 128, 256, 512), (1, 48, 72, 64, 64),
+          (2, 32, 32, 64, 32), (1, 64, 64, 128, 32)]      # 32 output channels: the decoder's last 3x3 layer
 
 
 def _close(out, ref, rtol=1e-2):
@@ -57,6 +58,8 @@ def test_dgrad_all_plans(plan_reset, NB, H, W, Cin, Cout):
                                      dy.float().permute(0, 3, 1, 2), padding=1).permute(0, 2, 3, 1)
     refm = torch.where(x.float() > 0, ref, torch.zeros_like(ref))
     for halo, bn, sub in PLANS:
+        if not halo and Cout % 64:
+            continue                       # the per-tap form reduces over whole 64-channel blocks
         tc.set_conv_plan(halo, bn, sub)
         _close(tc.conv3x3_dgrad_nhwc(dy, w), ref)
         _close(tc.conv3x3_dgrad_nhwc(dy, w, mask_src=x), refm)

@@ -150,7 +150,7 @@ def test_decoder_tensor_core_path(cuda_lib, monkeypatch):
         return real(*a, **k)
     monkeypatch.setattr(common_net, "conv_in_act_tc", spy)
     ya, yb = dec(xa, xb)
-    assert len(calls) == 14, "6 residual convolutions + 1 up-sampling convolution per decoder"
+    assert len(calls) == 16, "6 residual convolutions + 2 up-sampling convolutions per decoder"
     (ya.square().mean() + yb.mean()).backward()
     monkeypatch.setattr(common_net, "conv_in_act_tc_supported", lambda x, conv: False)
     monkeypatch.setattr(common_net, "_fused_ok", lambda x: False)

@@ -125,7 +125,7 @@ def test_linear_wgrad(cuda_lib, rows, nout, kin):
 
 
 @pytest.mark.parametrize("NB,H,W,Cin,Cout", [(1, 8, 16, 64, 128), (1, 32, 64, 512, 512), (2, 32, 32, 128, 64),
-                                             (1, 64, 128, 64, 64), (1, 128, 256, 128, 256)])
+                                             (1, 64, 128, 64, 64), (1, 128, 256, 128, 256), (2, 64, 64, 64, 32)])
 def test_conv3x3_wgrad(cuda_lib, NB, H, W, Cin, Cout):
     import torch
     from scda_b200 import tc
