@@ -174,6 +174,18 @@ int scda_bce_sigmoid_rows_fwd(int K, int M, const float *logits, const float *la
 int scda_bce_sigmoid_rows_bwd(int K, int M, const float *logits, const float *labels, int label_stride,
                               const float *grad_rows, float *grad_logits, cudaStream_t stream);
 
+/* decoder head: nn.ConvTranspose2d(Cin = 32, Cout <= 4, kernel_size = 1) + nn.Tanh, the last two layers of each
+ * decoder (models/faster_rcnn/faster_rcnn_adver_expansion_reweight_cluster.py:380-383), one streaming pass each
+ * way.  x [P, Cin], y / dy [P, Cout], dx [P, Cin] fp32 with the channel innermost (channels-last); w [Cin][Cout]
+ * (the ConvTranspose2d weight [Cin, Cout, 1, 1] as stored); b [Cout] or NULL; dx may be NULL; dw [Cin][Cout],
+ * db [Cout] (or NULL) are overwritten.  Reductions in a fixed order (deterministic). */
+size_t scda_conv1x1_tanh_workspace_bytes(long long P, int Cin, int Cout);
+int scda_conv1x1_tanh_fwd(long long P, int Cin, int Cout, const float *x, const float *w, const float *b,
+                          float *y, cudaStream_t stream);
+int scda_conv1x1_tanh_bwd(long long P, int Cin, int Cout, const float *x, const float *w, const float *y,
+                          const float *dy, float *dx, float *dw, float *db, void *workspace,
+                          size_t workspace_bytes, cudaStream_t stream);
+
 /* --- tensor-core GEMM / 3x3 convolution (tcgen05 + TMA) ----------------- */
 /* flags for both entry points */
 #define SCDA_TC_RELU        1   /* y = max(y, 0)                                        */

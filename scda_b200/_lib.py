@@ -67,6 +67,9 @@ SIGNATURES = {
     "scda_smooth_l1_sigma_sum_bwd": (_i, [C.c_longlong, _p, _p, _p, _f, _p, _p, _p]),
     "scda_bce_sigmoid_rows_fwd": (_i, [_i, _i, _p, _p, _i, _p, _p]),
     "scda_bce_sigmoid_rows_bwd": (_i, [_i, _i, _p, _p, _i, _p, _p, _p]),
+    "scda_conv1x1_tanh_workspace_bytes": (_z, [C.c_longlong, _i, _i]),
+    "scda_conv1x1_tanh_fwd": (_i, [C.c_longlong, _i, _i, _p, _p, _p, _p, _p]),
+    "scda_conv1x1_tanh_bwd": (_i, [C.c_longlong, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _z, _p]),
     "scda_conv3x3_set_plan": (_i, [_i, _i, _i]),
     "scda_conv3x3_wgrad_set_form": (_i, [_i]),
     "scda_adam_step": (_i, [_p, _p, _p, _p, _p, C.c_longlong, _i, _f, _f, _f, _f, _f, _f, _p, _p]),
@@ -106,7 +109,7 @@ def load(path: str | None = None) -> C.CDLL:
 # the total inside its timed region as `gpu_launches`
 KERNELS_PER_CALL = {
     "scda_nms": 2, "scda_nms_dyn": 2, "scda_instnorm_act_fwd_nhwc_f32": 3, "scda_instnorm_act_bwd_nhwc_f32": 3,
-    "scda_instnorm_act_fwd_nhwc": 3, "scda_instnorm_act_bwd_nhwc": 3, "SoftmaxFocalLossForwardLaucher": 1,
+    "scda_instnorm_act_fwd_nhwc": 3, "scda_instnorm_act_bwd_nhwc": 3, "scda_conv1x1_tanh_bwd": 2, "SoftmaxFocalLossForwardLaucher": 1,
     "SoftmaxFocalLossBackwardLaucher": 1,
 }
 LAUNCHES = 0

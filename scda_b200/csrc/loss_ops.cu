@@ -146,3 +146,170 @@ SCDA_API int scda_bce_sigmoid_rows_bwd(int K, int M, const float *logits, const 
                                                                        grad_logits);
     return scda_launch_status();
 }
+
+// ---------------------------------------------------------------------------------------------------
+// Decoder head: nn.ConvTranspose2d(Cin, Cout, kernel_size=1) + nn.Tanh (the last two layers of each decoder,
+// models/faster_rcnn/faster_rcnn_adver_expansion_reweight_cluster.py:380-383 of the reference: 32 -> 3
+// channels over 4 x 256 x 256 pixels).  cuDNN / cuBLAS run this 0.05-GFLOP layer as GEMMs with a 3-wide
+// dimension (100 us for the data gradient alone); it is one streaming pass each way:
+//   forward : y[p, co] = tanh(b[co] + sum_ci x[p, ci] W[ci, co])                      (x, y channels-last)
+//   backward: g = dy * (1 - y^2);  dx[p, ci] = sum_co W[ci, co] g[co];
+//             dW[ci, co] = sum_p x[p, ci] g[co],  db[co] = sum_p g[co]  — per-thread register sums over a
+//             grid-stride pixel loop, a fixed-order block tree, one partial row per block, then a second
+//             kernel adds the block rows in order (deterministic).
+namespace {
+
+constexpr int kHeadCin = 32, kHeadCoutMax = 4, kHeadThreads = 256;
+
+template <int kCout>
+__global__ void __launch_bounds__(kHeadThreads)
+head_fwd_kernel(const float *__restrict__ x, const float *__restrict__ w, const float *__restrict__ b,
+                float *__restrict__ y, long long P)
+{
+    __shared__ float sw[kHeadCin * kCout + kCout];
+    for (int i = threadIdx.x; i < kHeadCin * kCout + kCout; i += kHeadThreads)
+        sw[i] = i < kHeadCin * kCout ? w[i] : (b ? b[i - kHeadCin * kCout] : 0.f);
+    __syncthreads();
+    for (long long p = (long long)blockIdx.x * kHeadThreads + threadIdx.x; p < P;
+         p += (long long)gridDim.x * kHeadThreads) {
+        float acc[kCout];
+#pragma unroll
+        for (int c = 0; c < kCout; ++c) acc[c] = sw[kHeadCin * kCout + c];
+        const float4 *xp = reinterpret_cast<const float4 *>(x + p * kHeadCin);
+#pragma unroll
+        for (int q = 0; q < kHeadCin / 4; ++q) {
+            const float4 v = ld_stream_f4(reinterpret_cast<const float *>(xp + q));
+            const float xv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+#pragma unroll
+                for (int c = 0; c < kCout; ++c) acc[c] = fmaf(xv[e], sw[(q * 4 + e) * kCout + c], acc[c]);
+        }
+#pragma unroll
+        for (int c = 0; c < kCout; ++c) y[p * kCout + c] = tanhf(acc[c]);
+    }
+}
+
+template <int kCout>
+__global__ void __launch_bounds__(kHeadThreads)
+head_bwd_kernel(const float *__restrict__ x, const float *__restrict__ w, const float *__restrict__ y,
+                const float *__restrict__ dy, float *__restrict__ dx, float *__restrict__ partial, long long P)
+{
+    constexpr int kNW = kHeadCin * kCout;
+    __shared__ float sw[kNW];
+    __shared__ float red[kHeadThreads / 32][kNW + kCout];
+    for (int i = threadIdx.x; i < kNW; i += kHeadThreads) sw[i] = w[i];
+    __syncthreads();
+    float aw[kNW], ab[kCout];
+#pragma unroll
+    for (int i = 0; i < kNW; ++i) aw[i] = 0.f;
+#pragma unroll
+    for (int c = 0; c < kCout; ++c) ab[c] = 0.f;
+    for (long long p = (long long)blockIdx.x * kHeadThreads + threadIdx.x; p < P;
+         p += (long long)gridDim.x * kHeadThreads) {
+        float g[kCout];
+#pragma unroll
+        for (int c = 0; c < kCout; ++c) {
+            const float yy = y[p * kCout + c];
+            g[c] = dy[p * kCout + c] * (1.f - yy * yy);
+            ab[c] += g[c];
+        }
+        const float4 *xp = reinterpret_cast<const float4 *>(x + p * kHeadCin);
+#pragma unroll
+        for (int q = 0; q < kHeadCin / 4; ++q) {
+            const float4 v = ld_stream_f4(reinterpret_cast<const float *>(xp + q));
+            const float xv[4] = {v.x, v.y, v.z, v.w};
+            float o[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                float s = 0.f;
+#pragma unroll
+                for (int c = 0; c < kCout; ++c) {
+                    s = fmaf(sw[(q * 4 + e) * kCout + c], g[c], s);
+                    aw[(q * 4 + e) * kCout + c] = fmaf(xv[e], g[c], aw[(q * 4 + e) * kCout + c]);
+                }
+                o[e] = s;
+            }
+            if (dx) *reinterpret_cast<float4 *>(dx + p * kHeadCin + q * 4) = make_float4(o[0], o[1], o[2], o[3]);
+        }
+    }
+    const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < kNW; ++i) {
+        const float s = warp_sum(aw[i]);
+        if (lane == 0) red[wp][i] = s;
+    }
+#pragma unroll
+    for (int c = 0; c < kCout; ++c) {
+        const float s = warp_sum(ab[c]);
+        if (lane == 0) red[wp][kNW + c] = s;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < kNW + kCout; i += kHeadThreads) {
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < kHeadThreads / 32; ++k) s += red[k][i];
+        partial[(long long)blockIdx.x * (kNW + kCout) + i] = s;
+    }
+}
+
+__global__ void head_bwd_final_kernel(const float *__restrict__ partial, int blocks, int n, float *__restrict__ dw,
+                                      float *__restrict__ db, int nw)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float s = 0.f;
+    for (int k = 0; k < blocks; ++k) s += partial[(long long)k * n + i];
+    if (i < nw) dw[i] = s; else if (db) db[i - nw] = s;
+}
+
+int head_blocks(long long P)
+{
+    long long b = (P + kHeadThreads - 1) / kHeadThreads;
+    const long long cap = (long long)kNumSMs * 4;
+    return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+}  // namespace
+
+SCDA_API size_t scda_conv1x1_tanh_workspace_bytes(long long P, int Cin, int Cout)
+{
+    if (P <= 0 || Cin != kHeadCin || Cout < 1 || Cout > kHeadCoutMax) return 0;
+    return sizeof(float) * (size_t)head_blocks(P) * (size_t)(Cin * Cout + Cout);
+}
+
+SCDA_API int scda_conv1x1_tanh_fwd(long long P, int Cin, int Cout, const float *x, const float *w, const float *b,
+                                   float *y, cudaStream_t stream)
+{
+    if (P <= 0 || Cin != kHeadCin || Cout < 1 || Cout > kHeadCoutMax || !x || !w || !y) return 0;
+    if ((uintptr_t)x % 16) return 0;
+    const int g = head_blocks(P);
+    switch (Cout) {
+    case 1: head_fwd_kernel<1><<<g, kHeadThreads, 0, stream>>>(x, w, b, y, P); break;
+    case 2: head_fwd_kernel<2><<<g, kHeadThreads, 0, stream>>>(x, w, b, y, P); break;
+    case 3: head_fwd_kernel<3><<<g, kHeadThreads, 0, stream>>>(x, w, b, y, P); break;
+    default: head_fwd_kernel<4><<<g, kHeadThreads, 0, stream>>>(x, w, b, y, P); break;
+    }
+    return scda_launch_status();
+}
+
+SCDA_API int scda_conv1x1_tanh_bwd(long long P, int Cin, int Cout, const float *x, const float *w, const float *y,
+                                   const float *dy, float *dx, float *dw, float *db, void *workspace,
+                                   size_t workspace_bytes, cudaStream_t stream)
+{
+    if (P <= 0 || Cin != kHeadCin || Cout < 1 || Cout > kHeadCoutMax || !x || !w || !y || !dy || !dw || !workspace)
+        return 0;
+    if (((uintptr_t)x % 16) || (dx && ((uintptr_t)dx % 16))) return 0;
+    if (workspace_bytes < scda_conv1x1_tanh_workspace_bytes(P, Cin, Cout)) return 0;
+    const int g = head_blocks(P);
+    float *part = (float *)workspace;
+    switch (Cout) {
+    case 1: head_bwd_kernel<1><<<g, kHeadThreads, 0, stream>>>(x, w, y, dy, dx, part, P); break;
+    case 2: head_bwd_kernel<2><<<g, kHeadThreads, 0, stream>>>(x, w, y, dy, dx, part, P); break;
+    case 3: head_bwd_kernel<3><<<g, kHeadThreads, 0, stream>>>(x, w, y, dy, dx, part, P); break;
+    default: head_bwd_kernel<4><<<g, kHeadThreads, 0, stream>>>(x, w, y, dy, dx, part, P); break;
+    }
+    const int n = Cin * Cout + Cout;
+    head_bwd_final_kernel<<<(n + 127) / 128, 128, 0, stream>>>(part, g, n, dw, db, Cin * Cout);
+    return scda_launch_status();
+}

@@ -293,3 +293,63 @@ def conv_in_act_tc(x, conv, act=None, negative_slope=0.01, eps=1e-5, out_bf16=Fa
     (fp32, or bf16 with out_bf16)."""
     return _ConvINActTC.apply(x, conv.weight, conv.bias, _ACT[act], float(negative_slope), float(eps),
                               bool(out_bf16))
+
+
+# ---------------------------------------------------------------------------------------
+# Decoder head: ConvTranspose2d(32 -> 3, k = 1) + Tanh as one streaming kernel each way
+# (csrc/loss_ops.cu: scda_conv1x1_tanh_*).
+class _Conv1x1Tanh(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        require_cuda(x)
+        if not x.is_contiguous(memory_format=torch.channels_last):
+            x = x.contiguous(memory_format=torch.channels_last)
+        N, Cin, H, W = x.shape
+        Cout = weight.shape[1]
+        w2 = weight.detach().reshape(Cin, Cout).contiguous()
+        y = torch.empty(N, H, W, Cout, dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            check(load().scda_conv1x1_tanh_fwd(N * H * W, Cin, Cout, x.data_ptr(), w2.data_ptr(),
+                                               bias.data_ptr() if bias is not None else None, y.data_ptr(),
+                                               stream_ptr(x.device)), "scda_conv1x1_tanh_fwd")
+        ctx.save_for_backward(x, w2, y)
+        ctx.has_bias = bias is not None
+        ctx.wshape = tuple(weight.shape)
+        return y.permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w2, y = ctx.saved_tensors
+        N, Cin, H, W = x.shape
+        Cout = w2.shape[1]
+        dy = dy.float()
+        if not dy.is_contiguous(memory_format=torch.channels_last):
+            dy = dy.contiguous(memory_format=torch.channels_last)
+        lib = load()
+        P = N * H * W
+        wsb = lib.scda_conv1x1_tanh_workspace_bytes(P, Cin, Cout)
+        ws = torch.empty(wsb, dtype=torch.uint8, device=x.device)
+        dx = torch.empty(N, H, W, Cin, dtype=torch.float32, device=x.device) if ctx.needs_input_grad[0] else None
+        dw = torch.empty(Cin, Cout, dtype=torch.float32, device=x.device)
+        db = torch.empty(Cout, dtype=torch.float32, device=x.device) if ctx.has_bias else None
+        with torch.cuda.device(x.device):
+            check(lib.scda_conv1x1_tanh_bwd(P, Cin, Cout, x.data_ptr(), w2.data_ptr(), y.data_ptr(), dy.data_ptr(),
+                                            dx.data_ptr() if dx is not None else None, dw.data_ptr(),
+                                            db.data_ptr() if db is not None else None, ws.data_ptr(), wsb,
+                                            stream_ptr(x.device)), "scda_conv1x1_tanh_bwd")
+        return (dx.permute(0, 3, 1, 2) if dx is not None else None), dw.view(ctx.wshape), db
+
+
+def conv1x1_tanh_supported(x, convt):
+    return (TC_GAN and x.is_cuda and x.dim() == 4 and x.dtype == torch.float32 and convt.in_channels == 32
+            and 1 <= convt.out_channels <= 4 and convt.kernel_size == (1, 1) and convt.stride == (1, 1)
+            and convt.padding == (0, 0) and convt.output_padding == (0, 0) and convt.groups == 1
+            and convt.weight.dtype == torch.float32)
+
+
+def conv1x1_tanh(x, convt):
+    """tanh(convt(x)) for an nn.ConvTranspose2d(32, <= 4, kernel_size=1); returns a channels_last tensor
+    tagged `_scda_tanh_applied` so that the nn.Tanh module behind it passes it through."""
+    y = _Conv1x1Tanh.apply(x, convt.weight, convt.bias)
+    y._scda_tanh_applied = True
+    return y

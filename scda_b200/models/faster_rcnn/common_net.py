@@ -6,8 +6,9 @@ Module / parameter names match the reference so state dicts are interchangeable.
 import torch
 import torch.nn as nn
 
-from ...gan_ops import (conv2d_bias_cl, conv_bias_supported, conv_in_act_tc, conv_in_act_tc_supported,
-                        instance_norm_act, supported as _fused_ok, upsample_bilinear2x, upsample_supported)
+from ...gan_ops import (conv1x1_tanh, conv1x1_tanh_supported, conv2d_bias_cl, conv_bias_supported, conv_in_act_tc,
+                        conv_in_act_tc_supported, instance_norm_act, supported as _fused_ok, upsample_bilinear2x,
+                        upsample_supported)
 
 
 class Conv2dCL(nn.Conv2d):
@@ -124,9 +125,22 @@ class ConvTranspose1x1(nn.ConvTranspose2d):
     per call (profiles/r1_launches_b_*: cutlass_80 s1688gemm tn_align1); the convolution
     form takes the regular wgrad path."""
 
+    fuse_tanh = False      # set by the decoder when an nn.Tanh follows: one kernel computes both
+
     def forward(self, x, output_size=None):
         assert self.kernel_size == (1, 1) and self.stride == (1, 1) and self.padding == (0, 0)
+        if self.fuse_tanh and conv1x1_tanh_supported(x, self):
+            return conv1x1_tanh(x, self)         # tagged: the TanhAfterHead behind it passes it through
         return nn.functional.conv2d(x, self.weight.permute(1, 0, 2, 3), self.bias)
+
+
+class TanhAfterHead(nn.Tanh):
+    """nn.Tanh, except that a tensor the fused decoder head already passed through tanh is returned as is."""
+
+    def forward(self, x):
+        if getattr(x, "_scda_tanh_applied", False):
+            return x
+        return super(TanhAfterHead, self).forward(x)
 
 
 class LeakyReLUConv2d(nn.Module):

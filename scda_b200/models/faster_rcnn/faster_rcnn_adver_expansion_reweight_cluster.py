@@ -24,7 +24,7 @@ from ...functions.proposal_target import compute_proposal_targets, proposal_targ
 from ...functions.rpn_proposal import compute_rpn_proposals, rpn_proposals_device
 from ...gan_ops import run_pair
 from ...loss_ops import smooth_l1_masked_sum
-from .common_net import (ConvTranspose1x1, INSResBlock, LeakyReLUConv2d, LeakyReLUConvTranspose2d_2,
+from .common_net import (ConvTranspose1x1, TanhAfterHead, INSResBlock, LeakyReLUConv2d, LeakyReLUConvTranspose2d_2,
                          LinUnsRes_cluster, ResDis_cluster, gaussian_weights_init)
 
 logger = logging.getLogger('global')
@@ -354,8 +354,10 @@ class GAN_decoder_AE(nn.Module):
                 dec += [LeakyReLUConvTranspose2d_2(tch, tch // 2, kernel_size=3, stride=1,
                                                    padding=1, output_padding=0)]
                 tch = tch // 2
-            dec += [ConvTranspose1x1(tch, input_dim_b, kernel_size=1, stride=1, padding=0)]
-            dec += [nn.Tanh()]
+            head = ConvTranspose1x1(tch, input_dim_b, kernel_size=1, stride=1, padding=0)
+            head.fuse_tanh = True
+            dec += [head]
+            dec += [TanhAfterHead()]
             return nn.Sequential(*dec)
 
         # construction order B then A, as in the reference (it fixes the RNG stream of the init)

@@ -80,6 +80,7 @@ def test_decoder_fused_equals_torch_modules(cuda_lib, monkeypatch):
     (ya.square().mean() + yb.mean()).backward()
     monkeypatch.setattr(common_net, "_fused_ok", lambda x: False)
     monkeypatch.setattr(common_net, "upsample_supported", lambda x, s, m: False)
+    monkeypatch.setattr(common_net, "conv1x1_tanh_supported", lambda x, c: False)
     ra, rb = ref(xa, xb)
     (ra.square().mean() + rb.mean()).backward()
     assert ya.shape == (4, 3, 256, 256)
@@ -155,6 +156,7 @@ def test_decoder_tensor_core_path(cuda_lib, monkeypatch):
     monkeypatch.setattr(common_net, "conv_in_act_tc_supported", lambda x, conv: False)
     monkeypatch.setattr(common_net, "_fused_ok", lambda x: False)
     monkeypatch.setattr(common_net, "upsample_supported", lambda x, s, m: False)
+    monkeypatch.setattr(common_net, "conv1x1_tanh_supported", lambda x, c: False)
     ra, rb = ref(xr, xb)
     (ra.square().mean() + rb.mean()).backward()
     assert _rel(ya, ra) < 5e-2 and _rel(yb, rb) < 5e-2
@@ -198,3 +200,33 @@ def test_instance_norm_bf16_io(cuda_lib, dy_bf16, dx_bf16):
                                          mean.data_ptr(), rstd.data_ptr(), dx.data_ptr(), 1 if dx_bf16 else 0, 2, 0.01,
                                          ws.data_ptr(), wsb, stream_ptr()), "bwd")
     assert torch.equal(dx, dx_ref.bfloat16() if dx_bf16 else dx_ref)
+
+
+@pytest.mark.parametrize("cout,hw,bias", [(3, 256, True), (3, 40, False), (1, 64, True), (4, 33, True)])
+def test_decoder_head_conv1x1_tanh(cuda_lib, cout, hw, bias):
+    """scda_conv1x1_tanh_{fwd,bwd} = nn.ConvTranspose2d(32, cout, 1) + nn.Tanh (fp32, 1e-5 relative)."""
+    import torch
+    from scda_b200.gan_ops import conv1x1_tanh, conv1x1_tanh_supported
+    torch.manual_seed(cout * 100 + hw)
+    convt = torch.nn.ConvTranspose2d(32, cout, 1, bias=bias).cuda()
+    x = torch.randn(4, 32, hw, hw, device="cuda").contiguous(memory_format=torch.channels_last)
+    dy = torch.randn(4, cout, hw, hw, device="cuda")
+    assert conv1x1_tanh_supported(x, convt)
+    xa = x.clone().requires_grad_(True)
+    y = conv1x1_tanh(xa, convt)
+    assert getattr(y, "_scda_tanh_applied", False) and y.shape == (4, cout, hw, hw)
+    y.backward(dy)
+    got = [xa.grad.clone(), convt.weight.grad.clone()] + ([convt.bias.grad.clone()] if bias else [])
+    convt.zero_grad()
+    xr = x.clone().double().requires_grad_(True)
+    ref_mod = torch.nn.ConvTranspose2d(32, cout, 1, bias=bias).cuda().double()
+    ref_mod.load_state_dict({k: v.double() for k, v in convt.state_dict().items()})
+    r = torch.tanh(ref_mod(xr))
+    r.backward(dy.double())
+    want = [xr.grad, ref_mod.weight.grad] + ([ref_mod.bias.grad] if bias else [])
+    assert _rel(y.double(), r.detach()) < 1e-5
+    for a, b in zip(got, want):
+        assert _rel(a.double(), b) < 2e-5
+    # deterministic
+    y2 = conv1x1_tanh(x.clone().requires_grad_(True), convt)
+    assert torch.equal(y2, y.detach())
