@@ -43,6 +43,15 @@ __device__ __forceinline__ bool suppresses(float ax1, float ay1, float ax2, floa
     const float h = fmaxf(__fadd_rn(__fsub_rn(bottom, top), 1.f), 0.f);
     const float inter = __fmul_rn(w, h);
     const float den = __fsub_rn(__fmaf_rn(b.w, b.h, Sa), inter);
+    // The verdict must be that of the IEEE division.  Most pairs do not need it: disjoint boxes
+    // (inter == 0: 0 / den > thresh is false for any den when thresh >= 0), and pairs whose
+    // approximate quotient (2 ulp) is further than 1e-6 relative from the threshold.
+    if (thresh >= 0.f && den > 0.f) {
+        if (!(inter > 0.f)) return false;
+        const float q = __fdividef(inter, den);
+        if (q > thresh * 1.000001f) return true;
+        if (q < thresh * 0.999999f) return false;
+    }
     return __fdiv_rn(inter, den) > thresh;
 }
 
