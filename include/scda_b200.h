@@ -154,6 +154,17 @@ int scda_softmax_focal_loss_sum(const int N, const float *logits, const int *tar
                                 const int num_classes, float *losses, float *priors,
                                 float *loss_sum, cudaStream_t stream);
 
+/* --- RPN proposal decode ------------------------------------------------ */
+/* the stretch of compute_rpn_proposals between the top-k and the NMS (functions/rpn_proposal.py:53-64,
+ * utils/bbox_helper.py:88-111): rows i < pre take anchor / delta order[i]; decode in the reference's dtypes
+ * (float32 exp, float64 products, every operation rounded on its own), clip to [0, img_w - 1] x [0, img_h - 1],
+ * drop boxes with w + 1 or h + 1 < min_size, compact the survivors in order into packed[pre][5] =
+ * (x1, y1, x2, y2, score) float32 (zero rows behind them) and write their number to count[0].
+ * anchors [KA][4] float64, deltas [KA][4] float32, order [pre] int64, top_scores [pre]. */
+int scda_rpn_decode_pack(int pre, const double *anchors, const float *deltas, const long long *order,
+                         const float *top_scores, double img_h, double img_w, double min_size, float *packed,
+                         int *count, cudaStream_t stream);
+
 /* --- fused detector / adversarial losses -------------------------------- */
 /* smooth_l1_loss_with_sigma(pred * mask, target) of the reference
  * (models/faster_rcnn/faster_rcnn_adver_expansion_reweight_cluster.py:238-246; RPN :54-55, RCNN :64-66):

@@ -15,6 +15,7 @@ returning fixed-capacity device buffers plus counts for the in-graph training pa
 import numpy as np
 import torch
 
+from .._lib import check, load, stream_ptr
 from ..extensions._nms.pth_nms import nms_device
 from ..utils import anchor_helper
 from ..utils.bbox_helper import clip_t, decode_t
@@ -50,16 +51,16 @@ def rpn_proposals_device(conv_cls, conv_loc, cfg, image_info):
         else:
             top, order = torch.topk(scores, pre, sorted=True)
         h, w = _image_hw(image_info, b)
-        boxes = clip_t(decode_t(anchors[order], loc_view[b][order].float()), h, w)   # float64
-        ms = cfg['roi_min_size']
-        ok = ((boxes[:, 2] - boxes[:, 0] + 1) >= ms) & ((boxes[:, 3] - boxes[:, 1] + 1) >= ms)
-        n = boxes.shape[0]
-        pos = torch.cumsum(ok.to(torch.int64), 0)
-        count = pos[-1].to(torch.int32).reshape(1)
-        packed = torch.zeros(n + 1, 5, dtype=torch.float32, device=dev)
-        rows = torch.cat([boxes.float(), top.float().unsqueeze(1)], dim=1)
-        packed.index_copy_(0, torch.where(ok, pos - 1, torch.full_like(pos, n)), rows)
-        packed = packed[:n].contiguous()
+        n = int(order.shape[0])
+        # decode + clip + min-size filter + stable compaction: one kernel (csrc/proposal_ops.cu)
+        packed = torch.empty(n, 5, dtype=torch.float32, device=dev)
+        count = torch.empty(1, dtype=torch.int32, device=dev)
+        deltas = loc_view[b].float().contiguous()
+        with torch.cuda.device(dev):
+            check(load().scda_rpn_decode_pack(n, anchors.data_ptr(), deltas.data_ptr(), order.data_ptr(),
+                                              top.float().contiguous().data_ptr(), float(h), float(w),
+                                              float(cfg['roi_min_size']), packed.data_ptr(), count.data_ptr(),
+                                              stream_ptr(dev)), "scda_rpn_decode_pack")
         keep, n_keep = nms_device(packed, cfg['nms_iou_thresh'], max_keep=max(post, 0),
                                   n_dev=count)
         cap = min(post, n) if post > 0 else n
