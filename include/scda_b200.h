@@ -165,6 +165,12 @@ int scda_rpn_decode_pack(int pre, const double *anchors, const float *deltas, co
                          const float *top_scores, double img_h, double img_w, double min_size, float *packed,
                          int *count, cudaStream_t stream);
 
+/* crops around the cluster centres (tools/faster_rcnn_train_val.py:411-438, 528-557): K windows of R x R pixels,
+ * corner = clamp(int(centre) - R/2, 0, size - R) per axis, gathered from image [C, H, W] fp32 into
+ * out [K, C, R, R]; centers [K][2] = (x, y) fp32 on the device.  R even, R <= H, W. */
+int scda_crop_regions(int K, int C, int H, int W, int R, const float *image, const float *centers, float *out,
+                      cudaStream_t stream);
+
 /* --- fused detector / adversarial losses -------------------------------- */
 /* smooth_l1_loss_with_sigma(pred * mask, target) of the reference
  * (models/faster_rcnn/faster_rcnn_adver_expansion_reweight_cluster.py:238-246; RPN :54-55, RCNN :64-66):

@@ -101,3 +101,43 @@ SCDA_API int scda_rpn_decode_pack(int pre, const double *anchors, const float *d
                                                   packed, count);
     return scda_launch_status();
 }
+
+// ---------------------------------------------------------------------------------------------------
+// Crops around the cluster centres: `get_corner_from_center` + the slicing loop of the reference driver
+// (tools/faster_rcnn_train_val.py:411-438, 528-557).  The branchy corner rule is a clamp of
+// int(c) - R/2 to [0, size - R]; centres stay on the device.  out[k, c, y, x] = image[c, y1_k + y, x1_k + x].
+namespace {
+
+__global__ void __launch_bounds__(256)
+crop_regions_kernel(const float *__restrict__ image, const float *__restrict__ centers, float *__restrict__ out,
+                    int K, int C, int H, int W, int R)
+{
+    const long long total = (long long)K * C * R * R;
+    const int half = R / 2;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int x = (int)(i % R);
+        long long t = i / R;
+        const int y = (int)(t % R);
+        t /= R;
+        const int c = (int)(t % C), k = (int)(t / C);
+        long long x1 = (long long)centers[2 * k] - half, y1 = (long long)centers[2 * k + 1] - half;
+        x1 = x1 < 0 ? 0 : (x1 > W - R ? W - R : x1);
+        y1 = y1 < 0 ? 0 : (y1 > H - R ? H - R : y1);
+        out[i] = __ldg(image + ((long long)c * H + (y1 + y)) * W + (x1 + x));
+    }
+}
+
+}  // namespace
+
+SCDA_API int scda_crop_regions(int K, int C, int H, int W, int R, const float *image, const float *centers,
+                               float *out, cudaStream_t stream)
+{
+    if (K <= 0 || C <= 0 || R <= 0 || R > H || R > W || (R & 1) || !image || !centers || !out) return 0;
+    const long long total = (long long)K * C * R * R;
+    long long blocks = (total + 255) / 256;
+    const long long cap = (long long)kNumSMs * 16;
+    if (blocks > cap) blocks = cap;
+    crop_regions_kernel<<<(unsigned)blocks, 256, 0, stream>>>(image, centers, out, K, C, H, W, R);
+    return scda_launch_status();
+}

@@ -548,6 +548,16 @@ def crops_device(image, centers, recon_size, new_w, new_h):
     if not torch.is_tensor(centers):
         centers = torch.as_tensor(np.asarray(centers), dtype=torch.float32, device=image.device)
     assert recon_size % 2 == 0 and image.shape[0] == 1
+    if (image.is_cuda and image.dtype == torch.float32 and image.is_contiguous() and centers.is_cuda
+            and tuple(image.shape[2:]) == (new_h, new_w)):
+        # one gather kernel (csrc/proposal_ops.cu) instead of ~13 index / arange / clamp launches
+        cen = centers.float().contiguous()
+        K, C = cen.shape[0], image.shape[1]
+        out = torch.empty(K, C, recon_size, recon_size, dtype=torch.float32, device=image.device)
+        with torch.cuda.device(image.device):
+            check(load().scda_crop_regions(K, C, new_h, new_w, recon_size, image.data_ptr(), cen.data_ptr(),
+                                           out.data_ptr(), stream_ptr(image.device)), "scda_crop_regions")
+        return out
     half = recon_size // 2
     x1 = (centers[:, 0].to(torch.int64) - half).clamp(0, new_w - recon_size)
     y1 = (centers[:, 1].to(torch.int64) - half).clamp(0, new_h - recon_size)

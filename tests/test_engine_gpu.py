@@ -146,3 +146,19 @@ def test_direct_gradient_sink_equals_autograd_gradients(cuda_lib):
         assert g is not None, n
         tol = 1e-4 * float(g.abs().max()) + 1e-7
         assert float((d - g).abs().max()) <= tol, (n, float((d - g).abs().max()), tol)
+
+
+def test_crops_kernel_equals_reference_corner_rule(cuda_lib):
+    """scda_crop_regions against the reference's get_corner_from_center + slicing
+    (tools/faster_rcnn_train_val.py:411-438, 528-557), centres at and beyond every border."""
+    import torch
+    from scda_b200.engine import _crops, crops_device, get_corner_from_center
+    Hh, Ww, R = 512, 1024, 256
+    g = torch.Generator().manual_seed(4)
+    image = torch.randn(1, 3, Hh, Ww, generator=g)
+    centers = np.array([[0.0, 0.0], [1023.9, 511.9], [127.99, 128.0], [128.0, 127.99], [896.0, 384.0],
+                        [895.99, 383.99], [512.5, 256.5], [900.2, 10.7], [3.3, 500.1]], np.float32)
+    want = _crops(image, get_corner_from_center(centers, R, Ww, Hh), R)
+    got = crops_device(image.cuda(), torch.from_numpy(centers).cuda(), R, Ww, Hh)
+    assert got.shape == (len(centers), 3, R, R)
+    assert torch.equal(got.cpu(), want)
