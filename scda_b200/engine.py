@@ -18,7 +18,15 @@ Mechanism differences (results are the same):
     compute the stray gradients the reference accumulates into the other networks and
     then discards with the next zero_grad();
   * the "Max Grad" logging loops (:607-611, 695-699, 741-745: one host sync per parameter
-    tensor) are off unless asked for.
+    tensor) are off unless asked for;
+  * the phases that do not depend on each other run side by side on separate CUDA streams
+    (`overlap`): the target-image branch of the detector forward beside the source branch, the
+    anchor targets beside the backbone, the detector's backward + Adam (phase 4) beside phases
+    1-3 — the cluster features are detached (functions/mask.py:234), so phase 4's gradient never
+    depended on them — and phase 2 beside phase 1.  The whole iteration, all streams included,
+    is replayed from one CUDA graph (world 1) or from eight graphs cut at the four gradient
+    all-reduces (world > 1).  `overlap=False` gives the reference's single-stream order; the
+    tests compare the two.
 """
 from __future__ import annotations
 
