@@ -323,7 +323,7 @@ def our_arm(args):
                            "execution": ("eager" if args.no_graphs else
                                          "one CUDA graph per iteration" + (", NCCL all-reduces captured" if world > 1 else "")
                                          if tr._whole_graph() else
-                                         "eight CUDA graphs per iteration, cut at the gradient all-reduces "
+                                         "eleven CUDA graphs per iteration on three streams, cut at the gradient all-reduces "
                                          "(NCCL issued between them)")
                            + (", detector backward + Adam overlapped with the reconstruction/discriminator "
                               "updates on a second stream, target-image branch beside the source branch"

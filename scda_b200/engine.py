@@ -235,7 +235,14 @@ class SCDATrainer(object):
             n.train()
 
     # ------------------------------------------------------------------ phases 1-3 (+ 4 forward)
-    def _seg_dis(self, patch_stream=None, reduce=None):
+    def _seg_patch_fwd(self):
+        """forwards of the patch discriminator on both cluster-feature blocks (used by phases 1 and 2)"""
+        b, st = self._static, self._st
+        st['t_patch_pro'] = self.dis_model_patch(b['xt'])
+        st['t_patch_mean'] = torch.mean(st['t_patch_pro'], 1)
+        st['s_patch_pro'] = self.dis_model_patch(b['xs'])
+
+    def _seg_dis(self, patch_stream=None, reduce=None, patch_done=False):
         """(1) image discriminator: forward + backward (tools/faster_rcnn_train_val.py:567-611).
         With `patch_stream` the patch discriminator's two forwards AND its whole update (phase 2:
         loss, backward, all-reduce, Adam) run on that stream beside this phase: phase 2 needs
@@ -263,7 +270,9 @@ class SCDATrainer(object):
         score_1 = soft_label(1, s_real[:1])
         score_0 = soft_label(0, s_dis[:1])
         adloss_source = (_bce_rows(s_dis, score_1) + _bce_rows(s_real, score_0)).sum()
-        if patch_stream is None:
+        if patch_done:                       # cut plan: an earlier stretch on the patch stream ran them
+            t_patch_mean = st['t_patch_mean']
+        elif patch_stream is None:
             st['t_patch_pro'] = self.dis_model_patch(xt)
             t_patch_mean = torch.mean(st['t_patch_pro'], 1)
             st['s_patch_pro'] = self.dis_model_patch(xs)
@@ -311,7 +320,7 @@ class SCDATrainer(object):
         recon_loss = (fake_loss1_source + fake_loss1_target) / ws
         recon_loss.backward(inputs=self.opt_dec.params)
         st['dec_loss'] = recon_loss.detach()
-        st.pop('recon'), st.pop('t_patch_pro'), st.pop('s_patch_pro')
+        st.pop('recon'), st.pop('t_patch_pro'), st.pop('s_patch_pro'), st.pop('t_patch_mean', None)
 
     def _seg_fake(self):
         """(3) step; forward of (4): decoders swapped, values only (:704-732).  The cluster
@@ -444,16 +453,28 @@ class SCDATrainer(object):
 
     def _segments(self):
         """world > 1 with the collectives NOT captured: the iteration cut at its four gradient
-        all-reduces -> (stretch, stream it runs on, optimiser whose gradients are all-reduced
-        after it).  With `overlap` the reconstruction / discriminator stretches replay on the side
-        stream beside the detector's backward; the collectives are issued from the host in one
-        fixed order on every rank (dis, patch, dec, detector)."""
-        side = 'side' if self.overlap else 'main'
+        all-reduces -> (name, stretch, stream it replays on, optimiser whose gradients are
+        all-reduced after it).  With `overlap` three streams replay side by side: `main` (detector
+        backward + Adam), `side` (phases 1, 3 and the forward of 4) and `patch` (the patch
+        discriminator's forwards and phase 2); the collectives are issued from the host in one
+        fixed order on every rank (patch, dis, dec, detector)."""
+        if not self.overlap:
+            return (('fwd', self._seg_forward, 'main', None),
+                    ('dis', self._seg_dis, 'main', self.opt_dis),
+                    ('dis_patch', self._seg_dis_patch, 'main', self.opt_dis_patch),
+                    ('dec', self._seg_dec, 'main', self.opt_dec),
+                    ('fake', self._seg_fake, 'main', None),
+                    ('det_bwd', self._seg_det_backward, 'main', self.opt),
+                    ('step', self._seg_step, 'main', None),
+                    ('out', self._seg_outputs, 'main', None))
         return (('fwd', self._seg_forward, 'main', None),
-                ('dis', self._seg_dis, side, self.opt_dis),
-                ('dis_patch', self._seg_dis_patch, side, self.opt_dis_patch),
-                ('dec', self._seg_dec, side, self.opt_dec),
-                ('fake', self._seg_fake, side, None),
+                ('patch_fwd', self._seg_patch_fwd, 'patch', None),
+                ('patch_upd', self._patch_update, 'patch', self.opt_dis_patch),
+                ('patch_step', self.opt_dis_patch.step_dev, 'patch', None),
+                ('dis', lambda: self._seg_dis(patch_done=True), 'side', self.opt_dis),
+                ('dis_step', self.opt_dis.step_dev, 'side', None),
+                ('dec', self._dec_update, 'side', self.opt_dec),
+                ('fake', self._seg_fake, 'side', None),
                 ('det_bwd', self._seg_det_backward, 'main', self.opt),
                 ('step', self._seg_step, 'main', None),
                 ('out', self._seg_outputs, 'main', None))
@@ -476,7 +497,7 @@ class SCDATrainer(object):
             with torch.cuda.graph(g, pool=torch.cuda.graph_pool_handle()):
                 self._body(reduce)
             return [g]
-        pools = {'main': torch.cuda.graph_pool_handle(), 'side': torch.cuda.graph_pool_handle()}
+        pools = {k: torch.cuda.graph_pool_handle() for k in ('main', 'side', 'patch')}
         graphs = []
         for _, fn, where, _ in self._segments():
             g = torch.cuda.CUDAGraph()
@@ -486,11 +507,11 @@ class SCDATrainer(object):
         return graphs
 
     def _replay_cut(self, graphs):
-        """replay of the cut form: main-stream stretches on the current stream, side-stream
-        stretches (and their all-reduces) on the side stream, forked after the forward and
-        joined before the losses are assembled"""
+        """replay of the cut form: every stretch on its stream (and its all-reduce behind it on
+        the same stream), the streams forked after the forward and joined before the losses are
+        assembled; phase 1 waits for the patch forwards (it needs their mean), phase 3 for the
+        whole patch stream (it needs the updated patch discriminator)"""
         main = torch.cuda.current_stream()
-        side = self._side_stream() if self.overlap else main
         segs = self._segments()
         by_name = {name: (g, opt) for g, (name, _, _, opt) in zip(graphs, segs)}
 
@@ -501,14 +522,24 @@ class SCDATrainer(object):
                 if opt is not None:
                     opt.all_reduce()
         run(['fwd'])
-        if self.overlap:
-            side.wait_stream(main)
-            with torch.cuda.stream(side):
-                run(['dis', 'dis_patch', 'dec', 'fake'])
-            run(['det_bwd', 'step'])
-            main.wait_stream(side)
-        else:
-            run(['dis', 'dis_patch', 'dec', 'fake', 'det_bwd', 'step'])
+        if not self.overlap:
+            run(['dis', 'dis_patch', 'dec', 'fake', 'det_bwd', 'step', 'out'])
+            return
+        side, patch = self._side_stream(), self._patch_stream()
+        patch.wait_stream(main)
+        side.wait_stream(main)
+        with torch.cuda.stream(patch):
+            run(['patch_fwd'])
+            have_mean = torch.cuda.Event()
+            have_mean.record(patch)
+            run(['patch_upd', 'patch_step'])
+        with torch.cuda.stream(side):
+            side.wait_event(have_mean)
+            run(['dis', 'dis_step'])
+            side.wait_stream(patch)
+            run(['dec', 'fake'])
+        run(['det_bwd', 'step'])
+        main.wait_stream(side)
         run(['out'])
 
     def iteration(self, cfg, image, image_info, gts, target, lr=None):

@@ -100,8 +100,8 @@ def test_graph_replay_equals_eager(cuda_lib, monkeypatch):
             grads.append([o.bucket.flat.clone() for o in (tr.opt, tr.opt_dec, tr.opt_dis, tr.opt_dis_patch)])
         torch.cuda.synchronize()
         if use_graphs:
-            # one graph, or (the plan used when world > 1) eight stretches on two streams
-            assert tr._graphs is not None and len(tr._graphs) == (8 if cut else 1)
+            # one graph, or (the plan used when world > 1) eleven stretches on three streams
+            assert tr._graphs is not None and len(tr._graphs) == (11 if cut else 1)
         results.append((losses, grads))
     (l_e, g_e) = results[0]
     for mode, (l_g, g_g) in zip(("one graph", "cut"), results[1:]):
