@@ -4,21 +4,20 @@ Reference flow per image: D2H of the class and delta maps -> numpy argpartition/
 top-k -> float64 decode -> clip -> min-size filter -> H2D -> GPU bitmask NMS -> D2H of
 the 18 MB mask -> host scan -> slice -> numpy stack -> CPU tensor.
 Here everything up to the final slice stays on the device and nothing synchronises:
-top-k (descending) -> decode/clip in float64 (the dtype numpy gives the reference) ->
-stable compaction of the min-size survivors with a device-side count -> scda_nms_dyn
-(count read on the device, scan stops after post_nms_top_n survivors) -> gather.
+top-k (descending) -> scda_rpn_decode_pack (csrc/proposal_ops.cu: decode/clip in float64, the
+dtype numpy gives the reference, min-size filter, stable compaction of the survivors with a
+device-side count; utils.bbox_helper.decode_t / clip_t are the same arithmetic as tensor ops)
+-> scda_nms_dyn (count read on the device, scan stops after post_nms_top_n survivors) -> gather.
 
 `compute_rpn_proposals` keeps the reference's signature and return type (CPU float tensor
 [N, 6] = batch, x1, y1, x2, y2, score); `rpn_proposals_device` is the same computation
 returning fixed-capacity device buffers plus counts for the in-graph training path.
 """
-import numpy as np
 import torch
 
 from .._lib import check, load, stream_ptr
 from ..extensions._nms.pth_nms import nms_device
 from ..utils import anchor_helper
-from ..utils.bbox_helper import clip_t, decode_t
 
 
 def _image_hw(image_info, b):
