@@ -8,7 +8,9 @@
  *   - the caller allocates every output (and the workspace, sized by the
  *     matching *_workspace_bytes query); nothing is allocated or freed inside;
  *   - work is enqueued on the cudaStream_t passed in and the call returns
- *     without synchronising; no global state, re-entrant;
+ *     without synchronising; re-entrant, and no global state apart from the two
+ *     process-wide tuning / test hooks (scda_conv3x3_set_plan,
+ *     scda_conv3x3_wgrad_set_form), which select between equivalent kernels;
  *   - return value: 1 = launched, 0 = rejected arguments, negative =
  *     -(cudaError_t) of the failed launch.  Never exit()s (the reference
  *     launchers do: extensions/_roi_pooling/src/roi_pooling_kernel.cu:117-122).

@@ -69,3 +69,21 @@ def test_product_does_not_import_oracle():
                 src = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "import oracle" not in src and "from oracle" not in src, f
                 assert "liboracle" not in src and "oracle/" not in src, f
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/scda_b200.h compiles on its own as C99 and as C++ (no CUDA, torch or STL header needed):
+    it is the whole drop-in boundary a maintainer binds from cffi / ctypes / cgo."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        import pytest
+        pytest.skip("no gcc")
+    hdr = os.path.join(ROOT, "include", "scda_b200.h")
+    src = tmp_path / "t.c"
+    src.write_text('#include "%s"\nint main(void) { return scda_abi_version() == 0; }\n' % hdr)
+    for lang, std in (("c", "-std=c99"), ("c++", "-std=c++11")):
+        r = subprocess.run([gcc, "-x", lang, std, "-Wall", "-Werror", "-pedantic", "-fsyntax-only", str(src)],
+                           capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
