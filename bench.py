@@ -25,7 +25,6 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
@@ -48,12 +47,12 @@ def peaks():
 
 
 def load_cfg():
-    import _inputs
-    return _inputs.load_cfg()
+    from scda_b200 import synthetic
+    return synthetic.load_cfg()
 
 
 def synth_batch(rank, pinned):
-    import _inputs
+    from scda_b200 import synthetic as _inputs
     r = np.random.RandomState(1000 + rank)
     mk = lambda: torch.from_numpy(r.standard_normal((1, 3, IMG_H, IMG_W)).astype(np.float32))
     image, target = mk(), mk()
@@ -98,12 +97,22 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(self.samples)}
 
 
+def host_cores():
+    """every core this process may run on (torchrun exports OMP_NUM_THREADS=1: ignored on purpose)"""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_reference_run(steps, warmup, budget_s, threads=None):
-    """The reference CPU-extension path (oracle/model_cpu.py) timed on the host cores."""
+    """The reference CPU-extension path (oracle/model_cpu.py) timed on ALL the host cores:
+    torch's intra-op pool and the OpenMP loops of the C restatement are both set explicitly."""
+    import oracle
     from oracle.model_cpu import CPUTrainer
-    if threads:
-        torch.set_num_threads(threads)
-    cores = torch.get_num_threads()
+    cores = int(threads) if threads else host_cores()
+    torch.set_num_threads(cores)
+    oracle.set_threads(cores)
     cfg = load_cfg()
     tr = CPUTrainer(cfg)
     image, target, gts, info = synth_batch(0, pinned=False)
@@ -122,14 +131,17 @@ def cpu_reference_run(steps, warmup, budget_s, threads=None):
         if time.perf_counter() - t_all > budget_s and len(times) >= 1:
             break
     sec = float(np.mean(times))
-    return {"value": 1.0 / sec, "unit": UNIT, "cores": cores, "kind": "port",
+    return {"value": 1.0 / sec, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
             "sample": "%d warm-up + %d timed full iterations of the same workload (1 image each) on the "
                       "host, torch CPU fp32 + OpenMP C restatements of the reference's CUDA ops + the "
-                      "reference's numpy/sklearn plumbing (time-boxed to %ds)" % (done_w, len(times), budget_s),
+                      "reference's numpy/sklearn plumbing, %d threads (time-boxed to %ds)"
+                      % (done_w, len(times), cores, budget_s),
             "ms_per_step": sec * 1e3, "steps_done": len(times), "warmup_done": done_w}
 
 
 def reference_arm(args):
+    """--impl reference: the CPU path on all host cores.  Under torchrun rank 0 alone runs it (the
+    CPU path is ONE image stream whatever --gpus says; the line says so) and the other ranks exit."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -138,7 +150,9 @@ def reference_arm(args):
             "n_gpus": args.gpus, "steps": r["steps_done"], "warmup": r["warmup_done"],
             "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "note": "CPU path runs one image stream regardless of --gpus"},
+            "config": {"workload": WORKLOAD, "parallelism": "cpu x%d threads" % r["cores"],
+                       "note": "the CPU path runs ONE image stream on all host cores regardless of --gpus: "
+                               "only the N=1 ratio is like for like"},
             "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -199,8 +213,8 @@ def aux_ops(dev):
     (1x256x64x64 features, 128 RoIs, 7x7), the RoI max-pool the model really uses (NHWC bf16, 512 RoIs on the
     1x512x32x64 map) and NMS(0.7) over 12 000 score-sorted synthetic proposals (config 5 generator), each through
     the C ABI, CUDA events on the launch stream, L2 flushed, median of 10."""
-    import _inputs
     from scda_b200 import _lib, tc
+    from scda_b200 import synthetic as _inputs
     lib = _lib.load()
     st = torch.cuda.current_stream().cuda_stream
     flush = torch.zeros(64 * 1024 * 1024, device=dev)
@@ -351,7 +365,7 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--cpu-budget", type=int, default=150, help="seconds for the --impl reference arm")
+    ap.add_argument("--cpu-budget", type=int, default=240, help="seconds for the --impl reference arm")
     ap.add_argument("--cpu-budget-inline", type=int, default=45)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graphs", action="store_true", help="eager execution (for kernel profilers)")

@@ -365,6 +365,42 @@ int scda_roi_pool_nhwc_bf16_bwd(const void *dout, const unsigned short *argmax, 
                                 int num_rois, int batch, int H, int W, int C, int PH, int PW,
                                 float *dfeat, cudaStream_t stream);
 
+/* the same on an fp32 feature map / fp32 out and dout (the fp32-parity precision mode below) */
+int scda_roi_pool_nhwc_f32_fwd(const float *feat, float spatial_scale, int num_rois, int batch, int H,
+                               int W, int C, int PH, int PW, const float *rois, float *out,
+                               unsigned short *argmax, cudaStream_t stream);
+int scda_roi_pool_nhwc_f32_bwd(const float *dout, const unsigned short *argmax, const float *rois,
+                               int num_rois, int batch, int H, int W, int C, int PH, int PW,
+                               float *dfeat, cudaStream_t stream);
+
+/* --- fp32-parity precision mode ("bf16x3") ------------------------------- */
+/* The reference's convolutions / linear layers are fp32 (cuDNN / cuBLAS of torch 0.4.1:
+ * vgg_adver_expansion_cluster.py:46-60,101-114, models/head.py:13-18, common_net.py).  In this
+ * mode activations and gradients stay fp32 NHWC and the tensor-core entry points above are fed
+ * operands split into bf16 halves (x = hi + lo) concatenated along the reduction dimension,
+ * A = [hi|lo|hi], B = [hi|hi|lo]: three MMAs per product, ~2^-16 relative error per product.
+ * The epilogue flag 64 (mask_src holds fp32) goes with it.
+ * scda_split3_f32_bf16: x fp32 [rows, C] (row stride ldx) -> y bf16 [rows, 3C] = [hi|lo|hi]; C % 8 == 0.
+ * scda_split_weights_f32_bf16: w fp32 [rows, K] (row stride ldw) -> fwd bf16 [rows, 3K] = [hi|hi|lo]
+ * (K-major B operand of the forward GEMM / convolution) and / or stk bf16 [3 rows, K] = [hi;hi;lo]
+ * (the MN-major B operand of the data gradient); either may be NULL.  K % 8 == 0. */
+int scda_split3_f32_bf16(long long rows, int C, const float *x, long long ldx, void *y, cudaStream_t stream);
+int scda_split_weights_f32_bf16(long long rows, int K, const float *w, long long ldw, void *fwd, void *stk,
+                                cudaStream_t stream);
+/* scda_conv3x3_wgrad_bf16_nhwc on channel sub-blocks of wider tensors: ldx / ldy = elements between
+ * consecutive pixels (how the hi / lo halves of a split tensor are addressed) */
+int scda_conv3x3_wgrad_bf16_nhwc_ld(int NB, int H, int W, int Cin, int Cout, const void *x, long long ldx,
+                                    const void *dy, long long ldy, float *dw_partials, int splits,
+                                    cudaStream_t stream);
+/* fp32 NHWC forms of scda_maxpool2x2_*_bf16 / scda_nchw_f32_to_nhwc_bf16 (C % 4 == 0) */
+int scda_maxpool2x2_nhwc_f32(int NB, int H, int W, int C, const float *x, float *y, cudaStream_t stream);
+int scda_maxpool2x2_bwd_nhwc_f32(int NB, int H, int W, int C, const float *x, const float *dy, float *dx,
+                                 int relu_mask, cudaStream_t stream);
+int scda_nchw_f32_to_nhwc_f32(int NB, int C, int H, int W, int Cpad, const float *x, float *y,
+                              cudaStream_t stream);
+/* out[N] += column sums of x fp32 [M, ld] (any N, any ld >= N) */
+int scda_colsum_f32_ld(long long M, int N, const float *x, long long ld, float *out, cudaStream_t stream);
+
 /* --- optimiser -------------------------------------------------------- */
 /* replaces torch.optim.Adam(...).step() on each of the four networks
  * (tools/faster_rcnn_train_val.py:305-316 construct, :616,:635,:704,:750 step): one pass

@@ -39,6 +39,11 @@ def lib() -> C.CDLL:
     return _LIB
 
 
+def set_threads(n: int) -> int:
+    """thread count of the C restatement's OpenMP loops; returns what is in force"""
+    return int(lib().oracle_set_num_threads(int(n)))
+
+
 def _c(a, dt):
     return np.ascontiguousarray(a, dtype=dt)
 

@@ -28,7 +28,24 @@
 #include <stdlib.h>
 #include <string.h>
 
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
 #define ORACLE_API __attribute__((visibility("default")))
+
+/* Thread count of the OpenMP loops below (test / bench infrastructure: torchrun exports
+ * OMP_NUM_THREADS=1, which would otherwise time the baseline on one core). */
+ORACLE_API int oracle_set_num_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+    return omp_get_max_threads();
+#else
+    (void)n;
+    return 1;
+#endif
+}
 
 /* ------------------------------------------------------------------ */
 /* RoI max pooling                                                      */

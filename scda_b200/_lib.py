@@ -61,6 +61,15 @@ SIGNATURES = {
     "scda_upsample_bilinear2x_bwd_nhwc_f32": (_i, [_i, _i, _i, _i, _p, _p, _p]),
     "scda_roi_pool_nhwc_bf16_fwd": (_i, [_p, _f, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p]),
     "scda_roi_pool_nhwc_bf16_bwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p]),
+    "scda_roi_pool_nhwc_f32_fwd": (_i, [_p, _f, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p]),
+    "scda_roi_pool_nhwc_f32_bwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p]),
+    "scda_split3_f32_bf16": (_i, [C.c_longlong, _i, _p, C.c_longlong, _p, _p]),
+    "scda_split_weights_f32_bf16": (_i, [C.c_longlong, _i, _p, C.c_longlong, _p, _p, _p]),
+    "scda_conv3x3_wgrad_bf16_nhwc_ld": (_i, [_i, _i, _i, _i, _i, _p, C.c_longlong, _p, C.c_longlong, _p, _i, _p]),
+    "scda_maxpool2x2_nhwc_f32": (_i, [_i, _i, _i, _i, _p, _p, _p]),
+    "scda_maxpool2x2_bwd_nhwc_f32": (_i, [_i, _i, _i, _i, _p, _p, _p, _i, _p]),
+    "scda_nchw_f32_to_nhwc_f32": (_i, [_i, _i, _i, _i, _i, _p, _p, _p]),
+    "scda_colsum_f32_ld": (_i, [C.c_longlong, _i, _p, C.c_longlong, _p, _p]),
     "scda_kmeans_workspace_bytes": (_z, [_i, _i]),
     "scda_kmeans_regions": (_i, [_p, _i, _i, _i, _i, _p, _i, _i, _f, _p, _i, _p, _p, _p, _p, _p, _z, _p]),
     "scda_smooth_l1_sigma_sum_fwd": (_i, [C.c_longlong, _p, _p, _p, _f, _p, _p]),

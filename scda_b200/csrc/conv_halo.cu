@@ -286,6 +286,18 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             halo_epilogue<kBlockN, kSub, kFlagMaskPos>(p, e, tmem_base, bar_tfull, bar_tempty, warp - 4, lane);
         else if (e.flags == 0)
             halo_epilogue<kBlockN, kSub, 0>(p, e, tmem_base, bar_tfull, bar_tempty, warp - 4, lane);
+        // fp32-parity mode (x3_ops.cu): fp32 outputs, fp32 ReLU masks
+        else if (e.flags == (kFlagRelu | kFlagBias | kFlagOutF32))
+            halo_epilogue<kBlockN, kSub, kFlagRelu | kFlagBias | kFlagOutF32>(p, e, tmem_base, bar_tfull, bar_tempty,
+                                                                              warp - 4, lane);
+        else if (e.flags == (kFlagMaskPos | kFlagMaskF32 | kFlagOutF32))
+            halo_epilogue<kBlockN, kSub, kFlagMaskPos | kFlagMaskF32 | kFlagOutF32>(p, e, tmem_base, bar_tfull,
+                                                                                   bar_tempty, warp - 4, lane);
+        else if (e.flags == kFlagOutF32)
+            halo_epilogue<kBlockN, kSub, kFlagOutF32>(p, e, tmem_base, bar_tfull, bar_tempty, warp - 4, lane);
+        else if (e.flags == (kFlagOutF32 | kFlagBias))      // (also the decoder's conv -> InstanceNorm layers)
+            halo_epilogue<kBlockN, kSub, kFlagOutF32 | kFlagBias>(p, e, tmem_base, bar_tfull, bar_tempty, warp - 4,
+                                                                  lane);
         else
             halo_epilogue<kBlockN, kSub, -1>(p, e, tmem_base, bar_tfull, bar_tempty, warp - 4, lane);
     }

@@ -311,6 +311,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         else if (e.flags == kFlagMaskPos) SCDA_EPI(kFlagMaskPos);
         else if (e.flags == (kFlagMaskPos | kFlagMulSrc)) SCDA_EPI(kFlagMaskPos | kFlagMulSrc);
         else if (e.flags == 0) SCDA_EPI(0);
+        // fp32-parity mode (x3_ops.cu): fp32 outputs, fp32 ReLU masks
+        else if (e.flags == (kFlagRelu | kFlagBias | kFlagOutF32)) SCDA_EPI(kFlagRelu | kFlagBias | kFlagOutF32);
+        else if (e.flags == (kFlagMaskPos | kFlagMaskF32 | kFlagOutF32)) SCDA_EPI(kFlagMaskPos | kFlagMaskF32 | kFlagOutF32);
+        else if (e.flags == kFlagOutF32) SCDA_EPI(kFlagOutF32);
         else SCDA_EPI(-1);
 #undef SCDA_EPI
     }
@@ -961,12 +965,16 @@ SCDA_API int scda_conv3x3_wgrad_set_form(int three_taps)
     return 1;
 }
 
-SCDA_API int scda_conv3x3_wgrad_bf16_nhwc(int NB, int H, int W, int Cin, int Cout, const void *x, const void *dy,
-                                          float *dw_partials, int splits, cudaStream_t stream)
+SCDA_API int scda_conv3x3_wgrad_bf16_nhwc_ld(int NB, int H, int W, int Cin, int Cout, const void *x, long long ldx,
+                                             const void *dy, long long ldy, float *dw_partials, int splits,
+                                             cudaStream_t stream)
 {
-    // dw_partials: [splits][Cout][3][3][Cin] fp32; the caller sums the slabs
+    // dw_partials: [splits][Cout][3][3][Cin] fp32; the caller sums the slabs.  ldx / ldy: elements between
+    // consecutive pixels of x / dy (>= Cin / Cout: the operands may be channel sub-blocks of wider tensors,
+    // which is how the fp32-parity mode addresses the hi / lo halves of a split tensor, x3_ops.cu)
     if (NB <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0 || !x || !dy || !dw_partials || splits < 1) return 0;
     if (Cin % 64 || Cout % 32) return 0;      // Cout = 32: the upper half of the 64-wide dY box is TMA zero fill
+    if (ldx < Cin || ldy < Cout || ldx % 8 || ldy % 8 || ((uintptr_t)x | (uintptr_t)dy) % 16) return 0;
     int TW = 16, TH = 8;
     if (W % 16) {
         if (W % 8 == 0) { TW = 8; TH = 16; } else return 0;
@@ -976,9 +984,9 @@ SCDA_API int scda_conv3x3_wgrad_bf16_nhwc(int NB, int H, int W, int Cin, int Cou
     const int bn = Cin <= 64 ? 64 : 128;
     CUtensorMap ma, mb;
     cuuint64_t da[4] = {(cuuint64_t)Cout, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)NB};
-    cuuint64_t sa[3] = {(cuuint64_t)Cout * 2, (cuuint64_t)W * Cout * 2, (cuuint64_t)H * W * Cout * 2};
+    cuuint64_t sa[3] = {(cuuint64_t)ldy * 2, (cuuint64_t)W * ldy * 2, (cuuint64_t)H * W * ldy * 2};
     cuuint64_t db[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)NB};
-    cuuint64_t sb[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)W * Cin * 2, (cuuint64_t)H * W * Cin * 2};
+    cuuint64_t sb[3] = {(cuuint64_t)ldx * 2, (cuuint64_t)W * ldx * 2, (cuuint64_t)H * W * ldx * 2};
     cuuint32_t box[4] = {64, (cuuint32_t)TW, (cuuint32_t)TH, 1};
     if (!make_map(&ma, dy, 4, da, sa, box) || !make_map(&mb, x, 4, db, sb, box)) return 0;
     WgParams p = {};
@@ -999,4 +1007,10 @@ SCDA_API int scda_conv3x3_wgrad_bf16_nhwc(int NB, int H, int W, int Cin, int Cou
     }
     if (bn == 64) return launch_wg<64, 4>(ma, mb, p, 9, splits, stream);
     return launch_wg<128, 3>(ma, mb, p, 9, splits, stream);
+}
+
+SCDA_API int scda_conv3x3_wgrad_bf16_nhwc(int NB, int H, int W, int Cin, int Cout, const void *x, const void *dy,
+                                          float *dw_partials, int splits, cudaStream_t stream)
+{
+    return scda_conv3x3_wgrad_bf16_nhwc_ld(NB, H, W, Cin, Cout, x, Cin, dy, Cout, dw_partials, splits, stream);
 }

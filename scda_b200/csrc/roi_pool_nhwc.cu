@@ -51,15 +51,35 @@ __device__ __forceinline__ PoolRoiN load_roi(const float *r, float scale, int PH
 
 __device__ __forceinline__ int clamp_e(int v, int hi) { return (int)fminf(fmaxf((float)v, 0.f), (float)hi); }
 
+// 8 consecutive channels of one pixel as floats (T = bf16: one 16-byte load; T = float: two)
+__device__ __forceinline__ void load8(const __nv_bfloat16 *p, float (&f)[8])
+{
+    const uint4 v = __ldg(reinterpret_cast<const uint4 *>(p));
+    const __nv_bfloat16 *e = reinterpret_cast<const __nv_bfloat16 *>(&v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = __bfloat162float(e[j]);
+}
+__device__ __forceinline__ void load8(const float *p, float (&f)[8])
+{
+    const float4 a = __ldg(reinterpret_cast<const float4 *>(p)), b = __ldg(reinterpret_cast<const float4 *>(p) + 1);
+    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+__device__ __forceinline__ void store1(__nv_bfloat16 *p, float v) { *p = __float2bfloat16_rn(v); }
+__device__ __forceinline__ void store1(float *p, float v) { *p = v; }
+__device__ __forceinline__ float as_float(__nv_bfloat16 v) { return __bfloat162float(v); }
+__device__ __forceinline__ float as_float(float v) { return v; }
+
+// T = __nv_bfloat16: the throughput mode's feature map; T = float: the fp32-parity mode (tc.set_precision)
+template <typename T>
 __global__ void __launch_bounds__(kThreadsRP)
-roi_pool_nhwc_fwd_kernel(const __nv_bfloat16 *__restrict__ feat, float scale, int NB, int H, int W, int C, int PH,
-                         int PW, const float *__restrict__ rois, __nv_bfloat16 *__restrict__ out,
+roi_pool_nhwc_fwd_kernel(const T *__restrict__ feat, float scale, int NB, int H, int W, int C, int PH,
+                         int PW, const float *__restrict__ rois, T *__restrict__ out,
                          unsigned short *__restrict__ argmax)
 {
     extern __shared__ __align__(16) unsigned char rp_smem[];
     const int bins = PH * PW;
     // [C][bins] values, [C][bins] argmax, then the bin edges
-    __nv_bfloat16 *s_val = reinterpret_cast<__nv_bfloat16 *>(rp_smem);
+    T *s_val = reinterpret_cast<T *>(rp_smem);
     unsigned short *s_arg = reinterpret_cast<unsigned short *>(s_val + (size_t)C * bins);
     int *hs = reinterpret_cast<int *>(s_arg + (size_t)C * bins + ((C * bins) & 1));
     int *he = hs + PH, *ws = he + PH, *we = ws + PW;
@@ -79,7 +99,7 @@ roi_pool_nhwc_fwd_kernel(const __nv_bfloat16 *__restrict__ feat, float scale, in
     __syncthreads();
     const int groups = C >> 3;                       // 8-channel (16-byte) groups
     const int b_ok = q.batch >= 0 && q.batch < NB;
-    const __nv_bfloat16 *img = feat + (long long)(b_ok ? q.batch : 0) * H * W * C;
+    const T *img = feat + (long long)(b_ok ? q.batch : 0) * H * W * C;
     for (int b = warp; b < bins; b += kWarpsRP) {
         const int ph = b / PW, pw = b - ph * PW;
         const int h0 = hs[ph], h1 = he[ph], w0 = ws[pw], w1 = we[pw];
@@ -91,15 +111,14 @@ roi_pool_nhwc_fwd_kernel(const __nv_bfloat16 *__restrict__ feat, float scale, in
             for (int j = 0; j < 8; ++j) { best[j] = empty ? 0.f : -3.4e38f; where[j] = 0xFFFF; }
             if (!empty) {
                 for (int h = h0; h < h1; ++h) {
-                    const __nv_bfloat16 *row = img + ((long long)h * W) * C + g * 8;
+                    const T *row = img + ((long long)h * W) * C + g * 8;
                     for (int w = w0; w < w1; ++w) {
-                        const uint4 v = __ldg(reinterpret_cast<const uint4 *>(row + (long long)w * C));
-                        const __nv_bfloat16 *e = reinterpret_cast<const __nv_bfloat16 *>(&v);
+                        float f[8];
+                        load8(row + (long long)w * C, f);
                         const int pos = h * W + w;
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
-                            const float f = __bfloat162float(e[j]);
-                            if (f > best[j]) { best[j] = f; where[j] = pos; }
+                            if (f[j] > best[j]) { best[j] = f[j]; where[j] = pos; }
                         }
                     }
                 }
@@ -107,7 +126,7 @@ roi_pool_nhwc_fwd_kernel(const __nv_bfloat16 *__restrict__ feat, float scale, in
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const int c = g * 8 + j;
-                s_val[c * bins + b] = __float2bfloat16_rn(best[j]);
+                store1(s_val + c * bins + b, best[j]);
                 s_arg[c * bins + b] = (unsigned short)where[j];
             }
         }
@@ -121,10 +140,8 @@ roi_pool_nhwc_fwd_kernel(const __nv_bfloat16 *__restrict__ feat, float scale, in
         const uint4 *sa = reinterpret_cast<const uint4 *>(s_arg);
         uint4 *ov = reinterpret_cast<uint4 *>(out + obase);
         uint4 *oa = reinterpret_cast<uint4 *>(argmax + obase);
-        for (int i = threadIdx.x; i < total / 8; i += kThreadsRP) {
-            ov[i] = sv[i];
-            oa[i] = sa[i];
-        }
+        for (int i = threadIdx.x; i < total / 8; i += kThreadsRP) oa[i] = sa[i];
+        for (int i = threadIdx.x; i < total * (int)sizeof(T) / 16; i += kThreadsRP) ov[i] = sv[i];
     } else {
         for (int i = threadIdx.x; i < total; i += kThreadsRP) {
             out[obase + i] = s_val[i];
@@ -133,8 +150,9 @@ roi_pool_nhwc_fwd_kernel(const __nv_bfloat16 *__restrict__ feat, float scale, in
     }
 }
 
+template <typename T>
 __global__ void __launch_bounds__(kThreadsRP)
-roi_pool_nhwc_bwd_kernel(const __nv_bfloat16 *__restrict__ dout, const unsigned short *__restrict__ argmax,
+roi_pool_nhwc_bwd_kernel(const T *__restrict__ dout, const unsigned short *__restrict__ argmax,
                          const float *__restrict__ rois, int NB, int HW, int C, int bins,
                          float *__restrict__ dfeat)
 {
@@ -146,39 +164,37 @@ roi_pool_nhwc_bwd_kernel(const __nv_bfloat16 *__restrict__ dout, const unsigned 
     const long long base = (long long)n * C * bins;
     const int total = C * bins;
     if ((total & 7) == 0) {
-        const uint4 *gv = reinterpret_cast<const uint4 *>(dout + base);
         const uint4 *av = reinterpret_cast<const uint4 *>(argmax + base);
         for (int i = threadIdx.x; i < total / 8; i += kThreadsRP) {
-            const uint4 g = __ldg(gv + i), a = __ldg(av + i);
-            const __nv_bfloat16 *ge = reinterpret_cast<const __nv_bfloat16 *>(&g);
+            const uint4 a = __ldg(av + i);
+            float ge[8];
+            load8(dout + base + (long long)i * 8, ge);
             const unsigned short *ae = reinterpret_cast<const unsigned short *>(&a);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const int e = i * 8 + j;
-                const float gj = __bfloat162float(ge[j]);
+                const float gj = ge[j];
                 if (ae[j] != 0xFFFF && gj != 0.f) red_add_f32(img + (long long)ae[j] * C + e / bins, gj);
             }
         }
     } else {
         for (int e = threadIdx.x; e < total; e += kThreadsRP) {
             const unsigned short a = argmax[base + e];
-            const float gj = __bfloat162float(dout[base + e]);
+            const float gj = as_float(dout[base + e]);
             if (a != 0xFFFF && gj != 0.f) red_add_f32(img + (long long)a * C + e / bins, gj);
         }
     }
 }
 
-size_t fwd_smem(int C, int PH, int PW)
+size_t fwd_smem(int C, int PH, int PW, size_t elem)
 {
     const size_t bins = (size_t)PH * PW;
-    return 4 * (size_t)C * bins + 4 + sizeof(int) * 2 * (size_t)(PH + PW) + 16;
+    return (elem + 2) * (size_t)C * bins + 4 + sizeof(int) * 2 * (size_t)(PH + PW) + 16;
 }
 
-}  // namespace
-
-SCDA_API int scda_roi_pool_nhwc_bf16_fwd(const void *feat, float spatial_scale, int num_rois, int batch, int H,
-                                         int W, int C, int PH, int PW, const float *rois, void *out,
-                                         unsigned short *argmax, cudaStream_t stream)
+template <typename T>
+int roi_pool_nhwc_fwd(const void *feat, float spatial_scale, int num_rois, int batch, int H, int W, int C, int PH,
+                      int PW, const float *rois, void *out, unsigned short *argmax, cudaStream_t stream)
 {
     if (num_rois < 0 || batch <= 0 || H <= 0 || W <= 0 || C <= 0 || PH <= 0 || PW <= 0 || !feat || !rois || !out ||
         !argmax)
@@ -186,24 +202,23 @@ SCDA_API int scda_roi_pool_nhwc_bf16_fwd(const void *feat, float spatial_scale, 
     if (C % 8 || (long long)H * W >= 0xFFFF) return 0;
     if (((uintptr_t)feat | (uintptr_t)out | (uintptr_t)argmax) % 16) return 0;
     if (num_rois == 0) return 1;
-    const size_t smem = fwd_smem(C, PH, PW);
+    const size_t smem = fwd_smem(C, PH, PW, sizeof(T));
     if (smem > 220 * 1024) return 0;
     static size_t attr_smem = 0;
     if (smem > 48 * 1024 && smem > attr_smem) {
-        cudaError_t e = cudaFuncSetAttribute(roi_pool_nhwc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(roi_pool_nhwc_fwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)smem);
         if (e != cudaSuccess) return -(int)e;
         attr_smem = smem;
     }
-    roi_pool_nhwc_fwd_kernel<<<num_rois, kThreadsRP, smem, stream>>>((const __nv_bfloat16 *)feat, spatial_scale, batch,
-                                                                      H, W, C, PH, PW, rois, (__nv_bfloat16 *)out,
-                                                                      argmax);
+    roi_pool_nhwc_fwd_kernel<T><<<num_rois, kThreadsRP, smem, stream>>>((const T *)feat, spatial_scale, batch, H, W, C,
+                                                                         PH, PW, rois, (T *)out, argmax);
     return scda_launch_status();
 }
 
-SCDA_API int scda_roi_pool_nhwc_bf16_bwd(const void *dout, const unsigned short *argmax, const float *rois,
-                                         int num_rois, int batch, int H, int W, int C, int PH, int PW,
-                                         float *dfeat, cudaStream_t stream)
+template <typename T>
+int roi_pool_nhwc_bwd(const void *dout, const unsigned short *argmax, const float *rois, int num_rois, int batch,
+                      int H, int W, int C, int PH, int PW, float *dfeat, cudaStream_t stream)
 {
     if (num_rois < 0 || batch <= 0 || H <= 0 || W <= 0 || C <= 0 || PH <= 0 || PW <= 0 || !dout || !argmax || !rois ||
         !dfeat)
@@ -212,7 +227,38 @@ SCDA_API int scda_roi_pool_nhwc_bf16_bwd(const void *dout, const unsigned short 
     cudaError_t e = cudaMemsetAsync(dfeat, 0, sizeof(float) * (size_t)batch * H * W * C, stream);
     if (e != cudaSuccess) return -(int)e;
     if (num_rois == 0) return 1;
-    roi_pool_nhwc_bwd_kernel<<<num_rois, kThreadsRP, 0, stream>>>((const __nv_bfloat16 *)dout, argmax, rois, batch,
-                                                                   H * W, C, PH * PW, dfeat);
+    roi_pool_nhwc_bwd_kernel<T><<<num_rois, kThreadsRP, 0, stream>>>((const T *)dout, argmax, rois, batch, H * W, C,
+                                                                      PH * PW, dfeat);
     return scda_launch_status();
+}
+
+}  // namespace
+
+SCDA_API int scda_roi_pool_nhwc_bf16_fwd(const void *feat, float spatial_scale, int num_rois, int batch, int H,
+                                         int W, int C, int PH, int PW, const float *rois, void *out,
+                                         unsigned short *argmax, cudaStream_t stream)
+{
+    return roi_pool_nhwc_fwd<__nv_bfloat16>(feat, spatial_scale, num_rois, batch, H, W, C, PH, PW, rois, out, argmax,
+                                            stream);
+}
+
+SCDA_API int scda_roi_pool_nhwc_bf16_bwd(const void *dout, const unsigned short *argmax, const float *rois,
+                                         int num_rois, int batch, int H, int W, int C, int PH, int PW,
+                                         float *dfeat, cudaStream_t stream)
+{
+    return roi_pool_nhwc_bwd<__nv_bfloat16>(dout, argmax, rois, num_rois, batch, H, W, C, PH, PW, dfeat, stream);
+}
+
+SCDA_API int scda_roi_pool_nhwc_f32_fwd(const float *feat, float spatial_scale, int num_rois, int batch, int H,
+                                        int W, int C, int PH, int PW, const float *rois, float *out,
+                                        unsigned short *argmax, cudaStream_t stream)
+{
+    return roi_pool_nhwc_fwd<float>(feat, spatial_scale, num_rois, batch, H, W, C, PH, PW, rois, out, argmax, stream);
+}
+
+SCDA_API int scda_roi_pool_nhwc_f32_bwd(const float *dout, const unsigned short *argmax, const float *rois,
+                                        int num_rois, int batch, int H, int W, int C, int PH, int PW,
+                                        float *dfeat, cudaStream_t stream)
+{
+    return roi_pool_nhwc_bwd<float>(dout, argmax, rois, num_rois, batch, H, W, C, PH, PW, dfeat, stream);
 }

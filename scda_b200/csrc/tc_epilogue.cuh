@@ -18,6 +18,7 @@ enum : int {
     kFlagAccumulate = 8,  // y += previous contents (fp32 output only)
     kFlagMulSrc = 16,     // y *= mul_src            (dropout keep/scale tensor, bf16)
     kFlagBias = 32,       // internal: bias pointer present
+    kFlagMaskF32 = 64,    // mask_src holds fp32 (the fp32-parity mode keeps activations in fp32)
 };
 
 struct EpiParams {
@@ -55,7 +56,17 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], const Ep
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
         }
-        if (flags & kFlagMaskPos) {
+        if ((flags & kFlagMaskPos) && (flags & kFlagMaskF32)) {
+            const float *mf = reinterpret_cast<const float *>(e.mask_src) + o;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+                const float4 q = __ldg(reinterpret_cast<const float4 *>(mf + j));
+                if (!(q.x > 0.f)) f[j] = 0.f;
+                if (!(q.y > 0.f)) f[j + 1] = 0.f;
+                if (!(q.z > 0.f)) f[j + 2] = 0.f;
+                if (!(q.w > 0.f)) f[j + 3] = 0.f;
+            }
+        } else if (flags & kFlagMaskPos) {
 #pragma unroll
             for (int j = 0; j < 32; j += 8) {
                 const uint4 q = __ldg(reinterpret_cast<const uint4 *>(e.mask_src + o + j));
@@ -115,7 +126,11 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], const Ep
         for (int t = 1; t < 32; ++t) x = (t == j) ? __uint_as_float(v[t]) : x;
         if (flags & kFlagBias) x += __ldg(e.bias + col0 + j);
         if (flags & kFlagRelu) x = fmaxf(x, 0.f);
-        if ((flags & kFlagMaskPos) && !(__bfloat162float(e.mask_src[o + j]) > 0.f)) x = 0.f;
+        if (flags & kFlagMaskPos) {
+            const float m = (flags & kFlagMaskF32) ? reinterpret_cast<const float *>(e.mask_src)[o + j]
+                                                   : __bfloat162float(e.mask_src[o + j]);
+            if (!(m > 0.f)) x = 0.f;
+        }
         if (flags & kFlagMulSrc) x *= __bfloat162float(e.mul_src[o + j]);
         if (flags & kFlagOutF32) {
             float *dst = reinterpret_cast<float *>(e.out) + o + j;

@@ -169,11 +169,9 @@ def soft_label(flag, like, generator=None):
 
 def _bce_rows(logits, label_row):
     """per-cluster vector of F.binary_cross_entropy(sigmoid(logits[c:c+1]), label_row)
-    (tools/faster_rcnn_train_val.py:577-600): one fused kernel each way (csrc/loss_ops.cu)."""
-    if logits.is_cuda:
-        return bce_sigmoid_rows(logits, label_row)
-    p = torch.sigmoid(logits)
-    return F.binary_cross_entropy(p, label_row.expand_as(p), reduction='none').mean(dim=1)
+    (tools/faster_rcnn_train_val.py:577-600): one fused kernel each way (csrc/loss_ops.cu).
+    CUDA only — there is no CPU path (loss_ops raises on host tensors)."""
+    return bce_sigmoid_rows(logits, label_row)
 
 
 class SCDATrainer(object):
@@ -226,6 +224,11 @@ class SCDATrainer(object):
         self._static, self._st = None, {}
         self._graphs = None
         self._by_shape = {}
+        # parity-test hooks (tests/test_iteration_parity_gpu.py); all None in production:
+        #   rng  {'anchor': rng, 'proposal': rng}  prescribed sampling keys (functions/_sampling.ArrayRng)
+        #   soft {'score_1', 'score_0' [1, M]; 'score_0_patch', 'score_1_patch' [K, P]}  soft-label rows
+        #   taps {}  receives the detector's intermediate decisions (forces eager execution)
+        self.rng, self.soft, self.taps = None, None, None
 
     def nets(self):
         return (self.model, self.dec_model, self.dis_model, self.dis_model_patch)
@@ -267,8 +270,8 @@ class SCDATrainer(object):
         on_recon, on_real = run_pair(lambda: self.dis_model(x_source_recon, x_target_recon),
                                      lambda: self.dis_model(cs, ct))
         (s_dis, t_dis), (s_real, t_real) = on_recon, on_real        # logits: the sigmoid lives in _bce_rows
-        score_1 = soft_label(1, s_real[:1])
-        score_0 = soft_label(0, s_dis[:1])
+        score_1 = self._soft('score_1', 1, s_real[:1])
+        score_0 = self._soft('score_0', 0, s_dis[:1])
         adloss_source = (_bce_rows(s_dis, score_1) + _bce_rows(s_real, score_0)).sum()
         if patch_done:                       # cut plan: an earlier stretch on the patch stream ran them
             t_patch_mean = st['t_patch_mean']
@@ -284,12 +287,17 @@ class SCDATrainer(object):
         adloss.backward(retain_graph=True, inputs=self.opt_dis.params)
         st['dis_loss'] = adloss.detach()
 
+    def _soft(self, name, flag, like):
+        if self.soft is not None and name in self.soft:
+            return self.soft[name].to(like.device, like.dtype).view_as(like)
+        return soft_label(flag, like)
+
     def _patch_update(self):
         """(2) patch discriminator: loss + backward (:616-630)"""
         st, ws = self._st, float(self.world_size)
         self.opt_dis_patch.zero_grad()
-        score_0_patch = soft_label(0, st['t_patch_pro'])
-        score_1_patch = soft_label(1, st['s_patch_pro'])
+        score_0_patch = self._soft('score_0_patch', 0, st['t_patch_pro'])
+        score_1_patch = self._soft('score_1_patch', 1, st['s_patch_pro'])
         dis_patch_loss = (F.binary_cross_entropy(st['s_patch_pro'], score_1_patch)
                           + F.binary_cross_entropy(st['t_patch_pro'], score_0_patch)) / ws
         dis_patch_loss.backward(retain_graph=True, inputs=self.opt_dis_patch.params)
@@ -345,6 +353,10 @@ class SCDATrainer(object):
         if self.overlap:
             x['target_stream'] = self._target_stream()
             x['aux_stream'] = self._aux_stream()
+        if self.rng is not None:
+            x['rng'] = self.rng
+        if self.taps is not None:
+            x['taps'] = self.taps
         outputs = self.model(x, b['target'])
         st['det_losses'] = outputs['losses']
         st['acc'] = outputs['accuracy']
@@ -373,6 +385,7 @@ class SCDATrainer(object):
         st['out'] = {'loss': loss, 'rpn_cls': rpn_cls_loss.detach(),
                      'rpn_loc': rpn_loc_loss.detach(), 'rcnn_cls': rcnn_cls_loss.detach(),
                      'rcnn_loc': rcnn_loc_loss.detach(), 'fake_loss': st['fake_loss_target'],
+                     'fake_loss_source': st['fake_loss_source'],
                      'dec_loss': st['dec_loss'], 'dis_loss': st['dis_loss'],
                      'dis_patch_loss': st['dis_patch_loss'],
                      'rpn_acc': st['acc'][0], 'rcnn_acc': st['acc'][1]}
@@ -565,7 +578,7 @@ class SCDATrainer(object):
         b['gts'].copy_(gts, non_blocking=True)
         for o in (self.opt_dis, self.opt_dis_patch, self.opt_dec, self.opt):
             o.begin_step(lr)
-        if not self.use_graphs or ent['calls'] == 0:
+        if not self.use_graphs or ent['calls'] == 0 or self.taps is not None or self.rng is not None:
             self._body(self._reduce_fn())           # eager (also the warm-up before a capture)
         else:
             if ent['graphs'] is None:
@@ -579,31 +592,36 @@ class SCDATrainer(object):
         return {k: v.clone() for k, v in self._st['out'].items()}
 
 
-def crops_device(image, centers, recon_size, new_w, new_h):
-    """recon_size windows around the cluster centres, shifted to stay inside the image —
-    `get_corner_from_center` (tools/faster_rcnn_train_val.py:411-438) is a clamp of
-    int(c) - recon_size // 2 to [0, size - recon_size] — gathered on the device from
-    centres that never visited the host.  image [1,3,H,W], centers [K,2] -> [K,3,R,R]."""
-    if not torch.is_tensor(centers):
-        centers = torch.as_tensor(np.asarray(centers), dtype=torch.float32, device=image.device)
-    assert recon_size % 2 == 0 and image.shape[0] == 1
-    if (image.is_cuda and image.dtype == torch.float32 and image.is_contiguous() and centers.is_cuda
-            and tuple(image.shape[2:]) == (new_h, new_w)):
-        # one gather kernel (csrc/proposal_ops.cu) instead of ~13 index / arange / clamp launches
-        cen = centers.float().contiguous()
-        K, C = cen.shape[0], image.shape[1]
-        out = torch.empty(K, C, recon_size, recon_size, dtype=torch.float32, device=image.device)
-        with torch.cuda.device(image.device):
-            check(load().scda_crop_regions(K, C, new_h, new_w, recon_size, image.data_ptr(), cen.data_ptr(),
-                                           out.data_ptr(), stream_ptr(image.device)), "scda_crop_regions")
-        return out
+def crop_corners(centers, recon_size, new_w, new_h):
+    """(x1, y1) of the recon_size windows: `get_corner_from_center`
+    (tools/faster_rcnn_train_val.py:411-438) is a clamp of int(c) - recon_size // 2 to
+    [0, size - recon_size].  The rule scda_crop_regions implements, as tensor ops (host logic,
+    tests/test_engine_cpu.py)."""
     half = recon_size // 2
     x1 = (centers[:, 0].to(torch.int64) - half).clamp(0, new_w - recon_size)
     y1 = (centers[:, 1].to(torch.int64) - half).clamp(0, new_h - recon_size)
-    ar = torch.arange(recon_size, device=image.device)
-    ys = (y1[:, None] + ar)[:, :, None]
-    xs = (x1[:, None] + ar)[:, None, :]
-    return image[0][:, ys, xs].permute(1, 0, 2, 3).contiguous()
+    return x1, y1
+
+
+def crops_device(image, centers, recon_size, new_w, new_h):
+    """recon_size windows around the cluster centres, shifted to stay inside the image (the rule
+    of `crop_corners`), gathered by one kernel (csrc/proposal_ops.cu) from centres that never
+    visited the host.  image [1,3,H,W] fp32 CUDA, centers [K,2] -> [K,3,R,R].  CUDA only."""
+    if not torch.is_tensor(centers):
+        centers = torch.as_tensor(np.asarray(centers), dtype=torch.float32, device=image.device)
+    assert recon_size % 2 == 0 and image.shape[0] == 1
+    if not (image.is_cuda and centers.is_cuda):
+        raise RuntimeError("crops_device: CUDA tensors required (scda_b200 has no CPU path)")
+    if tuple(image.shape[2:]) != (new_h, new_w):
+        raise ValueError("crops_device: image is %s, expected (%d, %d)" % (tuple(image.shape[2:]), new_h, new_w))
+    image = image.float().contiguous()
+    cen = centers.float().contiguous()
+    K, C = cen.shape[0], image.shape[1]
+    out = torch.empty(K, C, recon_size, recon_size, dtype=torch.float32, device=image.device)
+    with torch.cuda.device(image.device):
+        check(load().scda_crop_regions(K, C, new_h, new_w, recon_size, image.data_ptr(), cen.data_ptr(),
+                                       out.data_ptr(), stream_ptr(image.device)), "scda_crop_regions")
+    return out
 
 
 def builder_gan(cluster_num=4, threshold=128, recon_size=256, neww=64, newh=64):

@@ -78,11 +78,14 @@ def kmeans_regions_device(proposals, N_cluster, threshold, max_iter=300, tol=1e-
     return labels, centers, counts, index
 
 
-def cluster_targets_device(proposals, features, N_cluster=4, threshold=128):
-    """-> batch_rois [N_cluster, threshold, F] (detached) and centres as a DEVICE fp32 [K, 2]"""
+def cluster_targets_device(proposals, features, N_cluster=4, threshold=128, taps=None):
+    """-> batch_rois [N_cluster, threshold, F] (detached) and centres as a DEVICE fp32 [K, 2];
+    `taps` (a dict, tests only) receives the row index and the labels the gather used"""
     assert features.is_cuda
-    _, centers, _, index = kmeans_regions_device(proposals.detach().float(), N_cluster, threshold)
+    labels, centers, _, index = kmeans_regions_device(proposals.detach().float(), N_cluster, threshold)
     rows = features.detach().float().index_select(0, index)
+    if taps is not None:
+        taps.update(index=index, labels=labels, centers=centers)
     return rows.view(N_cluster, threshold, features.shape[1]), centers
 
 

@@ -101,8 +101,9 @@ class _Upsample2x(torch.autograd.Function):
 def upsample_bilinear2x(x, out_bf16=False):
     """F.interpolate(x, scale_factor=2, mode='bilinear', align_corners=True) on a channels_last
     fp32 CUDA tensor (C % 4 == 0, H, W >= 2); out_bf16 writes the result as bf16 (the operand
-    dtype of the tensor-core convolution behind it)."""
-    return _Upsample2x.apply(x, bool(out_bf16))
+    dtype of the tensor-core convolution behind it; ignored in the fp32-parity mode)."""
+    from . import tc
+    return _Upsample2x.apply(x, bool(out_bf16) and not tc.x3())
 
 
 def upsample_supported(x, scale_factor, mode):
@@ -222,14 +223,20 @@ class _ConvINActTC(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias, act, slope, eps, out_bf16):
         from . import tc
-        from .tc_detector import shadow_of
+        from .tc_detector import shadow3_of, shadow_of
         require_cuda(x)
+        x3 = tc.x3()          # fp32-parity mode: fp32 activations, split operands (csrc/x3_ops.cu)
+        out_bf16 = out_bf16 and not x3
         if not x.is_contiguous(memory_format=torch.channels_last):
             x = x.contiguous(memory_format=torch.channels_last)
-        xb = x if x.dtype == torch.bfloat16 else x.to(torch.bfloat16)       # keeps channels_last
+        if x3:
+            xb = tc.split3(x.float().permute(0, 2, 3, 1)).permute(0, 3, 1, 2)   # [N,3C,H,W] view of NHWC
+            w = shadow3_of(weight)[0]                                           # bf16 [O,3,3,3I]
+        else:
+            xb = x if x.dtype == torch.bfloat16 else x.to(torch.bfloat16)       # keeps channels_last
+            w = shadow_of(weight)                                               # bf16 [O,3,3,I]
         xn = xb.permute(0, 2, 3, 1)                                         # [N,H,W,C] contiguous view
         N, H, W, _ = xn.shape
-        w = shadow_of(weight)                                               # bf16 [O,3,3,I]
         O = w.shape[0]
         c = tc.conv3x3_nhwc(xn, w, bias.detach() if bias is not None else None, out_dtype=torch.float32)
         y = torch.empty(N, H, W, O, dtype=torch.bfloat16 if out_bf16 else torch.float32, device=x.device)
@@ -246,34 +253,43 @@ class _ConvINActTC(torch.autograd.Function):
                                                  wsb, stream_ptr(x.device)), "scda_instnorm_act_fwd_nhwc")
         ctx.save_for_backward(xb, c, mean, rstd)
         ctx.params = (weight, bias)
-        ctx.cfg = (act, slope, x.dtype)
+        ctx.cfg = (act, slope, x.dtype, x3)
         return y.permute(0, 3, 1, 2)
 
     @staticmethod
     def backward(ctx, dy):
         from . import tc
-        from .tc_detector import _sink_bias, _sink_conv_wgrad, shadow_of
+        from .tc_detector import (_sink_bias, _sink_bias_f32, _sink_conv_wgrad, _sink_conv_wgrad_x3, shadow3_of,
+                                  shadow_of)
         xb, c, mean, rstd = ctx.saved_tensors
         weight, bias = ctx.params
-        act, slope, x_dtype = ctx.cfg
+        act, slope, x_dtype, x3 = ctx.cfg
         N, H, W, O = c.shape
         if dy.dtype not in (torch.float32, torch.bfloat16):
             dy = dy.float()
         if not dy.is_contiguous(memory_format=torch.channels_last):
             dy = dy.contiguous(memory_format=torch.channels_last)
-        dc = torch.empty(N, H, W, O, dtype=torch.bfloat16, device=c.device)
+        dc = torch.empty(N, H, W, O, dtype=torch.float32 if x3 else torch.bfloat16, device=c.device)
         lib = load()
         wsb = lib.scda_instnorm_workspace_bytes(N, H * W, O) + 8 * N * O
         ws = torch.empty(wsb, dtype=torch.uint8, device=c.device)
         with torch.cuda.device(c.device):
             check(lib.scda_instnorm_act_bwd_nhwc(N, H * W, O, c.data_ptr(), dy.data_ptr(),
                                                  1 if dy.dtype == torch.bfloat16 else 0, mean.data_ptr(),
-                                                 rstd.data_ptr(), dc.data_ptr(), 1, act, slope, ws.data_ptr(), wsb,
-                                                 stream_ptr(c.device)), "scda_instnorm_act_bwd_nhwc")
+                                                 rstd.data_ptr(), dc.data_ptr(), 0 if x3 else 1, act, slope,
+                                                 ws.data_ptr(), wsb, stream_ptr(c.device)),
+                  "scda_instnorm_act_bwd_nhwc")
         xn = xb.permute(0, 2, 3, 1)
+        dx = None
+        if x3:
+            gb = _sink_bias_f32(bias, dc.view(-1, O)) if bias is not None and ctx.needs_input_grad[2] else None
+            ds = tc.split3(dc)
+            gw = _sink_conv_wgrad_x3(weight, xn, ds) if ctx.needs_input_grad[1] else None
+            if ctx.needs_input_grad[0]:
+                dx = tc.conv3x3_dgrad_nhwc(ds, shadow3_of(weight)[1], out_dtype=torch.float32).permute(0, 3, 1, 2)
+            return dx, gw, gb, None, None, None, None
         gb = _sink_bias(bias, dc.view(-1, O)) if bias is not None and ctx.needs_input_grad[2] else None
         gw = _sink_conv_wgrad(weight, xn, dc) if ctx.needs_input_grad[1] else None
-        dx = None
         if ctx.needs_input_grad[0]:
             dx = tc.conv3x3_dgrad_nhwc(dc, shadow_of(weight), out_dtype=x_dtype).permute(0, 3, 1, 2)
         return dx, gw, gb, None, None, None, None

@@ -66,13 +66,13 @@ class FasterRCNN_AdEx(nn.Module):
         acc = accuracy(rcnn_pred_cls, cls_targets)[0]
         return rcnn_loss_cls, rcnn_loss_loc, acc
 
-    def _pin_args_to_fn(self, cfg, ground_truth_bboxes, image_info, ignore_regions):
+    def _pin_args_to_fn(self, cfg, ground_truth_bboxes, image_info, ignore_regions, rng=None):
         partial_fn = {}
         if self.training:
             partial_fn['anchor_target_fn'] = functools.partial(
                 compute_anchor_targets, cfg=cfg['train_anchor_target_cfg'],
                 ground_truth_bboxes=ground_truth_bboxes, ignore_regions=ignore_regions,
-                image_info=image_info)
+                image_info=image_info, rng=(rng or {}).get('anchor'))
             partial_fn['proposal_target_fn'] = functools.partial(
                 compute_proposal_targets, cfg=cfg['train_proposal_target_cfg'],
                 ground_truth_bboxes=ground_truth_bboxes, ignore_regions=ignore_regions,
@@ -93,14 +93,14 @@ class FasterRCNN_AdEx(nn.Module):
         x = F.softmax(x.view(-1, 2), dim=1).view_as(x)
         return x.permute(0, 3, 1, 2)
 
-    def _train_rois(self, cfg, proposals_per_image, ground_truth_bboxes, image_info):
+    def _train_rois(self, cfg, proposals_per_image, ground_truth_bboxes, image_info, rng=None):
         """proposal targets straight from the device-side proposal buffers (no host hop)."""
         info = _host_info(image_info)
         outs = []
         for b, (boxes, n_keep) in enumerate(proposals_per_image):
             outs.append(proposal_targets_device(
                 boxes, n_keep, ground_truth_bboxes[b].float(), cfg['train_proposal_target_cfg'],
-                (float(info[b][0]), float(info[b][1])), batch_ix=b))
+                (float(info[b][0]), float(info[b][1])), batch_ix=b, rng=rng))
         return tuple(torch.cat([o[i] for o in outs], 0).contiguous() for i in range(4))
 
     def forward(self, input, target=None):
@@ -118,7 +118,20 @@ class FasterRCNN_AdEx(nn.Module):
         ignore_regions = input['ignore_regions']
         if self.training and ground_truth_bboxes is not None and not ground_truth_bboxes.is_cuda:
             ground_truth_bboxes = ground_truth_bboxes.to(x_input.device, non_blocking=True)
-        partial_fn = self._pin_args_to_fn(cfg, ground_truth_bboxes, image_info, ignore_regions)
+        # tests only: input['rng'] = {'anchor': rng, 'proposal': rng} replays prescribed sampling keys
+        # (functions/_sampling.ArrayRng); input['taps'] (a dict) receives the intermediate decisions
+        rng = input.get('rng') or {}
+        taps = input.get('taps')
+        partial_fn = self._pin_args_to_fn(cfg, ground_truth_bboxes, image_info, ignore_regions, rng)
+        if taps is not None and self.training:
+            raw_fn, memo = partial_fn['anchor_target_fn'], {}
+
+            def anchor_once(size):          # computed once per forward, also when the taps ask for it again
+                key = tuple(int(v) for v in size)
+                if key not in memo:
+                    memo[key] = raw_fn(size)
+                return memo[key]
+            partial_fn['anchor_target_fn'] = anchor_once
 
         outputs = {'losses': [], 'predict': [], 'accuracy': []}
         if not self.training:
@@ -159,8 +172,14 @@ class FasterRCNN_AdEx(nn.Module):
                     x_fea_gan, _, _ = self.rcnn(x_gan, proposals_gan)
                 clusters = None
                 if on_dev and proposals_gan.shape[0] == n_t:
+                    ktap = {} if taps is not None else None
                     clusters = cluster_targets_device(proposals_gan, x_fea_gan, N_cluster=input['cluster_num'],
-                                                      threshold=input['threshold'])
+                                                      threshold=input['threshold'], taps=ktap)
+                    if taps is not None:
+                        taps.update(cluster_tgt=ktap)
+                if taps is not None:
+                    taps.update(rois_gan=proposals_gan, enough=enough, feat_gan=x_gan, fc7_gan=x_fea_gan,
+                                rpn_cls_gan=rpn_pred_cls_gan, rpn_loc_gan=rpn_pred_loc_gan)
                 return x_gan, proposals_gan, enough, x_fea_gan, clusters
 
             # input['target_stream']: run the target branch on that stream, beside the source
@@ -206,11 +225,20 @@ class FasterRCNN_AdEx(nn.Module):
             props = rpn_proposals_device(self._rpn_scores(rpn_pred_cls).data, rpn_pred_loc.data,
                                          pcfg, image_info)
             rois, cls_targets, loc_targets, loc_weights = self._train_rois(
-                cfg, props, ground_truth_bboxes, image_info)
+                cfg, props, ground_truth_bboxes, image_info, rng.get('proposal'))
             assert rois.shape[1] == 5
             x_fea, rcnn_pred_cls, rcnn_pred_loc = self.rcnn(x, rois)
-            x_cluster_fea, x_center_cluster = cluster_fn(
-                rois, x_fea, N_cluster=input['cluster_num'], threshold=input['threshold'])
+            if taps is not None and on_dev:
+                ktap = {}
+                x_cluster_fea, x_center_cluster = cluster_targets_device(
+                    rois, x_fea, N_cluster=input['cluster_num'], threshold=input['threshold'], taps=ktap)
+                taps.update(cluster_src=ktap, anchor_targets=partial_fn['anchor_target_fn'](rpn_pred_loc.size()),
+                            rois_targets=(rois, cls_targets, loc_targets, loc_weights), feat=x,
+                            rpn_cls=rpn_pred_cls, rpn_loc=rpn_pred_loc, fc7=x_fea, rcnn_cls=rcnn_pred_cls,
+                            rcnn_loc=rcnn_pred_loc, proposals=props)
+            else:
+                x_cluster_fea, x_center_cluster = cluster_fn(
+                    rois, x_fea, N_cluster=input['cluster_num'], threshold=input['threshold'])
 
             if tstream is not None:
                 cur_stream.wait_stream(tstream)

@@ -10,7 +10,30 @@ import torch
 
 from ._lib import check, load, require_cuda, stream_ptr
 
-RELU, OUT_F32, MASK_POS, ACCUMULATE, MUL_SRC = 1, 2, 4, 8, 16
+RELU, OUT_F32, MASK_POS, ACCUMULATE, MUL_SRC, MASK_F32 = 1, 2, 4, 8, 16, 64
+
+# Precision mode of the detector / decoder contractions (one process-wide switch):
+#   'bf16'    operands rounded to bf16, fp32 accumulation — the throughput mode (default);
+#   'bf16x3'  the fp32-parity mode: activations / gradients stay fp32 NHWC, every operand is split
+#             into bf16 halves hi + lo and each product is three MMAs (csrc/x3_ops.cu): ~2^-16
+#             relative error per product (TF32: 2^-11) at one third of the bf16 rate.  The
+#             reference computes these layers in fp32 (cuDNN / cuBLAS of torch 0.4.1).
+PRECISION = os.environ.get("SCDA_PRECISION", "bf16")
+
+
+def set_precision(mode):
+    global PRECISION
+    if mode not in ("bf16", "bf16x3"):
+        raise ValueError("precision mode must be 'bf16' or 'bf16x3', got %r" % (mode,))
+    PRECISION = mode
+    if mode == "bf16x3":
+        # the layers still on cuDNN (discriminators) must not drop to TF32 in the parity mode
+        torch.backends.cudnn.allow_tf32 = False
+        torch.backends.cuda.matmul.allow_tf32 = False
+
+
+def x3():
+    return PRECISION == "bf16x3"
 
 
 def _ptr(t):
@@ -20,11 +43,13 @@ def _ptr(t):
 def _flags(relu, out_dtype, mask_src, accumulate=False, mul_src=None):
     return (RELU if relu else 0) | (OUT_F32 if out_dtype == torch.float32 else 0) \
         | (MASK_POS if mask_src is not None else 0) | (ACCUMULATE if accumulate else 0) \
-        | (MUL_SRC if mul_src is not None else 0)
+        | (MUL_SRC if mul_src is not None else 0) \
+        | (MASK_F32 if mask_src is not None and mask_src.dtype == torch.float32 else 0)
 
 
-def _check_side(t, out, what):
-    assert t.dtype == torch.bfloat16 and t.shape == out.shape and t.stride() == out.stride(), what
+def _check_side(t, out, what, f32_ok=False):
+    assert t.dtype == torch.bfloat16 or (f32_ok and t.dtype == torch.float32), what
+    assert t.shape == out.shape and t.stride() == out.stride(), what
 
 
 def gemm_tn(a, b, bias=None, relu=False, out_dtype=torch.bfloat16, mask_src=None, out=None,
@@ -44,7 +69,7 @@ def gemm_tn(a, b, bias=None, relu=False, out_dtype=torch.bfloat16, mask_src=None
     if bias is not None:
         assert bias.dtype == torch.float32 and bias.numel() == N and bias.is_contiguous()
     if mask_src is not None:
-        _check_side(mask_src, out, "mask_src must match the output")
+        _check_side(mask_src, out, "mask_src must match the output", f32_ok=True)
     if mul_src is not None:
         _check_side(mul_src, out, "mul_src must match the output")
     with torch.cuda.device(a.device):
@@ -66,7 +91,7 @@ def gemm_nn(a, b, bias=None, relu=False, out_dtype=torch.bfloat16, mask_src=None
     out = torch.empty(M, N, dtype=out_dtype, device=a.device)
     flags = _flags(relu, out_dtype, mask_src, False, mul_src)
     if mask_src is not None:
-        _check_side(mask_src, out, "mask_src must match the output")
+        _check_side(mask_src, out, "mask_src must match the output", f32_ok=True)
     if mul_src is not None:
         _check_side(mul_src, out, "mul_src must match the output")
     with torch.cuda.device(a.device):
@@ -90,7 +115,8 @@ def conv3x3_nhwc(x, w_krsc, bias=None, relu=False, out_dtype=torch.bfloat16, mas
     if bias is not None:
         assert bias.dtype == torch.float32 and bias.numel() == Cout and bias.is_contiguous()
     if mask_src is not None:
-        assert mask_src.dtype == torch.bfloat16 and mask_src.shape == y.shape and mask_src.is_contiguous()
+        assert mask_src.dtype in (torch.bfloat16, torch.float32) and mask_src.shape == y.shape \
+            and mask_src.is_contiguous()
     with torch.cuda.device(x.device):
         check(load().scda_conv3x3_bf16_nhwc(NB, H, W, Cin, Cout, x.data_ptr(), w_krsc.data_ptr(),
                                             _ptr(bias), y.data_ptr(), flags, _ptr(mask_src),
@@ -116,7 +142,8 @@ def conv3x3_dgrad_nhwc(dy, w_krsc, mask_src=None, out_dtype=torch.bfloat16):
     dx = torch.empty(NB, H, W, Cin, dtype=out_dtype, device=dy.device)
     flags = _flags(False, out_dtype, mask_src)
     if mask_src is not None:
-        assert mask_src.dtype == torch.bfloat16 and mask_src.shape == dx.shape and mask_src.is_contiguous()
+        assert mask_src.dtype in (torch.bfloat16, torch.float32) and mask_src.shape == dx.shape \
+            and mask_src.is_contiguous()
     with torch.cuda.device(dy.device):
         check(load().scda_conv3x3_dgrad_bf16_nhwc(NB, H, W, Cin, Cout, dy.data_ptr(), w_krsc.data_ptr(),
                                                   dx.data_ptr(), flags, _ptr(mask_src),
@@ -287,4 +314,152 @@ def roi_pool_nhwc_bwd(dout, argmax, rois, geom, pooled_height, pooled_width):
                                                  rois.shape[0], NB, H, W, C, pooled_height, pooled_width,
                                                  dfeat.data_ptr(), stream_ptr(dout.device)),
               "scda_roi_pool_nhwc_bf16_bwd")
+    return dfeat
+
+
+# ---------------------------------------------------------------------------------------
+# fp32-parity mode (PRECISION == 'bf16x3'): operand splits and fp32 NHWC companions (csrc/x3_ops.cu)
+def split3(x):
+    """x fp32 [..., C] (last dim contiguous, uniform row stride) -> bf16 [..., 3C] = [hi | lo | hi]"""
+    require_cuda(x)
+    assert x.dtype == torch.float32 and x.stride(-1) == 1
+    C = x.shape[-1]
+    if x.dim() == 2:
+        rows, ld = x.shape[0], x.stride(0)
+    else:
+        assert x.is_contiguous()
+        rows, ld = x.numel() // C, C
+    y = torch.empty(x.shape[:-1] + (3 * C,), dtype=torch.bfloat16, device=x.device)
+    with torch.cuda.device(x.device):
+        check(load().scda_split3_f32_bf16(rows, C, x.data_ptr(), ld, y.data_ptr(), stream_ptr(x.device)),
+              "scda_split3_f32_bf16")
+    return y
+
+
+def split_weights(w2d, want_fwd=True, want_stk=True):
+    """w fp32 [rows, K] contiguous -> (fwd bf16 [rows, 3K] = [hi|hi|lo], stk bf16 [3 rows, K] = [hi;hi;lo])"""
+    require_cuda(w2d)
+    assert w2d.dtype == torch.float32 and w2d.dim() == 2 and w2d.is_contiguous()
+    rows, K = w2d.shape
+    fwd = torch.empty(rows, 3 * K, dtype=torch.bfloat16, device=w2d.device) if want_fwd else None
+    stk = torch.empty(3 * rows, K, dtype=torch.bfloat16, device=w2d.device) if want_stk else None
+    with torch.cuda.device(w2d.device):
+        check(load().scda_split_weights_f32_bf16(rows, K, w2d.data_ptr(), K, _ptr(fwd), _ptr(stk),
+                                                 stream_ptr(w2d.device)), "scda_split_weights_f32_bf16")
+    return fwd, stk
+
+
+def conv3x3_wgrad_x3(xs, gs, out=None, accumulate=False, target_ctas=None):
+    """dW[Cout,3,3,Cin] fp32 from the SPLIT operands xs bf16 [N,H,W,3Cin] = [hi|lo|hi] and gs bf16
+    [N,H,W,3Cout]: x_hi g_hi + x_lo g_hi + x_hi g_lo, three launches of the strided weight-gradient
+    kernel into separate split-K slabs, one slab reduction."""
+    require_cuda(xs, gs)
+    assert xs.dtype == torch.bfloat16 and gs.dtype == torch.bfloat16 and xs.is_contiguous() and gs.is_contiguous()
+    NB, H, W, C3 = xs.shape
+    Cin, Cout = C3 // 3, gs.shape[3] // 3
+    if target_ctas is None:
+        target_ctas = 148 if WGRAD3 else 296
+    splits = _wgrad_splits(NB, H, W, Cin, Cout, target_ctas)
+    part = torch.empty(3 * splits, Cout, 3, 3, Cin, dtype=torch.float32, device=xs.device)
+    lib = load()
+    pairs = ((0, 0), (1, 0), (0, 1))              # (x block, g block): hi.hi, lo.hi, hi.lo
+    with torch.cuda.device(xs.device):
+        for k, (bx, bg) in enumerate(pairs):
+            check(lib.scda_conv3x3_wgrad_bf16_nhwc_ld(
+                NB, H, W, Cin, Cout, xs.data_ptr() + 2 * bx * Cin, 3 * Cin, gs.data_ptr() + 2 * bg * Cout, 3 * Cout,
+                part[k * splits].data_ptr(), splits, stream_ptr(xs.device)), "scda_conv3x3_wgrad_bf16_nhwc_ld")
+    if out is None:
+        return part.sum(0)
+    assert out.dtype == torch.float32 and out.numel() == part[0].numel()
+    reduce_slabs(part, out, accumulate)
+    return out
+
+
+def linear_wgrad_x3(gs, xs, out=None, accumulate=False):
+    """dW[Nout, Kin] fp32 (+)= dY^T X from the split operands gs bf16 [rows, 3Nout], xs bf16 [rows, 3Kin]"""
+    nout, kin = gs.shape[1] // 3, xs.shape[1] // 3
+    if out is None:
+        assert not accumulate
+        out = torch.empty(nout, kin, dtype=torch.float32, device=xs.device)
+    for k, (bg, bx) in enumerate(((0, 0), (0, 1), (1, 0))):
+        linear_wgrad(gs[:, bg * nout:(bg + 1) * nout], xs[:, bx * kin:(bx + 1) * kin], out=out,
+                     accumulate=accumulate or k > 0)
+    return out
+
+
+def maxpool2x2_nhwc_f32(x):
+    require_cuda(x)
+    assert x.dtype == torch.float32 and x.is_contiguous() and x.dim() == 4
+    NB, H, W, C = x.shape
+    y = torch.empty(NB, H // 2, W // 2, C, dtype=x.dtype, device=x.device)
+    with torch.cuda.device(x.device):
+        check(load().scda_maxpool2x2_nhwc_f32(NB, H, W, C, x.data_ptr(), y.data_ptr(), stream_ptr(x.device)),
+              "scda_maxpool2x2_nhwc_f32")
+    return y
+
+
+def maxpool2x2_bwd_nhwc_f32(x, dy, relu_mask=True):
+    require_cuda(x, dy)
+    assert x.dtype == torch.float32 and dy.dtype == torch.float32 and x.is_contiguous() and dy.is_contiguous()
+    NB, H, W, C = x.shape
+    assert tuple(dy.shape) == (NB, H // 2, W // 2, C)
+    dx = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        check(load().scda_maxpool2x2_bwd_nhwc_f32(NB, H, W, C, x.data_ptr(), dy.data_ptr(), dx.data_ptr(),
+                                                  1 if relu_mask else 0, stream_ptr(x.device)),
+              "scda_maxpool2x2_bwd_nhwc_f32")
+    return dx
+
+
+def nchw_f32_to_nhwc_f32(x, c_pad=None):
+    require_cuda(x)
+    assert x.dtype == torch.float32 and x.is_contiguous() and x.dim() == 4
+    NB, C, H, W = x.shape
+    c_pad = C if c_pad is None else c_pad
+    y = torch.empty(NB, H, W, c_pad, dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        check(load().scda_nchw_f32_to_nhwc_f32(NB, C, H, W, c_pad, x.data_ptr(), y.data_ptr(),
+                                               stream_ptr(x.device)), "scda_nchw_f32_to_nhwc_f32")
+    return y
+
+
+def colsum_f32_into(x2d, out):
+    """out[N] (fp32) += column sums of x2d[M, N] (fp32, any row stride)."""
+    require_cuda(x2d, out)
+    assert x2d.dtype == torch.float32 and x2d.dim() == 2 and x2d.stride(1) == 1
+    assert out.dtype == torch.float32 and out.is_contiguous() and out.numel() == x2d.shape[1]
+    with torch.cuda.device(x2d.device):
+        check(load().scda_colsum_f32_ld(x2d.shape[0], x2d.shape[1], x2d.data_ptr(), x2d.stride(0),
+                                        out.data_ptr(), stream_ptr(x2d.device)), "scda_colsum_f32_ld")
+    return out
+
+
+def roi_pool_nhwc_f32(feat, rois, pooled_height, pooled_width, spatial_scale):
+    """feat [NB,H,W,C] fp32, rois [R,5] fp32 -> (out [R, C*PH*PW] fp32 channel-major, argmax int16 bits)"""
+    require_cuda(feat, rois)
+    assert feat.dtype == torch.float32 and feat.is_contiguous() and feat.dim() == 4
+    assert rois.dtype == torch.float32 and rois.is_contiguous() and rois.dim() == 2 and rois.shape[1] == 5
+    NB, H, W, C = feat.shape
+    R = rois.shape[0]
+    n = C * pooled_height * pooled_width
+    out = torch.empty(R, n, dtype=torch.float32, device=feat.device)
+    argmax = torch.empty(R, n, dtype=torch.int16, device=feat.device)
+    with torch.cuda.device(feat.device):
+        check(load().scda_roi_pool_nhwc_f32_fwd(feat.data_ptr(), spatial_scale, R, NB, H, W, C, pooled_height,
+                                                pooled_width, rois.data_ptr(), out.data_ptr(),
+                                                argmax.data_ptr(), stream_ptr(feat.device)),
+              "scda_roi_pool_nhwc_f32_fwd")
+    return out, argmax
+
+
+def roi_pool_nhwc_f32_bwd(dout, argmax, rois, geom, pooled_height, pooled_width):
+    require_cuda(dout, argmax, rois)
+    NB, H, W, C = geom
+    assert dout.dtype == torch.float32 and dout.is_contiguous() and argmax.is_contiguous()
+    dfeat = torch.empty(NB, H, W, C, dtype=torch.float32, device=dout.device)
+    with torch.cuda.device(dout.device):
+        check(load().scda_roi_pool_nhwc_f32_bwd(dout.data_ptr(), argmax.data_ptr(), rois.data_ptr(),
+                                                rois.shape[0], NB, H, W, C, pooled_height, pooled_width,
+                                                dfeat.data_ptr(), stream_ptr(dout.device)),
+              "scda_roi_pool_nhwc_f32_bwd")
     return dfeat

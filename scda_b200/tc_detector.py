@@ -47,6 +47,33 @@ def shadow_of(p):
     return sh
 
 
+def shadow3_of(p, pad_in=None):
+    """(fwd, stk) split shadows of parameter p for the 'bf16x3' mode (csrc/x3_ops.cu), cached on the
+    parameter and re-derived when it changed (`_version`, or the optimiser's `_scda_epoch`):
+    conv [O,I,3,3] -> fwd bf16 [O,3,3,3I] ([hi|hi|lo] per tap), stk bf16 [3O,3,3,I] ([hi;hi;lo]);
+    linear [N,K] -> fwd [N,3K], stk [3N,K].  pad_in zero-pads the input channels first (conv1_1)."""
+    stamp = (p._version, getattr(p, "_scda_epoch", 0), pad_in)
+    ent = getattr(p, "_scda_x3", None)
+    if ent is not None and ent[0] == stamp:
+        return ent[1]
+    src = p.detach()
+    if p.dim() == 4:
+        O, I = p.shape[0], p.shape[1]
+        w = src.permute(0, 2, 3, 1)
+        if pad_in is not None and pad_in > I:
+            wp = torch.zeros(O, 3, 3, pad_in, dtype=torch.float32, device=p.device)
+            wp[..., :I].copy_(w)
+            w, I = wp, pad_in
+        w = w.contiguous()
+        fwd, _ = tc.split_weights(w.view(O * 9, I), want_stk=False)
+        _, stk = tc.split_weights(w.view(O, 9 * I), want_fwd=False)
+        val = (fwd.view(O, 3, 3, 3 * I), stk.view(3 * O, 3, 3, I))
+    else:
+        val = tc.split_weights(src.contiguous())
+    p._scda_x3 = (stamp, val)
+    return val
+
+
 class TcDetector(object):
     def __init__(self, vgg):
         import torch.nn as nn
@@ -114,24 +141,49 @@ class TcDetector(object):
             return w, b, nc, nl
         return self._derive("rcnn", ps, build)
 
+    # ------------------------------------------------------------------ fp32-parity mode shadows
+    def shadow3(self, p, pad_in=None):
+        return shadow3_of(p, pad_in)
+
+    def cat3(self, key):
+        """split shadows of the concatenated (cls | loc) head, rows zero-padded to a multiple of 8"""
+        if key == "rpn":
+            h = self.vgg.rpn_head
+            ps = (h.conv_cls.weight, h.conv_cls.bias, h.conv_loc.weight, h.conv_loc.bias)
+        else:
+            v = self.vgg
+            ps = (v.fc_rcnn_cls.weight, v.fc_rcnn_cls.bias, v.fc_rcnn_loc.weight, v.fc_rcnn_loc.bias)
+
+        def build():
+            nc, nl, k = ps[0].shape[0], ps[2].shape[0], ps[0].shape[1]
+            n = nc + nl
+            w = torch.zeros((n + 7) // 8 * 8, k, dtype=torch.float32, device=ps[0].device)
+            w[:nc].copy_(ps[0].detach().reshape(nc, k))
+            w[nc:n].copy_(ps[2].detach().reshape(nl, k))
+            fwd, stk = tc.split_weights(w)
+            b = torch.cat([ps[1].detach(), ps[3].detach()]).float().contiguous()
+            return fwd, stk, b, nc, nl
+        return self._derive("x3" + key, ps, build)
+
     # ------------------------------------------------------------------ stages
     def features(self, image):
         params = []
         for m, _ in self.convs:
             params += [m.weight, m.bias]
-        return _BackboneFn.apply(image, self, *params)
+        return (_BackboneFnX3 if tc.x3() else _BackboneFn).apply(image, self, *params)
 
     def rpn(self, feat):
         h = self.vgg.rpn_head
-        return _RpnHeadFn.apply(feat, self, h.conv3x3.weight, h.conv3x3.bias, h.conv_cls.weight,
-                                h.conv_cls.bias, h.conv_loc.weight, h.conv_loc.bias)
+        return (_RpnHeadFnX3 if tc.x3() else _RpnHeadFn).apply(
+            feat, self, h.conv3x3.weight, h.conv3x3.bias, h.conv_cls.weight, h.conv_cls.bias, h.conv_loc.weight,
+            h.conv_loc.bias)
 
     def rcnn(self, feat, rois):
         v = self.vgg
         fc6, fc7 = v.classifier[0], v.classifier[3]
         p_drop = (v.classifier[2].p, v.classifier[5].p) if v.training else (0.0, 0.0)
         pool = v.roipooling
-        return _RcnnHeadFn.apply(feat, rois, self, (pool.pooled_height, pool.pooled_width,
+        return (_RcnnHeadFnX3 if tc.x3() else _RcnnHeadFn).apply(feat, rois, self, (pool.pooled_height, pool.pooled_width,
                                                     pool.spatial_scale), p_drop,
                                  fc6.weight, fc6.bias, fc7.weight, fc7.bias,
                                  v.fc_rcnn_cls.weight, v.fc_rcnn_cls.bias,
@@ -376,4 +428,208 @@ class _RcnnHeadFn(torch.autograd.Function):
         gw6 = _sink_linear_wgrad(w6, d6, x)
         dx = tc.gemm_nn(d6, rt.shadow(w6))                                    # [R, C*ph*pw] bf16
         d_feat = tc.roi_pool_nhwc_bwd(dx, argmax, rois, (NB, H, W, C), ph, pw).to(torch.bfloat16)
+        return d_feat, None, None, None, None, gw6, gb6, gw7, gb7, gwc, gbc, gwl, gbl
+
+
+# ======================================================================================
+# fp32-parity mode ('bf16x3', tc.set_precision): the same three stages with fp32 NHWC activations
+# and gradients; every contraction runs on the same tcgen05 kernels with split operands
+# (A = [hi|lo|hi], B = [hi|hi|lo]: csrc/x3_ops.cu).  Reference arithmetic: fp32 cuDNN / cuBLAS
+# (vgg_adver_expansion_cluster.py:46-60,101-114, models/head.py:13-18).
+def _sink_conv_wgrad_x3(p, xs, gs, cin_real=None):
+    if cin_real is None and _direct(p) and _is_krsc(p.grad):
+        tc.conv3x3_wgrad_x3(xs, gs, out=p.grad, accumulate=not _take_fresh(p))
+        return None
+    dw = tc.conv3x3_wgrad_x3(xs, gs)                       # [O,3,3,Ipad]
+    if cin_real is not None:
+        dw = dw[..., :cin_real]
+    dw = dw.permute(0, 3, 1, 2)
+    if _direct(p):
+        if _take_fresh(p):
+            p.grad.copy_(dw)
+        else:
+            p.grad.add_(dw)
+        return None
+    return dw.contiguous()
+
+
+def _sink_linear_wgrad_x3(p, gs, xs):
+    if _direct(p) and p.grad.stride(-1) == 1 and p.grad.dim() == 2:
+        tc.linear_wgrad_x3(gs, xs, out=p.grad, accumulate=not _take_fresh(p))
+        return None
+    return tc.linear_wgrad_x3(gs, xs)
+
+
+def _sink_bias_f32(p, g2d):
+    if _direct(p) and p.grad.is_contiguous():
+        if _take_fresh(p):
+            p.grad.zero_()
+        tc.colsum_f32_into(g2d, p.grad)
+        return None
+    out = torch.zeros(p.shape, dtype=torch.float32, device=p.device)
+    tc.colsum_f32_into(g2d, out)
+    return out
+
+
+class _BackboneFnX3(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, image, rt, *params):
+        assert image.is_cuda and image.dtype == torch.float32 and image.dim() == 4
+        x = tc.nchw_f32_to_nhwc_f32(image.contiguous(), 64)
+        saved = []
+        for i, (m, pool) in enumerate(rt.convs):
+            xs = tc.split3(x)
+            wf, _ = rt.shadow3(m.weight, pad_in=64 if i == 0 else None)
+            y = tc.conv3x3_nhwc(xs, wf, m.bias.detach(), relu=True, out_dtype=torch.float32)
+            saved += [xs, y]
+            x = tc.maxpool2x2_nhwc_f32(y) if pool else y
+        ctx.rt = rt
+        ctx.cin = image.shape[1]
+        ctx.save_for_backward(*saved)
+        return x
+
+    @staticmethod
+    def backward(ctx, g_feat):
+        rt = ctx.rt
+        saved = list(ctx.saved_tensors)
+        ins = saved[0::2]           # split input of conv i
+        outs = saved[1::2]          # fp32 output (after ReLU) of conv i
+        last = len(rt.convs) - 1
+        assert not rt.convs[last][1], "the stack ends with a convolution (last pool dropped)"
+        g = g_feat.contiguous().float()
+        g = torch.where(outs[last] > 0, g, torch.zeros_like(g))
+        grads = [None] * (2 * len(rt.convs))
+        for i in range(last, -1, -1):
+            m, _ = rt.convs[i]
+            cout = m.weight.shape[0]
+            grads[2 * i + 1] = _sink_bias_f32(m.bias, g.view(-1, cout))
+            gs = tc.split3(g)
+            if i == 0:
+                grads[0] = _sink_conv_wgrad_x3(m.weight, ins[0], gs, cin_real=ctx.cin)
+                break
+            grads[2 * i] = _sink_conv_wgrad_x3(m.weight, ins[i], gs)
+            _, ws = rt.shadow3(m.weight)
+            if rt.convs[i - 1][1]:
+                d_pooled = tc.conv3x3_dgrad_nhwc(gs, ws, out_dtype=torch.float32)
+                g = tc.maxpool2x2_bwd_nhwc_f32(outs[i - 1], d_pooled, relu_mask=True)
+            else:
+                g = tc.conv3x3_dgrad_nhwc(gs, ws, mask_src=outs[i - 1], out_dtype=torch.float32)
+        return (None, None) + tuple(grads)
+
+
+class _RpnHeadFnX3(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, feat, rt, w3, b3, wc, bc, wl, bl):
+        NB, H, W, C = feat.shape
+        fs = tc.split3(feat.contiguous().float())
+        w3f, _ = rt.shadow3(w3)
+        hidden = tc.conv3x3_nhwc(fs, w3f, b3.detach(), relu=True, out_dtype=torch.float32)
+        hs = tc.split3(hidden)
+        wf, _, bcat, nc, nl = rt.cat3("rpn")
+        out = tc.gemm_tn(hs.view(-1, hs.shape[3]), wf[:nc + nl], bcat, out_dtype=torch.float32)
+        out = out.view(NB, H, W, nc + nl)
+        cls = out[..., :nc].permute(0, 3, 1, 2).contiguous()
+        loc = out[..., nc:].permute(0, 3, 1, 2).contiguous()
+        ctx.rt = rt
+        ctx.save_for_backward(fs, hidden, hs)
+        return cls, loc
+
+    @staticmethod
+    def backward(ctx, g_cls, g_loc):
+        rt = ctx.rt
+        fs, hidden, hs = ctx.saved_tensors
+        h = rt.vgg.rpn_head
+        w3, b3, wc, bc, wl, bl = (h.conv3x3.weight, h.conv3x3.bias, h.conv_cls.weight, h.conv_cls.bias,
+                                  h.conv_loc.weight, h.conv_loc.bias)
+        NB, H, W, C = hidden.shape
+        wf, wstk, _, nc, nl = rt.cat3("rpn")
+        npad = wf.shape[0]
+        g = torch.zeros(NB, H, W, npad, dtype=torch.float32, device=hidden.device)
+        gb = [None, None]
+        if g_cls is not None:
+            g[..., :nc].copy_(g_cls.permute(0, 2, 3, 1))
+            gb[0] = _sink_small(bc, g_cls.sum((0, 2, 3)))
+        if g_loc is not None:
+            g[..., nc:nc + nl].copy_(g_loc.permute(0, 2, 3, 1))
+            gb[1] = _sink_small(bl, g_loc.sum((0, 2, 3)))
+        gs = tc.split3(g.view(-1, npad))
+        dwcat = tc.linear_wgrad_x3(gs, hs.view(-1, hs.shape[3]))          # [npad, C] fp32
+        gwc = _sink_small(wc, dwcat[:nc])
+        gwl = _sink_small(wl, dwcat[nc:nc + nl])
+        d_hidden = tc.gemm_nn(gs, wstk, mask_src=hidden.view(-1, C), out_dtype=torch.float32).view(NB, H, W, C)
+        gb3 = _sink_bias_f32(b3, d_hidden.view(-1, C))
+        ds = tc.split3(d_hidden)
+        gw3 = _sink_conv_wgrad_x3(w3, fs, ds)
+        _, w3s = rt.shadow3(w3)
+        d_feat = tc.conv3x3_dgrad_nhwc(ds, w3s, out_dtype=torch.float32)
+        return d_feat, None, gw3, gb3, gwc, gb[0], gwl, gb[1]
+
+
+class _RcnnHeadFnX3(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, feat, rois, rt, pool, p_drop, w6, b6, w7, b7, wc, bc, wl, bl):
+        ph, pw, scale = pool
+        NB, H, W, C = feat.shape
+        R = rois.shape[0]
+        rois = rois.contiguous().float()
+        x, argmax = tc.roi_pool_nhwc_f32(feat.contiguous().float(), rois, ph, pw, scale)    # [R, C*ph*pw] fp32
+        dm6 = _dropout_scale((R, w6.shape[0]), p_drop[0], feat.device)
+        dm7 = _dropout_scale((R, w7.shape[0]), p_drop[1], feat.device)
+        xs = tc.split3(x)
+        h6 = tc.gemm_tn(xs, rt.shadow3(w6)[0], b6.detach(), relu=True, mul_src=dm6, out_dtype=torch.float32)
+        h6s = tc.split3(h6)
+        h7 = tc.gemm_tn(h6s, rt.shadow3(w7)[0], b7.detach(), relu=True, mul_src=dm7, out_dtype=torch.float32)
+        h7s = tc.split3(h7)
+        wf, _, bcat, nc, nl = rt.cat3("rcnn")
+        out = tc.gemm_tn(h7s, wf[:nc + nl], bcat, out_dtype=torch.float32)
+        ctx.rt, ctx.pool, ctx.geom = rt, pool, (NB, H, W, C)
+        ctx.has_drop = (dm6 is not None, dm7 is not None)
+        keep = [rois, argmax, xs, h6, h6s, h7, h7s] + [t for t in (dm6, dm7) if t is not None]
+        ctx.save_for_backward(*keep)
+        ctx.set_materialize_grads(False)
+        return h7, out[:, :nc].contiguous(), out[:, nc:].contiguous()
+
+    @staticmethod
+    def backward(ctx, g_fea, g_cls, g_loc):
+        rt = ctx.rt
+        saved = list(ctx.saved_tensors)
+        rois, argmax, xs, h6, h6s, h7, h7s = saved[:7]
+        rest = saved[7:]
+        dm6 = rest.pop(0) if ctx.has_drop[0] else None
+        dm7 = rest.pop(0) if ctx.has_drop[1] else None
+        v = rt.vgg
+        w6, b6, w7, b7 = v.classifier[0].weight, v.classifier[0].bias, v.classifier[3].weight, v.classifier[3].bias
+        wc, bc, wl, bl = v.fc_rcnn_cls.weight, v.fc_rcnn_cls.bias, v.fc_rcnn_loc.weight, v.fc_rcnn_loc.bias
+        ph, pw, scale = ctx.pool
+        NB, H, W, C = ctx.geom
+        R = xs.shape[0]
+        wf, wstk, _, nc, nl = rt.cat3("rcnn")
+        npad = wf.shape[0]
+        g = torch.zeros(R, npad, dtype=torch.float32, device=xs.device)
+        gbc = gbl = None
+        if g_cls is not None:
+            g[:, :nc].copy_(g_cls)
+            gbc = _sink_small(bc, g_cls.sum(0))
+        if g_loc is not None:
+            g[:, nc:nc + nl].copy_(g_loc)
+            gbl = _sink_small(bl, g_loc.sum(0))
+        gs = tc.split3(g)
+        dwcat = tc.linear_wgrad_x3(gs, h7s)
+        gwc = _sink_small(wc, dwcat[:nc])
+        gwl = _sink_small(wl, dwcat[nc:nc + nl])
+        d7 = tc.gemm_nn(gs, wstk, mask_src=h7, mul_src=dm7, out_dtype=torch.float32)
+        if g_fea is not None:
+            extra = g_fea.float()
+            if dm7 is not None:
+                extra = extra * dm7.float()
+            d7 = d7 + torch.where(h7 > 0, extra, torch.zeros_like(extra))
+        gb7 = _sink_bias_f32(b7, d7)
+        d7s = tc.split3(d7)
+        gw7 = _sink_linear_wgrad_x3(w7, d7s, h6s)
+        d6 = tc.gemm_nn(d7s, rt.shadow3(w7)[1], mask_src=h6, mul_src=dm6, out_dtype=torch.float32)
+        gb6 = _sink_bias_f32(b6, d6)
+        d6s = tc.split3(d6)
+        gw6 = _sink_linear_wgrad_x3(w6, d6s, xs)
+        dx = tc.gemm_nn(d6s, rt.shadow3(w6)[1], out_dtype=torch.float32)               # [R, C*ph*pw] fp32
+        d_feat = tc.roi_pool_nhwc_f32_bwd(dx, argmax, rois, (NB, H, W, C), ph, pw)
         return d_feat, None, None, None, None, gw6, gb6, gw7, gb7, gwc, gbc, gwl, gbl

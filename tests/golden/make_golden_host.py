@@ -106,7 +106,7 @@ def main():
     # fixtures stay small: the RPN maps are regenerated from the seed by the tests
     del out["rpn_cls"], out["rpn_loc"]
     np.savez_compressed(os.path.join(HERE, "host_plumbing.npz"), **out)
-    json.dump(c, open(os.path.join(HERE, "config_512_merged.json"), "w"), indent=1)
+    json.dump(c, open(os.path.join(HERE, "..", "..", "scda_b200", "configs", "config_512_merged.json"), "w"), indent=1)
     print({k: getattr(v, "shape", v) for k, v in out.items()})
 
 
