@@ -200,28 +200,27 @@ class FasterRCNN_AdEx(nn.Module):
             conv_loc = getattr(getattr(self, 'rpn_head', None), 'conv_loc', None)
             anchor_pre = None
             if astream is not None and conv_loc is not None:
-                stride = int(cfg['train_anchor_target_cfg']['anchor_stride'])
-                size_pre = (x_input.shape[0], conv_loc.out_channels, x_input.shape[2] // stride,
-                            x_input.shape[3] // stride)
+                # forked from HERE (an event in front of the backbone) but issued BEHIND the backbone:
+                # a replayed CUDA graph dispatches its nodes roughly in creation order, and ~110 tiny
+                # kernels created first held the backbone's first node back by 0.58 ms
+                # (profiles/r2_timeline_a_forward.txt)
                 main_stream = torch.cuda.current_stream()
-                astream.wait_stream(main_stream)
-                with torch.cuda.stream(astream):
-                    anchor_pre = (size_pre, partial_fn['anchor_target_fn'](size_pre))
+                fork_point = torch.cuda.Event()
+                fork_point.record(main_stream)
 
             x = self.feature_extractor(x_input)
             rpn_pred_cls, rpn_pred_loc = self.rpn(x)
-            if anchor_pre is not None:
-                main_stream.wait_stream(astream)
-                if tuple(rpn_pred_loc.size()) == tuple(anchor_pre[0]):
-                    pre = anchor_pre[1]
-                    partial_fn['anchor_target_fn'] = lambda size: pre
+            if astream is not None and conv_loc is not None:
+                astream.wait_event(fork_point)
+                with torch.cuda.stream(astream):
+                    pre = partial_fn['anchor_target_fn'](rpn_pred_loc.size())
+                anchor_pre = pre
+                partial_fn['anchor_target_fn'] = lambda size: pre
             if tstream is not None and not early:
                 cur_stream = torch.cuda.current_stream()
                 tstream.wait_stream(cur_stream)
                 with torch.cuda.stream(tstream):
                     tgt = run_target()
-            rpn_loss_cls, rpn_loss_loc, rpn_acc = self._add_rpn_loss(
-                partial_fn['anchor_target_fn'], rpn_pred_cls, rpn_pred_loc)
             props = rpn_proposals_device(self._rpn_scores(rpn_pred_cls).data, rpn_pred_loc.data,
                                          pcfg, image_info)
             rois, cls_targets, loc_targets, loc_weights = self._train_rois(
@@ -232,7 +231,7 @@ class FasterRCNN_AdEx(nn.Module):
                 ktap = {}
                 x_cluster_fea, x_center_cluster = cluster_targets_device(
                     rois, x_fea, N_cluster=input['cluster_num'], threshold=input['threshold'], taps=ktap)
-                taps.update(cluster_src=ktap, anchor_targets=partial_fn['anchor_target_fn'](rpn_pred_loc.size()),
+                taps.update(cluster_src=ktap,
                             rois_targets=(rois, cls_targets, loc_targets, loc_weights), feat=x,
                             rpn_cls=rpn_pred_cls, rpn_loc=rpn_pred_loc, fc7=x_fea, rcnn_cls=rcnn_pred_cls,
                             rcnn_loc=rcnn_pred_loc, proposals=props)
@@ -247,6 +246,17 @@ class FasterRCNN_AdEx(nn.Module):
             x_gan, proposals_gan, enough, x_fea_gan, clusters_gan = tgt
             assert x_gan.size() == x.size(), "gan_features does not match the backbone"
 
+            # the RPN losses are only needed by the backward: computed here, at the end of the forward,
+            # so that the proposal / RoI stages above never wait for the anchor targets
+            if anchor_pre is not None:
+                torch.cuda.current_stream().wait_stream(astream)
+                for t_ in anchor_pre:
+                    if torch.is_tensor(t_):
+                        t_.record_stream(torch.cuda.current_stream())
+            if taps is not None:
+                taps.update(anchor_targets=partial_fn['anchor_target_fn'](rpn_pred_loc.size()))
+            rpn_loss_cls, rpn_loss_loc, rpn_acc = self._add_rpn_loss(
+                partial_fn['anchor_target_fn'], rpn_pred_cls, rpn_pred_loc)
             rcnn_loss_cls, rcnn_loss_loc, rcnn_acc = self._add_rcnn_loss(
                 rcnn_pred_cls, rcnn_pred_loc, cls_targets, loc_targets, loc_weights)
             outputs['losses'] = [rpn_loss_cls, rpn_loss_loc, rcnn_loss_cls, rcnn_loss_loc]
