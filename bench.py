@@ -170,17 +170,20 @@ VGG_CONVS = [(3, 64, 512, 1024), (64, 64, 512, 1024), (64, 128, 256, 512), (128,
              (512, 512, 32, 64)]     # (Cin, Cout, H, W) of the 13 backbone convolutions at 512 x 1024
 
 
-def roofline_probe(dev):
+def roofline_probe(dev, x3=False):
     """Dominant hand-written kernel = the tcgen05 halo convolution (conv_halo_kernel):
     the 13 backbone launches of one image timed back to back with CUDA events on the launch
     stream (L2 flushed before each pass).  Algorithmic work = 2 * H * W * Cin * Cout * 9 per
     layer (conv1_1 counted with its 3 real input channels) = 320.71 GFLOP per image
-    (SURVEY.md section 8d); achieved = that / the time of the 13 launches."""
+    (SURVEY.md section 8d); achieved = that / the time of the 13 launches.
+    x3: the fp32-parity mode — the same kernel on split operands (three bf16 MMAs per product,
+    csrc/x3_ops.cu), fp32 output; the peak it is held against is bf16_tflops / 3."""
     from scda_b200 import tc
     hbm, tf, tf_sus, src = peaks()
     xs, ws, bs = [], [], []
+    mult = 3 if x3 else 1
     for cin, cout, h, w in VGG_CONVS:
-        cp = max(cin, 64)
+        cp = max(cin, 64) * mult
         xs.append(torch.randn(1, h, w, cp, device=dev).bfloat16())
         ws.append((torch.randn(cout, 3, 3, cp, device=dev) / (9 * cp) ** 0.5).bfloat16())
         bs.append(torch.zeros(cout, device=dev))
@@ -192,18 +195,21 @@ def roofline_probe(dev):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         for x, w, bias in zip(xs, ws, bs):
-            tc.conv3x3_nhwc(x, w, bias, relu=True)
+            tc.conv3x3_nhwc(x, w, bias, relu=True, out_dtype=torch.float32 if x3 else torch.bfloat16)
         b.record()
         b.synchronize()
         if i >= 3:
             ts.append(a.elapsed_time(b) * 1e-3)
     t = float(np.mean(ts))
-    return {"bound": "tensor", "achieved": flops / t / 1e12, "peak": tf, "unit": "TFLOP/s",
-            "frac": flops / t / 1e12 / tf, "traffic": NCU_DRAM_BYTES_PER_LAUNCH,
-            "traffic_source": NCU_TRAFFIC_SOURCE,
+    peak = tf / mult
+    return {"bound": "tensor", "achieved": flops / t / 1e12, "peak": peak, "unit": "TFLOP/s",
+            "frac": flops / t / 1e12 / peak, "traffic": None if x3 else NCU_DRAM_BYTES_PER_LAUNCH,
+            "traffic_source": None if x3 else NCU_TRAFFIC_SOURCE,
             "kernel": "conv_halo_kernel (tcgen05 + TMA 3x3 convolution, input halo staged once for the nine taps, "
-                      "+ bias + ReLU), 13 backbone launches",
-            "peak_source": src + " (MEASURED_PEAKS.json bf16_tflops, burst: kernels timed alone)",
+                      "+ bias + ReLU), 13 backbone launches"
+                      + (" on hi/lo split operands (3 bf16 MMAs per fp32 product), fp32 output" if x3 else ""),
+            "peak_source": src + " (MEASURED_PEAKS.json bf16_tflops, burst: kernels timed alone)"
+                           + (" / 3: three tensor-core products per algorithmic product" if x3 else ""),
             "algorithmic_flops_per_launch": flops / len(VGG_CONVS),
             "avg_launch_us": t / len(VGG_CONVS) * 1e6}
 
@@ -267,6 +273,8 @@ def our_arm(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     _lib.load()
+    from scda_b200 import gan_ops, tc
+    tc.set_precision(args.precision)
     cfg = load_cfg()
     tr = build_trainer(cfg, world_size=world, seed=0, use_graphs=not args.no_graphs,
                        overlap=not args.no_overlap,
@@ -323,32 +331,63 @@ def our_arm(args):
     barrier()
     ms2 = a2.elapsed_time(b2)
 
+    whole_graph, overlap_on = tr._whole_graph(), tr.overlap
     if world > 1:
         t = torch.tensor([ms, ms2], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, ms2 = float(t[0]), float(t[1])
+    parity = None
+    if rank == 0 and world == 1 and args.precision == "bf16" and not args.no_parity_line:
+        # the same iteration in the fp32-parity precision mode (tc.set_precision('bf16x3')), timed in
+        # this process right after the headline run: a second trainer, 3 warm-up + 10 timed steps
+        del tr
+        torch.cuda.empty_cache()
+        tc.set_precision("bf16x3")
+        tr3 = build_trainer(cfg, world_size=1, seed=0, use_graphs=not args.no_graphs, overlap=not args.no_overlap)
+        for _ in range(4):
+            tr3.iteration(cfg, d_image, info, d_gts, d_target)
+        torch.cuda.synchronize()
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0.record()
+        for _ in range(10):
+            tr3.iteration(cfg, d_image, info, d_gts, d_target)
+        p1.record()
+        torch.cuda.synchronize()
+        pms = p0.elapsed_time(p1) / 10
+        roof3 = roofline_probe(dev, x3=True)
+        parity = {"dtype": "bf16x3 (fp32 activations; operands split into bf16 hi + lo, 3 MMAs per product, "
+                           "~2^-16 per product; the reference's arithmetic is fp32)",
+                  "value": 1e3 / pms, "unit": UNIT, "ms_per_step": pms, "steps": 10, "warmup": 4,
+                  "roofline": {k: roof3[k] for k in ("bound", "achieved", "peak", "unit", "frac", "peak_source")},
+                  "parity": "tests/test_iteration_parity_gpu.py, profiles/r2_iteration_parity.txt"}
+        del tr3
+        tc.set_precision("bf16")
+        tr = None
     if rank == 0:
-        roof = roofline_probe(dev)
+        roof = roofline_probe(dev, x3=args.precision == "bf16x3")
         line = {"metric": METRIC, "value": world * args.steps / (ms / 1e3), "unit": UNIT,
                 "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
                 "config": {"workload": WORKLOAD, "parallelism": "dp%d" % world,
                            "execution": ("eager" if args.no_graphs else
                                          "one CUDA graph per iteration" + (", NCCL all-reduces captured" if world > 1 else "")
-                                         if tr._whole_graph() else
+                                         if whole_graph else
                                          "eleven CUDA graphs per iteration on three streams, cut at the gradient all-reduces "
                                          "(NCCL issued between them)")
                            + (", detector backward + Adam overlapped with the reconstruction/discriminator "
                               "updates on a second stream, target-image branch beside the source branch"
-                              if tr.overlap else ""),
+                              if overlap_on else ""),
                            "l2": "per-step working set (547 MB of fp32 weights + activations) exceeds the "
                                  "126 MB L2; no explicit flush"},
                 "clocks": clocks,
                 "e2e": {"value": world * args.steps / (ms2 / 1e3), "unit": UNIT,
                         "h2d_bytes_per_step": int(h_image.numel() * 4 + h_target.numel() * 4 + h_gts.numel() * 4),
                         "d2h_bytes_per_step": 4, "last_loss": last},
-                "gpu_launches": launches, "roofline": roof}
+                "gpu_launches": launches, "roofline": roof,
+                "library_fallbacks": dict(gan_ops.LIBRARY_CALLS)}
+        if parity is not None:
+            line["parity_mode"] = parity
         if world == 1:
             line["aux"] = aux_ops(dev)
         if world == 1 and not args.no_cpu_baseline:
@@ -371,6 +410,9 @@ def main():
     ap.add_argument("--no-graphs", action="store_true", help="eager execution (for kernel profilers)")
     ap.add_argument("--no-overlap", action="store_true", help="single stream (no detector/GAN overlap)")
     ap.add_argument("--force-cut", action="store_true", help="1 GPU: replay the cut (world > 1) graph plan")
+    ap.add_argument("--precision", "--dtype", dest="precision", default="bf16", choices=["bf16", "bf16x3"],
+                    help="bf16: throughput mode; bf16x3: fp32-parity mode (3 bf16 MMAs per product)")
+    ap.add_argument("--no-parity-line", action="store_true", help="skip the bf16x3 sub-measurement")
     ap.add_argument("--no-graph-collectives", action="store_true",
                     help="world > 1: cut the graph at the all-reduces instead of capturing NCCL")
     args = ap.parse_args()

@@ -401,6 +401,25 @@ int scda_nchw_f32_to_nhwc_f32(int NB, int C, int H, int W, int Cpad, const float
 /* out[N] += column sums of x fp32 [M, ld] (any N, any ld >= N) */
 int scda_colsum_f32_ld(long long M, int N, const float *x, long long ld, float *out, cudaStream_t stream);
 
+/* --- detector losses -------------------------------------------------- */
+/* F.cross_entropy(logits, targets, ignore_index) (mean over the counted rows) AND the reference's
+ * top-1 `accuracy` in one pass (_add_rpn_loss / _add_rcnn_loss,
+ * faster_rcnn_adver_expansion_reweight_cluster.py:36-68, 249-267).  logits fp32 [M, C] with row stride
+ * ld, C <= 32; targets int64 [M].  out3 = {loss, accuracy in percent, rows counted} (device floats; loss
+ * is NaN when no row is counted, as torch).  workspace >= scda_softmax_ce_workspace_bytes(M).
+ * Backward: dlogits[m, c] = grad_loss[0] * (softmax - onehot) / rows counted, 0 for ignored rows. */
+size_t scda_softmax_ce_workspace_bytes(long long M);
+int scda_softmax_ce_acc_fwd(long long M, int C, const float *logits, long long ld, const long long *targets,
+                            long long ignore_index, float *out3, void *workspace, size_t workspace_bytes,
+                            cudaStream_t stream);
+int scda_softmax_ce_bwd(long long M, int C, const float *logits, long long ld, const long long *targets,
+                        long long ignore_index, const float *stats3, const float *grad_loss, float *dlogits,
+                        long long lddx, cudaStream_t stream);
+/* RPN objectness (…reweight_cluster.py:153-155, functions/rpn_proposal.py:44-49): 2-way softmax over each
+ * anchor's (bg, fg) channel pair of the NCHW class map [B, 2A, H, W]; the foreground probability is written
+ * in the proposal stage's anchor order, scores[b, (h*W + w)*A + a]. */
+int scda_rpn_fg_scores(int B, int A, int H, int W, const float *cls_nchw, float *scores, cudaStream_t stream);
+
 /* --- optimiser -------------------------------------------------------- */
 /* replaces torch.optim.Adam(...).step() on each of the four networks
  * (tools/faster_rcnn_train_val.py:305-316 construct, :616,:635,:704,:750 step): one pass

@@ -76,6 +76,10 @@ SIGNATURES = {
     "scda_smooth_l1_sigma_sum_bwd": (_i, [C.c_longlong, _p, _p, _p, _f, _p, _p, _p]),
     "scda_bce_sigmoid_rows_fwd": (_i, [_i, _i, _p, _p, _i, _p, _p]),
     "scda_bce_sigmoid_rows_bwd": (_i, [_i, _i, _p, _p, _i, _p, _p, _p]),
+    "scda_softmax_ce_workspace_bytes": (_z, [C.c_longlong]),
+    "scda_softmax_ce_acc_fwd": (_i, [C.c_longlong, _i, _p, C.c_longlong, _p, C.c_longlong, _p, _p, _z, _p]),
+    "scda_softmax_ce_bwd": (_i, [C.c_longlong, _i, _p, C.c_longlong, _p, C.c_longlong, _p, _p, _p, C.c_longlong, _p]),
+    "scda_rpn_fg_scores": (_i, [_i, _i, _i, _i, _p, _p, _p]),
     "scda_conv1x1_tanh_workspace_bytes": (_z, [C.c_longlong, _i, _i]),
     "scda_conv1x1_tanh_fwd": (_i, [C.c_longlong, _i, _i, _p, _p, _p, _p, _p]),
     "scda_conv1x1_tanh_bwd": (_i, [C.c_longlong, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _z, _p]),
@@ -120,7 +124,8 @@ def load(path: str | None = None) -> C.CDLL:
 # the total inside its timed region as `gpu_launches`
 KERNELS_PER_CALL = {
     "scda_nms": 2, "scda_nms_dyn": 2, "scda_instnorm_act_fwd_nhwc_f32": 3, "scda_instnorm_act_bwd_nhwc_f32": 3,
-    "scda_instnorm_act_fwd_nhwc": 3, "scda_instnorm_act_bwd_nhwc": 3, "scda_conv1x1_tanh_bwd": 2, "SoftmaxFocalLossForwardLaucher": 1,
+    "scda_instnorm_act_fwd_nhwc": 3, "scda_instnorm_act_bwd_nhwc": 3, "scda_conv1x1_tanh_bwd": 2,
+    "scda_softmax_ce_acc_fwd": 2, "SoftmaxFocalLossForwardLaucher": 1,
     "SoftmaxFocalLossBackwardLaucher": 1,
 }
 LAUNCHES = 0

@@ -105,6 +105,112 @@ bce_rows_bwd_kernel(const float *__restrict__ x, const float *__restrict__ y, in
     }
 }
 
+// ------------------------------------------------------------------ softmax cross-entropy + top-1 accuracy
+// F.cross_entropy(logits, targets, ignore_index) (mean over the rows whose target != ignore_index) and
+// `accuracy(output, target, topk=(1,))` of the reference in ONE pass over the logits:
+// _add_rpn_loss / _add_rcnn_loss, models/faster_rcnn/faster_rcnn_adver_expansion_reweight_cluster.py:36-68,
+// 249-267 (there: log_softmax + nll_loss + topk + eq + nonzero/index + sum, ~15 launches and a host
+// synchronisation in `accuracy`).  One thread per row (C <= 32 classes: 2 for the RPN, 9 for the RCNN head);
+// per-block partials (sum of -log p_target, rows counted, rows whose argmax is the target) in a fixed
+// order, a one-block finish: deterministic.
+constexpr int kCeThreads = 256;
+
+__global__ void __launch_bounds__(kCeThreads)
+softmax_ce_partial_kernel(const float *__restrict__ x, long long ld, const long long *__restrict__ target,
+                          long long M, int C, long long ignore_index, float *__restrict__ partial)
+{
+    __shared__ float sh[32];
+    float nll = 0.f, cnt = 0.f, hit = 0.f;
+    for (long long m = (long long)blockIdx.x * kCeThreads + threadIdx.x; m < M;
+         m += (long long)gridDim.x * kCeThreads) {
+        const long long t = target[m];
+        if (t == ignore_index) continue;
+        const float *row = x + m * ld;
+        float mx = row[0];
+        int am = 0;
+        for (int c = 1; c < C; ++c) {
+            const float v = row[c];
+            if (v > mx) { mx = v; am = c; }
+        }
+        float sum = 0.f;
+        for (int c = 0; c < C; ++c) sum += expf(row[c] - mx);
+        const float xt = (t >= 0 && t < C) ? row[t] : 0.f;
+        nll += (logf(sum) + mx) - xt;
+        cnt += 1.f;
+        hit += (am == (int)t) ? 1.f : 0.f;
+    }
+    nll = block_sum(nll, sh);
+    cnt = block_sum(cnt, sh);
+    hit = block_sum(hit, sh);
+    if (threadIdx.x == 0) {
+        partial[3 * blockIdx.x] = nll;
+        partial[3 * blockIdx.x + 1] = cnt;
+        partial[3 * blockIdx.x + 2] = hit;
+    }
+}
+
+// out[0] = mean loss (NaN if no row counted, as torch), out[1] = top-1 accuracy in percent, out[2] = rows counted
+__global__ void softmax_ce_finish_kernel(const float *__restrict__ partial, int blocks, float *__restrict__ out)
+{
+    if (threadIdx.x != 0) return;
+    float nll = 0.f, cnt = 0.f, hit = 0.f;
+    for (int b = 0; b < blocks; ++b) {
+        nll += partial[3 * b];
+        cnt += partial[3 * b + 1];
+        hit += partial[3 * b + 2];
+    }
+    out[0] = nll / cnt;
+    out[1] = hit * (100.f / fmaxf(cnt, 1.f));
+    out[2] = cnt;
+}
+
+// dx[m, c] = gout * (softmax(x[m])[c] - [c == target[m]]) / rows counted; 0 for ignored rows
+__global__ void __launch_bounds__(kCeThreads)
+softmax_ce_bwd_kernel(const float *__restrict__ x, long long ld, const long long *__restrict__ target, long long M,
+                      int C, long long ignore_index, const float *__restrict__ stats,
+                      const float *__restrict__ gout, float *__restrict__ dx, long long lddx)
+{
+    const float scale = gout[0] / stats[2];
+    for (long long m = (long long)blockIdx.x * kCeThreads + threadIdx.x; m < M;
+         m += (long long)gridDim.x * kCeThreads) {
+        const long long t = target[m];
+        float *drow = dx + m * lddx;
+        if (t == ignore_index) {
+            for (int c = 0; c < C; ++c) drow[c] = 0.f;
+            continue;
+        }
+        const float *row = x + m * ld;
+        float mx = row[0];
+        for (int c = 1; c < C; ++c) mx = fmaxf(mx, row[c]);
+        float sum = 0.f;
+        for (int c = 0; c < C; ++c) sum += expf(row[c] - mx);
+        const float inv = 1.f / sum;
+        for (int c = 0; c < C; ++c) drow[c] = scale * (expf(row[c] - mx) * inv - (c == (int)t ? 1.f : 0.f));
+    }
+}
+
+// RPN objectness: 2-way softmax over each anchor's (bg, fg) channel pair of the NCHW class map,
+// foreground probability written straight in the proposal stage's anchor order
+// (…reweight_cluster.py:153-155 + functions/rpn_proposal.py:44-49: permute to NHWC, view(-1, 2), softmax,
+// permute back, permute again, reshape, take column 1: five layout passes and a softmax there).
+// cls [B, 2A, H, W] -> score [B, H*W*A], score[b, (h*W + w)*A + a] = softmax(cls[b, 2a : 2a+2, h, w])[1]
+__global__ void __launch_bounds__(256)
+rpn_fg_score_kernel(const float *__restrict__ cls, int B, int A, long long HW, float *__restrict__ score)
+{
+    const long long total = (long long)B * HW * A;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int a = (int)(i % A);
+        const long long hw = (i / A) % HW;
+        const long long b = i / (A * HW);
+        const float *p = cls + (b * 2 * A + 2 * a) * HW + hw;
+        const float l0 = p[0], l1 = p[HW];
+        const float mx = fmaxf(l0, l1);
+        const float e0 = expf(l0 - mx), e1 = expf(l1 - mx);
+        score[i] = e1 / (e0 + e1);
+    }
+}
+
 int ew_grid(long long n)
 {
     long long b = (n + 255) / 256;
@@ -311,5 +417,45 @@ SCDA_API int scda_conv1x1_tanh_bwd(long long P, int Cin, int Cout, const float *
     }
     const int n = Cin * Cout + Cout;
     head_bwd_final_kernel<<<(n + 127) / 128, 128, 0, stream>>>(part, g, n, dw, db, Cin * Cout);
+    return scda_launch_status();
+}
+
+SCDA_API size_t scda_softmax_ce_workspace_bytes(long long M)
+{
+    long long blocks = (M + kCeThreads - 1) / kCeThreads;
+    if (blocks > kNumSMs * 4) blocks = kNumSMs * 4;
+    if (blocks < 1) blocks = 1;
+    return (size_t)blocks * 3 * sizeof(float);
+}
+
+SCDA_API int scda_softmax_ce_acc_fwd(long long M, int C, const float *logits, long long ld, const long long *targets,
+                                     long long ignore_index, float *out3, void *workspace, size_t workspace_bytes,
+                                     cudaStream_t stream)
+{
+    if (M <= 0 || C <= 0 || C > 32 || ld < C || !logits || !targets || !out3 || !workspace) return 0;
+    if (workspace_bytes < scda_softmax_ce_workspace_bytes(M)) return 0;
+    const int blocks = (int)(scda_softmax_ce_workspace_bytes(M) / (3 * sizeof(float)));
+    softmax_ce_partial_kernel<<<blocks, kCeThreads, 0, stream>>>(logits, ld, targets, M, C, ignore_index,
+                                                                 (float *)workspace);
+    softmax_ce_finish_kernel<<<1, 32, 0, stream>>>((const float *)workspace, blocks, out3);
+    return scda_launch_status();
+}
+
+SCDA_API int scda_softmax_ce_bwd(long long M, int C, const float *logits, long long ld, const long long *targets,
+                                 long long ignore_index, const float *stats3, const float *grad_loss, float *dlogits,
+                                 long long lddx, cudaStream_t stream)
+{
+    if (M <= 0 || C <= 0 || C > 32 || ld < C || lddx < C || !logits || !targets || !stats3 || !grad_loss || !dlogits)
+        return 0;
+    softmax_ce_bwd_kernel<<<ew_grid(M), kCeThreads, 0, stream>>>(logits, ld, targets, M, C, ignore_index, stats3,
+                                                                 grad_loss, dlogits, lddx);
+    return scda_launch_status();
+}
+
+SCDA_API int scda_rpn_fg_scores(int B, int A, int H, int W, const float *cls_nchw, float *scores, cudaStream_t stream)
+{
+    if (B <= 0 || A <= 0 || H <= 0 || W <= 0 || !cls_nchw || !scores) return 0;
+    rpn_fg_score_kernel<<<ew_grid((long long)B * A * H * W), 256, 0, stream>>>(cls_nchw, B, A, (long long)H * W,
+                                                                               scores);
     return scda_launch_status();
 }

@@ -30,6 +30,8 @@ Mechanism differences (results are the same):
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 import torch
 import torch.nn.functional as F
@@ -84,17 +86,39 @@ class FlatAdam(object):
                     p._scda_shadow = seg.view(p.shape)
                 p._scda_shadow_version = p._version
                 p._scda_direct_grad = True
+                p.register_hook(self._stale_guard(p))
         self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
         self.t = 0
         self.lr_t_dev = torch.zeros(1, dtype=torch.float32, device=dev)
 
+    @staticmethod
+    def _stale_guard(p):
+        """FlatGradBucket.zero() leaves the big direct-written gradients un-zeroed and only marks them
+        fresh (the tensor-core sinks overwrite them).  If a gradient reaches such a parameter through
+        ordinary autograd instead (`_fp32_graph`, a sink's fall-through), it would be ADDED onto last
+        step's values: this hook runs before that accumulation and zeroes the stale contents first."""
+        def hook(grad):
+            if getattr(p, "_scda_grad_fresh", False):
+                if p.grad is not None:
+                    p.grad.zero_()
+                p._scda_grad_fresh = False
+            return grad
+        return hook
+
     def zero_grad(self):
         self.bucket.zero()
 
-    def all_reduce(self):
+    def all_reduce(self, lo=0, hi=None):
         self.bucket.rebind()
-        self.bucket.settle()
-        self.bucket.all_reduce()
+        self.bucket.settle(lo, hi)
+        self.bucket.all_reduce(lo=lo, hi=hi)
+
+    def offset_of(self, param):
+        """start of `param`'s segment in the flat buffers (bucket boundaries)"""
+        for p, off in zip(self.params, self.offsets):
+            if p is param:
+                return off
+        raise KeyError("parameter is not owned by this optimiser")
 
     def begin_step(self, lr=None):
         """host side of one optimiser step: count it and publish the step size"""
@@ -105,19 +129,25 @@ class FlatAdam(object):
         # pinned scalar could be overtaken by the next step's value (the host runs ahead)
         self.lr_t_dev.fill_(lr * (bc2 ** 0.5) / bc1)
 
-    def step_dev(self, grad_scale=1.0):
-        """device side: one fused kernel over the flat buffers (graph-capturable)"""
+    def step_dev(self, grad_scale=1.0, lo=0, hi=None):
+        """device side: one fused kernel over the flat buffers, or over their slice [lo, hi) — a bucket
+        of whole parameter segments (graph-capturable)"""
+        hi = self.n if hi is None else hi
+        assert 0 <= lo < hi <= self.n and lo % 64 == 0
         self.bucket.rebind()
-        self.bucket.settle()
+        self.bucket.settle(lo, hi)
         with torch.cuda.device(self.flat.device):
             check(load().scda_adam_step(
-                self.flat.data_ptr(), self.bucket.flat.data_ptr(), self.exp_avg.data_ptr(),
-                self.exp_avg_sq.data_ptr(), self.shadow.data_ptr() if self.shadow is not None else None,
-                self.n, max(self.t, 1), float(self.lr), self.betas[0], self.betas[1], self.eps,
+                self.flat.data_ptr() + 4 * lo, self.bucket.flat.data_ptr() + 4 * lo, self.exp_avg.data_ptr() + 4 * lo,
+                self.exp_avg_sq.data_ptr() + 4 * lo,
+                self.shadow.data_ptr() + 2 * lo if self.shadow is not None else None,
+                hi - lo, max(self.t, 1), float(self.lr), self.betas[0], self.betas[1], self.eps,
                 self.weight_decay, float(grad_scale), self.lr_t_dev.data_ptr(),
                 stream_ptr(self.flat.device)), "scda_adam_step")
         # the kernel wrote the parameters through raw pointers: stamp what is (not) in sync
-        for p in self.params:
+        for p, off in zip(self.params, self.offsets):
+            if off < lo or off >= hi:
+                continue
             p._scda_epoch = getattr(p, "_scda_epoch", 0) + 1
             if self.shadow is not None:
                 p._scda_shadow_version = p._version
@@ -206,13 +236,13 @@ class SCDATrainer(object):
         # captured form hung (NCCL 2.28.9 / torch 2.11, profiles/r1_ddp2_check.txt), the cut form is
         # what the multi-GPU numbers are measured with.
         self.overlap = overlap
-        import os
         self.pair_streams = os.environ.get("SCDA_PAIR_STREAMS", "1") != "0"
         if graph_collectives is None:
-            import os
             graph_collectives = os.environ.get("SCDA_GRAPH_COLLECTIVES", "0") != "0"
         self.graph_collectives = graph_collectives
         self.force_cut = force_cut          # tests: the cut (world > 1) replay plan on one GPU
+        self.split_detector = os.environ.get("SCDA_SPLIT_DETECTOR", "1") != "0"
+        self._det_head_lo, self._oside = None, None
         self._side = None
         self._tside = None
         self._aside = None
@@ -359,6 +389,7 @@ class SCDATrainer(object):
             x['taps'] = self.taps
         outputs = self.model(x, b['target'])
         st['det_losses'] = outputs['losses']
+        st['feat'] = outputs['feature_map']
         st['acc'] = outputs['accuracy']
         centers_source, centers_target = outputs['cluster_centers']
         b['cs'] = crops_device(b['image'], centers_source, self.recon_size, self.new_w, self.new_h)
@@ -377,6 +408,45 @@ class SCDATrainer(object):
 
     def _seg_step(self):
         self.opt.step_dev()
+
+    # The same backward CUT AT THE FEATURE MAP into two buckets (">= 2 buckets, head
+    # first"): the RCNN head's gradients (fc6 + fc7 + cls / loc = 478 of the detector's 547 MB) are complete
+    # ~0.6 ms into the backward; their all-reduce and their Adam sweep (HBM bound) then run on a side stream
+    # beside the backbone's backward (tensor-core bound) instead of behind it.
+    def _head_lo(self):
+        if self._det_head_lo is None:
+            self._det_head_lo = self.opt.offset_of(self.model.classifier[0].weight)
+        return self._det_head_lo
+
+    def _seg_det_backward_head(self):
+        st, ws = self._st, float(self.world_size)
+        rpn_cls_loss, rpn_loc_loss, rcnn_cls_loss, rcnn_loc_loss = st['det_losses']
+        st['det_loss_sum'] = rpn_cls_loss + rpn_loc_loss + rcnn_cls_loss + rcnn_loc_loss
+        self.opt.zero_grad()
+        # every head parameter takes its gradient through the direct sinks of tc_detector (written into
+        # the flat buffer as a side effect), so differentiating w.r.t. the feature map alone runs the
+        # whole head backward
+        (st['g_feat'],) = torch.autograd.grad((rcnn_cls_loss + rcnn_loc_loss) / ws, [st['feat']])
+
+    def _seg_det_backward_body(self):
+        st, ws = self._st, float(self.world_size)
+        rpn_cls_loss, rpn_loc_loss = st['det_losses'][:2]
+        lo = self._head_lo()
+        front = [p for p, off in zip(self.opt.params, self.opt.offsets) if off < lo]
+        torch.autograd.backward([(rpn_cls_loss + rpn_loc_loss) / ws, st['feat']], [None, st.pop('g_feat')],
+                                inputs=front)
+        st.pop('feat')
+
+    def _seg_step_head(self):
+        self.opt.step_dev(lo=self._head_lo())
+
+    def _seg_step_body(self):
+        self.opt.step_dev(lo=0, hi=self._head_lo())
+
+    def _opt_stream(self):
+        if self._oside is None:
+            self._oside = torch.cuda.Stream(device=self.opt.flat.device)
+        return self._oside
 
     def _seg_outputs(self):
         st = self._st
@@ -417,9 +487,23 @@ class SCDATrainer(object):
         return self._pside
 
     def _det_chain(self, reduce):
-        self._seg_det_backward()
-        reduce(self.opt)
-        self._seg_step()
+        if not (self.overlap and self.split_detector):
+            self._st.pop('feat', None)
+            self._seg_det_backward()
+            reduce(self.opt)
+            self._seg_step()
+            return
+        lo = self._head_lo()
+        self._seg_det_backward_head()
+        cur, osd = torch.cuda.current_stream(), self._opt_stream()
+        osd.wait_stream(cur)
+        with torch.cuda.stream(osd):
+            reduce(self.opt, lo, None)
+            self._seg_step_head()
+        self._seg_det_backward_body()
+        reduce(self.opt, 0, lo)
+        self._seg_step_body()
+        cur.wait_stream(osd)
 
     def _side_stream(self):
         """stream of the reconstruction / discriminator chain: the longer of the two chains,
@@ -461,8 +545,8 @@ class SCDATrainer(object):
 
     def _reduce_fn(self):
         if self.world_size > 1:
-            return lambda opt: opt.all_reduce()
-        return lambda opt: None
+            return lambda opt, lo=0, hi=None: opt.all_reduce(lo, hi)
+        return lambda opt, lo=0, hi=None: None
 
     def _segments(self):
         """world > 1 with the collectives NOT captured: the iteration cut at its four gradient
@@ -480,17 +564,26 @@ class SCDATrainer(object):
                     ('det_bwd', self._seg_det_backward, 'main', self.opt),
                     ('step', self._seg_step, 'main', None),
                     ('out', self._seg_outputs, 'main', None))
-        return (('fwd', self._seg_forward, 'main', None),
+        head = (('fwd', self._seg_forward, 'main', None),
                 ('patch_fwd', self._seg_patch_fwd, 'patch', None),
                 ('patch_upd', self._patch_update, 'patch', self.opt_dis_patch),
                 ('patch_step', self.opt_dis_patch.step_dev, 'patch', None),
                 ('dis', lambda: self._seg_dis(patch_done=True), 'side', self.opt_dis),
                 ('dis_step', self.opt_dis.step_dev, 'side', None),
                 ('dec', self._dec_update, 'side', self.opt_dec),
-                ('fake', self._seg_fake, 'side', None),
-                ('det_bwd', self._seg_det_backward, 'main', self.opt),
-                ('step', self._seg_step, 'main', None),
-                ('out', self._seg_outputs, 'main', None))
+                ('fake', self._seg_fake, 'side', None))
+        if self.split_detector:
+            # the detector's backward in two stretches (head bucket, then backbone + RPN bucket): the head
+            # bucket's all-reduce and Adam go to the `opt` stream beside the second stretch
+            lo = self._head_lo()
+            det = (('det_bwd_head', self._seg_det_backward_head, 'main', None),
+                   ('step_head', self._seg_step_head, 'opt', None),
+                   ('det_bwd_body', self._seg_det_backward_body, 'main', (self.opt, 0, lo)),
+                   ('step_body', self._seg_step_body, 'main', None))
+        else:
+            det = (('det_bwd', self._seg_det_backward, 'main', self.opt),
+                   ('step', self._seg_step, 'main', None))
+        return head + det + (('out', self._seg_outputs, 'main', None),)
 
     def _whole_graph(self):
         """world 1, or world > 1 with the all-reduces captured: ONE graph holds the iteration"""
@@ -510,7 +603,7 @@ class SCDATrainer(object):
             with torch.cuda.graph(g, pool=torch.cuda.graph_pool_handle()):
                 self._body(reduce)
             return [g]
-        pools = {k: torch.cuda.graph_pool_handle() for k in ('main', 'side', 'patch')}
+        pools = {k: torch.cuda.graph_pool_handle() for k in ('main', 'side', 'patch', 'opt')}
         graphs = []
         for _, fn, where, _ in self._segments():
             g = torch.cuda.CUDAGraph()
@@ -532,7 +625,9 @@ class SCDATrainer(object):
             for n in names:
                 g, opt = by_name[n]
                 g.replay()
-                if opt is not None:
+                if isinstance(opt, tuple):
+                    opt[0].all_reduce(opt[1], opt[2])
+                elif opt is not None:
                     opt.all_reduce()
         run(['fwd'])
         if not self.overlap:
@@ -551,7 +646,17 @@ class SCDATrainer(object):
             run(['dis', 'dis_step'])
             side.wait_stream(patch)
             run(['dec', 'fake'])
-        run(['det_bwd', 'step'])
+        if self.split_detector:
+            osd = self._opt_stream()
+            run(['det_bwd_head'])
+            osd.wait_stream(main)
+            with torch.cuda.stream(osd):
+                self.opt.all_reduce(self._head_lo(), None)
+                run(['step_head'])
+            run(['det_bwd_body', 'step_body'])
+            main.wait_stream(osd)
+        else:
+            run(['det_bwd', 'step'])
         main.wait_stream(side)
         run(['out'])
 

@@ -28,10 +28,12 @@ def _image_hw(image_info, b):
     return float(image_info[b][0]), float(image_info[b][1])
 
 
-def rpn_proposals_device(conv_cls, conv_loc, cfg, image_info):
+def rpn_proposals_device(conv_cls, conv_loc, cfg, image_info, fg_scores=None):
     """Returns a list (one per image) of (boxes5 float32 [cap, 5] = x1,y1,x2,y2,score sorted
-    by descending score with the NMS survivors first, n_keep int64 0-dim tensor)."""
-    assert conv_cls.is_cuda and conv_loc.is_cuda
+    by descending score with the NMS survivors first, n_keep int64 0-dim tensor).
+    fg_scores: [B, K*A] foreground probabilities already in anchor order (loss_ops.rpn_fg_scores on the
+    raw class map) — then conv_cls is not read."""
+    assert conv_loc.is_cuda and (fg_scores is not None or conv_cls.is_cuda)
     B, A4, fh, fw = conv_loc.shape
     A = A4 // 4
     assert A * 4 == A4
@@ -39,12 +41,12 @@ def rpn_proposals_device(conv_cls, conv_loc, cfg, image_info):
     dev = conv_loc.device
     anchors = anchor_helper.anchors_device(fh, fw, cfg['anchor_ratios'], cfg['anchor_scales'],
                                            cfg['anchor_stride'], dev)
-    cls_view = conv_cls.permute(0, 2, 3, 1).reshape(B, KA, -1)
+    cls_view = conv_cls.permute(0, 2, 3, 1).reshape(B, KA, -1) if fg_scores is None else None
     loc_view = conv_loc.permute(0, 2, 3, 1).reshape(B, KA, 4)
     pre, post = cfg['pre_nms_top_n'], cfg['post_nms_top_n']
     out = []
     for b in range(B):
-        scores = cls_view[b, :, -1].contiguous()
+        scores = cls_view[b, :, -1].contiguous() if fg_scores is None else fg_scores[b]
         if pre <= 0 or pre > KA:
             top, order = torch.sort(scores, descending=True)
         else:

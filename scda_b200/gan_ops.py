@@ -4,6 +4,7 @@
 ReLU / LeakyReLU, on a channels_last fp32 CUDA tensor, forward and backward, without the
 NCHW round trip torch's instance norm forces (models/faster_rcnn/common_net.py:59-80,
 279-293 of the reference use the torch modules)."""
+import logging
 import os
 
 import torch
@@ -11,6 +12,19 @@ import torch
 from ._lib import check, load, require_cuda, stream_ptr
 
 _ACT = {None: 0, "none": 0, "relu": 1, "leaky_relu": 2}
+
+# CUDA-path calls that went to a LIBRARY (cuDNN / torch) instead of a hand-written kernel, by layer kind:
+# counted, logged once per kind at WARNING, and reported by bench.py as `library_fallbacks`
+LIBRARY_CALLS = {}
+_log = logging.getLogger("scda_b200")
+
+
+def note_library_call(kind, why=""):
+    n = LIBRARY_CALLS.get(kind, 0)
+    if n == 0:
+        _log.warning("scda_b200: %s runs on a library kernel (cuDNN / torch), not a hand-written one%s",
+                     kind, (": " + why) if why else "")
+    LIBRARY_CALLS[kind] = n + 1
 
 
 class _InstNormAct(torch.autograd.Function):

@@ -83,3 +83,57 @@ class _BceSigmoidRows(torch.autograd.Function):
 def bce_sigmoid_rows(logits, label):
     """[K] vector: mean over M of BCE(sigmoid(logits[k]), label) — label [1, M] / [M] or a 1-element tensor."""
     return _BceSigmoidRows.apply(logits, label)
+
+
+class _SoftmaxCEAcc(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, targets, ignore_index):
+        require_cuda(logits, targets)
+        assert logits.dim() == 2 and logits.dtype == torch.float32 and logits.stride(1) == 1
+        x = logits
+        t = targets.contiguous()
+        assert t.dtype == torch.int64 and t.numel() == x.shape[0]
+        M, C = x.shape
+        lib = load()
+        wsb = lib.scda_softmax_ce_workspace_bytes(M)
+        ws = torch.empty(wsb, dtype=torch.uint8, device=x.device)
+        out3 = torch.empty(3, dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            check(lib.scda_softmax_ce_acc_fwd(M, C, x.data_ptr(), x.stride(0), t.data_ptr(), int(ignore_index),
+                                              out3.data_ptr(), ws.data_ptr(), wsb, stream_ptr(x.device)),
+                  "scda_softmax_ce_acc_fwd")
+        ctx.save_for_backward(x, t, out3)
+        ctx.ignore_index = int(ignore_index)
+        acc = out3[1:2]
+        ctx.mark_non_differentiable(acc)
+        return out3[0], acc
+
+    @staticmethod
+    def backward(ctx, g, _g_acc):
+        x, t, out3 = ctx.saved_tensors
+        M, C = x.shape
+        g = g.contiguous().float().reshape(1)
+        dx = torch.empty(M, C, dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            check(load().scda_softmax_ce_bwd(M, C, x.data_ptr(), x.stride(0), t.data_ptr(), ctx.ignore_index,
+                                             out3.data_ptr(), g.data_ptr(), dx.data_ptr(), C,
+                                             stream_ptr(x.device)), "scda_softmax_ce_bwd")
+        return dx, None, None
+
+
+def softmax_ce_acc(logits, targets, ignore_index=-100):
+    """(F.cross_entropy(logits, targets, ignore_index=ignore_index), top-1 accuracy in percent as a
+    1-element tensor): one pass over logits [M, C <= 32] fp32, int64 targets (csrc/loss_ops.cu)."""
+    return _SoftmaxCEAcc.apply(logits, targets, int(ignore_index))
+
+
+def rpn_fg_scores(cls_nchw):
+    """[B, 2A, H, W] RPN class map -> [B, H*W*A] foreground probabilities in anchor order."""
+    require_cuda(cls_nchw)
+    x = cls_nchw.detach().contiguous().float()
+    B, A2, H, W = x.shape
+    out = torch.empty(B, H * W * (A2 // 2), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        check(load().scda_rpn_fg_scores(B, A2 // 2, H, W, x.data_ptr(), out.data_ptr(), stream_ptr(x.device)),
+              "scda_rpn_fg_scores")
+    return out

@@ -7,8 +7,8 @@ import torch
 import torch.nn as nn
 
 from ...gan_ops import (conv1x1_tanh, conv1x1_tanh_supported, conv2d_bias_cl, conv_bias_supported, conv_in_act_tc,
-                        conv_in_act_tc_supported, instance_norm_act, supported as _fused_ok, upsample_bilinear2x,
-                        upsample_supported)
+                        conv_in_act_tc_supported, instance_norm_act, note_library_call, supported as _fused_ok,
+                        upsample_bilinear2x, upsample_supported)
 
 
 class Conv2dCL(nn.Conv2d):
@@ -16,6 +16,8 @@ class Conv2dCL(nn.Conv2d):
     the library's channels-last column-sum kernel instead of torch's strided reduction."""
 
     def forward(self, x):
+        if x.is_cuda:
+            note_library_call("Conv2dCL %dx%d s%d" % (self.kernel_size + self.stride[:1]), "cuDNN convolution")
         if conv_bias_supported(x, self):
             return conv2d_bias_cl(x, self)
         return super(Conv2dCL, self).forward(x)
@@ -52,6 +54,8 @@ class INSResBlock(nn.Module):
             if len(m) > 5:
                 out = m[5](out)
             return out + x
+        if x.is_cuda:
+            note_library_call("INSResBlock", "shape outside conv_in_act_tc_supported")
         if _fused_ok(x):
             # same layers, InstanceNorm + ReLU as one channels-last kernel (csrc/norm_ops.cu)
             out = instance_norm_act(m[0](x), "relu", eps=m[1].eps)
@@ -86,6 +90,8 @@ class Interpolate(nn.Module):
     def forward(self, x):
         if upsample_supported(x, self.scale_factor, self.mode):
             return upsample_bilinear2x(x)          # channels-last kernel, csrc/norm_ops.cu
+        if x.is_cuda:
+            note_library_call("Interpolate", "scale / mode / shape outside upsample_supported")
         return nn.functional.interpolate(x, scale_factor=self.scale_factor, mode=self.mode,
                                          align_corners=True)
 
@@ -112,6 +118,7 @@ class ResDis_cluster(nn.Module):
         x1 = x1.view(self.cluster_num, self.channel, self.w, self.h)
         if x1.is_cuda:
             x1 = x1.contiguous(memory_format=torch.channels_last)
+            note_library_call("ResDis_cluster", "stride-2 convolutions + BatchNorm on cuDNN")
         out = self.model(x1)
         out = nn.functional.avg_pool2d(out, out.size()[2:])
         return torch.squeeze(out)
@@ -131,6 +138,8 @@ class ConvTranspose1x1(nn.ConvTranspose2d):
         assert self.kernel_size == (1, 1) and self.stride == (1, 1) and self.padding == (0, 0)
         if self.fuse_tanh and conv1x1_tanh_supported(x, self):
             return conv1x1_tanh(x, self)         # tagged: the TanhAfterHead behind it passes it through
+        if x.is_cuda:
+            note_library_call("ConvTranspose1x1", "outside conv1x1_tanh_supported")
         return nn.functional.conv2d(x, self.weight.permute(1, 0, 2, 3), self.bias)
 
 
@@ -157,6 +166,7 @@ class LeakyReLUConv2d(nn.Module):
             out = m[1](m[0](x))
             if _fused_ok(out):
                 return instance_norm_act(out, "leaky_relu", m[3].negative_slope, m[2].eps)
+            note_library_call("LeakyReLUConv2d InstanceNorm", "shape outside the fused kernel")
             return m[3](m[2](out))
         return self.model(x)
 
@@ -180,6 +190,7 @@ class LeakyReLUConvTranspose2d_2(nn.Module):
             if conv_in_act_tc_supported(x, m[1]) and upsample_supported(x, m[0].scale_factor, m[0].mode):
                 up = upsample_bilinear2x(x, out_bf16=True)        # written as the MMA operand dtype
                 return conv_in_act_tc(up, m[1], "leaky_relu", m[3].negative_slope, m[2].eps)
+            note_library_call("LeakyReLUConvTranspose2d_2", "shape outside conv_in_act_tc_supported")
             out = m[1](m[0](x))
             if _fused_ok(out):
                 return instance_norm_act(out, "leaky_relu", m[3].negative_slope, m[2].eps)

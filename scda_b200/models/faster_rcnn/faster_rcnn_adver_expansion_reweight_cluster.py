@@ -23,7 +23,7 @@ from ...functions.predict_bbox import compute_predicted_bboxes
 from ...functions.proposal_target import compute_proposal_targets, proposal_targets_device
 from ...functions.rpn_proposal import compute_rpn_proposals, rpn_proposals_device
 from ...gan_ops import run_pair
-from ...loss_ops import smooth_l1_masked_sum
+from ...loss_ops import rpn_fg_scores, smooth_l1_masked_sum, softmax_ce_acc
 from .common_net import (ConvTranspose1x1, TanhAfterHead, INSResBlock, LeakyReLUConv2d, LeakyReLUConvTranspose2d_2,
                          LinUnsRes_cluster, ResDis_cluster, gaussian_weights_init)
 
@@ -54,15 +54,21 @@ class FasterRCNN_AdEx(nn.Module):
             compute_anchor_targets_fn(rpn_pred_loc.size())
         rpn_pred_cls = rpn_pred_cls.permute(0, 2, 3, 1).contiguous().view(-1, 2)
         cls_targets = cls_targets.permute(0, 2, 3, 1).contiguous().view(-1)
-        rpn_loss_cls = F.cross_entropy(rpn_pred_cls, cls_targets, ignore_index=-1)
         rpn_loss_loc = _smooth_l1_masked(rpn_pred_loc, loc_masks, loc_targets) / loc_normalizer
+        if rpn_pred_cls.is_cuda:        # cross entropy (ignore -1) + top-1 accuracy: one pass (csrc/loss_ops.cu)
+            rpn_loss_cls, acc = softmax_ce_acc(rpn_pred_cls, cls_targets, ignore_index=-1)
+            return rpn_loss_cls, rpn_loss_loc, acc
+        rpn_loss_cls = F.cross_entropy(rpn_pred_cls, cls_targets, ignore_index=-1)
         acc = accuracy(rpn_pred_cls.data, cls_targets.data)[0]
         return rpn_loss_cls, rpn_loss_loc, acc
 
     def _add_rcnn_loss(self, rcnn_pred_cls, rcnn_pred_loc, cls_targets, loc_targets, loc_weights):
-        rcnn_loss_cls = F.cross_entropy(rcnn_pred_cls, cls_targets)
         loc_normalizer = cls_targets.shape[0]
         rcnn_loss_loc = _smooth_l1_masked(rcnn_pred_loc, loc_weights, loc_targets) / loc_normalizer
+        if rcnn_pred_cls.is_cuda:
+            rcnn_loss_cls, acc = softmax_ce_acc(rcnn_pred_cls.contiguous(), cls_targets, ignore_index=-100)
+            return rcnn_loss_cls, rcnn_loss_loc, acc
+        rcnn_loss_cls = F.cross_entropy(rcnn_pred_cls, cls_targets)
         acc = accuracy(rcnn_pred_cls, cls_targets)[0]
         return rcnn_loss_cls, rcnn_loss_loc, acc
 
@@ -154,8 +160,8 @@ class FasterRCNN_AdEx(nn.Module):
                 with torch.no_grad():
                     x_gan = self.feature_extractor(target)
                     rpn_pred_cls_gan, rpn_pred_loc_gan = self.rpn(x_gan)
-                props_gan = rpn_proposals_device(self._rpn_scores(rpn_pred_cls_gan).data,
-                                                 rpn_pred_loc_gan.data, pcfg, image_info)
+                props_gan = rpn_proposals_device(None, rpn_pred_loc_gan.data, pcfg, image_info,
+                                                 fg_scores=rpn_fg_scores(rpn_pred_cls_gan))
                 gan_rows = []
                 for b, (boxes, n_keep) in enumerate(props_gan):
                     gan_rows.append((torch.cat([torch.full((boxes.shape[0], 1), float(b),
@@ -216,17 +222,29 @@ class FasterRCNN_AdEx(nn.Module):
                     pre = partial_fn['anchor_target_fn'](rpn_pred_loc.size())
                 anchor_pre = pre
                 partial_fn['anchor_target_fn'] = lambda size: pre
+            late = os.environ.get("SCDA_TARGET_LATE", "0")
             if tstream is not None and not early:
                 cur_stream = torch.cuda.current_stream()
-                tstream.wait_stream(cur_stream)
+                after_rpn = torch.cuda.Event()
+                after_rpn.record(cur_stream)
+                if late == "0":
+                    tstream.wait_event(after_rpn)
+                    with torch.cuda.stream(tstream):
+                        tgt = run_target()
+            fg = rpn_fg_scores(rpn_pred_cls)
+            props = rpn_proposals_device(None, rpn_pred_loc.data, pcfg, image_info, fg_scores=fg)
+            if tstream is not None and not early and late == "1":
+                tstream.wait_event(after_rpn)
                 with torch.cuda.stream(tstream):
                     tgt = run_target()
-            props = rpn_proposals_device(self._rpn_scores(rpn_pred_cls).data, rpn_pred_loc.data,
-                                         pcfg, image_info)
             rois, cls_targets, loc_targets, loc_weights = self._train_rois(
                 cfg, props, ground_truth_bboxes, image_info, rng.get('proposal'))
             assert rois.shape[1] == 5
             x_fea, rcnn_pred_cls, rcnn_pred_loc = self.rcnn(x, rois)
+            if tstream is not None and not early and late == "2":
+                tstream.wait_event(after_rpn)
+                with torch.cuda.stream(tstream):
+                    tgt = run_target()
             if taps is not None and on_dev:
                 ktap = {}
                 x_cluster_fea, x_center_cluster = cluster_targets_device(
@@ -234,7 +252,7 @@ class FasterRCNN_AdEx(nn.Module):
                 taps.update(cluster_src=ktap,
                             rois_targets=(rois, cls_targets, loc_targets, loc_weights), feat=x,
                             rpn_cls=rpn_pred_cls, rpn_loc=rpn_pred_loc, fc7=x_fea, rcnn_cls=rcnn_pred_cls,
-                            rcnn_loc=rcnn_pred_loc, proposals=props)
+                            rcnn_loc=rcnn_pred_loc, proposals=props, fg_scores=fg)
             else:
                 x_cluster_fea, x_center_cluster = cluster_fn(
                     rois, x_fea, N_cluster=input['cluster_num'], threshold=input['threshold'])
@@ -262,6 +280,7 @@ class FasterRCNN_AdEx(nn.Module):
             outputs['losses'] = [rpn_loss_cls, rpn_loss_loc, rcnn_loss_cls, rcnn_loss_loc]
             outputs['accuracy'] = [rpn_acc, rcnn_acc]
             outputs['predict'] = [props]
+            outputs['feature_map'] = x          # (engine: the detector's backward is cut here, see SCDATrainer)
             # fewer than 512 surviving target proposals: reuse the source clusters (:207-215)
             if proposals_gan.shape[0] != n_t:
                 logger.info("Different channels {} at target image".format(x_fea_gan.size(0)))

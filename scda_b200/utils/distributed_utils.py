@@ -121,9 +121,12 @@ class FlatGradBucket(object):
         if pos < self.flat.numel():
             self.flat[pos:].zero_()
 
-    def settle(self):
-        """a gradient still marked fresh was never written this step: it is zero"""
-        for p, v in zip(self.params, self._views):
+    def settle(self, lo=0, hi=None):
+        """a gradient still marked fresh was never written this step: it is zero
+        (lo, hi: only the parameters whose segment starts inside [lo, hi) of the flat buffer)"""
+        for p, v, off in zip(self.params, self._views, self.offsets):
+            if off < lo or (hi is not None and off >= hi):
+                continue
             if getattr(p, "_scda_grad_fresh", False):
                 if p.numel() >= (1 << 20):
                     v.zero_()
@@ -137,9 +140,11 @@ class FlatGradBucket(object):
                     view.copy_(p.grad)
                 p.grad = view
 
-    def all_reduce(self, async_op=False):
+    def all_reduce(self, async_op=False, lo=0, hi=None):
+        """SUM all-reduce of the flat buffer, or of its slice [lo, hi) (a gradient bucket)"""
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            return dist.all_reduce(self.flat, async_op=async_op)
+            buf = self.flat if (lo == 0 and hi is None) else self.flat[lo:hi]
+            return dist.all_reduce(buf, async_op=async_op)
         return None
 
 

@@ -100,8 +100,8 @@ def test_graph_replay_equals_eager(cuda_lib, monkeypatch):
             grads.append([o.bucket.flat.clone() for o in (tr.opt, tr.opt_dec, tr.opt_dis, tr.opt_dis_patch)])
         torch.cuda.synchronize()
         if use_graphs:
-            # one graph, or (the plan used when world > 1) eleven stretches on three streams
-            assert tr._graphs is not None and len(tr._graphs) == (11 if cut else 1)
+            # one graph, or (the plan used when world > 1) one stretch per segment on four streams
+            assert tr._graphs is not None and len(tr._graphs) == (len(tr._segments()) if cut else 1)
         results.append((losses, grads))
     (l_e, g_e) = results[0]
     for mode, (l_g, g_g) in zip(("one graph", "cut"), results[1:]):
@@ -162,3 +162,32 @@ def test_crops_kernel_equals_reference_corner_rule(cuda_lib):
     got = crops_device(image.cuda(), torch.from_numpy(centers).cuda(), R, Ww, Hh)
     assert got.shape == (len(centers), 3, R, R)
     assert torch.equal(got.cpu(), want)
+
+
+def test_stale_direct_gradient_is_zeroed_before_autograd_accumulates(cuda_lib):
+    """FlatGradBucket.zero() leaves the big direct-written gradients un-zeroed (the tensor-core
+    sinks overwrite them).  A gradient that reaches such a parameter through ordinary autograd — here the
+    detector run through the plain fp32 torch graph under FlatAdam(tensor_core=True) — must not be added
+    onto last step's values."""
+    import torch
+    from scda_b200.engine import FlatAdam
+    from scda_b200.models.faster_rcnn.vgg_adver_expansion_cluster import vgg16
+    cfg = _inputs.load_cfg()
+    torch.manual_seed(0)
+    model = vgg16(cfg=cfg["shared"]).cuda()
+    opt = FlatAdam(model, 1e-4, tensor_core=True)
+    model._fp32_graph = True
+    fc6 = model.classifier[0].weight                      # 102.8 M elements: never zeroed by zero()
+    feat = torch.randn(1, 512, 16, 32, device="cuda")
+    rois = torch.from_numpy(_inputs.rois_uniform(16, 2, img_w=512, img_h=256, wh=(16, 128))).cuda()
+    grads = []
+    for it in range(2):
+        opt.zero_grad()
+        fea, cls, loc = model.rcnn(feat, rois)
+        (cls.sum() + loc.sum()).backward()
+        opt.bucket.rebind()
+        opt.bucket.settle()
+        grads.append(fc6.grad.detach().clone())
+    model._fp32_graph = False
+    assert float(grads[0].abs().max()) > 0
+    assert torch.allclose(grads[0], grads[1], rtol=1e-5, atol=1e-7), "second step accumulated onto stale gradients"

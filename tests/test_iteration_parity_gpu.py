@@ -126,11 +126,16 @@ def _run(precision, torch, host, ArrayRng):
     np.testing.assert_allclose(_np(a_got[1]), a_ref[1], rtol=1e-5, atol=1e-6)
     assert np.array_equal(_np(a_got[2]), a_ref[2]) and int(a_got[3]) == a_ref[3]
 
-    def scores(cls):
+    def scores(cls, fg):
+        """the class map the oracle's proposal stage reads (softmax over each (bg, fg) pair, NCHW), with the
+        foreground plane taken from the GPU's own fused score kernel so that near-ties rank identically"""
         x = cls.float().permute(0, 2, 3, 1).contiguous()
-        return torch.softmax(x.view(-1, 2), dim=1).view_as(x).permute(0, 3, 1, 2).contiguous()
-    p_ref = host.compute_rpn_proposals(_np(scores(t['rpn_cls'])), _np(t['rpn_loc']), cfg['train_rpn_proposal_cfg'],
-                                       info_np)
+        p = torch.softmax(x.view(-1, 2), dim=1)
+        assert float((p[:, 1] - fg.reshape(-1)).abs().max()) < 1e-6, "rpn_fg_scores != softmax"
+        p[:, 1] = fg.reshape(-1)
+        return p.view_as(x).permute(0, 3, 1, 2).contiguous()
+    p_ref = host.compute_rpn_proposals(_np(scores(t['rpn_cls'], t['fg_scores'])), _np(t['rpn_loc']),
+                                       cfg['train_rpn_proposal_cfg'], info_np)
     boxes, n_keep = t['proposals'][0]
     n_keep = int(n_keep)
     p_got = _np(boxes)[:n_keep]

@@ -69,3 +69,48 @@ def test_bce_sigmoid_rows(cuda_lib, K, M, label):
     assert torch.allclose(xa.grad, xr.grad, rtol=1e-4, atol=1e-8)
     # deterministic
     assert torch.equal(bce_sigmoid_rows(x.cuda(), y.cuda()), out.detach())
+
+
+@pytest.mark.parametrize("M,C,ignore", [(30720, 2, -1), (512, 9, -100), (7, 3, -1), (1000, 32, -1)])
+def test_softmax_ce_acc_matches_torch(cuda_lib, M, C, ignore):
+    """fused cross entropy (+ ignore index) and top-1 accuracy against F.cross_entropy and the reference's
+    accuracy() (faster_rcnn_adver_expansion_reweight_cluster.py:249-267), forward and backward"""
+    import torch
+    import torch.nn.functional as F
+    from scda_b200.loss_ops import softmax_ce_acc
+    from scda_b200.models.faster_rcnn.faster_rcnn_adver_expansion_reweight_cluster import accuracy
+    g = torch.Generator(device="cuda").manual_seed(M + C)
+    x = (torch.randn(M, C, device="cuda", generator=g) * 2).requires_grad_(True)
+    t = torch.randint(0, C, (M,), device="cuda", generator=g)
+    if ignore == -1:
+        t = torch.where(torch.rand(M, device="cuda", generator=g) < 0.6, torch.full_like(t, -1), t)
+    loss, acc = softmax_ce_acc(x, t, ignore_index=ignore)
+    (loss * 1.7).backward()
+    gx = x.grad.clone()
+    x.grad = None
+    ref = F.cross_entropy(x, t, ignore_index=ignore)
+    (ref * 1.7).backward()
+    assert abs(float(loss) - float(ref)) <= 2e-6 * max(1.0, abs(float(ref)))
+    assert torch.allclose(gx, x.grad, rtol=1e-5, atol=1e-8)
+    ref_acc = accuracy(x.detach(), t, ignore_index=ignore)[0]
+    assert abs(float(acc) - float(ref_acc)) < 1e-3
+
+
+def test_softmax_ce_all_ignored_is_nan(cuda_lib):
+    import torch
+    from scda_b200.loss_ops import softmax_ce_acc
+    x = torch.randn(64, 2, device="cuda")
+    loss, acc = softmax_ce_acc(x, torch.full((64,), -1, device="cuda"), ignore_index=-1)
+    assert bool(torch.isnan(loss)) and float(acc) == 0.0
+
+
+def test_rpn_fg_scores_matches_softmax(cuda_lib):
+    import torch
+    import torch.nn.functional as F
+    from scda_b200.loss_ops import rpn_fg_scores
+    g = torch.Generator(device="cuda").manual_seed(5)
+    cls = torch.randn(2, 30, 32, 64, device="cuda", generator=g) * 3
+    x = cls.permute(0, 2, 3, 1).contiguous()
+    ref = F.softmax(x.view(-1, 2), dim=1).view(2, -1, 2)[..., 1]
+    got = rpn_fg_scores(cls)
+    assert got.shape == ref.shape and float((got - ref).abs().max()) < 1e-6
