@@ -401,6 +401,56 @@ int scda_nchw_f32_to_nhwc_f32(int NB, int C, int H, int W, int Cpad, const float
 /* out[N] += column sums of x fp32 [M, ld] (any N, any ld >= N) */
 int scda_colsum_f32_ld(long long M, int N, const float *x, long long ld, float *out, cudaStream_t stream);
 
+/* --- discriminators (GAN_dis_AE, GAN_dis_AE_patch) ---------------------- */
+/* replaces cuDNN / torch behind nn.Conv2d(k=3, s=2, p=1) (+ LeakyReLU / BatchNorm2d) and the 1x1 head of
+ * faster_rcnn_adver_expansion_reweight_cluster.py:270-333, common_net.py:205-261.
+ * Stride-2 3x3 convolution on the tcgen05 halo kernel: x bf16 NHWC [NB, 2Ho, 2Wo, C] (C % 32 == 0), wd bf16
+ * [Cout][3][3][4C] = the phase-decomposed weight layout written by scda_conv_s2_weights from bf16
+ * [Cout][3][3][C]; flags / slope: epilogue flags of the GEMM entry points (1 ReLU, 2 fp32 out, 4 mask,
+ * 64 fp32 mask, 128 LeakyReLU(slope), 256 mask with LeakyReLU gradient). */
+int scda_conv_s2_weights(int Cout, int C, const void *w_krsc_bf16, void *wd_bf16, cudaStream_t stream);
+int scda_conv3x3_s2_bf16_nhwc(int NB, int Ho, int Wo, int C, int Cout, const void *x, const void *wd,
+                              const float *bias, void *y, int flags, float slope, cudaStream_t stream);
+/* dx [NB, 2Ho, 2Wo, C] from dy [NB, Ho, Wo, Cout]; mask_src (indexed like dx) = the input activation */
+int scda_conv3x3_s2_dgrad_bf16_nhwc(int NB, int Ho, int Wo, int C, int Cout, const void *dy, const void *wd,
+                                    void *dx, int flags, const void *mask_src, float slope, cudaStream_t stream);
+/* dw_partials fp32 [splits][Cout][9][4C] (taps 0, 1, 3, 4 written); scda_conv_s2_wgrad_gather sums the
+ * slabs and folds them to dw fp32 [Cout][3][3][C] (+= when accumulate) */
+int scda_conv3x3_s2_wgrad_bf16_nhwc(int NB, int Ho, int Wo, int C, int Cout, const void *x, const void *dy,
+                                    float *dw_partials, int splits, cudaStream_t stream);
+int scda_conv_s2_wgrad_gather(int Cout, int C, const float *partials, int splits, float *dw, int accumulate,
+                              cudaStream_t stream);
+/* first layer Conv2d(3, 32, 3, s 2, p 1) + LeakyReLU, direct: x fp32 [N, 3, H, W] with element strides
+ * (sn, sc, sh, sw); w fp32 [32][3][3][3] (o, r, s, c); y NHWC [N, H/2, W/2, 32] bf16 (y_f32 = 0) or fp32.
+ * Backward: g = gradient w.r.t. the pre-activation; dw [32][3][3][3], db [32] (= or +=), dx fp32 NHWC
+ * [N, H, W, 3]; any of dw / dx may be NULL.  workspace >= scda_disc_l1_workspace_bytes when dw != NULL. */
+int scda_disc_l1_fwd(int N, int H, int W, const float *x, long long sn, long long sc, long long sh,
+                     long long sw, const float *w_orsc, const float *bias, float slope, void *y, int y_f32,
+                     cudaStream_t stream);
+size_t scda_disc_l1_workspace_bytes(int N, int H, int W);
+int scda_disc_l1_bwd(int N, int H, int W, const float *x, long long sn, long long sc, long long sh,
+                     long long sw, const float *w_orsc, const void *g, int g_f32, float *dw, float *db,
+                     float *dx, int accumulate, void *workspace, size_t workspace_bytes, cudaStream_t stream);
+/* 1x1 head Conv2d(C, 1, 1): out[p] = bias + x[p, :] . w.  Backward: dx[p, c] = g[p] w[c] (x > 0 ? 1 : slope)
+ * (through the LeakyReLU that produced x), dw[c] += sum_p g x, db += sum g (dw / db must be zeroed or hold
+ * the running sum).  C divides 256. */
+int scda_head_dot_fwd(long long P, int C, const void *x, int x_f32, const float *w, const float *bias,
+                      float *out, cudaStream_t stream);
+int scda_head_dot_bwd(long long P, int C, const void *x, int x_f32, const float *w, const float *g,
+                      float slope, void *dx, float *dw, float *db, cudaStream_t stream);
+/* nn.BatchNorm2d in training mode + LeakyReLU over x fp32 [P, C] (P = N*H*W): batch statistics, running
+ * statistics updated (momentum, unbiased variance) when the pointers are not NULL; mean / rstd [C] saved for
+ * the backward.  Backward: dgamma, dbeta (= or +=), dx (may be NULL). */
+int scda_bn_lrelu_fwd(long long P, int C, const float *x, const float *gamma, const float *beta, float eps,
+                      float slope, float momentum, float *running_mean, float *running_var, float *mean,
+                      float *rstd, void *y, int y_f32, cudaStream_t stream);
+int scda_bn_lrelu_bwd(long long P, int C, const float *x, const void *dy, int dy_f32, const float *gamma,
+                      const float *beta, const float *mean, const float *rstd, float slope, void *dx,
+                      int dx_f32, float *dgamma, float *dbeta, int accumulate, cudaStream_t stream);
+/* global average pool x fp32 [N, HW, C] -> [N, C] and its backward (dx bf16 or fp32 [N, HW, C]) */
+int scda_avgpool_fwd(int N, int HW, int C, const float *x, float *out, cudaStream_t stream);
+int scda_avgpool_bwd(int N, int HW, int C, const float *g, void *dx, int dx_f32, cudaStream_t stream);
+
 /* --- detector losses -------------------------------------------------- */
 /* F.cross_entropy(logits, targets, ignore_index) (mean over the counted rows) AND the reference's
  * top-1 `accuracy` in one pass (_add_rpn_loss / _add_rcnn_loss,

@@ -76,6 +76,21 @@ SIGNATURES = {
     "scda_smooth_l1_sigma_sum_bwd": (_i, [C.c_longlong, _p, _p, _p, _f, _p, _p, _p]),
     "scda_bce_sigmoid_rows_fwd": (_i, [_i, _i, _p, _p, _i, _p, _p]),
     "scda_bce_sigmoid_rows_bwd": (_i, [_i, _i, _p, _p, _i, _p, _p, _p]),
+    "scda_conv_s2_weights": (_i, [_i, _i, _p, _p, _p]),
+    "scda_conv3x3_s2_bf16_nhwc": (_i, [_i, _i, _i, _i, _i, _p, _p, _p, _p, _i, _f, _p]),
+    "scda_conv3x3_s2_dgrad_bf16_nhwc": (_i, [_i, _i, _i, _i, _i, _p, _p, _p, _i, _p, _f, _p]),
+    "scda_conv3x3_s2_wgrad_bf16_nhwc": (_i, [_i, _i, _i, _i, _i, _p, _p, _p, _i, _p]),
+    "scda_conv_s2_wgrad_gather": (_i, [_i, _i, _p, _i, _p, _i, _p]),
+    "scda_disc_l1_fwd": (_i, [_i, _i, _i, _p, C.c_longlong, C.c_longlong, C.c_longlong, C.c_longlong, _p, _p, _f, _p, _i, _p]),
+    "scda_disc_l1_workspace_bytes": (_z, [_i, _i, _i]),
+    "scda_disc_l1_bwd": (_i, [_i, _i, _i, _p, C.c_longlong, C.c_longlong, C.c_longlong, C.c_longlong, _p, _p, _i, _p, _p, _p,
+                              _i, _p, _z, _p]),
+    "scda_head_dot_fwd": (_i, [C.c_longlong, _i, _p, _i, _p, _p, _p, _p]),
+    "scda_head_dot_bwd": (_i, [C.c_longlong, _i, _p, _i, _p, _p, _f, _p, _p, _p, _p]),
+    "scda_bn_lrelu_fwd": (_i, [C.c_longlong, _i, _p, _p, _p, _f, _f, _f, _p, _p, _p, _p, _p, _i, _p]),
+    "scda_bn_lrelu_bwd": (_i, [C.c_longlong, _i, _p, _p, _i, _p, _p, _p, _p, _f, _p, _i, _p, _p, _i, _p]),
+    "scda_avgpool_fwd": (_i, [_i, _i, _i, _p, _p, _p]),
+    "scda_avgpool_bwd": (_i, [_i, _i, _i, _p, _p, _i, _p]),
     "scda_softmax_ce_workspace_bytes": (_z, [C.c_longlong]),
     "scda_softmax_ce_acc_fwd": (_i, [C.c_longlong, _i, _p, C.c_longlong, _p, C.c_longlong, _p, _p, _z, _p]),
     "scda_softmax_ce_bwd": (_i, [C.c_longlong, _i, _p, C.c_longlong, _p, C.c_longlong, _p, _p, _p, C.c_longlong, _p]),
@@ -125,7 +140,7 @@ def load(path: str | None = None) -> C.CDLL:
 KERNELS_PER_CALL = {
     "scda_nms": 2, "scda_nms_dyn": 2, "scda_instnorm_act_fwd_nhwc_f32": 3, "scda_instnorm_act_bwd_nhwc_f32": 3,
     "scda_instnorm_act_fwd_nhwc": 3, "scda_instnorm_act_bwd_nhwc": 3, "scda_conv1x1_tanh_bwd": 2,
-    "scda_softmax_ce_acc_fwd": 2, "SoftmaxFocalLossForwardLaucher": 1,
+    "scda_softmax_ce_acc_fwd": 2, "scda_disc_l1_bwd": 3, "SoftmaxFocalLossForwardLaucher": 1,
     "SoftmaxFocalLossBackwardLaucher": 1,
 }
 LAUNCHES = 0

@@ -52,6 +52,11 @@ struct HaloParams {
     long long ldc;
     const __nv_bfloat16 *mask_src;
     int flags;
+    // stride-2 form (kS2): the convolution runs on the (H, W) = OUTPUT grid over 4 * C virtual input channels
+    // (row phase, column phase, channel); c2 = 2 * C = the channels of one row phase
+    int c2;
+    int tap_mask;                // taps (bit r * 3 + s) that carry non-zero weights
+    float slope;                 // LeakyReLU slope of the epilogue
 };
 
 // Halo stages: with 64 output channels a tile retires its nine taps in ~2.3 k clocks, about the
@@ -94,7 +99,7 @@ __device__ __forceinline__ HaloTile halo_tile(const HaloParams &p, int tile)
     return t;
 }
 
-template <int kBlockN, int kSub, int kSpec>
+template <int kBlockN, int kSub, int kSpec, bool kS2Dgrad = false>
 __device__ __forceinline__ void halo_epilogue(const HaloParams &p, const EpiParams &e, uint32_t tmem_base,
                                               uint32_t bar_tfull, uint32_t bar_tempty, int ew, int lane)
 {
@@ -114,7 +119,15 @@ __device__ __forceinline__ void halo_epilogue(const HaloParams &p, const EpiPara
         const int row = q * 32 + lane;
         const int h = t.h0 + (row >> 3), w = t.w0 + (row & 7) + kSubW * sub;
         const bool row_ok = h < p.H && w < p.W;
-        const long long out_row = ((long long)t.img * p.H + h) * p.W + w;
+        long long out_row = ((long long)t.img * p.H + h) * p.W + w;
+        int col_base = t.n0;
+        if (kS2Dgrad) {
+            // data gradient of the stride-2 convolution: N tile = virtual channels (py, px, c) of the input
+            // seen as [NB, 2H, W, 2C]; row phase py = n0 / 2C selects the image row 2h + py
+            const int py = t.n0 / p.c2;
+            col_base = t.n0 - py * p.c2;
+            out_row = (((long long)t.img * p.H + h) * 2 + py) * p.W + w;
+        }
 #pragma unroll 1
         for (int c0 = 0; c0 < kBlockN; c0 += 32) {
             uint32_t v[32];
@@ -125,12 +138,18 @@ __device__ __forceinline__ void halo_epilogue(const HaloParams &p, const EpiPara
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_tempty + acc * 8);
             }
-            if (row_ok) epilogue_chunk<kSpec>(v, e, out_row, t.n0 + c0, vec_ok);
+            if (row_ok) epilogue_chunk<kSpec>(v, e, out_row, col_base + c0, vec_ok);
         }
     }
 }
 
-template <int kBlockN, int kSub, bool kBMn, int kBStages>
+// kS2: the stride-2 form (discriminators: models/faster_rcnn/common_net.py:205-261 of the reference,
+// nn.Conv2d(k=3, s=2, p=1)).  out(i, j) = sum_{r,s} x(2i + r - 1, 2j + s - 1) W[r, s] is a 2 x 2-tap stride-1
+// convolution over the input's four phase images: the A tensor map views x as [NB, Hin, Win/2, 2C] and walks
+// the row dimension with element stride 2, so the halo box of virtual channel block (py, 64 of 2C) is the
+// phase image's tile, zero-filled outside; the weights are laid out [Cout][3x3 taps][4C] with the taps of the
+// two offsets {-1, 0} (tap_mask) — taps that are structurally zero are neither loaded nor multiplied.
+template <int kBlockN, int kSub, bool kBMn, int kBStages, bool kS2 = false>
 __global__ void __launch_bounds__(128 + 128 * kSub, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                  const HaloParams p)
@@ -192,8 +211,14 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                     const int s = it % kAStages;
                     mbar_wait(bar_aempty + s * 8, ((it / kAStages) & 1) ^ 1);
                     mbar_expect_tx(bar_afull + s * 8, L::kABox);
-                    tma_load_4d(base + s * L::kABytes, &map_a, bar_afull + s * 8, cb * 64, t.w0 - 1, t.h0 - 1,
-                                t.img);
+                    if (kS2 && !kBMn) {
+                        const int py = (cb * 64) / p.c2;
+                        tma_load_4d(base + s * L::kABytes, &map_a, bar_afull + s * 8, cb * 64 - py * p.c2, t.w0 - 1,
+                                    2 * (t.h0 - 1) + py, t.img);
+                    } else {
+                        tma_load_4d(base + s * L::kABytes, &map_a, bar_afull + s * 8, cb * 64, t.w0 - 1, t.h0 - 1,
+                                    t.img);
+                    }
                 }
             }
         }
@@ -207,9 +232,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                  tile += gridDim.x) {
                 const HaloTile t = halo_tile<kBlockN, kSub>(p, tile);
                 for (int cb = 0; cb < p.cblocks; ++cb) {
-                    for (int tap = 0; tap < 9; ++tap, ++it) {
+                    for (int tap = 0; tap < 9; ++tap) {
+                        if (kS2 && !((p.tap_mask >> tap) & 1)) continue;
                         const int s = it % kBStages;
-                        if (!kBRes) mbar_wait(bar_bempty + s * 8, ((it / kBStages) & 1) ^ 1);
+                        ++it;
+                        if (!kBRes) mbar_wait(bar_bempty + s * 8, (((it - 1) / kBStages) & 1) ^ 1);
                         mbar_expect_tx(bar_bfull + s * 8, L::kBBytes);
                         const uint32_t b_dst = base + L::kBOffset + s * L::kBBytes;
                         if (kBMn) {
@@ -250,14 +277,18 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                     const uint32_t as = ait % kAStages;
                     mbar_wait(bar_afull + as * 8, (ait / kAStages) & 1);
                     const uint32_t a_lo = a_lo0 + as * (L::kABytes >> 4);
+                    uint32_t done_taps = 0;          // (kS2) MMAs already issued for this channel block
 #pragma unroll
-                    for (int tap = 0; tap < 9; ++tap, ++bit) {
+                    for (int tap = 0; tap < 9; ++tap) {
+                        if (kS2 && !((p.tap_mask >> tap) & 1)) continue;
                         const uint32_t bs = kBRes ? (uint32_t)tap : bit % kBStages;
                         // (resident: the slot's first and only phase; later waits return at once)
                         mbar_wait(bar_bfull + bs * 8, kBRes ? 0u : (bit / kBStages) & 1);
+                        ++bit;
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                         const uint32_t b_lo = b_lo0 + bs * (L::kBBytes >> 4);
-                        const uint32_t first = (uint32_t)(cb | tap);
+                        const uint32_t first = kS2 ? (uint32_t)cb | done_taps : (uint32_t)(cb | tap);
+                        done_taps = 1;
 #pragma unroll
                         for (int sub = 0; sub < kSub; ++sub) {
                             // rows (tap/3) * HW + tap%3 + 8*sub of 128 B each = 8 units of 16 B per row
@@ -280,26 +311,27 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         e.bias = p.bias; e.out = p.out; e.ldc = p.ldc; e.mask_src = p.mask_src; e.mul_src = nullptr;
         e.flags = p.flags | (p.bias ? kFlagBias : 0);
         e.N = p.N;
-        if (e.flags == (kFlagRelu | kFlagBias))
-            halo_epilogue<kBlockN, kSub, kFlagRelu | kFlagBias>(p, e, tmem_base, bar_tfull, bar_tempty, warp - 4, lane);
-        else if (e.flags == kFlagMaskPos)
-            halo_epilogue<kBlockN, kSub, kFlagMaskPos>(p, e, tmem_base, bar_tfull, bar_tempty, warp - 4, lane);
-        else if (e.flags == 0)
-            halo_epilogue<kBlockN, kSub, 0>(p, e, tmem_base, bar_tfull, bar_tempty, warp - 4, lane);
+        e.slope = p.slope;
+#define SCDA_HEPI(SPEC)                                                                                          \
+    halo_epilogue<kBlockN, kSub, SPEC, kS2 && kBMn>(p, e, tmem_base, bar_tfull, bar_tempty, warp - 4, lane)
+        if (kS2) {
+            // discriminator layers: conv + bias + LeakyReLU; its data gradient through the LeakyReLU below
+            if (kBMn) { e.N = p.c2; }
+            if (e.flags == (kFlagLeaky | kFlagBias)) SCDA_HEPI(kFlagLeaky | kFlagBias);
+            else if (e.flags == (kFlagMaskPos | kFlagMaskLeaky)) SCDA_HEPI(kFlagMaskPos | kFlagMaskLeaky);
+            else if (e.flags == kFlagOutF32) SCDA_HEPI(kFlagOutF32);
+            else if (e.flags == 0) SCDA_HEPI(0);
+            else SCDA_HEPI(-1);
+        } else if (e.flags == (kFlagRelu | kFlagBias)) SCDA_HEPI(kFlagRelu | kFlagBias);
+        else if (e.flags == kFlagMaskPos) SCDA_HEPI(kFlagMaskPos);
+        else if (e.flags == 0) SCDA_HEPI(0);
         // fp32-parity mode (x3_ops.cu): fp32 outputs, fp32 ReLU masks
-        else if (e.flags == (kFlagRelu | kFlagBias | kFlagOutF32))
-            halo_epilogue<kBlockN, kSub, kFlagRelu | kFlagBias | kFlagOutF32>(p, e, tmem_base, bar_tfull, bar_tempty,
-                                                                              warp - 4, lane);
-        else if (e.flags == (kFlagMaskPos | kFlagMaskF32 | kFlagOutF32))
-            halo_epilogue<kBlockN, kSub, kFlagMaskPos | kFlagMaskF32 | kFlagOutF32>(p, e, tmem_base, bar_tfull,
-                                                                                   bar_tempty, warp - 4, lane);
-        else if (e.flags == kFlagOutF32)
-            halo_epilogue<kBlockN, kSub, kFlagOutF32>(p, e, tmem_base, bar_tfull, bar_tempty, warp - 4, lane);
-        else if (e.flags == (kFlagOutF32 | kFlagBias))      // (also the decoder's conv -> InstanceNorm layers)
-            halo_epilogue<kBlockN, kSub, kFlagOutF32 | kFlagBias>(p, e, tmem_base, bar_tfull, bar_tempty, warp - 4,
-                                                                  lane);
-        else
-            halo_epilogue<kBlockN, kSub, -1>(p, e, tmem_base, bar_tfull, bar_tempty, warp - 4, lane);
+        else if (e.flags == (kFlagRelu | kFlagBias | kFlagOutF32)) SCDA_HEPI(kFlagRelu | kFlagBias | kFlagOutF32);
+        else if (e.flags == (kFlagMaskPos | kFlagMaskF32 | kFlagOutF32)) SCDA_HEPI(kFlagMaskPos | kFlagMaskF32 | kFlagOutF32);
+        else if (e.flags == kFlagOutF32) SCDA_HEPI(kFlagOutF32);
+        else if (e.flags == (kFlagOutF32 | kFlagBias)) SCDA_HEPI(kFlagOutF32 | kFlagBias);      // (decoder conv -> IN)
+        else SCDA_HEPI(-1);
+#undef SCDA_HEPI
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -310,21 +342,21 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     }
 }
 
-template <int kBlockN, int kSub, bool kBMn, int kBStages>
+template <int kBlockN, int kSub, bool kBMn, int kBStages, bool kS2 = false>
 int launch_halo(const CUtensorMap &ma, const CUtensorMap &mb, const HaloParams &p, cudaStream_t stream)
 {
     using L = HaloSmem<kBlockN, kSub, kBStages>;
     static_assert(L::kTotal <= 227 * 1024, "shared memory budget");
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<kBlockN, kSub, kBMn, kBStages>,
+        cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<kBlockN, kSub, kBMn, kBStages, kS2>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
         if (e != cudaSuccess) return -(int)e;
         attr_done = true;
     }
     const long long tiles = (long long)p.m_tiles * p.n_tiles;
     const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
-    conv_halo_kernel<kBlockN, kSub, kBMn, kBStages><<<grid, 128 + 128 * kSub, L::kTotal, stream>>>(ma, mb, p);
+    conv_halo_kernel<kBlockN, kSub, kBMn, kBStages, kS2><<<grid, 128 + 128 * kSub, L::kTotal, stream>>>(ma, mb, p);
     return scda_launch_status();
 }
 
@@ -438,4 +470,63 @@ int scda_conv_halo_launch(int NB, int H, int W, int Cred, int Nout, const void *
                                   : launch_halo<64, 2, false, 8>(ma, mb, p, stream);
     return sub == 1 ? launch_halo<128, 1, false, 8>(ma, mb, p, stream)
                     : launch_halo<128, 2, false, 8>(ma, mb, p, stream);
+}
+
+// Stride-2 3x3 convolution (padding 1) and its data gradient on the halo kernel (see conv_halo_kernel, kS2).
+//   forward: x bf16 [NB, 2*Ho, 2*Wo, C] (C % 32 == 0), wd bf16 [Cout][3][3][4C] = the s2d weight layout written by
+//            scda_conv_s2_weights (disc_ops.cu) -> y [NB, Ho, Wo, Cout]
+//   dgrad  : dy bf16 [NB, Ho, Wo, Cout], the same wd -> dx [NB, 2*Ho, 2*Wo, C]
+// flags / bias / mask_src / slope: the epilogue of tc_epilogue.cuh (mask_src is indexed like the output).
+int scda_conv_halo_s2_launch(int NB, int Ho, int Wo, int C, int Cout, const void *a, const void *wd,
+                             const float *bias, void *out, int flags, const void *mask_src, float slope,
+                             bool dgrad, cudaStream_t stream)
+{
+    if (C % 32 || Cout % 32 || NB <= 0 || Ho <= 0 || Wo <= 0) return 0;
+    const int c2 = 2 * C, c4 = 4 * C;
+    if (c2 % 64) return 0;
+    const int Cred = dgrad ? Cout : c4, Nout = dgrad ? c4 : Cout;
+    // N tile: 64 unless 128 fits (a data-gradient tile must stay inside one row phase of 2C channels)
+    int bn = (Nout % 128 == 0 && (!dgrad || c2 % 128 == 0)) ? 128 : 64;
+    const long long th = ceil_div(Ho, kTileH);
+    if ((long long)NB * th * ceil_div(Wo, kSubW) * ceil_div(Nout, bn) < (long long)num_sms() * 3 / 4) bn = 64;
+    const int sub = 1;
+    HaloParams p = {};
+    p.H = Ho; p.W = Wo; p.Cred = Cred; p.N = Nout;
+    p.cblocks = ceil_div(Cred, 64);
+    p.tiles_w = ceil_div(Wo, kSubW * sub);
+    p.tiles_h = ceil_div(Ho, kTileH);
+    p.m_tiles = NB * p.tiles_h * p.tiles_w;
+    p.n_tiles = ceil_div(Nout, bn);
+    p.bias = bias; p.out = out;
+    p.ldc = dgrad ? c2 : Nout;
+    p.mask_src = (const __nv_bfloat16 *)mask_src;
+    p.flags = flags;
+    p.c2 = c2;
+    p.slope = slope;
+    // forward taps: offsets (a, b) in {-1, 0}^2 of the 3x3 grid = taps 0, 1, 3, 4; the data gradient walks the
+    // mirrored offsets {0, +1}^2 = taps 4, 5, 7, 8 (and reads weight tap 8 - tap)
+    p.tap_mask = dgrad ? ((1 << 4) | (1 << 5) | (1 << 7) | (1 << 8)) : ((1 << 0) | (1 << 1) | (1 << 3) | (1 << 4));
+    CUtensorMap ma, mb;
+    if (dgrad) {
+        cuuint64_t da[4] = {(cuuint64_t)Cout, (cuuint64_t)Wo, (cuuint64_t)Ho, (cuuint64_t)NB};
+        cuuint64_t sa[3] = {(cuuint64_t)Cout * 2, (cuuint64_t)Wo * Cout * 2, (cuuint64_t)Ho * Wo * Cout * 2};
+        cuuint32_t ba[4] = {64, (cuuint32_t)(kSubW * sub + 2), (cuuint32_t)kHaloH, 1};
+        if (!make_map(&ma, a, 4, da, sa, ba)) return 0;
+        cuuint64_t db[2] = {(cuuint64_t)9 * Nout, (cuuint64_t)Cred}, sb[1] = {(cuuint64_t)9 * Nout * 2};
+        cuuint32_t bb[2] = {64, 64};
+        if (!make_map(&mb, wd, 2, db, sb, bb)) return 0;
+        return bn == 64 ? launch_halo<64, 1, true, 8, true>(ma, mb, p, stream)
+                        : launch_halo<128, 1, true, 8, true>(ma, mb, p, stream);
+    }
+    // x seen as [NB, Hin = 2Ho, Wo (pixel pairs), 2C]; rows walked with element stride 2 (one row phase per box)
+    cuuint64_t da[4] = {(cuuint64_t)c2, (cuuint64_t)Wo, (cuuint64_t)2 * Ho, (cuuint64_t)NB};
+    cuuint64_t sa[3] = {(cuuint64_t)c2 * 2, (cuuint64_t)Wo * c2 * 2, (cuuint64_t)2 * Ho * Wo * c2 * 2};
+    cuuint32_t ba[4] = {64, (cuuint32_t)(kSubW * sub + 2), (cuuint32_t)(2 * kHaloH), 1};
+    cuuint32_t es[4] = {1, 1, 2, 1};
+    if (!make_map_strided(&ma, a, 4, da, sa, ba, es)) return 0;
+    cuuint64_t db[2] = {(cuuint64_t)9 * Cred, (cuuint64_t)Nout}, sb[1] = {(cuuint64_t)9 * Cred * 2};
+    cuuint32_t bb[2] = {64, (cuuint32_t)bn};
+    if (!make_map(&mb, wd, 2, db, sb, bb)) return 0;
+    return bn == 64 ? launch_halo<64, 1, false, 8, true>(ma, mb, p, stream)
+                    : launch_halo<128, 1, false, 8, true>(ma, mb, p, stream);
 }

@@ -8,3 +8,8 @@ bool scda_conv_halo_plan(int NB, int H, int W, int Cred, int Nout, bool dgrad, i
 int scda_conv_halo_launch(int NB, int H, int W, int Cred, int Nout, const void *a, const void *w_krsc,
                           const float *bias, void *out, int flags, const void *mask_src, bool dgrad, int bn,
                           int sub, cudaStream_t stream);
+
+// stride-2 3x3 convolution (padding 1) / its data gradient; wd = the [Cout][3][3][4C] layout of scda_conv_s2_weights
+int scda_conv_halo_s2_launch(int NB, int Ho, int Wo, int C, int Cout, const void *a, const void *wd,
+                             const float *bias, void *out, int flags, const void *mask_src, float slope,
+                             bool dgrad, cudaStream_t stream);

@@ -302,6 +302,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         e.bias = p.bias; e.out = p.out; e.ldc = p.ldc; e.mask_src = p.mask_src; e.mul_src = p.mul_src;
         e.flags = p.flags | (p.bias ? kFlagBias : 0);
         e.N = p.N;
+        e.slope = 0.f;
         const uint32_t tempty_remote = kPair ? map_to_cta(bar_tempty, 0) : bar_tempty;
 #define SCDA_EPI(SPEC)                                                                                         \
     gemm_epilogue<kBlockN, kCluster, SPEC>(p, e, tmem_base, bar_tfull, bar_tempty, tempty_remote, warp - 4,   \
@@ -450,6 +451,11 @@ struct WgParams {
     long long ldo;               // row stride of the output (conv: 9*Cin)
     long long split_stride;
     int accumulate;              // dst += (linear form only)
+    // stride-2 convolution (conv_halo.cu, kS2): No = 4C virtual input channels (row phase, column phase,
+    // channel), c2 = 2C; the X map views the input as [NB, 2H, W, 2C] with element stride 2 along rows;
+    // tap_list holds the ntaps taps of the 3x3 grid that are computed, 4 bits each (0 = all nine in order)
+    int s2, c2, ntaps;
+    unsigned long long tap_list;
 };
 
 template <int kBlockN, int kStages>
@@ -479,8 +485,9 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.x * kBlockM;                 // Cout offset
     const int n_tiles = (p.No + kBlockN - 1) / kBlockN;
-    const int tap = p.conv ? blockIdx.y / n_tiles : 0;
-    const int n0 = (blockIdx.y - tap * n_tiles) * kBlockN;   // Cin offset
+    const int tap_ix = p.conv ? blockIdx.y / n_tiles : 0;
+    const int tap = p.ntaps ? (int)((p.tap_list >> (4 * tap_ix)) & 15) : tap_ix;
+    const int n0 = (blockIdx.y - tap_ix * n_tiles) * kBlockN;   // Cin offset
     const int split = blockIdx.z;
     const int kb0 = split * p.k_per_split;
     const int kb1 = min(kb0 + p.k_per_split, p.total_k_blocks);
@@ -521,10 +528,18 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 #pragma unroll
                     for (int c = 0; c < 2; ++c)
                         tma_load_4d(a_dst + c * L::kChunk, &map_a, bar_full + s * 8, m0 + c * 64, w0, h0, img);
+                    if (p.s2) {
+                        const int py = n0 / p.c2;
 #pragma unroll
-                    for (int c = 0; c < kBlockN / 64; ++c)
-                        tma_load_4d(b_dst + c * L::kChunk, &map_b, bar_full + s * 8, n0 + c * 64, w0 + sx - 1,
-                                    h0 + r - 1, img);
+                        for (int c = 0; c < kBlockN / 64; ++c)
+                            tma_load_4d(b_dst + c * L::kChunk, &map_b, bar_full + s * 8, n0 - py * p.c2 + c * 64,
+                                        w0 + sx - 1, 2 * (h0 + r - 1) + py, img);
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < kBlockN / 64; ++c)
+                            tma_load_4d(b_dst + c * L::kChunk, &map_b, bar_full + s * 8, n0 + c * 64, w0 + sx - 1,
+                                        h0 + r - 1, img);
+                    }
                 } else {
 #pragma unroll
                     for (int c = 0; c < 2; ++c)
@@ -1013,4 +1028,62 @@ SCDA_API int scda_conv3x3_wgrad_bf16_nhwc(int NB, int H, int W, int Cin, int Cou
                                           float *dw_partials, int splits, cudaStream_t stream)
 {
     return scda_conv3x3_wgrad_bf16_nhwc_ld(NB, H, W, Cin, Cout, x, Cin, dy, Cout, dw_partials, splits, stream);
+}
+
+// Weight gradient of the stride-2 3x3 convolution (conv_halo.cu, kS2): x bf16 [NB, 2Ho, 2Wo, C], dy bf16
+// [NB, Ho, Wo, Cout] -> dw_partials fp32 [splits][Cout][9][4C] in the s2d weight layout; only the four taps
+// {0, 1, 3, 4} are written (scda_conv_s2_wgrad_gather of disc_ops.cu folds them back to [Cout][3][3][C]).
+SCDA_API int scda_conv3x3_s2_wgrad_bf16_nhwc(int NB, int Ho, int Wo, int C, int Cout, const void *x, const void *dy,
+                                             float *dw_partials, int splits, cudaStream_t stream)
+{
+    if (NB <= 0 || Ho <= 0 || Wo <= 0 || C <= 0 || Cout <= 0 || !x || !dy || !dw_partials || splits < 1) return 0;
+    if (C % 32 || Cout % 32) return 0;
+    const int c2 = 2 * C, c4 = 4 * C;
+    int TW = 16, TH = 8;
+    if (Wo % 16) {
+        if (Wo % 8 == 0) { TW = 8; TH = 16; } else return 0;
+    }
+    // (a tile taller than the map is fine: TMA zero-fills the rows outside on BOTH operands)
+    const int tiles_w = Wo / TW, tiles_h = ceil_div(Ho, TH);
+    const int bn = c2 % 128 == 0 ? 128 : 64;          // a Cin tile stays inside one row phase
+    CUtensorMap ma, mb;
+    cuuint64_t da[4] = {(cuuint64_t)Cout, (cuuint64_t)Wo, (cuuint64_t)Ho, (cuuint64_t)NB};
+    cuuint64_t sa[3] = {(cuuint64_t)Cout * 2, (cuuint64_t)Wo * Cout * 2, (cuuint64_t)Ho * Wo * Cout * 2};
+    cuuint32_t box[4] = {64, (cuuint32_t)TW, (cuuint32_t)TH, 1};
+    cuuint64_t db[4] = {(cuuint64_t)c2, (cuuint64_t)Wo, (cuuint64_t)2 * Ho, (cuuint64_t)NB};
+    cuuint64_t sb[3] = {(cuuint64_t)c2 * 2, (cuuint64_t)Wo * c2 * 2, (cuuint64_t)2 * Ho * Wo * c2 * 2};
+    cuuint32_t boxb[4] = {64, (cuuint32_t)TW, (cuuint32_t)(2 * TH), 1};
+    cuuint32_t es[4] = {1, 1, 2, 1};
+    if (!make_map(&ma, dy, 4, da, sa, box) || !make_map_strided(&mb, x, 4, db, sb, boxb, es)) return 0;
+    WgParams p = {};
+    p.Mo = Cout; p.No = c4; p.conv = 1;
+    p.H = Ho; p.W = Wo; p.TH = TH; p.TW = TW; p.tiles_w = tiles_w; p.tiles_h = tiles_h;
+    p.total_k_blocks = NB * tiles_h * tiles_w;
+    if (splits > p.total_k_blocks) return 0;
+    p.k_per_split = ceil_div(p.total_k_blocks, splits);
+    if (ceil_div(p.total_k_blocks, p.k_per_split) != splits) return 0;
+    p.out = dw_partials; p.ldo = 9ll * c4; p.split_stride = (long long)Cout * 9 * c4;
+    p.s2 = 1; p.c2 = c2; p.ntaps = 4;
+    p.tap_list = 0ull | (1ull << 4) | (3ull << 8) | (4ull << 12);
+    if (bn == 64) return launch_wg<64, 4>(ma, mb, p, 4, splits, stream);
+    return launch_wg<128, 3>(ma, mb, p, 4, splits, stream);
+}
+
+// the halo convolution's stride-2 form behind the C ABI (conv_halo.cu: scda_conv_halo_s2_launch)
+SCDA_API int scda_conv3x3_s2_bf16_nhwc(int NB, int Ho, int Wo, int C, int Cout, const void *x, const void *wd,
+                                       const float *bias, void *y, int flags, float slope, cudaStream_t stream)
+{
+    if (!x || !wd || !y) return 0;
+    if (flags & (kFlagMaskPos | kFlagMulSrc | kFlagAccumulate)) return 0;
+    return scda_conv_halo_s2_launch(NB, Ho, Wo, C, Cout, x, wd, bias, y, flags, nullptr, slope, false, stream);
+}
+
+SCDA_API int scda_conv3x3_s2_dgrad_bf16_nhwc(int NB, int Ho, int Wo, int C, int Cout, const void *dy, const void *wd,
+                                             void *dx, int flags, const void *mask_src, float slope,
+                                             cudaStream_t stream)
+{
+    if (!dy || !wd || !dx) return 0;
+    if ((flags & kFlagMaskPos) && !mask_src) return 0;
+    if (flags & (kFlagRelu | kFlagLeaky | kFlagMulSrc | kFlagAccumulate)) return 0;
+    return scda_conv_halo_s2_launch(NB, Ho, Wo, C, Cout, dy, wd, nullptr, dx, flags, mask_src, slope, true, stream);
 }

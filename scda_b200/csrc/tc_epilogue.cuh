@@ -19,6 +19,8 @@ enum : int {
     kFlagMulSrc = 16,     // y *= mul_src            (dropout keep/scale tensor, bf16)
     kFlagBias = 32,       // internal: bias pointer present
     kFlagMaskF32 = 64,    // mask_src holds fp32 (the fp32-parity mode keeps activations in fp32)
+    kFlagLeaky = 128,     // y = y > 0 ? y : slope * y            (LeakyReLU forward)
+    kFlagMaskLeaky = 256, // with kFlagMaskPos: y = mask_src > 0 ? y : slope * y   (LeakyReLU backward)
 };
 
 struct EpiParams {
@@ -29,6 +31,7 @@ struct EpiParams {
     const __nv_bfloat16 *mul_src;    // [rows, ldc]
     int flags;                       // run-time flag set (| kFlagBias)
     int N;
+    float slope;                     // LeakyReLU negative slope (kFlagLeaky / kFlagMaskLeaky)
 };
 
 // kSpec >= 0: the flag set is the compile-time constant kSpec; kSpec < 0: e.flags at run time.
@@ -56,15 +59,20 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], const Ep
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
         }
+        if (flags & kFlagLeaky) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = f[j] > 0.f ? f[j] : f[j] * e.slope;
+        }
+#define SCDA_MASKED(x) ((flags & kFlagMaskLeaky) ? (x) * e.slope : 0.f)     /* value where the mask is <= 0 */
         if ((flags & kFlagMaskPos) && (flags & kFlagMaskF32)) {
             const float *mf = reinterpret_cast<const float *>(e.mask_src) + o;
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
                 const float4 q = __ldg(reinterpret_cast<const float4 *>(mf + j));
-                if (!(q.x > 0.f)) f[j] = 0.f;
-                if (!(q.y > 0.f)) f[j + 1] = 0.f;
-                if (!(q.z > 0.f)) f[j + 2] = 0.f;
-                if (!(q.w > 0.f)) f[j + 3] = 0.f;
+                if (!(q.x > 0.f)) f[j] = SCDA_MASKED(f[j]);
+                if (!(q.y > 0.f)) f[j + 1] = SCDA_MASKED(f[j + 1]);
+                if (!(q.z > 0.f)) f[j + 2] = SCDA_MASKED(f[j + 2]);
+                if (!(q.w > 0.f)) f[j + 3] = SCDA_MASKED(f[j + 3]);
             }
         } else if (flags & kFlagMaskPos) {
 #pragma unroll
@@ -73,7 +81,7 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], const Ep
                 const __nv_bfloat16 *qb = reinterpret_cast<const __nv_bfloat16 *>(&q);
 #pragma unroll
                 for (int t = 0; t < 8; ++t)
-                    if (!(__bfloat162float(qb[t]) > 0.f)) f[j + t] = 0.f;
+                    if (!(__bfloat162float(qb[t]) > 0.f)) f[j + t] = SCDA_MASKED(f[j + t]);
             }
         }
         if (flags & kFlagMulSrc) {
@@ -126,10 +134,11 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], const Ep
         for (int t = 1; t < 32; ++t) x = (t == j) ? __uint_as_float(v[t]) : x;
         if (flags & kFlagBias) x += __ldg(e.bias + col0 + j);
         if (flags & kFlagRelu) x = fmaxf(x, 0.f);
+        if (flags & kFlagLeaky) x = x > 0.f ? x : x * e.slope;
         if (flags & kFlagMaskPos) {
             const float m = (flags & kFlagMaskF32) ? reinterpret_cast<const float *>(e.mask_src)[o + j]
                                                    : __bfloat162float(e.mask_src[o + j]);
-            if (!(m > 0.f)) x = 0.f;
+            if (!(m > 0.f)) x = SCDA_MASKED(x);
         }
         if (flags & kFlagMulSrc) x *= __bfloat162float(e.mul_src[o + j]);
         if (flags & kFlagOutF32) {
@@ -140,5 +149,7 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], const Ep
         }
     }
 }
+
+#undef SCDA_MASKED
 
 }  // namespace tcptx

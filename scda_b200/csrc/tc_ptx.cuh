@@ -293,5 +293,17 @@ inline bool make_map(CUtensorMap *map, const void *ptr, int rank, const cuuint64
     return r == CUDA_SUCCESS;
 }
 
+// the same with per-dimension element strides (a box of boxDim[i] positions delivers
+// ceil(boxDim[i] / elem_strides[i]) elements along dimension i): the row-phase view of the stride-2 convolutions
+inline bool make_map_strided(CUtensorMap *map, const void *ptr, int rank, const cuuint64_t *dims,
+                             const cuuint64_t *strides_bytes, const cuuint32_t *box, const cuuint32_t *elem_strides)
+{
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return false;
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void *>(ptr), dims,
+                    strides_bytes, box, elem_strides, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
 
 }  // namespace tcptx

@@ -223,8 +223,11 @@ class SCDATrainer(object):
         # (the decoder's 64-multiple 3x3 convolutions run on the tensor-core kernels: bf16 shadows)
         self.opt_dec = FlatAdam(dec_model, lr, weight_decay=weight_decay, tensor_core=gan_ops.TC_GAN,
                                 channels_last=True)
-        self.opt_dis = FlatAdam(dis_model, lr, weight_decay=weight_decay, channels_last=True)
-        self.opt_dis_patch = FlatAdam(dis_model_patch, lr, weight_decay=weight_decay, channels_last=True)
+        # (the discriminators' stride-2 convolutions run on the tensor-core kernels too: bf16 shadows, direct sinks)
+        self.opt_dis = FlatAdam(dis_model, lr, weight_decay=weight_decay, tensor_core=gan_ops.TC_GAN,
+                                channels_last=True)
+        self.opt_dis_patch = FlatAdam(dis_model_patch, lr, weight_decay=weight_decay, tensor_core=gan_ops.TC_GAN,
+                                      channels_last=True)
         self.cluster_num, self.threshold, self.recon_size = cluster_num, threshold, recon_size
         self.new_w, self.new_h, self.world_size = new_w, new_h, world_size
         self.use_graphs = use_graphs

@@ -117,8 +117,13 @@ class ResDis_cluster(nn.Module):
     def forward(self, x1):
         x1 = x1.view(self.cluster_num, self.channel, self.w, self.h)
         if x1.is_cuda:
+            from ... import disc_ops
+            if disc_ops.patch_dis_supported(self.model, x1):
+                # the whole trunk as one autograd node on hand-written kernels (scda_b200/disc_ops.py)
+                return torch.squeeze(disc_ops.patch_dis(self.model, x1))
             x1 = x1.contiguous(memory_format=torch.channels_last)
-            note_library_call("ResDis_cluster", "stride-2 convolutions + BatchNorm on cuDNN")
+            note_library_call("ResDis_cluster", "stride-2 convolutions + BatchNorm on cuDNN "
+                              "(fp32-parity mode, eval mode or an unsupported shape)")
         out = self.model(x1)
         out = nn.functional.avg_pool2d(out, out.size()[2:])
         return torch.squeeze(out)

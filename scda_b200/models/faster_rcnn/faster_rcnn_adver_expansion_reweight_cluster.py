@@ -364,11 +364,20 @@ class GAN_dis_AE(nn.Module):
         model += [nn.Conv2d(tch, 1, kernel_size=1, stride=1, padding=0)]
         return nn.Sequential(*model)
 
+    @staticmethod
+    def _run(seq, x):
+        if x.is_cuda:
+            from ... import disc_ops
+            if disc_ops.image_dis_supported(seq, x):
+                # one autograd node on hand-written kernels (scda_b200/disc_ops.py): direct first layer,
+                # stride-2 tcgen05 convolutions with bias + LeakyReLU in the epilogue, dot-product head
+                return disc_ops.image_dis(seq, x)
+            # NHWC end to end: no cuDNN layout transposes around the convolutions
+            x = x.contiguous(memory_format=torch.channels_last)
+        return seq(x)
+
     def forward(self, x_aa, x_bb):
-        if x_aa.is_cuda:      # NHWC end to end: no cuDNN layout transposes around the convolutions
-            x_aa = x_aa.contiguous(memory_format=torch.channels_last)
-            x_bb = x_bb.contiguous(memory_format=torch.channels_last)
-        out_A, out_B = run_pair(lambda: self.model_A(x_aa), lambda: self.model_B(x_bb))
+        out_A, out_B = run_pair(lambda: self._run(self.model_A, x_aa), lambda: self._run(self.model_B, x_bb))
         return out_A.reshape(out_A.size(0), -1), out_B.reshape(out_B.size(0), -1)
 
 

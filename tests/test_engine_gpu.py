@@ -176,6 +176,7 @@ def test_stale_direct_gradient_is_zeroed_before_autograd_accumulates(cuda_lib):
     torch.manual_seed(0)
     model = vgg16(cfg=cfg["shared"]).cuda()
     opt = FlatAdam(model, 1e-4, tensor_core=True)
+    model.eval()                                          # dropout off: the two steps compute the same gradient
     model._fp32_graph = True
     fc6 = model.classifier[0].weight                      # 102.8 M elements: never zeroed by zero()
     feat = torch.randn(1, 512, 16, 32, device="cuda")
