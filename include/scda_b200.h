@@ -131,6 +131,12 @@ int scda_nms_dyn(int n_cap, const int *n_dev, const float *boxes, float thresh, 
                  int64_t *keep_out, int64_t *num_out, void *workspace, size_t workspace_bytes,
                  cudaStream_t stream);
 /* the bitmask alone, on a stream (the _nms symbol above is the stream-less form) */
+/* `groups` independent NMS problems in one launch (the eight per-class calls per image of
+ * compute_predicted_bboxes, functions/predict_bbox.py:36-52): boxes [groups][n_cap][5] each sorted by
+ * descending score, n_dev[g] <= n_cap <= 1024 live boxes; keep_out [groups][n_cap] ascending survivor
+ * indices, num_out [groups].  Same survivors as scda_nms on each group. */
+int scda_nms_groups(int groups, int n_cap, const int *n_dev, const float *boxes, float thresh,
+                    int64_t *keep_out, int64_t *num_out, cudaStream_t stream);
 int scda_nms_mask(int n, const float *boxes, unsigned long long *mask, float thresh,
                   cudaStream_t stream);
 
@@ -450,6 +456,14 @@ int scda_bn_lrelu_bwd(long long P, int C, const float *x, const void *dy, int dy
 /* global average pool x fp32 [N, HW, C] -> [N, C] and its backward (dx bf16 or fp32 [N, HW, C]) */
 int scda_avgpool_fwd(int N, int HW, int C, const float *x, float *out, cudaStream_t stream);
 int scda_avgpool_bwd(int N, int HW, int C, const float *g, void *dx, int dx_f32, cudaStream_t stream);
+
+/* --- input pipeline ---------------------------------------------------- */
+/* decoded uint8 HWC image [H0, W0, 3] (device) -> fp32 CHW [3, H, W]: resize (mode 0 nearest as Pillow < 7's
+ * Image.resize, 1 bilinear), optional left-right mirror, / 255, (x - mean) / std — what
+ * datasets/example_dataset.py:86-104,129-145 and target_dataset.py:41-71 do on the host with PIL + torchvision.
+ * mean3 / std3: HOST pointers to three floats. */
+int scda_image_prepare(const unsigned char *src_hwc, int H0, int W0, float *dst_chw, int H, int W, int mode,
+                       int flip, const float *mean3, const float *std3, cudaStream_t stream);
 
 /* --- detector losses -------------------------------------------------- */
 /* F.cross_entropy(logits, targets, ignore_index) (mean over the counted rows) AND the reference's

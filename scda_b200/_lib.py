@@ -34,6 +34,7 @@ SIGNATURES = {
     "scda_nms": (_i, [_i, _p, _f, _i, _p, _p, _p, _z, _p]),
     "scda_nms_dyn": (_i, [_i, _p, _p, _f, _i, _p, _p, _p, _z, _p]),
     "scda_nms_mask": (_i, [_i, _p, _p, _f, _p]),
+    "scda_nms_groups": (_i, [_i, _i, _p, _p, _f, _p, _p, _p]),
     "scda_bbox_overlaps": (_i, [_i, _p, _i, _p, _p, _p]),
     "scda_sigmoid_focal_loss_sum": (_i, [_i, _p, _p, _f, _f, _f, _i, _p, _p, _p]),
     "scda_softmax_focal_loss_sum": (_i, [_i, _p, _p, _f, _f, _f, _i, _p, _p, _p, _p]),
@@ -91,6 +92,7 @@ SIGNATURES = {
     "scda_bn_lrelu_bwd": (_i, [C.c_longlong, _i, _p, _p, _i, _p, _p, _p, _p, _f, _p, _i, _p, _p, _i, _p]),
     "scda_avgpool_fwd": (_i, [_i, _i, _i, _p, _p, _p]),
     "scda_avgpool_bwd": (_i, [_i, _i, _i, _p, _p, _i, _p]),
+    "scda_image_prepare": (_i, [_p, _i, _i, _p, _i, _i, _i, _i, _p, _p, _p]),
     "scda_softmax_ce_workspace_bytes": (_z, [C.c_longlong]),
     "scda_softmax_ce_acc_fwd": (_i, [C.c_longlong, _i, _p, C.c_longlong, _p, C.c_longlong, _p, _p, _z, _p]),
     "scda_softmax_ce_bwd": (_i, [C.c_longlong, _i, _p, C.c_longlong, _p, C.c_longlong, _p, _p, _p, C.c_longlong, _p]),

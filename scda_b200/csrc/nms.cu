@@ -280,6 +280,90 @@ int nms_impl(int n, const int *n_dev, const float *boxes, float thresh, int max_
 
 }  // namespace
 
+// ---------------------------------------------------------------------------------------
+// Many small independent NMS problems in ONE launch: group g = n_dev[g] (<= n_cap <= 1024) boxes sorted by
+// descending score, boxes[g][n_cap][5].  The reference's compute_predicted_bboxes
+// (functions/predict_bbox.py:36-52) runs one gpu_nms round trip (mask kernel, 18-line host scan, two PCIe
+// copies) per class per image: 8 per image.  One CTA per group: the boxes and the whole suppression bitmask
+// live in shared memory (n_cap 1024: 32 KB + 128 KB), the greedy scan walks it with one warp.
+// Same IoU arithmetic and `> thresh` verdict as nms_mask_kernel, hence the same survivors as scda_nms per group.
+constexpr int kGroupThreads = 256;
+
+__global__ void __launch_bounds__(kGroupThreads)
+nms_groups_kernel(int n_cap, const int *__restrict__ n_dev, const float *__restrict__ boxes, float thresh,
+                  long long *__restrict__ keep, long long *__restrict__ num_out)
+{
+    extern __shared__ __align__(16) unsigned char g_smem[];
+    const int g = blockIdx.x;
+    const int n = max(0, min(n_cap, n_dev[g]));
+    const int words = (n_cap + 63) / 64;
+    ColBox *s_box = reinterpret_cast<ColBox *>(g_smem);
+    unsigned long long *s_mask = reinterpret_cast<unsigned long long *>(s_box + n_cap);
+    unsigned long long *s_removed = s_mask + (size_t)n_cap * words;
+    const float *gb = boxes + (long long)g * n_cap * 5;
+    for (int j = threadIdx.x; j < n; j += kGroupThreads) {
+        ColBox c;
+        c.x1 = gb[5 * j]; c.y1 = gb[5 * j + 1]; c.x2 = gb[5 * j + 2]; c.y2 = gb[5 * j + 3];
+        c.w = __fadd_rn(__fsub_rn(c.x2, c.x1), 1.f);
+        c.h = __fadd_rn(__fsub_rn(c.y2, c.y1), 1.f);
+        c.pad0 = c.pad1 = 0.f;
+        s_box[j] = c;
+    }
+    for (int w = threadIdx.x; w < words; w += kGroupThreads) s_removed[w] = 0ull;
+    __syncthreads();
+    // (row i, word w): bits of the boxes j > i that box i suppresses
+    for (int t = threadIdx.x; t < n * words; t += kGroupThreads) {
+        const int i = t / words, w = t - i * words;
+        unsigned long long word = 0ull;
+        if (w * 64 + 63 > i) {
+            const ColBox a = s_box[i];
+            const float Sa = __fmul_rn(a.w, a.h);
+            const int j0 = max(w * 64, i + 1), j1 = min(n, w * 64 + 64);
+            for (int j = j0; j < j1; ++j)
+                if (suppresses(a.x1, a.y1, a.x2, a.y2, Sa, s_box[j], thresh)) word |= 1ull << (j - w * 64);
+        }
+        s_mask[(size_t)i * words + w] = word;
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        int kept = 0;
+        for (int i = 0; i < n; ++i) {
+            const unsigned long long rem = s_removed[i >> 6];          // same value in every lane
+            if ((rem >> (i & 63)) & 1ull) continue;
+            if (lane == 0) keep[(long long)g * n_cap + kept] = i;
+            ++kept;
+            for (int w = lane; w < words; w += 32) s_removed[w] |= s_mask[(size_t)i * words + w];
+            __syncwarp();
+        }
+        if (lane == 0) num_out[g] = kept;
+    }
+}
+
+static size_t scda_nms_groups_smem_bytes(int n_cap)
+{
+    const size_t words = (size_t)(n_cap + 63) / 64;
+    return (size_t)n_cap * sizeof(ColBox) + ((size_t)n_cap * words + words) * sizeof(unsigned long long);
+}
+
+SCDA_API int scda_nms_groups(int groups, int n_cap, const int *n_dev, const float *boxes, float thresh,
+                             int64_t *keep_out, int64_t *num_out, cudaStream_t stream)
+{
+    if (groups < 0 || n_cap <= 0 || n_cap > 1024 || !n_dev || !boxes || !keep_out || !num_out) return 0;
+    if (groups == 0) return 1;
+    const size_t smem = scda_nms_groups_smem_bytes(n_cap);
+    if (smem > 220 * 1024) return 0;
+    static size_t attr = 0;
+    if (smem > 48 * 1024 && smem > attr) {
+        cudaError_t e = cudaFuncSetAttribute(nms_groups_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return -(int)e;
+        attr = smem;
+    }
+    nms_groups_kernel<<<groups, kGroupThreads, smem, stream>>>(n_cap, n_dev, boxes, thresh, (long long *)keep_out,
+                                                               (long long *)num_out);
+    return scda_launch_status();
+}
+
 SCDA_API void _nms(int boxes_num, float *boxes_dev, unsigned long long *mask_dev,
                    float nms_overlap_thresh)
 {

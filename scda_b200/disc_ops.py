@@ -18,6 +18,22 @@ from .tc_detector import _direct, _is_krsc, _take_fresh, shadow_of
 
 LEAKY, OUT_F32, MASK_POS, MASK_LEAKY = 128, 2, 4, 256
 
+# `loss.backward(inputs=other_network.params)` still reports needs_input_grad = True for the discriminator's
+# own weights (the flag is static), so the decoder's update (phase 3) would compute — and write into the
+# discriminator's gradient buffer — weight gradients nobody uses.  The engine sets this around that backward:
+# only the input gradient is produced.
+FREEZE_PARAMS = False
+
+
+class frozen_params(object):
+    def __enter__(self):
+        global FREEZE_PARAMS
+        self.prev, FREEZE_PARAMS = FREEZE_PARAMS, True
+
+    def __exit__(self, *exc):
+        global FREEZE_PARAMS
+        FREEZE_PARAMS = self.prev
+
 
 def _ptr(t):
     return t.data_ptr() if t is not None else None
@@ -147,6 +163,8 @@ class _ImageDisFn(torch.autograd.Function):
         x, y1, y2, y3 = ctx.saved_tensors
         w1, b1, w2, b2, w3, b3, w4, b4 = ctx.params
         need = ctx.needs_input_grad                     # x, w1, b1, w2, b2, w3, b3, w4, b4, slope
+        if FREEZE_PARAMS:
+            need = (need[0],) + (False,) * 9
         slope, dev, lib = ctx.slope, x.device, load()
         N, _, H, W = x.shape
         P, C = y3.numel() // y3.shape[3], y3.shape[3]

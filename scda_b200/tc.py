@@ -80,16 +80,23 @@ def gemm_tn(a, b, bias=None, relu=False, out_dtype=torch.bfloat16, mask_src=None
     return out
 
 
-def gemm_nn(a, b, bias=None, relu=False, out_dtype=torch.bfloat16, mask_src=None, mul_src=None):
-    """out[M, N] = a[M, K] @ b[K, N] — b row-major with N contiguous (e.g. dX = dY @ W)."""
+def gemm_nn(a, b, bias=None, relu=False, out_dtype=torch.bfloat16, mask_src=None, mul_src=None, out=None,
+            accumulate=False):
+    """out[M, N] = a[M, K] @ b[K, N] — b row-major with N contiguous (e.g. dX = dY @ W).
+    With `out` (fp32 when accumulate) the result is written / added there."""
     require_cuda(a, b)
     assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16
     assert a.dim() == 2 and b.dim() == 2 and a.shape[1] == b.shape[0]
     assert a.stride(1) == 1 and b.stride(1) == 1
     M, K = a.shape
     N = b.shape[1]
-    out = torch.empty(M, N, dtype=out_dtype, device=a.device)
-    flags = _flags(relu, out_dtype, mask_src, False, mul_src)
+    if out is None:
+        assert not accumulate
+        out = torch.empty(M, N, dtype=out_dtype, device=a.device)
+    else:
+        assert out.shape == (M, N) and out.stride(1) == 1
+        out_dtype = out.dtype
+    flags = _flags(relu, out_dtype, mask_src, accumulate, mul_src)
     if mask_src is not None:
         _check_side(mask_src, out, "mask_src must match the output", f32_ok=True)
     if mul_src is not None:
@@ -151,6 +158,9 @@ def conv3x3_dgrad_nhwc(dy, w_krsc, mask_src=None, out_dtype=torch.bfloat16):
     return dx
 
 
+WGRAD_GEMM = os.environ.get("SCDA_WGRAD_GEMM", "1") != "0"
+
+
 def linear_wgrad(dy, x, out=None, accumulate=False):
     """dW[Nout, Kin] fp32 (+)= dy[rows, Nout]^T @ x[rows, Kin]."""
     require_cuda(dy, x)
@@ -158,6 +168,15 @@ def linear_wgrad(dy, x, out=None, accumulate=False):
     assert dy.shape[0] == x.shape[0] and dy.stride(1) == 1 and x.stride(1) == 1
     rows, nout = dy.shape
     kin = x.shape[1]
+    if (WGRAD_GEMM and rows <= 2048 and rows % 64 == 0 and nout % 128 == 0 and kin % 256 == 0
+            and nout * kin >= (1 << 22) and x.stride(0) % 8 == 0
+            and (out is None or (out.dtype == torch.float32 and out.stride(1) == 1 and out.stride(0) % 8 == 0))):
+        # short reduction, big output (fc6: 512 rows -> 4096 x 25088 = 411 MB of fp32): the product is bound by
+        # WRITING the gradient.  The one-shot tc_wgrad_kernel (6272 CTAs of four k-blocks, no overlap of a tile's
+        # store with the next tile's MMAs) took 0.31 ms alone and 1.2 ms inside the iteration; the persistent
+        # GEMM kernel (256-wide tiles, double-buffered TMEM accumulators) does it on dY transposed
+        # (4 MB: one small copy) as out = dY^T[Nout, rows] . X[rows, Kin].
+        return gemm_nn(dy.t().contiguous(), x, out_dtype=torch.float32, out=out, accumulate=accumulate)
     if out is None:
         assert not accumulate
         out = torch.empty(nout, kin, dtype=torch.float32, device=x.device)

@@ -366,6 +366,14 @@ def _dropout_scale(shape, p, device):
     return keep.to(torch.bfloat16) * (1.0 / (1.0 - p))
 
 
+# Side stream for the big fc6 / fc7 weight gradients of the RCNN head's backward (set by the engine; None =
+# everything on the current stream).  Those two products are bound by WRITING 478 MB of gradient and nothing in
+# the rest of the backward reads them: on the side stream they run beside the data-gradient chain
+# (fc7 -> fc6 -> RoIPool backward -> backbone) instead of in front of it.  The engine joins the stream before
+# the head bucket's all-reduce / Adam.
+WGRAD_STREAM = None
+
+
 class _RcnnHeadFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, feat, rois, rt, pool, p_drop, w6, b6, w7, b7, wc, bc, wl, bl):
@@ -422,10 +430,20 @@ class _RcnnHeadFn(torch.autograd.Function):
                 extra = extra * dm7
             d7 = d7 + torch.where(h7 > 0, extra, torch.zeros_like(extra))
         gb7 = _sink_bias(b7, d7)
-        gw7 = _sink_linear_wgrad(w7, d7, h6)
         d6 = tc.gemm_nn(d7, rt.shadow(w7), mask_src=h6, mul_src=dm6)
         gb6 = _sink_bias(b6, d6)
-        gw6 = _sink_linear_wgrad(w6, d6, x)
+        side = WGRAD_STREAM if (d7.is_cuda and _direct(w6) and _direct(w7)) else None
+        if side is not None:
+            cur = torch.cuda.current_stream()
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                gw7 = _sink_linear_wgrad(w7, d7, h6)
+                gw6 = _sink_linear_wgrad(w6, d6, x)
+            for t in (d7, d6, h6, x):
+                t.record_stream(side)
+        else:
+            gw7 = _sink_linear_wgrad(w7, d7, h6)
+            gw6 = _sink_linear_wgrad(w6, d6, x)
         dx = tc.gemm_nn(d6, rt.shadow(w6))                                    # [R, C*ph*pw] bf16
         d_feat = tc.roi_pool_nhwc_bwd(dx, argmax, rois, (NB, H, W, C), ph, pw).to(torch.bfloat16)
         return d_feat, None, None, None, None, gw6, gb6, gw7, gb7, gwc, gbc, gwl, gbl

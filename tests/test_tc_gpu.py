@@ -162,3 +162,26 @@ def test_conv3x3_dgrad_via_flipped_weights(cuda_lib):
                                      dy.float().permute(0, 3, 1, 2), padding=1).permute(0, 2, 3, 1)
     ref = torch.where(x.float() > 0, ref, torch.zeros_like(ref))
     _close(dx, ref)
+
+
+def test_linear_wgrad_gemm_form_into_buffer(cuda_lib):
+    """the persistent-GEMM form of the big weight gradients (fc6 / fc7): written into, and accumulated onto, a
+    caller's fp32 buffer; equal to the one-shot weight-gradient kernel"""
+    import torch
+    from scda_b200 import tc
+    g = torch.Generator(device="cuda").manual_seed(11)
+    rows, nout, kin = 512, 512, 8192
+    dy = (torch.randn(rows, nout, device="cuda", generator=g) / rows ** 0.5).bfloat16()
+    x = torch.randn(rows, kin, device="cuda", generator=g).bfloat16()
+    ref = dy.float().t() @ x.float()
+    out = torch.full((nout, kin), 7.0, device="cuda")
+    assert tc.WGRAD_GEMM
+    tc.linear_wgrad(dy, x, out=out)
+    _close(out, ref, rtol=2e-3)
+    tc.linear_wgrad(dy, x, out=out, accumulate=True)
+    _close(out, 2 * ref, rtol=2e-3)
+    tc.WGRAD_GEMM = False
+    try:
+        _close(tc.linear_wgrad(dy, x), out / 2, rtol=1e-3)
+    finally:
+        tc.WGRAD_GEMM = True
