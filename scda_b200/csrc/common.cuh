@@ -32,6 +32,14 @@ __device__ __forceinline__ void st_stream_i4(int *p, int4 v)
                  "r"(v.w)
                  : "memory");
 }
+__device__ __forceinline__ void st_stream_f32(float *p, float v)
+{
+    asm volatile("st.global.cs.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+__device__ __forceinline__ void st_stream_s32(int *p, int v)
+{
+    asm volatile("st.global.cs.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 __device__ __forceinline__ float4 ld_stream_f4(const float *p)
 {
     float4 v;

@@ -17,6 +17,8 @@
 //     red.global.add per CTA.
 #include <float.h>
 
+#include <atomic>
+
 #include "common.cuh"
 
 namespace {
@@ -45,14 +47,21 @@ __device__ __forceinline__ double log_one_minus_sigmoid(float x)
     return -1.0 * (double)x * pos - (double)logf((float)(1.0 + (double)e));
 }
 
+// powf(x, gamma) for x in [0, 1]; gamma = 2 (the published setting) is one correctly rounded product
+// (libdevice powf: ~60 instructions and up to 2 ulp)
+__device__ __forceinline__ float pow_gamma(float x, float gamma)
+{
+    return gamma == 2.f ? __fmul_rn(x, x) : powf(x, gamma);
+}
+
 __device__ __forceinline__ float sigmoid_focal_elem(float x, int t, int d, float gamma,
                                                     FocalScale s)
 {
     const float c1 = (float)(t == d + 1);
     const float c2 = (float)((t != -1) & (t != d + 1));
     const float p = (float)(1.0 / (1.0 + (double)expf(-x)));
-    const float term1 = powf((float)(1.0 - (double)p), gamma) * logf(fmaxf(p, FLT_MIN));
-    const float term2 = (float)((double)powf(p, gamma) * log_one_minus_sigmoid(x));
+    const float term1 = pow_gamma((float)(1.0 - (double)p), gamma) * logf(fmaxf(p, FLT_MIN));
+    const float term2 = (float)((double)pow_gamma(p, gamma) * log_one_minus_sigmoid(x));
     float l = 0.f;
     l += -c1 * term1 * s.zp;
     l += -c2 * term2 * s.zn;
@@ -75,17 +84,45 @@ __device__ __forceinline__ float sigmoid_focal_grad_elem(float x, int t, int d, 
     return g;
 }
 
-// one red.global.add per CTA
-__device__ __forceinline__ void cta_accumulate(float v, float *dst)
+// The fused total, in ONE launch and in a fixed order: every CTA leaves its partial in a slot of module
+// memory and takes a ticket; the CTA that draws the last ticket adds the partials in index order, overwrites
+// loss_sum[0] and re-arms the ticket.  (A memset of loss_sum + one floating-point atomic per CTA was a second
+// graph node in front of a 5 us kernel and made the total depend on the arrival order.)  Concurrent calls
+// take different slots: the host hands them out round-robin, kFocalSlots calls can be in flight at once.
+constexpr int kFocalSlots = 64;
+constexpr int kFocalMaxGrid = kNumSMs * 8;
+__device__ float g_focal_partial[kFocalSlots][kFocalMaxGrid];
+__device__ unsigned int g_focal_ticket[kFocalSlots];
+
+__device__ __forceinline__ void cta_accumulate(float v, float *dst, int slot)
 {
     __shared__ float s_part[kFocalThreads / 32];
+    __shared__ bool s_last;
     v = warp_sum(v);
     if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = v;
     __syncthreads();
-    if (threadIdx.x < 32) {
-        float t = threadIdx.x < kFocalThreads / 32 ? s_part[threadIdx.x] : 0.f;
-        t = warp_sum(t);
-        if (threadIdx.x == 0) red_add_f32(dst, t);
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < kFocalThreads / 32; ++w) t += s_part[w];
+        g_focal_partial[slot][blockIdx.x] = t;
+        __threadfence();
+        s_last = atomicAdd(&g_focal_ticket[slot], 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    float t = 0.f;                                     // fixed order: thread k takes partials k, k + 256, ...
+    for (int i = threadIdx.x; i < (int)gridDim.x; i += kFocalThreads) t += __ldcg(&g_focal_partial[slot][i]);
+    t = warp_sum(t);
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = t;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float tot = 0.f;
+#pragma unroll
+        for (int w = 0; w < kFocalThreads / 32; ++w) tot += s_part[w];
+        *dst = tot;
+        g_focal_ticket[slot] = 0u;
     }
 }
 
@@ -93,7 +130,7 @@ template <bool kSum>
 __global__ void __launch_bounds__(kFocalThreads)
 sigmoid_focal_fwd_kernel(int N, const float *__restrict__ logits, const int *__restrict__ targets,
                          float weight_pos, float gamma, float alpha, int num_classes,
-                         float *__restrict__ losses, float *__restrict__ loss_sum)
+                         float *__restrict__ losses, float *__restrict__ loss_sum, int slot)
 {
     const FocalScale s = focal_scale(weight_pos, alpha);
     float acc = 0.f;
@@ -103,7 +140,7 @@ sigmoid_focal_fwd_kernel(int N, const float *__restrict__ logits, const int *__r
         if (losses) losses[i] = l;
         acc += l;
     }
-    if (kSum) cta_accumulate(acc, loss_sum);
+    if (kSum) cta_accumulate(acc, loss_sum, slot);
 }
 
 __global__ void __launch_bounds__(kFocalThreads)
@@ -129,7 +166,7 @@ __global__ void __launch_bounds__(kFocalThreads)
 softmax_focal_fwd_kernel(int rows, const float *__restrict__ logits,
                          const int *__restrict__ targets, float weight_pos, float gamma,
                          float alpha, int num_classes, float *__restrict__ losses,
-                         float *__restrict__ priors, float *__restrict__ loss_sum)
+                         float *__restrict__ priors, float *__restrict__ loss_sum, int slot)
 {
     const float Np = (float)fmax((double)weight_pos, 1.0);
     float acc = 0.f;
@@ -158,7 +195,7 @@ softmax_focal_fwd_kernel(int rows, const float *__restrict__ logits,
         if (losses) losses[i] = l;
         acc += l;
     }
-    if (kSum) cta_accumulate(acc, loss_sum);
+    if (kSum) cta_accumulate(acc, loss_sum, slot);
 }
 
 __global__ void __launch_bounds__(kFocalThreads)
@@ -187,8 +224,21 @@ softmax_focal_bwd_kernel(int rows, const int *__restrict__ targets, float *__res
 int focal_grid(long long work)
 {
     long long g = (work + kFocalThreads - 1) / kFocalThreads;
-    const long long cap = (long long)kNumSMs * 8;
+    const long long cap = kFocalMaxGrid;
     return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+// the fused-sum forms: two CTAs per SM (every CTA costs one ticket and one partial in the final pass)
+int focal_sum_grid(long long work)
+{
+    const int g = focal_grid(work);
+    return g > 2 * kNumSMs ? 2 * kNumSMs : g;
+}
+
+int focal_slot()
+{
+    static std::atomic<unsigned> next{0};
+    return (int)(next.fetch_add(1u, std::memory_order_relaxed) % kFocalSlots);
 }
 
 bool focal_args_ok(int N, int num_classes, const void *a, const void *b, const void *c)
@@ -206,7 +256,7 @@ SCDA_API int SigmoidFocalLossForwardLaucher(const int N, const float *logits, co
     if (!focal_args_ok(N, num_classes, logits, targets, losses)) return 0;
     if (N == 0) return 1;
     sigmoid_focal_fwd_kernel<false><<<focal_grid(N), kFocalThreads, 0, stream>>>(
-        N, logits, targets, weight_pos, gamma, alpha, num_classes, losses, nullptr);
+        N, logits, targets, weight_pos, gamma, alpha, num_classes, losses, nullptr, 0);
     return scda_launch_status();
 }
 
@@ -216,11 +266,12 @@ SCDA_API int scda_sigmoid_focal_loss_sum(const int N, const float *logits, const
                                          float *loss_sum, cudaStream_t stream)
 {
     if (!focal_args_ok(N, num_classes, logits, targets, loss_sum) || !loss_sum) return 0;
-    cudaError_t e = cudaMemsetAsync(loss_sum, 0, sizeof(float), stream);
-    if (e != cudaSuccess) return -(int)e;
-    if (N == 0) return 1;
-    sigmoid_focal_fwd_kernel<true><<<focal_grid(N), kFocalThreads, 0, stream>>>(
-        N, logits, targets, weight_pos, gamma, alpha, num_classes, losses, loss_sum);
+    if (N == 0) {
+        cudaError_t e = cudaMemsetAsync(loss_sum, 0, sizeof(float), stream);
+        return e == cudaSuccess ? 1 : -(int)e;
+    }
+    sigmoid_focal_fwd_kernel<true><<<focal_sum_grid(N), kFocalThreads, 0, stream>>>(
+        N, logits, targets, weight_pos, gamma, alpha, num_classes, losses, loss_sum, focal_slot());
     return scda_launch_status();
 }
 
@@ -245,7 +296,7 @@ SCDA_API int SoftmaxFocalLossForwardLaucher(const int N, const float *logits, co
     if (N == 0) return 1;
     const int rows = N / num_classes;
     softmax_focal_fwd_kernel<false><<<focal_grid(rows), kFocalThreads, 0, stream>>>(
-        rows, logits, targets, weight_pos, gamma, alpha, num_classes, losses, priors, nullptr);
+        rows, logits, targets, weight_pos, gamma, alpha, num_classes, losses, priors, nullptr, 0);
     return scda_launch_status();
 }
 
@@ -255,12 +306,13 @@ SCDA_API int scda_softmax_focal_loss_sum(const int N, const float *logits, const
                                          float *priors, float *loss_sum, cudaStream_t stream)
 {
     if (!focal_args_ok(N, num_classes, logits, targets, priors) || !loss_sum) return 0;
-    cudaError_t e = cudaMemsetAsync(loss_sum, 0, sizeof(float), stream);
-    if (e != cudaSuccess) return -(int)e;
-    if (N == 0) return 1;
+    if (N == 0) {
+        cudaError_t e = cudaMemsetAsync(loss_sum, 0, sizeof(float), stream);
+        return e == cudaSuccess ? 1 : -(int)e;
+    }
     const int rows = N / num_classes;
-    softmax_focal_fwd_kernel<true><<<focal_grid(rows), kFocalThreads, 0, stream>>>(
-        rows, logits, targets, weight_pos, gamma, alpha, num_classes, losses, priors, loss_sum);
+    softmax_focal_fwd_kernel<true><<<focal_sum_grid(rows), kFocalThreads, 0, stream>>>(
+        rows, logits, targets, weight_pos, gamma, alpha, num_classes, losses, priors, loss_sum, focal_slot());
     return scda_launch_status();
 }
 

@@ -19,6 +19,7 @@
 //             fire-and-forget red.global.add into the 4 MB input gradient,
 //             which lives in L2.
 #include <float.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -247,6 +248,230 @@ int launch_pool_fwd_warp(const float *feat, float scale, int R, int H, int W, in
     return scda_launch_status();
 }
 
+// ---------------------------------------------------------------------------
+// Forward, plane-resident form (the main one: any map whose channel plane fits in shared memory).
+//
+// The warp form above reads every RoI's window from L2 with one dependent load per row: at the model's
+// operating point (512 RoIs x 512 channels, windows of ~200 cells) that is ~210 MB of scattered L2 reads behind
+// chains of ~20 load latencies per (RoI, channel) — 235 us, 7 % of the HBM rate the 103 MB of output could be
+// written at.  Here the loop nest is turned inside out: a CTA owns FOUR channel planes of one image, stages
+// them once in shared memory interleaved per pixel ([h][w][4 channels]: one 16-byte shared-memory load feeds
+// four channels) and walks over its share of the RoIs, 32 at a time, whose integer bin edges are derived
+// cooperatively into shared memory.  A thread owns a (RoI, bin) and runs the reference's own row-major
+// strict-'>' scan (roi_pooling_kernel.cu:75-87) for the four channels at once — bit-identical values and
+// argmax, no tie rule to re-derive; the scan's loop and address arithmetic (the bulk of the instructions: the
+// first, one-channel-per-thread version of this kernel was issue bound at 160 us) is paid once per four
+// outputs.  Consecutive lanes own consecutive bins of one RoI, so each of a thread's four value stores (and
+// four argmax stores) lands in a stretch of up to 128 contiguous bytes per warp: streaming 4-byte stores.
+// Global memory sees the feature map read once per RoI split plus the output stream.
+constexpr int kPlaneThreads = 512;
+constexpr int kPlaneRoiBatch = 32;
+constexpr int kPlaneC = 4;
+
+// floor(x / d) for 0 <= x < 2^21 with inv = 1.f / d: (x + 0.5) / d is at least 0.5 / d away from an integer,
+// more than the rounding error of the two float operations
+__device__ __forceinline__ int div_small(int x, float inv)
+{
+    return __float2int_rz(__fmul_rn(__int2float_rn(x) + 0.5f, inv));
+}
+
+template <int kMinBlocks>
+__global__ void __launch_bounds__(kPlaneThreads, kMinBlocks)
+roi_pool_fwd_plane_kernel(const float *__restrict__ feat, float scale, int H, int W, int C, int PH, int PW,
+                          const float *__restrict__ rois, int R, float *__restrict__ out,
+                          int *__restrict__ argmax, int pitch, int rois_per_cta, int vec_in, int roi_batch)
+{
+    extern __shared__ __align__(16) unsigned char s_bytes[];
+    __shared__ int s_next;
+    __shared__ int s_img[kPlaneRoiBatch];
+    const int ne = PH + PW, ew = 2 * ne;
+    const int bins = PH * PW, HW = H * W;
+    float4 *s_plane = reinterpret_cast<float4 *>(s_bytes);                                   // [H][pitch] x 4 ch
+    unsigned short *s_edge = reinterpret_cast<unsigned short *>(s_plane + (size_t)H * pitch);   // [batch][hs he ws we]
+    const int tid = threadIdx.x;
+    const int c0 = blockIdx.x * kPlaneC, cn = min(kPlaneC, C - c0);
+    const int r0 = blockIdx.y * rois_per_cta, r1 = min(R, r0 + rois_per_cta);
+    const float inv_bins = 1.f / (float)bins, inv_pw = 1.f / (float)PW;
+    const float inv_h = 1.f / (float)H, inv_ne = 1.f / (float)ne;
+
+    int cur = -1;   // image whose planes are resident
+    for (;;) {
+        // next image index (ascending) referenced by one of this CTA's RoIs
+        if (tid == 0) s_next = 0x7fffffff;
+        __syncthreads();
+        for (int r = r0 + tid; r < r1; r += kPlaneThreads) {
+            const int b = (int)__ldg(rois + 5 * r);
+            if (b > cur) atomicMin(&s_next, b);
+        }
+        __syncthreads();
+        const int img = s_next;
+        if (img == 0x7fffffff) break;
+        {
+            // the cn planes are one contiguous stretch of the NCHW map: independent 16-byte loads, four in
+            // flight per thread (one dependent load per row made the staging alone ~13 us of memory latency)
+            float *sp = reinterpret_cast<float *>(s_plane);
+            const float *__restrict__ src = feat + ((long long)img * C + c0) * HW;
+            const float inv_w = 1.f / (float)W;
+            if (vec_in) {
+                const int n4 = (cn * HW) >> 2;
+                for (int i0 = tid; i0 < n4; i0 += 4 * kPlaneThreads) {
+                    float4 v[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int i = i0 + u * kPlaneThreads;
+                        if (i < n4) v[u] = __ldg(reinterpret_cast<const float4 *>(src) + i);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int i = i0 + u * kPlaneThreads;
+                        if (i >= n4) continue;
+                        const int row = div_small(i << 2, inv_w), w = (i << 2) - row * W;   // row = c * H + h
+                        const int c = div_small(row, inv_h), h = row - c * H;
+                        float *dst = sp + ((size_t)h * pitch + w) * kPlaneC + c;
+                        dst[0] = v[u].x; dst[kPlaneC] = v[u].y; dst[2 * kPlaneC] = v[u].z; dst[3 * kPlaneC] = v[u].w;
+                    }
+                }
+            } else {
+                const int n1 = cn * HW;
+                for (int i0 = tid; i0 < n1; i0 += 4 * kPlaneThreads) {
+                    float v[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int i = i0 + u * kPlaneThreads;
+                        if (i < n1) v[u] = __ldg(src + i);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int i = i0 + u * kPlaneThreads;
+                        if (i >= n1) continue;
+                        const int row = div_small(i, inv_w), w = i - row * W;
+                        const int c = div_small(row, inv_h), h = row - c * H;
+                        sp[((size_t)h * pitch + w) * kPlaneC + c] = v[u];
+                    }
+                }
+            }
+            if (cn < kPlaneC)
+                for (int i = tid; i < H * W; i += kPlaneThreads) {
+                    const int h = div_small(i, inv_w), w = i - h * W;
+                    for (int c = cn; c < kPlaneC; ++c) sp[((size_t)h * pitch + w) * kPlaneC + c] = 0.f;
+                }
+        }
+        for (int rb = r0; rb < r1; rb += roi_batch) {
+            const int nb = min(roi_batch, r1 - rb);
+            __syncthreads();   // planes staged / previous batch's edges and staged outputs no longer read
+            for (int t = tid; t < nb * ne; t += kPlaneThreads) {
+                const int j = div_small(t, inv_ne), i = t - j * ne;
+                const float *r = rois + 5 * (rb + j);
+                const PoolRoi q = load_pool_roi(r, scale, PH, PW);
+                unsigned short *e = s_edge + j * ew;
+                if (i < PH) {
+                    e[i] = clamp_edge((int)floorf(__fmul_rn((float)i, q.bin_h)) + q.y0, H);
+                    e[PH + i] = clamp_edge((int)ceilf(__fmul_rn((float)(i + 1), q.bin_h)) + q.y0, H);
+                } else {
+                    const int k = i - PH;
+                    e[2 * PH + k] = clamp_edge((int)floorf(__fmul_rn((float)k, q.bin_w)) + q.x0, W);
+                    e[2 * PH + PW + k] = clamp_edge((int)ceilf(__fmul_rn((float)(k + 1), q.bin_w)) + q.x0, W);
+                }
+                if (i == 0) s_img[j] = q.batch;
+            }
+            __syncthreads();
+            for (int o = tid; o < nb * bins; o += kPlaneThreads) {
+                const int j = div_small(o, inv_bins), b = o - j * bins;
+                const unsigned short *e = s_edge + j * ew;
+                if (s_img[j] != img) continue;
+                const int ph = div_small(b, inv_pw), pw = b - ph * PW;
+                const int h0 = e[ph], h1 = e[PH + ph], w0 = e[2 * PH + pw], w1 = e[2 * PH + PW + pw];
+                const float init = (h1 <= h0 || w1 <= w0) ? 0.f : -FLT_MAX;
+                float b0 = init, b1 = init, b2 = init, b3 = init;
+                int p0 = -1, p1 = -1, p2 = -1, p3 = -1;
+                for (int h = h0; h < h1; ++h) {
+                    const float4 *prow = s_plane + h * pitch;
+                    int pos = h * W + w0;
+                    for (int w = w0; w < w1; ++w, ++pos) {
+                        const float4 v = prow[w];
+                        if (v.x > b0) { b0 = v.x; p0 = pos; }
+                        if (v.y > b1) { b1 = v.y; p1 = pos; }
+                        if (v.z > b2) { b2 = v.z; p2 = pos; }
+                        if (v.w > b3) { b3 = v.w; p3 = pos; }
+                    }
+                }
+                // consecutive lanes = consecutive bins of one RoI: each of the 2 x cn stores below writes a
+                // contiguous stretch of up to 128 bytes
+                const long long oi = ((long long)(rb + j) * C + c0) * bins + b;
+                const int abase = (img * C + c0) * HW;
+                st_stream_f32(out + oi, b0);
+                if (cn > 1) st_stream_f32(out + oi + bins, b1);
+                if (cn > 2) st_stream_f32(out + oi + 2 * bins, b2);
+                if (cn > 3) st_stream_f32(out + oi + 3 * bins, b3);
+                if (argmax) {
+                    st_stream_s32(argmax + oi, p0 < 0 ? -1 : abase + p0);
+                    if (cn > 1) st_stream_s32(argmax + oi + bins, p1 < 0 ? -1 : abase + HW + p1);
+                    if (cn > 2) st_stream_s32(argmax + oi + 2 * bins, p2 < 0 ? -1 : abase + 2 * HW + p2);
+                    if (cn > 3) st_stream_s32(argmax + oi + 3 * bins, p3 < 0 ? -1 : abase + 3 * HW + p3);
+                }
+            }
+        }
+        cur = img;
+    }
+}
+
+// 1: launched, 2: not applicable (caller takes another form), <0: CUDA error
+int launch_pool_fwd_plane(const float *feat, float scale, int R, int H, int W, int C, int PH, int PW,
+                          const float *rois, float *out, int *argmax, cudaStream_t stream)
+{
+    const int pitch = W | 1, bins = PH * PW;
+    if (H > 0xFFFF || W > 0xFFFF || PH + PW > 256) return 2;            // edges are kept as 16 bits
+    const size_t plane = sizeof(float4) * (size_t)H * pitch;
+    const size_t edges = sizeof(short) * (size_t)kPlaneRoiBatch * 2 * (PH + PW) + 16;
+    const size_t smem = plane + edges;
+    if (smem > 200 * 1024 || (long long)kPlaneRoiBatch * kPlaneC * bins >= (1 << 21)) return 2;
+    static int occ = 0;
+    if (!occ) {
+        const char *e = getenv("SCDA_POOL_OCC");
+        occ = (e && *e == '3') ? 3 : 2;
+    }
+    static size_t attr = 0;
+    if (smem > 48 * 1024 && smem > attr) {
+        cudaError_t e = cudaFuncSetAttribute(roi_pool_fwd_plane_kernel<2>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(roi_pool_fwd_plane_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)smem);
+        if (e != cudaSuccess) return -(int)e;
+        attr = smem;
+    }
+    const int chunks = ceil_div(C, kPlaneC);
+    int per_sm = (int)((226 * 1024) / (smem + 1024));
+    if (per_sm > occ) per_sm = occ;                        // 512 threads x 64 (40) registers
+    if (per_sm < 1) per_sm = 1;
+    // RoIs per pass: the (RoI, bin) tasks of a pass should fill whole rounds of the CTA's threads
+    // (32 RoIs x 49 bins = 3 rounds of 512 + 32 stragglers: 31 RoIs fit in 3)
+    int roi_batch = kPlaneRoiBatch;
+    double best_fill = 0.0;
+    for (int n = kPlaneRoiBatch; n >= kPlaneRoiBatch / 2; --n) {
+        const int tasks = n * bins, rounds = ceil_div(tasks, kPlaneThreads);
+        const double fill = (double)tasks / ((double)rounds * kPlaneThreads);
+        if (fill > best_fill + 1e-9) { best_fill = fill; roi_batch = n; }
+    }
+    const int nbatch = ceil_div(R, roi_batch);
+    int rsplit = (kNumSMs * per_sm) / chunks;              // one wave, every CTA resident
+    if (rsplit > nbatch) rsplit = nbatch;
+    if (rsplit < 1) rsplit = 1;
+    const int per_cta = ceil_div(nbatch, rsplit) * roi_batch;
+    dim3 grid(chunks, ceil_div(R, per_cta));
+    const int vec_in = W % 4 == 0 && (uintptr_t)feat % 16 == 0;
+    if ((long long)kPlaneC * H * W >= (1 << 21)) return 2;
+    if (occ == 3)
+        roi_pool_fwd_plane_kernel<3><<<grid, kPlaneThreads, smem, stream>>>(feat, scale, H, W, C, PH, PW, rois, R,
+                                                                           out, argmax, pitch, per_cta, vec_in,
+                                                                           roi_batch);
+    else
+        roi_pool_fwd_plane_kernel<2><<<grid, kPlaneThreads, smem, stream>>>(feat, scale, H, W, C, PH, PW, rois, R,
+                                                                           out, argmax, pitch, per_cta, vec_in,
+                                                                           roi_batch);
+    return scda_launch_status();
+}
+
 template <bool kVec>
 __global__ void __launch_bounds__(256)
 roi_pool_bwd_scatter_kernel(const float *__restrict__ top_diff, const int *__restrict__ argmax,
@@ -282,7 +507,10 @@ SCDA_API int ROIPoolForwardLaucher(const float *bottom_data, const float spatial
         pooled_width <= 0 || !bottom_data || !bottom_rois || !top_data)
         return 0;
     if (num_rois == 0) return 1;
-    int st = 2;
+    int st = launch_pool_fwd_plane(bottom_data, spatial_scale, num_rois, height, width, channels,
+                                   pooled_height, pooled_width, bottom_rois, top_data, argmax_data, stream);
+    if (st != 2) return st;
+    // maps whose channel plane does not fit in shared memory
     switch (pooled_height) {
 #define SCDA_POOL_CASE(P)                                                                       \
     case P:                                                                                     \

@@ -37,6 +37,21 @@ def timeit(fn, iters, flush):
     return float(np.median(ts)), float(np.min(ts))
 
 
+def burst(fn, n=50):
+    """us per launch over n back-to-back launches (L2 warm): CUDA event timestamps tick every ~2 us on this
+    part, too coarse for a single launch of the small operators"""
+    s = torch.cuda.current_stream()
+    fn()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    a.record(s)
+    for _ in range(n):
+        fn()
+    b.record(s)
+    b.synchronize()
+    return a.elapsed_time(b) * 1e3 / n
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--iters", type=int, default=20)
@@ -52,10 +67,15 @@ def main():
         if bytes_alg:
             row["GBs"] = round(bytes_alg / med / 1e3, 1)
             row["frac_hbm"] = round(bytes_alg / med / 1e3 / PEAK, 3)
+        if med < 60:
+            row["us_burst"] = round(burst(fn_ours), 2)
         if fn_ref is not None:
             rmed, _ = timeit(fn_ref, a.iters, flush)
             row["ref_us"] = round(rmed, 2)
             row["speedup_vs_ref_kernel"] = round(rmed / med, 2)
+            if med < 60:
+                row["ref_us_burst"] = round(burst(fn_ref), 2)
+                row["speedup_burst"] = round(row["ref_us_burst"] / row["us_burst"], 2)
         if extra:
             row.update(extra)
         print(json.dumps(row), flush=True)

@@ -38,7 +38,11 @@ POOL_CASES = [
     ((1, 256, 64, 64), 128, (7, 7), 1024, 1024, (16, 512)),  # config 1 shape
     ((1, 8, 21, 70), 40, (7, 7), 1120, 336, (8, 1100)),    # W not a multiple of 32, wide RoIs
     ((1, 4, 40, 300), 24, (7, 9), 4800, 640, (8, 4800)),   # very wide map
-    ((2, 8, 16, 16), 30, (12, 3), 256, 256, (4, 250)),     # pooled_height > 8: generic kernel
+    ((2, 8, 16, 16), 30, (12, 3), 256, 256, (4, 250)),     # pooled_height > 8
+    ((1, 512, 32, 64), 512, (7, 7), 1024, 512, (16, 512)),   # the model's operating point (plane-resident form)
+    ((1, 2, 200, 300), 12, (7, 7), 4800, 3200, (8, 4000)),   # plane too large for shared memory: warp form
+    ((1, 2, 200, 300), 12, (9, 7), 4800, 3200, (8, 4000)),   # ... and pooled_height > 8: per-output form
+    ((3, 5, 12, 20), 50, (7, 7), 320, 192, (4, 300)),        # three images interleaved in the RoI list
 ]
 
 
@@ -61,7 +65,8 @@ def test_roi_pool_bit_exact(cuda_lib, ref_lib, oracle_mod, shape, R, pool, iw, i
     gi_rf = G.roi_pool_bwd(ref_lib, g, rois, arg, feat.shape, scale)
     gi_or = oracle_mod.roi_pool_backward(g, rois, arg, feat.shape, scale)
     assert np.array_equal(gi_rf, gi_or)              # oracle reproduces the reference's order
-    np.testing.assert_allclose(gi, gi_rf, rtol=RTOL, atol=1e-5)  # scatter order differs
+    # scatter order differs: sums of up to hundreds of terms, rel 1e-4 of the plane's scale
+    assert np.abs(gi - gi_rf).max() <= RTOL * max(1.0, float(np.abs(gi_rf).max()))
 
 
 def test_roi_pool_without_argmax_and_empty(cuda_lib):
@@ -84,6 +89,8 @@ def test_roi_pool_without_argmax_and_empty(cuda_lib):
     ((1, 256, 64, 64), 128, (7, 7), 1024, 1024, (16, 512)),   # BASELINE.json configs[0]
     ((1, 256, 64, 64), 128, (8, 8), 1024, 1024, (16, 512)),   # the RoIAlignAvg/Max intermediate
     ((2, 10, 20, 24), 33, (5, 3), 384, 320, (4, 300)),
+    ((3, 6, 13, 21), 40, (7, 7), 336, 208, (4, 300)),         # W % 4 != 0: scalar reductions in the backward
+    ((1, 2, 200, 300), 12, (7, 7), 4800, 3200, (8, 4000)),    # plane too large for shared memory: per-RoI form
 ])
 def test_roi_align_parity(cuda_lib, ref_lib, oracle_mod, shape, R, al, iw, ih, wh):
     feat = _inputs.features(shape, 0)
