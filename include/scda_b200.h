@@ -173,6 +173,40 @@ int scda_rpn_decode_pack(int pre, const double *anchors, const float *deltas, co
                          const float *top_scores, double img_h, double img_w, double min_size, float *packed,
                          int *count, cudaStream_t stream);
 
+/* the same rows straight from the scores: the top-`pre` selection and the descending sort of
+ * functions/rpn_proposal.py:49-55 (numpy argpartition + argsort on the host in the reference) run on the device
+ * too.  scores [KA] float32 (foreground probability per anchor); pre <= 0 or > KA takes every anchor.  Equal
+ * scores rank by ascending anchor index (the reference leaves that order to numpy's unstable sort).
+ * KA <= 51 200.  workspace: scda_rpn_proposal_rows_workspace_bytes(KA, pre) bytes, 16-byte aligned; two
+ * launches, no host synchronisation. */
+size_t scda_rpn_proposal_rows_workspace_bytes(int KA, int pre);
+int scda_rpn_proposal_rows(int KA, int pre, const float *scores, const double *anchors, const float *deltas,
+                           double img_h, double img_w, double min_size, float *packed, int *count,
+                           void *workspace, size_t workspace_bytes, cudaStream_t stream);
+
+/* --- runtime ------------------------------------------------------------ */
+/* identity of the stream capture `stream` is part of, 0 when it is not capturing (cudaStreamGetCaptureInfo) */
+unsigned long long scda_stream_capture_id(cudaStream_t stream);
+
+/* --- RCNN proposal targets --------------------------------------------- */
+/* compute_proposal_targets for one image (functions/proposal_target.py:17-177): boxes float32 [cap][ldb >= 4]
+ * = (x1, y1, x2, y2, ...) of which the first n_boxes[0] (device int64) are live; gts float32 [G][5] =
+ * (x1, y1, x2, y2, label), rows with x2 <= x1 + 1 or y2 <= y1 + 1 are padding; append_gts adds the valid gts to
+ * the candidates (:42-43).  Clip to the image, IoU (the cython_bbox arithmetic), positives iou > pos_thresh,
+ * negatives neg_lo <= iou < neg_hi; at most want_pos positives, the rest negatives, up to batch_size rows,
+ * padded by resampling.  Draws are key driven (functions/_sampling.py): candidate j (ascending index) owns
+ * keys[j], the k candidates with the smallest keys are chosen in key order; keys_pos / keys_neg [>= R],
+ * keys_pad [>= batch_size] float64 in [0, 1) on the device, R = cap (+ G).  Outputs (device): rois
+ * [batch_size][5] = (batch_ix, box), labels [batch_size] int64, loc_targets / loc_weights
+ * [batch_size][4 * num_classes] float32, class-specific, (t - mean) / std when `normalize` (means4 / stds4: HOST
+ * pointers to four doubles).  cap + G <= 4096, G <= 256.  One launch, no host synchronisation. */
+int scda_proposal_targets(int cap, int ldb, const float *boxes, const long long *n_boxes, int G, const float *gts,
+                          int append_gts, float img_h, float img_w, float pos_thresh, float neg_hi, float neg_lo,
+                          int want_pos, int batch_size, int num_classes, int normalize, const double *means4,
+                          const double *stds4, float batch_ix, const double *keys_pos, const double *keys_neg,
+                          const double *keys_pad, float *rois, long long *labels, float *loc_targets,
+                          float *loc_weights, cudaStream_t stream);
+
 /* crops around the cluster centres (tools/faster_rcnn_train_val.py:411-438, 528-557): K windows of R x R pixels,
  * corner = clamp(int(centre) - R/2, 0, size - R) per axis, gathered from image [C, H, W] fp32 into
  * out [K, C, R, R]; centers [K][2] = (x, y) fp32 on the device.  R even, R <= H, W. */

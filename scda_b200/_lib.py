@@ -101,6 +101,11 @@ SIGNATURES = {
     "scda_conv1x1_tanh_fwd": (_i, [C.c_longlong, _i, _i, _p, _p, _p, _p, _p]),
     "scda_conv1x1_tanh_bwd": (_i, [C.c_longlong, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _z, _p]),
     "scda_rpn_decode_pack": (_i, [_i, _p, _p, _p, _p, C.c_double, C.c_double, C.c_double, _p, _p, _p]),
+    "scda_rpn_proposal_rows_workspace_bytes": (_z, [_i, _i]),
+    "scda_rpn_proposal_rows": (_i, [_i, _i, _p, _p, _p, C.c_double, C.c_double, C.c_double, _p, _p, _p, _z, _p]),
+    "scda_stream_capture_id": (C.c_ulonglong, [_p]),
+    "scda_proposal_targets": (_i, [_i, _i, _p, _p, _i, _p, _i, _f, _f, _f, _f, _f, _i, _i, _i, _i, _p, _p, _f,
+                                   _p, _p, _p, _p, _p, _p, _p, _p]),
     "scda_crop_regions": (_i, [_i, _i, _i, _i, _i, _p, _p, _p, _p]),
     "scda_conv3x3_set_plan": (_i, [_i, _i, _i]),
     "scda_conv3x3_wgrad_set_form": (_i, [_i]),

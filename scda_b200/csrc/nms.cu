@@ -22,6 +22,8 @@
 // reference's `Sa + Sb - interS` (Sb being a product) into
 // fma(wb, hb, Sa) - interS and keeps an IEEE division (PTX of the unmodified
 // file, nvcc 12.9); the intrinsics below pin that sequence.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
@@ -238,6 +240,139 @@ nms_scan_kernel(const unsigned long long *__restrict__ mask, int n_cap,
     if (tid == 0) *num_out = (max_keep > 0 && base > max_keep) ? max_keep : base;
 }
 
+// Scan, wide form (n_cap <= kWideCap): the chain above costs one L2 round trip + two barriers per 64 boxes
+// (188 steps at 12 000 boxes: 160-210 us, as long as the mask kernel).  Here a step settles kWideW * 64 = 256
+// boxes: the pull walks a LIST of the boxes kept so far (ascending indices in shared memory: at most a couple of
+// thousand entries however many boxes were scanned, one round of independent loads) for the step's four column
+// blocks at once, and warp 0 runs the same fixpoint on the 256 x 256 diagonal (staged in shared memory; a lane owns 8 rows).
+// The list doubles as the output: it is the ascending survivor indices.
+constexpr int kWideW = 4;
+constexpr int kWideCap = 32768;
+
+__global__ void __launch_bounds__(kScanThreads)
+nms_scan_wide_kernel(const unsigned long long *__restrict__ mask, int n_cap, const int *__restrict__ n_dev,
+                     int max_keep, long long *__restrict__ keep_out, long long *__restrict__ num_out)
+{
+    extern __shared__ int s_list[];                  // [n_cap] kept indices, ascending
+    __shared__ unsigned long long s_red[kScanThreads / 32][kWideW];
+    __shared__ unsigned long long s_d[kWideW][kWideW * kTile];
+    __shared__ int s_total, s_done;
+    static_assert(kScanThreads == kWideW * kWideW * kTile, "one diagonal word per thread");
+    const int n = n_dev ? max(0, min(n_cap, __ldg(n_dev))) : n_cap;
+    const int cb = (n + kTile - 1) / kTile;
+    const int steps = (cb + kWideW - 1) / kWideW;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int kRows = kWideW * kTile;            // 256
+    constexpr int kPerLane = kRows / 32;             // 8 rows per lane: lane + 32 q
+    if (tid == 0) { s_total = 0; s_done = 0; }
+    __syncthreads();
+
+    for (int s = 0; s < steps; ++s) {
+        const int before = s * kRows;
+        const int cb0 = s * kWideW;                  // first column block of the step
+        // diagonal words of the step's rows: s_d[w][r] = mask[cb0 + w][before + r], zero below the diagonal;
+        // one word per thread, consumed by warp 0 after the barrier below
+        {
+            const int w = tid >> 8, r = tid & (kRows - 1);
+            const int i = before + r;
+            unsigned long long v = 0ull;
+            if (i < n && w >= (r >> 6) && cb0 + w < cb) v = __ldg(mask + (long long)(cb0 + w) * n_cap + i);
+            s_d[w][r] = v;
+        }
+        // pull: OR of the kept boxes' words for the step's column blocks
+        unsigned long long acc[kWideW];
+#pragma unroll
+        for (int w = 0; w < kWideW; ++w) acc[w] = 0ull;
+        const int nk = s_total;
+        for (int k0 = tid; k0 < nk; k0 += 2 * kScanThreads) {
+            unsigned long long v[2][kWideW];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int k = k0 + u * kScanThreads;
+                const int i = k < nk ? s_list[k] : -1;
+#pragma unroll
+                for (int w = 0; w < kWideW; ++w)
+                    v[u][w] = (i >= 0 && cb0 + w < cb) ? __ldg(mask + (long long)(cb0 + w) * n_cap + i) : 0ull;
+            }
+#pragma unroll
+            for (int w = 0; w < kWideW; ++w) acc[w] |= v[0][w] | v[1][w];
+        }
+#pragma unroll
+        for (int w = 0; w < kWideW; ++w) {
+            acc[w] = warp_or64(acc[w]);
+            if (lane == 0) s_red[warp][w] = acc[w];
+        }
+        __syncthreads();
+        if (warp == 0) {
+            unsigned long long und[kWideW], kept[kWideW];
+#pragma unroll
+            for (int w = 0; w < kWideW; ++w) {
+                const unsigned long long removed = warp_or64(s_red[lane][w]);
+                const int rows = min(max(n - (before + w * kTile), 0), kTile);
+                const unsigned long long valid = rows == 64 ? ~0ull : ((1ull << rows) - 1);
+                und[w] = ~removed & valid;
+                kept[w] = 0ull;
+            }
+            for (;;) {
+                unsigned long long any = 0ull;
+#pragma unroll
+                for (int w = 0; w < kWideW; ++w) any |= und[w];
+                if (!any) break;
+                // words of the undecided rows: what they would suppress if kept
+                unsigned long long con[kWideW];
+#pragma unroll
+                for (int w = 0; w < kWideW; ++w) con[w] = 0ull;
+#pragma unroll
+                for (int q = 0; q < kPerLane; ++q) {
+                    const bool u = (und[q >> 1] >> (lane + 32 * (q & 1))) & 1ull;
+#pragma unroll
+                    for (int w = 0; w < kWideW; ++w) con[w] |= u ? s_d[w][lane + 32 * q] : 0ull;
+                }
+                unsigned long long now[kWideW];
+#pragma unroll
+                for (int w = 0; w < kWideW; ++w) {
+                    now[w] = und[w] & ~warp_or64(con[w]);      // no earlier undecided overlapper: kept
+                    kept[w] |= now[w];
+                }
+                unsigned long long hit[kWideW];
+#pragma unroll
+                for (int w = 0; w < kWideW; ++w) hit[w] = 0ull;
+#pragma unroll
+                for (int q = 0; q < kPerLane; ++q) {
+                    const bool u = (now[q >> 1] >> (lane + 32 * (q & 1))) & 1ull;
+#pragma unroll
+                    for (int w = 0; w < kWideW; ++w) hit[w] |= u ? s_d[w][lane + 32 * q] : 0ull;
+                }
+#pragma unroll
+                for (int w = 0; w < kWideW; ++w) und[w] &= ~now[w] & ~warp_or64(hit[w]);
+            }
+            // ordered append of the step's survivors
+            int base = s_total;
+#pragma unroll
+            for (int w = 0; w < kWideW; ++w) {
+#pragma unroll
+                for (int hbit = 0; hbit < 2; ++hbit) {
+                    const int bit = lane + 32 * hbit;
+                    if ((kept[w] >> bit) & 1ull)
+                        s_list[base + __popcll(kept[w] & ((1ull << bit) - 1ull))] = before + w * kTile + bit;
+                }
+                base += __popcll(kept[w]);
+            }
+            if (lane == 0) {
+                s_total = base;
+                if (max_keep > 0 && base >= max_keep) s_done = 1;
+            }
+        }
+        __syncthreads();
+        if (s_done) break;
+    }
+    const int total = (max_keep > 0 && s_total > max_keep) ? max_keep : s_total;
+    for (int k = tid; k < total; k += kScanThreads) keep_out[k] = (long long)s_list[k];
+    if (tid == 0) *num_out = total;
+}
+
+int g_nms_wide_scan = -1;
+
 int launch_mask(int n, const int *n_dev, const float *boxes, unsigned long long *mask, float thresh,
                 bool row_major, cudaStream_t stream)
 {
@@ -267,6 +402,23 @@ int nms_impl(int n, const int *n_dev, const float *boxes, float thresh, int max_
     unsigned long long *mask = (unsigned long long *)workspace;
     int st = launch_mask(n, n_dev, boxes, mask, thresh, false, stream);
     if (st != 1) return st;
+    if (g_nms_wide_scan < 0) {
+        const char *e = getenv("SCDA_NMS_WIDE");
+        g_nms_wide_scan = (e && *e == '0') ? 0 : 1;
+    }
+    if (n <= kWideCap && g_nms_wide_scan) {
+        const size_t smem_w = sizeof(int) * (size_t)n;
+        static size_t attr = 0;
+        if (smem_w > 32 * 1024 && smem_w > attr) {     // + ~10 KB of static shared memory
+            cudaError_t e = cudaFuncSetAttribute(nms_scan_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 (int)smem_w);
+            if (e != cudaSuccess) return -(int)e;
+            attr = smem_w;
+        }
+        nms_scan_wide_kernel<<<1, kScanThreads, smem_w, stream>>>(mask, n, n_dev, max_keep, (long long *)keep_out,
+                                                                  (long long *)num_out);
+        return scda_launch_status();
+    }
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(nms_scan_kernel,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

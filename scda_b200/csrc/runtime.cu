@@ -1,0 +1,17 @@
+// Small runtime queries for the host side.
+#include "common.cuh"
+
+// Identity of the stream capture `stream` currently belongs to (0: not capturing).  The host side keeps lazily
+// derived tensors (concatenated / padded weight copies) that several streams share; a consumer may wait on the
+// builder's event only inside the SAME capture (or outside any capture) — waiting on an event of another
+// capture invalidates the one in progress.
+SCDA_API unsigned long long scda_stream_capture_id(cudaStream_t stream)
+{
+    cudaStreamCaptureStatus status = cudaStreamCaptureStatusNone;
+    unsigned long long id = 0;
+    if (cudaStreamGetCaptureInfo(stream, &status, &id) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return 0;
+    }
+    return status == cudaStreamCaptureStatusActive ? id : 0ull;
+}

@@ -11,17 +11,67 @@ device) and returns the same four CUDA tensors.  `proposal_targets_device` takes
 fixed-capacity buffer + device count produced by rpn_proposals_device and never
 synchronises.
 """
+import ctypes as C
+
 import torch
 
+from .._lib import check, load, stream_ptr
 from ..extensions._cython_bbox.cython_bbox import bbox_overlaps_device
 from ..utils.bbox_helper import clip_t, encode_t
 from . import _sampling
 
 
+import os as _os
+_FORCE_TENSOR_OPS = _os.environ.get('SCDA_PT_TENSOR_OPS', '0') == '1'      # debugging switch
+
+
 def proposal_targets_device(boxes, n_boxes, gts, cfg, image_hw, batch_ix=0, rng=None):
     """boxes float32 [cap, >=4] (x1,y1,x2,y2,...), n_boxes 0-dim int tensor (live rows),
     gts float32 [G, 5] (padded rows allowed).  Returns rois [bs,5], labels [bs] int64,
-    loc_targets / loc_weights [bs, num_classes*4] float32 with bs = cfg['batch_size']."""
+    loc_targets / loc_weights [bs, num_classes*4] float32 with bs = cfg['batch_size'].
+    ONE kernel (csrc/target_ops.cu) for up to 4096 boxes and 256 ground truths; the tensor-op form of the
+    same steps (`proposal_targets_tensor_ops`) beyond that."""
+    rng = rng or _sampling.TorchRng()
+    cap, G = boxes.shape[0], gts.shape[0]
+    R = cap + G if cfg['append_gts'] else cap
+    if not (boxes.is_cuda and R <= 4096 and 0 < G <= 256 and cfg['batch_size'] <= 4096) or _FORCE_TENSOR_OPS:
+        return proposal_targets_tensor_ops(boxes, n_boxes, gts, cfg, image_hw, batch_ix, rng)
+    dev = boxes.device
+    bs, nc = cfg['batch_size'], cfg['num_classes']
+    boxes = boxes.float()
+    if boxes.stride(1) != 1:
+        boxes = boxes.contiguous()
+    gts = gts.float().contiguous()
+    assert gts.shape[1] >= 5
+    if gts.shape[1] != 5:
+        gts = gts[:, :5].contiguous()
+    n_dev = n_boxes.to(device=dev, dtype=torch.int64).reshape(1) if torch.is_tensor(n_boxes) else \
+        torch.full((1,), int(n_boxes), dtype=torch.int64, device=dev)
+    # the three draws of the reference, in its order (positives, negatives, padding)
+    k_pos, k_neg, k_pad = rng.uniform(R, dev), rng.uniform(R, dev), rng.uniform(bs, dev)
+    rois = torch.empty(bs, 5, dtype=torch.float32, device=dev)
+    labels = torch.empty(bs, dtype=torch.int64, device=dev)
+    loc_t = torch.empty(bs, nc * 4, dtype=torch.float32, device=dev)
+    loc_w = torch.empty(bs, nc * 4, dtype=torch.float32, device=dev)
+    norm = bool(cfg['bbox_normalize_stats_precomputed'])
+    means = (C.c_double * 4)(*[float(v) for v in cfg['bbox_normalize_means']]) if norm else None
+    stds = (C.c_double * 4)(*[float(v) for v in cfg['bbox_normalize_stds']]) if norm else None
+    h, w = image_hw
+    with torch.cuda.device(dev):
+        check(load().scda_proposal_targets(
+            cap, boxes.stride(0), boxes.data_ptr(), n_dev.data_ptr(), G, gts.data_ptr(),
+            1 if cfg['append_gts'] else 0, float(h), float(w), float(cfg['positive_iou_thresh']),
+            float(cfg['negative_iou_thresh_hi']), float(cfg['negative_iou_thresh_lo']),
+            int(cfg['positive_percent'] * bs), bs, nc, 1 if norm else 0,
+            C.cast(means, C.c_void_p) if norm else None, C.cast(stds, C.c_void_p) if norm else None,
+            float(batch_ix), k_pos.data_ptr(), k_neg.data_ptr(), k_pad.data_ptr(), rois.data_ptr(),
+            labels.data_ptr(), loc_t.data_ptr(), loc_w.data_ptr(), stream_ptr(dev)), "scda_proposal_targets")
+    return rois, labels, loc_t, loc_w
+
+
+def proposal_targets_tensor_ops(boxes, n_boxes, gts, cfg, image_hw, batch_ix=0, rng=None):
+    """the same computation as ~150 tensor operations (shapes beyond the kernel's shared memory; also the
+    second implementation the kernel is tested against)"""
     rng = rng or _sampling.TorchRng()
     dev = boxes.device
     cap, G = boxes.shape[0], gts.shape[0]

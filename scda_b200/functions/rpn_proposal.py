@@ -4,9 +4,10 @@ Reference flow per image: D2H of the class and delta maps -> numpy argpartition/
 top-k -> float64 decode -> clip -> min-size filter -> H2D -> GPU bitmask NMS -> D2H of
 the 18 MB mask -> host scan -> slice -> numpy stack -> CPU tensor.
 Here everything up to the final slice stays on the device and nothing synchronises:
-top-k (descending) -> scda_rpn_decode_pack (csrc/proposal_ops.cu: decode/clip in float64, the
-dtype numpy gives the reference, min-size filter, stable compaction of the survivors with a
-device-side count; utils.bbox_helper.decode_t / clip_t are the same arithmetic as tensor ops)
+scda_rpn_proposal_rows (csrc/proposal_ops.cu: radix selection of the pre_nms_top_n best scores,
+their descending order by rank counting, decode/clip in float64 — the dtype numpy gives the
+reference —, min-size filter, stable compaction of the survivors with a device-side count;
+utils.bbox_helper.decode_t / clip_t are the same arithmetic as tensor ops)
 -> scda_nms_dyn (count read on the device, scan stops after post_nms_top_n survivors) -> gather.
 
 `compute_rpn_proposals` keeps the reference's signature and return type (CPU float tensor
@@ -18,6 +19,10 @@ import torch
 from .._lib import check, load, stream_ptr
 from ..extensions._nms.pth_nms import nms_device
 from ..utils import anchor_helper
+
+
+import os as _os
+_FORCE_TOPK = _os.environ.get('SCDA_RPN_TOPK', '0') == '1'      # debugging switch
 
 
 def _image_hw(image_info, b):
@@ -47,21 +52,36 @@ def rpn_proposals_device(conv_cls, conv_loc, cfg, image_info, fg_scores=None):
     out = []
     for b in range(B):
         scores = cls_view[b, :, -1].contiguous() if fg_scores is None else fg_scores[b]
-        if pre <= 0 or pre > KA:
-            top, order = torch.sort(scores, descending=True)
-        else:
-            top, order = torch.topk(scores, pre, sorted=True)
         h, w = _image_hw(image_info, b)
-        n = int(order.shape[0])
-        # decode + clip + min-size filter + stable compaction: one kernel (csrc/proposal_ops.cu)
+        deltas = loc_view[b].float().contiguous()
+        n = KA if (pre <= 0 or pre > KA) else pre
         packed = torch.empty(n, 5, dtype=torch.float32, device=dev)
         count = torch.empty(1, dtype=torch.int32, device=dev)
-        deltas = loc_view[b].float().contiguous()
-        with torch.cuda.device(dev):
-            check(load().scda_rpn_decode_pack(n, anchors.data_ptr(), deltas.data_ptr(), order.data_ptr(),
-                                              top.float().contiguous().data_ptr(), float(h), float(w),
-                                              float(cfg['roi_min_size']), packed.data_ptr(), count.data_ptr(),
-                                              stream_ptr(dev)), "scda_rpn_decode_pack")
+        if KA <= 51200 and not _FORCE_TOPK:
+            # selection, descending order, decode, clip, min-size filter, compaction: two launches
+            # (csrc/proposal_ops.cu)
+            lib = load()
+            scores = scores.float().contiguous()
+            wsb = lib.scda_rpn_proposal_rows_workspace_bytes(KA, pre)
+            ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+            with torch.cuda.device(dev):
+                check(lib.scda_rpn_proposal_rows(KA, pre, scores.data_ptr(), anchors.data_ptr(), deltas.data_ptr(),
+                                                 float(h), float(w), float(cfg['roi_min_size']), packed.data_ptr(),
+                                                 count.data_ptr(), ws.data_ptr(), wsb, stream_ptr(dev)),
+                      "scda_rpn_proposal_rows")
+        else:
+            # more anchors than the selection kernel's shared memory holds: library top-k, then the decode kernel
+            from .. import gan_ops
+            gan_ops.note_library_call("rpn top-k", ": more than 51200 anchors per image, torch.topk / torch.sort")
+            if pre <= 0 or pre > KA:
+                top, order = torch.sort(scores, descending=True)
+            else:
+                top, order = torch.topk(scores, pre, sorted=True)
+            with torch.cuda.device(dev):
+                check(load().scda_rpn_decode_pack(n, anchors.data_ptr(), deltas.data_ptr(), order.data_ptr(),
+                                                  top.float().contiguous().data_ptr(), float(h), float(w),
+                                                  float(cfg['roi_min_size']), packed.data_ptr(), count.data_ptr(),
+                                                  stream_ptr(dev)), "scda_rpn_decode_pack")
         keep, n_keep = nms_device(packed, cfg['nms_iou_thresh'], max_keep=max(post, 0),
                                   n_dev=count)
         cap = min(post, n) if post > 0 else n

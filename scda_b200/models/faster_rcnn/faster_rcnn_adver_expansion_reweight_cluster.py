@@ -240,6 +240,9 @@ class FasterRCNN_AdEx(nn.Module):
             rois, cls_targets, loc_targets, loc_weights = self._train_rois(
                 cfg, props, ground_truth_bboxes, image_info, rng.get('proposal'))
             assert rois.shape[1] == 5
+            if os.environ.get("SCDA_DEBUG_TARGETS") == "1":
+                self._dbg = dict(orig=(rois, cls_targets, loc_targets, loc_weights),
+                                 early=tuple(t.clone() for t in (rois, cls_targets, loc_targets, loc_weights)))
             x_fea, rcnn_pred_cls, rcnn_pred_loc = self.rcnn(x, rois)
             if tstream is not None and not early and late == "2":
                 tstream.wait_event(after_rpn)
@@ -277,6 +280,9 @@ class FasterRCNN_AdEx(nn.Module):
                 partial_fn['anchor_target_fn'], rpn_pred_cls, rpn_pred_loc)
             rcnn_loss_cls, rcnn_loss_loc, rcnn_acc = self._add_rcnn_loss(
                 rcnn_pred_cls, rcnn_pred_loc, cls_targets, loc_targets, loc_weights)
+            if os.environ.get("SCDA_DEBUG_TARGETS") == "1":
+                self._dbg['late'] = tuple(t.clone() for t in (rois, cls_targets, loc_targets, loc_weights))
+                self._dbg['pred'] = (rcnn_pred_cls.detach().clone(), rcnn_pred_loc.detach().clone())
             outputs['losses'] = [rpn_loss_cls, rpn_loss_loc, rcnn_loss_cls, rcnn_loss_loc]
             outputs['accuracy'] = [rpn_acc, rcnn_acc]
             outputs['predict'] = [props]

@@ -29,6 +29,39 @@ def _is_krsc(p):
     return p.dim() == 4 and p.permute(0, 2, 3, 1).is_contiguous()
 
 
+class _Published(object):
+    """a lazily derived tensor set shared by callers on DIFFERENT streams (the source and the target branch of
+    the detector forward both use the concatenated head weights): the builder's stream records an event, every
+    other stream waits on it before its first use.  Without it the second branch reads the buffer while the
+    first is still filling it — a race that stayed hidden as long as one branch was always the slower one."""
+    __slots__ = ("value", "event", "stream", "capture")
+
+    @staticmethod
+    def _capture_id(stream):
+        from ._lib import load
+        return int(load().scda_stream_capture_id(stream.cuda_stream))
+
+    def __init__(self, value):
+        self.value = value
+        self.event = self.stream = None
+        self.capture = 0
+        if torch.cuda.is_available() and torch.cuda.is_initialized():
+            self.stream = torch.cuda.current_stream()
+            self.capture = self._capture_id(self.stream)
+            self.event = torch.cuda.Event()
+            self.event.record(self.stream)
+
+    def get(self):
+        if self.event is not None:
+            cur = torch.cuda.current_stream()
+            # the wait is legal inside the builder's own capture (or outside any); an entry from before a
+            # capture is complete (captures begin behind a synchronisation), one from an earlier captured
+            # segment is ordered by the engine's segment plan
+            if cur != self.stream and self._capture_id(cur) == self.capture:
+                cur.wait_event(self.event)
+        return self.value
+
+
 def shadow_of(p):
     """bf16 copy of parameter p: conv weights as [O,3,3,I], everything else as stored.  Kept on
     the parameter (`_scda_shadow`) and re-derived only when `p._version` moved; engine.FlatAdam
@@ -55,7 +88,7 @@ def shadow3_of(p, pad_in=None):
     stamp = (p._version, getattr(p, "_scda_epoch", 0), pad_in)
     ent = getattr(p, "_scda_x3", None)
     if ent is not None and ent[0] == stamp:
-        return ent[1]
+        return ent[1].get()
     src = p.detach()
     if p.dim() == 4:
         O, I = p.shape[0], p.shape[1]
@@ -70,7 +103,7 @@ def shadow3_of(p, pad_in=None):
         val = (fwd.view(O, 3, 3, 3 * I), stk.view(3 * O, 3, 3, I))
     else:
         val = tc.split_weights(src.contiguous())
-    p._scda_x3 = (stamp, val)
+    p._scda_x3 = (stamp, _Published(val))
     return val
 
 
@@ -100,9 +133,9 @@ class TcDetector(object):
         stamp = tuple((p._version, getattr(p, "_scda_epoch", 0)) for p in params)
         ent = self._derived.get(key)
         if ent is None or ent[0] != stamp:
-            ent = (stamp, build())
+            ent = (stamp, _Published(build()))
             self._derived[key] = ent
-        return ent[1]
+        return ent[1].get()
 
     def conv1_weight(self):
         w = self.convs[0][0].weight

@@ -10,7 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def declared_symbols():
     text = open(os.path.join(ROOT, "include", "scda_b200.h")).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    names = re.findall(r"^\s*(?:int|void|size_t)\s+(\w+)\s*\(", text, flags=re.M)
+    names = re.findall(r"^\s*(?:int|void|size_t|unsigned long long)\s+(\w+)\s*\(", text, flags=re.M)
     assert len(names) >= 15
     return names
 

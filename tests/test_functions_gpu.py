@@ -80,6 +80,55 @@ def test_rpn_proposals_vs_oracle_other_seeds(cuda_lib, cfg, host, seed):
     np.testing.assert_allclose(out[:, 1:5], ref[:, 1:5], rtol=1e-5, atol=1e-4)
 
 
+@pytest.mark.parametrize("KA,pre,ties,min_size", [
+    (30720, 12000, False, 16.0),      # the training configuration
+    (30720, 6000, True, 16.0),        # quantised scores: long runs of equal keys across the selection boundary
+    (9000, 0, True, 2.0),             # pre <= 0: every anchor, sorted
+    (5001, 5001, False, 40.0),        # K not a multiple of four, many rows below the minimum size
+    (700, 33, True, 0.0),
+])
+def test_rpn_proposal_rows_kernel(cuda_lib, KA, pre, ties, min_size):
+    """scda_rpn_proposal_rows (selection + order by rank counting + decode + compaction, two launches) against
+    a stable descending sort on the host followed by the single-CTA decode kernel (scda_rpn_decode_pack, itself
+    pinned to the reference's golden proposals above): identical rows, bit for bit, ties by anchor index."""
+    import torch
+    from scda_b200._lib import check, load, stream_ptr
+    lib = load()
+    r = np.random.RandomState(KA + pre)
+    scores = r.uniform(0, 1, KA).astype(np.float32)
+    if ties:
+        scores = np.round(scores * 50) / 50
+        scores[r.randint(0, KA, KA // 10)] *= -1            # negative keys too
+        scores = scores + np.float32(0)                     # no -0.0: numpy ties it with +0.0
+    anchors = np.sort(r.uniform(0, 900, (KA, 2, 2)), axis=1).reshape(KA, 4)[:, [0, 2, 1, 3]].astype(np.float64)
+    deltas = (r.standard_normal((KA, 4)) * 0.3).astype(np.float32)
+    K = KA if pre <= 0 or pre > KA else pre
+    order = np.argsort(-scores.astype(np.float64), kind="stable")[:K]
+    dev = "cuda"
+    t_scores, t_anchors, t_deltas = (torch.from_numpy(x).to(dev) for x in (scores, anchors, deltas))
+    t_order = torch.from_numpy(order.astype(np.int64)).to(dev)
+    t_top = torch.from_numpy(scores[order]).to(dev)
+    want = torch.full((K, 5), 7.0, device=dev)
+    want_n = torch.zeros(1, dtype=torch.int32, device=dev)
+    check(lib.scda_rpn_decode_pack(K, t_anchors.data_ptr(), t_deltas.data_ptr(), t_order.data_ptr(), t_top.data_ptr(),
+                                   600.0, 1000.0, min_size, want.data_ptr(), want_n.data_ptr(), stream_ptr(dev)), "ref")
+    got = torch.full((K, 5), 9.0, device=dev)
+    got_n = torch.zeros(1, dtype=torch.int32, device=dev)
+    wsb = lib.scda_rpn_proposal_rows_workspace_bytes(KA, pre)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+    for _ in range(2):                                       # the ticket re-arms itself
+        got.fill_(9.0)
+        check(lib.scda_rpn_proposal_rows(KA, pre, t_scores.data_ptr(), t_anchors.data_ptr(), t_deltas.data_ptr(),
+                                         600.0, 1000.0, min_size, got.data_ptr(), got_n.data_ptr(), ws.data_ptr(),
+                                         wsb, stream_ptr(dev)), "scda_rpn_proposal_rows")
+        torch.cuda.synchronize()
+        assert int(got_n) == int(want_n)
+        assert 0 < int(got_n) <= K
+        assert torch.equal(got, want)
+    if min_size >= 40:
+        assert int(got_n) < K
+
+
 def _keys(seed, n, tags):
     r = np.random.RandomState(seed)
     return {t: r.uniform(0, 1, n) for t in tags}
