@@ -480,13 +480,17 @@ int scda_head_dot_bwd(long long P, int C, const void *x, int x_f32, const float 
                       float slope, void *dx, float *dw, float *db, cudaStream_t stream);
 /* nn.BatchNorm2d in training mode + LeakyReLU over x fp32 [P, C] (P = N*H*W): batch statistics, running
  * statistics updated (momentum, unbiased variance) when the pointers are not NULL; mean / rstd [C] saved for
- * the backward.  Backward: dgamma, dbeta (= or +=), dx (may be NULL). */
+ * the backward.  Backward: dgamma, dbeta (= or +=), dx (may be NULL).  Two launches each (per-chunk partial
+ * sums, then finish + apply); workspace: scda_bn_workspace_bytes(P, C) bytes, contents irrelevant. */
+size_t scda_bn_workspace_bytes(long long P, int C);
 int scda_bn_lrelu_fwd(long long P, int C, const float *x, const float *gamma, const float *beta, float eps,
                       float slope, float momentum, float *running_mean, float *running_var, float *mean,
-                      float *rstd, void *y, int y_f32, cudaStream_t stream);
+                      float *rstd, void *y, int y_f32, void *workspace, size_t workspace_bytes,
+                      cudaStream_t stream);
 int scda_bn_lrelu_bwd(long long P, int C, const float *x, const void *dy, int dy_f32, const float *gamma,
                       const float *beta, const float *mean, const float *rstd, float slope, void *dx,
-                      int dx_f32, float *dgamma, float *dbeta, int accumulate, cudaStream_t stream);
+                      int dx_f32, float *dgamma, float *dbeta, int accumulate, void *workspace,
+                      size_t workspace_bytes, cudaStream_t stream);
 /* global average pool x fp32 [N, HW, C] -> [N, C] and its backward (dx bf16 or fp32 [N, HW, C]) */
 int scda_avgpool_fwd(int N, int HW, int C, const float *x, float *out, cudaStream_t stream);
 int scda_avgpool_bwd(int N, int HW, int C, const float *g, void *dx, int dx_f32, cudaStream_t stream);

@@ -88,8 +88,9 @@ SIGNATURES = {
                               _i, _p, _z, _p]),
     "scda_head_dot_fwd": (_i, [C.c_longlong, _i, _p, _i, _p, _p, _p, _p]),
     "scda_head_dot_bwd": (_i, [C.c_longlong, _i, _p, _i, _p, _p, _f, _p, _p, _p, _p]),
-    "scda_bn_lrelu_fwd": (_i, [C.c_longlong, _i, _p, _p, _p, _f, _f, _f, _p, _p, _p, _p, _p, _i, _p]),
-    "scda_bn_lrelu_bwd": (_i, [C.c_longlong, _i, _p, _p, _i, _p, _p, _p, _p, _f, _p, _i, _p, _p, _i, _p]),
+    "scda_bn_workspace_bytes": (_z, [C.c_longlong, _i]),
+    "scda_bn_lrelu_fwd": (_i, [C.c_longlong, _i, _p, _p, _p, _f, _f, _f, _p, _p, _p, _p, _p, _i, _p, _z, _p]),
+    "scda_bn_lrelu_bwd": (_i, [C.c_longlong, _i, _p, _p, _i, _p, _p, _p, _p, _f, _p, _i, _p, _p, _i, _p, _z, _p]),
     "scda_avgpool_fwd": (_i, [_i, _i, _i, _p, _p, _p]),
     "scda_avgpool_bwd": (_i, [_i, _i, _i, _p, _p, _i, _p]),
     "scda_image_prepare": (_i, [_p, _i, _i, _p, _i, _i, _i, _i, _p, _p, _p]),

@@ -43,6 +43,8 @@ s2_weights_kernel(const __nv_bfloat16 *__restrict__ src, __nv_bfloat16 *__restri
 }
 
 // partial fp32 [splits][Cout][9][4C] (taps 0, 1, 3, 4 written) -> dw fp32 [Cout][3][3][C] (+)=
+// a thread owns one output and walks the slabs, four independent loads in flight; consecutive threads read
+// consecutive addresses of a slab (a CTA: 1 KB per slab step), which is what keeps this pass at HBM speed
 __global__ void __launch_bounds__(256)
 s2_wgrad_gather_kernel(const float *__restrict__ part, int splits, float *__restrict__ dw, int Cout, int C,
                        int accumulate)
@@ -56,9 +58,15 @@ s2_wgrad_gather_kernel(const float *__restrict__ part, int splits, float *__rest
         // r = 2a + py + 1 with a in {-1, 0}: r = 0 -> (a, py) = (-1, 1); r = 1 -> (0, 0); r = 2 -> (0, 1)
         const int a = r == 0 ? -1 : 0, py = r == 1 ? 0 : 1;
         const int b = s == 0 ? -1 : 0, px = s == 1 ? 0 : 1;
-        const long long src = ((o * 9 + (a + 1) * 3 + (b + 1)) * 4 + py * 2 + px) * C + c;
+        const float *src = part + ((o * 9 + (a + 1) * 3 + (b + 1)) * 4 + py * 2 + px) * C + c;
         float acc = accumulate ? dw[i] : 0.f;
-        for (int k = 0; k < splits; ++k) acc += part[k * slab + src];
+        int k = 0;
+        for (; k + 3 < splits; k += 4) {
+            const float v0 = __ldg(src + (long long)k * slab), v1 = __ldg(src + (long long)(k + 1) * slab);
+            const float v2 = __ldg(src + (long long)(k + 2) * slab), v3 = __ldg(src + (long long)(k + 3) * slab);
+            acc += v0; acc += v1; acc += v2; acc += v3;
+        }
+        for (; k < splits; ++k) acc += __ldg(src + (long long)k * slab);
         dw[i] = acc;
     }
 }
@@ -277,22 +285,34 @@ head_dot_bwd_kernel(const TX *__restrict__ x, const float *__restrict__ w, const
 // ------------------------------------------------------------------ BatchNorm2d (training) + LeakyReLU
 // x fp32 [P, C] (P = N * H * W pixels) -> y = lrelu(gamma * (x - mean) * rstd + beta), batch statistics (biased
 // variance) over the P rows; running_mean / running_var updated with `momentum` (unbiased variance), as
-// nn.BatchNorm2d.  One block per 32 channels: 32 x 32 threads, two passes over the block's columns.
-template <typename TY>
+// nn.BatchNorm2d.  Two launches each way, grid = (32-channel groups, pixel chunks):
+//   partial: a CTA (32 channels x 32 row lanes) reduces its pixel chunk -> partial[chunk][2][C]
+//   apply  : every CTA adds the chunk partials of its channels in chunk order (a few hundred floats out of L2:
+//            cheaper than a grid-wide barrier or a ticket, and the same bits in every CTA), then transforms its
+//            own pixel chunk; the CTAs of chunk 0 write the per-channel outputs.
+// (One CTA per 32 channels walking all pixels — 2 to 16 CTAs on 148 SMs — was 40 us forward / up to 180 us
+//  backward per layer on the critical path of the discriminator updates.)
+constexpr int kBnMaxChunks = 64;
+
+__device__ __forceinline__ void bn_chunk(long long P, int chunks, int chunk, long long *p0, long long *p1)
+{
+    const long long per = (P + chunks - 1) / chunks;
+    *p0 = min(P, per * chunk);
+    *p1 = min(P, *p0 + per);
+}
+
 __global__ void __launch_bounds__(1024)
-bn_lrelu_fwd_kernel(const float *__restrict__ x, long long P, int C, const float *__restrict__ gamma,
-                    const float *__restrict__ beta, float eps, float slope, float momentum,
-                    float *__restrict__ running_mean, float *__restrict__ running_var, float *__restrict__ mean,
-                    float *__restrict__ rstd, TY *__restrict__ y)
+bn_fwd_partial_kernel(const float *__restrict__ x, long long P, int C, float *__restrict__ partial)
 {
     __shared__ float s1[32][33], s2[32][33];
-    __shared__ float sm[32], sr[32];
     const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + cl;
+    long long p0, p1;
+    bn_chunk(P, gridDim.y, blockIdx.y, &p0, &p1);
     const float shift = c < C ? x[c] : 0.f;
     float a = 0.f, b = 0.f;
     if (c < C)
-        for (long long p = rl; p < P; p += 32) {
+        for (long long p = p0 + rl; p < p1; p += 32) {
             const float d = x[p * C + c] - shift;
             a += d;
             b = fmaf(d, d, b);
@@ -302,22 +322,48 @@ bn_lrelu_fwd_kernel(const float *__restrict__ x, long long P, int C, const float
     __syncthreads();
     if (rl == 0 && c < C) {
         for (int k = 1; k < 32; ++k) { a += s1[k][cl]; b += s2[k][cl]; }
+        partial[((long long)blockIdx.y * 2 + 0) * C + c] = a;
+        partial[((long long)blockIdx.y * 2 + 1) * C + c] = b;
+    }
+}
+
+template <typename TY>
+__global__ void __launch_bounds__(1024)
+bn_lrelu_fwd_apply_kernel(const float *__restrict__ x, long long P, int C, const float *__restrict__ gamma,
+                          const float *__restrict__ beta, float eps, float slope, float momentum,
+                          float *__restrict__ running_mean, float *__restrict__ running_var, float *__restrict__ mean,
+                          float *__restrict__ rstd, TY *__restrict__ y, const float *__restrict__ partial, int chunks)
+{
+    __shared__ float sm[32], sr[32];
+    const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + cl;
+    if (rl == 0 && c < C) {
+        float a = 0.f, b = 0.f;
+        for (int k = 0; k < chunks; ++k) {
+            a += partial[((long long)k * 2 + 0) * C + c];
+            b += partial[((long long)k * 2 + 1) * C + c];
+        }
+        const float shift = x[c];
         const float inv = 1.f / (float)P;
         const float m = a * inv;
         const float var = fmaxf(b * inv - m * m, 0.f);
         const float mu = shift + m, rs = rsqrtf(var + eps);
         sm[cl] = mu; sr[cl] = rs;
-        mean[c] = mu; rstd[c] = rs;
-        if (running_mean) {
-            running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mu;
-            const float unb = P > 1 ? var * ((float)P / (float)(P - 1)) : var;
-            running_var[c] = (1.f - momentum) * running_var[c] + momentum * unb;
+        if (blockIdx.y == 0) {
+            mean[c] = mu; rstd[c] = rs;
+            if (running_mean) {
+                running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mu;
+                const float unb = P > 1 ? var * ((float)P / (float)(P - 1)) : var;
+                running_var[c] = (1.f - momentum) * running_var[c] + momentum * unb;
+            }
         }
     }
     __syncthreads();
     if (c >= C) return;
+    long long p0, p1;
+    bn_chunk(P, gridDim.y, blockIdx.y, &p0, &p1);
     const float mu = sm[cl], ga = gamma[c] * sr[cl], be = beta[c];
-    for (long long p = rl; p < P; p += 32) {
+    for (long long p = p0 + rl; p < p1; p += 32) {
         const float v = lrelu(fmaf(x[p * C + c] - mu, ga, be), slope);
         if (sizeof(TY) == 2) reinterpret_cast<__nv_bfloat16 *>(y)[p * C + c] = __float2bfloat16_rn(v);
         else reinterpret_cast<float *>(y)[p * C + c] = v;
@@ -326,22 +372,22 @@ bn_lrelu_fwd_kernel(const float *__restrict__ x, long long P, int C, const float
 
 // dy [P, C] (bf16 or fp32) = gradient w.r.t. y; g = dy * lrelu'(gamma xhat + beta);
 // dgamma += sum g xhat, dbeta += sum g, dx = gamma rstd (g - mean(g) - xhat mean(g xhat))
-template <typename TDy, typename TDx>
+template <typename TDy>
 __global__ void __launch_bounds__(1024)
-bn_lrelu_bwd_kernel(const float *__restrict__ x, const TDy *__restrict__ dy, long long P, int C,
-                    const float *__restrict__ gamma, const float *__restrict__ beta, const float *__restrict__ mean,
-                    const float *__restrict__ rstd, float slope, TDx *__restrict__ dx, float *__restrict__ dgamma,
-                    float *__restrict__ dbeta, int accumulate)
+bn_bwd_partial_kernel(const float *__restrict__ x, const TDy *__restrict__ dy, long long P, int C,
+                      const float *__restrict__ gamma, const float *__restrict__ beta, const float *__restrict__ mean,
+                      const float *__restrict__ rstd, float slope, float *__restrict__ partial)
 {
     __shared__ float s1[32][33], s2[32][33];
-    __shared__ float sa[32], sb[32];
     const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + cl;
+    long long p0, p1;
+    bn_chunk(P, gridDim.y, blockIdx.y, &p0, &p1);
     const float mu = c < C ? mean[c] : 0.f, rs = c < C ? rstd[c] : 0.f, ga = c < C ? gamma[c] : 0.f,
                 be = c < C ? beta[c] : 0.f;
     float a = 0.f, b = 0.f;
     if (c < C)
-        for (long long p = rl; p < P; p += 32) {
+        for (long long p = p0 + rl; p < p1; p += 32) {
             const float xh = (x[p * C + c] - mu) * rs;
             float gy;
             if (sizeof(TDy) == 2) gy = __bfloat162float(reinterpret_cast<const __nv_bfloat16 *>(dy)[p * C + c]);
@@ -355,15 +401,42 @@ bn_lrelu_bwd_kernel(const float *__restrict__ x, const TDy *__restrict__ dy, lon
     __syncthreads();
     if (rl == 0 && c < C) {
         for (int k = 1; k < 32; ++k) { a += s1[k][cl]; b += s2[k][cl]; }
-        dbeta[c] = accumulate ? dbeta[c] + a : a;
-        dgamma[c] = accumulate ? dgamma[c] + b : b;
+        partial[((long long)blockIdx.y * 2 + 0) * C + c] = a;
+        partial[((long long)blockIdx.y * 2 + 1) * C + c] = b;
+    }
+}
+
+template <typename TDy, typename TDx>
+__global__ void __launch_bounds__(1024)
+bn_lrelu_bwd_apply_kernel(const float *__restrict__ x, const TDy *__restrict__ dy, long long P, int C,
+                          const float *__restrict__ gamma, const float *__restrict__ beta,
+                          const float *__restrict__ mean, const float *__restrict__ rstd, float slope,
+                          TDx *__restrict__ dx, float *__restrict__ dgamma, float *__restrict__ dbeta, int accumulate,
+                          const float *__restrict__ partial, int chunks)
+{
+    __shared__ float sa[32], sb[32];
+    const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + cl;
+    if (rl == 0 && c < C) {
+        float a = 0.f, b = 0.f;
+        for (int k = 0; k < chunks; ++k) {
+            a += partial[((long long)k * 2 + 0) * C + c];
+            b += partial[((long long)k * 2 + 1) * C + c];
+        }
+        if (blockIdx.y == 0) {
+            dbeta[c] = accumulate ? dbeta[c] + a : a;
+            dgamma[c] = accumulate ? dgamma[c] + b : b;
+        }
         sa[cl] = a / (float)P;
         sb[cl] = b / (float)P;
     }
     __syncthreads();
     if (c >= C || !dx) return;
+    long long p0, p1;
+    bn_chunk(P, gridDim.y, blockIdx.y, &p0, &p1);
+    const float mu = mean[c], rs = rstd[c], ga = gamma[c], be = beta[c];
     const float mg = sa[cl], mgx = sb[cl], k = ga * rs;
-    for (long long p = rl; p < P; p += 32) {
+    for (long long p = p0 + rl; p < p1; p += 32) {
         const float xh = (x[p * C + c] - mu) * rs;
         float gy;
         if (sizeof(TDy) == 2) gy = __bfloat162float(reinterpret_cast<const __nv_bfloat16 *>(dy)[p * C + c]);
@@ -373,6 +446,15 @@ bn_lrelu_bwd_kernel(const float *__restrict__ x, const TDy *__restrict__ dy, lon
         if (sizeof(TDx) == 2) reinterpret_cast<__nv_bfloat16 *>(dx)[p * C + c] = __float2bfloat16_rn(d);
         else reinterpret_cast<float *>(dx)[p * C + c] = d;
     }
+}
+
+int bn_chunks(long long P, int C)
+{
+    const int groups = (C + 31) / 32;
+    long long ch = (2 * kNumSMs + groups - 1) / groups;       // ~two CTAs of 1024 threads per SM
+    if (ch > (P + 255) / 256) ch = (P + 255) / 256;           // at least 8 rows per row lane
+    if (ch > kBnMaxChunks) ch = kBnMaxChunks;
+    return (int)(ch < 1 ? 1 : ch);
 }
 
 // global average pool of x fp32 [N, HW, C] -> out [N, C], and its backward written as bf16 / fp32 [N, HW, C]
@@ -494,29 +576,54 @@ SCDA_API int scda_head_dot_bwd(long long P, int C, const void *x, int x_f32, con
     return scda_launch_status();
 }
 
+SCDA_API size_t scda_bn_workspace_bytes(long long P, int C)
+{
+    if (P <= 0 || C <= 0) return 0;
+    return sizeof(float) * 2 * (size_t)bn_chunks(P, C) * (size_t)C;
+}
+
 SCDA_API int scda_bn_lrelu_fwd(long long P, int C, const float *x, const float *gamma, const float *beta, float eps,
                                float slope, float momentum, float *running_mean, float *running_var, float *mean,
-                               float *rstd, void *y, int y_f32, cudaStream_t stream)
+                               float *rstd, void *y, int y_f32, void *workspace, size_t workspace_bytes,
+                               cudaStream_t stream)
 {
-    if (P <= 0 || C <= 0 || !x || !gamma || !beta || !mean || !rstd || !y) return 0;
-    const int blocks = (C + 31) / 32;
-    if (y_f32) bn_lrelu_fwd_kernel<float><<<blocks, 1024, 0, stream>>>(x, P, C, gamma, beta, eps, slope, momentum,
-                                                                       running_mean, running_var, mean, rstd, (float *)y);
-    else bn_lrelu_fwd_kernel<__nv_bfloat16><<<blocks, 1024, 0, stream>>>(x, P, C, gamma, beta, eps, slope, momentum,
-                                                                         running_mean, running_var, mean, rstd,
-                                                                         (__nv_bfloat16 *)y);
+    if (P <= 0 || C <= 0 || !x || !gamma || !beta || !mean || !rstd || !y || !workspace) return 0;
+    if (workspace_bytes < scda_bn_workspace_bytes(P, C)) return 0;
+    const int chunks = bn_chunks(P, C);
+    const dim3 grid((C + 31) / 32, chunks);
+    float *partial = (float *)workspace;
+    bn_fwd_partial_kernel<<<grid, 1024, 0, stream>>>(x, P, C, partial);
+    if (y_f32)
+        bn_lrelu_fwd_apply_kernel<float><<<grid, 1024, 0, stream>>>(x, P, C, gamma, beta, eps, slope, momentum,
+                                                                    running_mean, running_var, mean, rstd, (float *)y,
+                                                                    partial, chunks);
+    else
+        bn_lrelu_fwd_apply_kernel<__nv_bfloat16><<<grid, 1024, 0, stream>>>(x, P, C, gamma, beta, eps, slope, momentum,
+                                                                            running_mean, running_var, mean, rstd,
+                                                                            (__nv_bfloat16 *)y, partial, chunks);
     return scda_launch_status();
 }
 
 SCDA_API int scda_bn_lrelu_bwd(long long P, int C, const float *x, const void *dy, int dy_f32, const float *gamma,
                                const float *beta, const float *mean, const float *rstd, float slope, void *dx,
-                               int dx_f32, float *dgamma, float *dbeta, int accumulate, cudaStream_t stream)
+                               int dx_f32, float *dgamma, float *dbeta, int accumulate, void *workspace,
+                               size_t workspace_bytes, cudaStream_t stream)
 {
-    if (P <= 0 || C <= 0 || !x || !dy || !gamma || !beta || !mean || !rstd || !dgamma || !dbeta) return 0;
-    const int blocks = (C + 31) / 32;
-#define SCDA_BN_BWD(TDY, TDX)                                                                                          \
-    bn_lrelu_bwd_kernel<TDY, TDX><<<blocks, 1024, 0, stream>>>(x, (const TDY *)dy, P, C, gamma, beta, mean, rstd, slope, \
-                                                               (TDX *)dx, dgamma, dbeta, accumulate)
+    if (P <= 0 || C <= 0 || !x || !dy || !gamma || !beta || !mean || !rstd || !dgamma || !dbeta || !workspace) return 0;
+    if (workspace_bytes < scda_bn_workspace_bytes(P, C)) return 0;
+    const int chunks = bn_chunks(P, C);
+    const dim3 grid((C + 31) / 32, chunks);
+    float *partial = (float *)workspace;
+    if (dy_f32)
+        bn_bwd_partial_kernel<float><<<grid, 1024, 0, stream>>>(x, (const float *)dy, P, C, gamma, beta, mean, rstd,
+                                                                slope, partial);
+    else
+        bn_bwd_partial_kernel<__nv_bfloat16><<<grid, 1024, 0, stream>>>(x, (const __nv_bfloat16 *)dy, P, C, gamma, beta,
+                                                                        mean, rstd, slope, partial);
+#define SCDA_BN_BWD(TDY, TDX)                                                                                         \
+    bn_lrelu_bwd_apply_kernel<TDY, TDX><<<grid, 1024, 0, stream>>>(x, (const TDY *)dy, P, C, gamma, beta, mean, rstd, \
+                                                                   slope, (TDX *)dx, dgamma, dbeta, accumulate,     \
+                                                                   partial, chunks)
     if (dy_f32 && dx_f32) SCDA_BN_BWD(float, float);
     else if (dy_f32) SCDA_BN_BWD(float, __nv_bfloat16);
     else if (dx_f32) SCDA_BN_BWD(__nv_bfloat16, float);

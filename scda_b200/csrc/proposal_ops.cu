@@ -258,7 +258,28 @@ rpn_rank_decode_kernel(int K, int Kpad, const unsigned *__restrict__ cand_key, c
     __shared__ int s_w[33];
     __shared__ bool s_last;
     const int tid = threadIdx.x;
-    for (int i = tid; i < Kpad; i += kRankThreads) s_k[i] = i < K ? __ldg(cand_key + i) : 0u;
+    {
+        const int n4 = Kpad >> 2;                    // 16-byte loads, four in flight per thread
+        uint4 *s4 = reinterpret_cast<uint4 *>(s_k);
+        for (int g0 = tid; g0 < n4; g0 += 4 * kRankThreads) {
+            uint4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int g = g0 + u * kRankThreads;
+                if (g < n4) v[u] = __ldg(reinterpret_cast<const uint4 *>(cand_key) + g);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int g = g0 + u * kRankThreads;
+                if (g >= n4) continue;
+                uint4 w = v[u];
+                if (4 * g + 1 >= K) w.y = 0u;
+                if (4 * g + 2 >= K) w.z = 0u;
+                if (4 * g + 3 >= K) w.w = 0u;
+                s4[g] = w;
+            }
+        }
+    }
     __syncthreads();
     const int i = blockIdx.x * kRankPerCta + tid / kRankLanes, part = tid % kRankLanes;
     const bool live = i < K;
@@ -314,19 +335,62 @@ rpn_rank_decode_kernel(int K, int Kpad, const unsigned *__restrict__ cand_key, c
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    const int per = (K + kRankThreads - 1) / kRankThreads;
-    const int r0 = min(K, tid * per), r1 = min(K, r0 + per);
+    // thread t owns the 16 * per16 consecutive ranks behind 16 * per16 * t: their flags are per16 aligned 16-byte
+    // loads, all in flight at once; a block scan gives every survivor its destination; the row copy then runs
+    // over DESTINATIONS through a source list in shared memory (the key array is dead by now), so that the
+    // gathers of consecutive threads are independent and the stores coalesced
+    int *s_src = reinterpret_cast<int *>(s_k);        // [<= K] rank of the row that lands at position d
+    const int per16 = (K + 16 * kRankThreads - 1) / (16 * kRankThreads);
+    const int r0 = tid * per16 * 16;
     int mine = 0;
-    for (int r = r0; r < r1; ++r) mine += __ldcg(ok_flag + r);
+    for (int v0 = 0; v0 < per16; v0 += 4) {
+        uint4 f[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int r = r0 + (v0 + u) * 16;
+            f[u] = (v0 + u < per16 && r < K) ? __ldcg(reinterpret_cast<const uint4 *>(ok_flag + r)) : make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int r = r0 + (v0 + u) * 16;
+            const unsigned w[4] = {f[u].x, f[u].y, f[u].z, f[u].w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+#pragma unroll
+                for (int bte = 0; bte < 4; ++bte)
+                    if (r + 4 * q + bte < K && ((w[q] >> (8 * bte)) & 1u)) ++mine;
+        }
+    }
     int total;
     int pos = block_exclusive_scan<kRankThreads>(mine, s_w, &total);
-    for (int r = r0; r < r1; ++r) {
-        if (!__ldcg(ok_flag + r)) continue;
-        const float *src = rows + 5ll * r;
-        float *dst = packed + 5ll * pos;
-        dst[0] = __ldcg(src); dst[1] = __ldcg(src + 1); dst[2] = __ldcg(src + 2); dst[3] = __ldcg(src + 3);
-        dst[4] = __ldcg(src + 4);
-        ++pos;
+    for (int v = 0; v < per16; ++v) {
+        const int r = r0 + v * 16;
+        if (r >= K) break;
+        const uint4 f = __ldcg(reinterpret_cast<const uint4 *>(ok_flag + r));
+        const unsigned w[4] = {f.x, f.y, f.z, f.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+            for (int bte = 0; bte < 4; ++bte)
+                if (r + 4 * q + bte < K && ((w[q] >> (8 * bte)) & 1u)) s_src[pos++] = r + 4 * q + bte;
+    }
+    __syncthreads();
+    const int n5 = total * 5;
+    for (int k0 = tid; k0 < n5; k0 += 8 * kRankThreads) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int k = k0 + u * kRankThreads;
+            if (k < n5) {
+                const int d = k / 5, c = k - 5 * d;
+                v[u] = __ldcg(rows + 5ll * s_src[d] + c);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int k = k0 + u * kRankThreads;
+            if (k < n5) packed[k] = v[u];
+        }
     }
     for (long long k = (long long)total * 5 + tid; k < (long long)K * 5; k += kRankThreads) packed[k] = 0.f;
     if (tid == 0) { count[0] = total; *ticket = 0u; }
@@ -339,7 +403,7 @@ size_t align16(size_t v) { return (v + 15) & ~(size_t)15; }
 SCDA_API size_t scda_rpn_proposal_rows_workspace_bytes(int KA, int pre)
 {
     const size_t K = (size_t)((pre <= 0 || pre > KA) ? KA : pre);
-    return align16(K * 4) + align16(K * 4) + align16(K * 20) + align16(K) + 16;
+    return align16(K * 4) + align16(K * 4) + align16(K * 20) + align16(K) + 16 + 16;
 }
 
 SCDA_API int scda_rpn_proposal_rows(int KA, int pre, const float *scores, const double *anchors, const float *deltas,

@@ -268,11 +268,14 @@ def _bn_fwd(c, bn, slope):
     rstd = torch.empty(C, dtype=torch.float32, device=c.device)
     mom = 0.1 if bn.momentum is None else float(bn.momentum)
     track = bn.training and bn.track_running_stats
+    lib = load()
+    wsb = lib.scda_bn_workspace_bytes(P, C)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=c.device)
     with torch.cuda.device(c.device):
-        check(load().scda_bn_lrelu_fwd(P, C, c.data_ptr(), bn.weight.data_ptr(), bn.bias.data_ptr(), float(bn.eps),
-                                       slope, mom, bn.running_mean.data_ptr() if track else None,
-                                       bn.running_var.data_ptr() if track else None, mean.data_ptr(), rstd.data_ptr(),
-                                       y.data_ptr(), 0, stream_ptr(c.device)), "scda_bn_lrelu_fwd")
+        check(lib.scda_bn_lrelu_fwd(P, C, c.data_ptr(), bn.weight.data_ptr(), bn.bias.data_ptr(), float(bn.eps),
+                                    slope, mom, bn.running_mean.data_ptr() if track else None,
+                                    bn.running_var.data_ptr() if track else None, mean.data_ptr(), rstd.data_ptr(),
+                                    y.data_ptr(), 0, ws.data_ptr(), wsb, stream_ptr(c.device)), "scda_bn_lrelu_fwd")
     if track and bn.num_batches_tracked is not None:
         bn.num_batches_tracked.add_(1)
     return y, mean, rstd
@@ -294,11 +297,14 @@ def _bn_bwd(c, dy, bn, mean, rstd, slope, need_params):
         acc = 0
         dg = torch.empty(C, dtype=torch.float32, device=c.device)
         db = torch.empty(C, dtype=torch.float32, device=c.device)
+    lib = load()
+    wsb = lib.scda_bn_workspace_bytes(P, C)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=c.device)
     with torch.cuda.device(c.device):
-        check(load().scda_bn_lrelu_bwd(P, C, c.data_ptr(), dy.data_ptr(), 1 if dy.dtype == torch.float32 else 0,
-                                       gw.data_ptr(), gb.data_ptr(), mean.data_ptr(), rstd.data_ptr(), slope,
-                                       dc.data_ptr(), 0, dg.data_ptr(), db.data_ptr(), acc, stream_ptr(c.device)),
-              "scda_bn_lrelu_bwd")
+        check(lib.scda_bn_lrelu_bwd(P, C, c.data_ptr(), dy.data_ptr(), 1 if dy.dtype == torch.float32 else 0,
+                                    gw.data_ptr(), gb.data_ptr(), mean.data_ptr(), rstd.data_ptr(), slope,
+                                    dc.data_ptr(), 0, dg.data_ptr(), db.data_ptr(), acc, ws.data_ptr(), wsb,
+                                    stream_ptr(c.device)), "scda_bn_lrelu_bwd")
     if not need_params or direct:
         return dc, None, None
     return dc, dg, db

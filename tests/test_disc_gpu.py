@@ -229,10 +229,14 @@ def test_bn_lrelu_kernels_match_torch(cuda_lib):
     mean, rstd = torch.empty(C, device="cuda"), torch.empty(C, device="cuda")
     y = torch.empty(P, C, device="cuda")
     st = stream_ptr(x.device)
+    wsb = lib.scda_bn_workspace_bytes(P, C)
+    ws = torch.full((wsb,), 0xAB, dtype=torch.uint8, device="cuda")     # contents irrelevant
     check(lib.scda_bn_lrelu_fwd(P, C, x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), 1e-5, 0.01, 0.1, rm.data_ptr(),
-                                rv.data_ptr(), mean.data_ptr(), rstd.data_ptr(), y.data_ptr(), 1, st), "bn")
+                                rv.data_ptr(), mean.data_ptr(), rstd.data_ptr(), y.data_ptr(), 1, ws.data_ptr(), wsb,
+                                st), "bn")
     assert _rel(y, ref) < 1e-5 and _rel(rm, rm2) < 1e-5 and _rel(rv, rv2) < 1e-5
     dx, dg, db = torch.empty(P, C, device="cuda"), torch.empty(C, device="cuda"), torch.empty(C, device="cuda")
     check(lib.scda_bn_lrelu_bwd(P, C, x.data_ptr(), dy.data_ptr(), 1, gamma.data_ptr(), beta.data_ptr(), mean.data_ptr(),
-                                rstd.data_ptr(), 0.01, dx.data_ptr(), 1, dg.data_ptr(), db.data_ptr(), 0, st), "bnb")
+                                rstd.data_ptr(), 0.01, dx.data_ptr(), 1, dg.data_ptr(), db.data_ptr(), 0, ws.data_ptr(),
+                                wsb, st), "bnb")
     assert _rel(dx, x.grad) < 1e-4 and _rel(dg, gamma.grad) < 1e-4 and _rel(db, beta.grad) < 1e-4
