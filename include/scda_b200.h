@@ -184,9 +184,15 @@ int scda_rpn_proposal_rows(int KA, int pre, const float *scores, const double *a
                            double img_h, double img_w, double min_size, float *packed, int *count,
                            void *workspace, size_t workspace_bytes, cudaStream_t stream);
 
+/* dst[c][r] = src[r][c], bf16 [rows][cols] -> [cols][rows]; lds / ldd: leading dimensions in elements */
+int scda_transpose_bf16(int rows, int cols, const void *src, long long lds, void *dst, long long ldd,
+                        cudaStream_t stream);
+
 /* --- runtime ------------------------------------------------------------ */
 /* identity of the stream capture `stream` is part of, 0 when it is not capturing (cudaStreamGetCaptureInfo) */
 unsigned long long scda_stream_capture_id(cudaStream_t stream);
+/* buf[slot] = %globaltimer (ns) in stream order: phase boundaries measured from inside a replayed graph */
+int scda_timestamp(unsigned long long *buf, int slot, cudaStream_t stream);
 
 /* --- RCNN proposal targets --------------------------------------------- */
 /* compute_proposal_targets for one image (functions/proposal_target.py:17-177): boxes float32 [cap][ldb >= 4]

@@ -105,6 +105,8 @@ SIGNATURES = {
     "scda_rpn_proposal_rows_workspace_bytes": (_z, [_i, _i]),
     "scda_rpn_proposal_rows": (_i, [_i, _i, _p, _p, _p, C.c_double, C.c_double, C.c_double, _p, _p, _p, _z, _p]),
     "scda_stream_capture_id": (C.c_ulonglong, [_p]),
+    "scda_timestamp": (_i, [_p, _i, _p]),
+    "scda_transpose_bf16": (_i, [_i, _i, _p, C.c_longlong, _p, C.c_longlong, _p]),
     "scda_proposal_targets": (_i, [_i, _i, _p, _p, _i, _p, _i, _f, _f, _f, _f, _f, _i, _i, _i, _i, _p, _p, _f,
                                    _p, _p, _p, _p, _p, _p, _p, _p]),
     "scda_crop_regions": (_i, [_i, _i, _i, _i, _i, _p, _p, _p, _p]),

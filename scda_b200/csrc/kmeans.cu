@@ -72,6 +72,12 @@ __device__ double block_sum(double v, double *red)
     return r;
 }
 
+// The sequential float32 sums below (numpy's row-by-row reductions, sklearn's chunked centre sums) are dependent
+// chains by definition; what made them slow was one shared-memory load latency per element in front of every
+// add.  kSeqBatch values are loaded first (independent loads, pipelined), then added in order: same sums, same
+// order, ~8x shorter.
+constexpr int kSeqBatch = 16;
+
 // sklearn.metrics.pairwise._euclidean_distances_upcast for one (centre, point) pair
 __device__ __forceinline__ float upcast_dist(const float cx, const float cy, const float px, const float py,
                                              const float ysq)
@@ -102,7 +108,14 @@ kmeans_kernel(const float *__restrict__ rois, int roi_stride, int n, int K, int 
     __syncthreads();
     if (t < 2) {                       // X.mean(axis=0): sequential float32 sum down the rows
         float acc = 0.f;
-        for (int i = 0; i < n; ++i) acc = __fadd_rn(acc, S.x[i][t]);
+        for (int i0 = 0; i0 < n; i0 += kSeqBatch) {
+            float v[kSeqBatch];
+#pragma unroll
+            for (int u = 0; u < kSeqBatch; ++u) v[u] = i0 + u < n ? S.x[i0 + u][t] : 0.f;
+#pragma unroll
+            for (int u = 0; u < kSeqBatch; ++u)
+                if (i0 + u < n) acc = __fadd_rn(acc, v[u]);
+        }
         S.mean[t] = __fdiv_rn(acc, (float)n);
     }
     __syncthreads();
@@ -116,12 +129,26 @@ kmeans_kernel(const float *__restrict__ rois, int roi_stride, int n, int K, int 
     __syncthreads();
     if (t < 2) {                       // np.var(X, axis=0) in float32, then tol = mean(var) * tol_rel
         float m = 0.f;
-        for (int i = 0; i < n; ++i) m = __fadd_rn(m, S.x[i][t]);
+        for (int i0 = 0; i0 < n; i0 += kSeqBatch) {
+            float xv[kSeqBatch];
+#pragma unroll
+            for (int u = 0; u < kSeqBatch; ++u) xv[u] = i0 + u < n ? S.x[i0 + u][t] : 0.f;
+#pragma unroll
+            for (int u = 0; u < kSeqBatch; ++u)
+                if (i0 + u < n) m = __fadd_rn(m, xv[u]);
+        }
         m = __fdiv_rn(m, (float)n);
         float v = 0.f;
-        for (int i = 0; i < n; ++i) {
-            const float d = __fsub_rn(S.x[i][t], m);
-            v = __fadd_rn(v, __fmul_rn(d, d));
+        for (int i0 = 0; i0 < n; i0 += kSeqBatch) {
+            float dd[kSeqBatch];
+#pragma unroll
+            for (int u = 0; u < kSeqBatch; ++u) {
+                const float d = i0 + u < n ? __fsub_rn(S.x[i0 + u][t], m) : 0.f;
+                dd[u] = __fmul_rn(d, d);
+            }
+#pragma unroll
+            for (int u = 0; u < kSeqBatch; ++u)
+                if (i0 + u < n) v = __fadd_rn(v, dd[u]);
         }
         S.cums[t] = __fdiv_rn(v, (float)n);
     }
@@ -146,9 +173,16 @@ kmeans_kernel(const float *__restrict__ rois, int roi_stride, int n, int K, int 
     for (int c = 1; c < K; ++c) {
         if (t == 0) {                  // np.cumsum in float32 is sequential
             float acc = 0.f;
-            for (int i = 0; i < n; ++i) {
-                acc = __fadd_rn(acc, S.closest[i]);
-                S.cums[i] = acc;
+            for (int i0 = 0; i0 < n; i0 += kSeqBatch) {
+                float v[kSeqBatch];
+#pragma unroll
+                for (int u = 0; u < kSeqBatch; ++u) v[u] = i0 + u < n ? S.closest[i0 + u] : 0.f;
+#pragma unroll
+                for (int u = 0; u < kSeqBatch; ++u)
+                    if (i0 + u < n) {
+                        acc = __fadd_rn(acc, v[u]);
+                        S.cums[i0 + u] = acc;
+                    }
             }
         }
         __syncthreads();
@@ -222,8 +256,19 @@ kmeans_kernel(const float *__restrict__ rois, int roi_stride, int n, int K, int 
             for (int ch = 0; ch < n_chunks; ++ch) {
                 float acc = 0.f, w = 0.f;
                 const int e = min(n, (ch + 1) * kChunk);
-                for (int i = ch * kChunk; i < e; ++i)
-                    if (S.label[i] == j) { acc = __fadd_rn(acc, S.x[i][k]); w += 1.f; }
+                for (int i0 = ch * kChunk; i0 < e; i0 += kSeqBatch) {
+                    float xv[kSeqBatch];
+                    bool in[kSeqBatch];
+#pragma unroll
+                    for (int u = 0; u < kSeqBatch; ++u) {
+                        const bool ok = i0 + u < e;
+                        in[u] = ok && S.label[i0 + u] == j;
+                        xv[u] = ok ? S.x[i0 + u][k] : 0.f;
+                    }
+#pragma unroll
+                    for (int u = 0; u < kSeqBatch; ++u)
+                        if (in[u]) { acc = __fadd_rn(acc, xv[u]); w += 1.f; }
+                }
                 tot = __fadd_rn(tot, acc);
                 wtot += w;
             }

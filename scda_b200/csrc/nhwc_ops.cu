@@ -238,6 +238,41 @@ int grid_for(long long work_items, int threads)
 
 }  // namespace
 
+// dst[c][r] = src[r][c] for a bf16 matrix (leading dimensions in elements): 32 x 32 tiles through shared memory,
+// coalesced both ways.  (torch's strided copy took 90 us for the 512 x 4096 gradient blocks whose transposes
+// feed the weight-gradient GEMMs of fc6 / fc7 — on the chain that the backbone's backward waits for.)
+namespace {
+__global__ void __launch_bounds__(256)
+transpose_bf16_kernel(const __nv_bfloat16 *__restrict__ src, long long lds, __nv_bfloat16 *__restrict__ dst,
+                      long long ldd, int rows, int cols)
+{
+    __shared__ __nv_bfloat16 tile[32][34];
+    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int r = r0 + ty + 8 * k, c = c0 + tx;
+        if (r < rows && c < cols) tile[ty + 8 * k][tx] = src[(long long)r * lds + c];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int c = c0 + ty + 8 * k, r = r0 + tx;
+        if (r < rows && c < cols) dst[(long long)c * ldd + r] = tile[tx][ty + 8 * k];
+    }
+}
+}  // namespace
+
+SCDA_API int scda_transpose_bf16(int rows, int cols, const void *src, long long lds, void *dst, long long ldd,
+                                 cudaStream_t stream)
+{
+    if (rows <= 0 || cols <= 0 || !src || !dst || lds < cols || ldd < rows) return 0;
+    dim3 grid((cols + 31) / 32, (rows + 31) / 32);
+    transpose_bf16_kernel<<<grid, 256, 0, stream>>>((const __nv_bfloat16 *)src, lds, (__nv_bfloat16 *)dst, ldd, rows,
+                                                   cols);
+    return scda_launch_status();
+}
+
 SCDA_API int scda_maxpool2x2_nhwc_bf16(int NB, int H, int W, int C, const void *x, void *y, cudaStream_t stream)
 {
     if (NB <= 0 || H <= 0 || W <= 0 || C <= 0 || !x || !y) return 0;

@@ -477,6 +477,8 @@ class SCDATrainer(object):
             reduce(self.opt_dis)
             self.opt_dis.step_dev()
             cur.wait_stream(helper)
+            from . import timestamps as ts
+            ts.mark("phase 1+2 done")
             self._dec_update()
         else:
             self._seg_dis()
@@ -511,10 +513,14 @@ class SCDATrainer(object):
         finally:
             tc_detector.WGRAD_STREAM = None
         osd.wait_stream(cur)
+        from . import timestamps as ts
+        ts.mark("det head backward done")
         with torch.cuda.stream(osd):
             reduce(self.opt, lo, None)
             self._seg_step_head()
+            ts.mark("head adam done")
         self._seg_det_backward_body()
+        ts.mark("det body backward done")
         reduce(self.opt, 0, lo)
         self._seg_step_body()
         cur.wait_stream(osd)
@@ -542,20 +548,26 @@ class SCDATrainer(object):
         and the forward of phase 4 (hundreds of small cuDNN / elementwise kernels, latency
         bound), the current stream runs the detector backward and Adam (tensor-core / HBM
         bound), and they join before the losses are assembled."""
+        from . import timestamps as ts
         gan_ops.PAIR_STREAMS = bool(self.overlap and self.pair_streams)
+        ts.mark("start")
         self._seg_forward()
+        ts.mark("forward done")
         if self.overlap:
             main = torch.cuda.current_stream()
             side = self._side_stream()
             side.wait_stream(main)
             with torch.cuda.stream(side):
                 self._gan_chain(reduce)
+                ts.mark("gan chain done")
             self._det_chain(reduce)
+            ts.mark("det chain done")
             main.wait_stream(side)
         else:
             self._gan_chain(reduce)
             self._det_chain(reduce)
         self._seg_outputs()
+        ts.mark("end")
 
     def _reduce_fn(self):
         if self.world_size > 1:

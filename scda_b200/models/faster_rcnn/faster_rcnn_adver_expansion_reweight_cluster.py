@@ -153,13 +153,17 @@ class FasterRCNN_AdEx(nn.Module):
             on_dev = bool(input.get('device_clusters', False))
             cluster_fn = cluster_targets_device if on_dev else compute_cluster_targets
 
-            def run_target():
-                """RPN + RCNN on the target image: top-512 proposals, no ground truth (:171-189)
-                (nothing downstream differentiates through this branch: its only product, the
-                cluster features, is detached by compute_cluster_targets — functions/mask.py:234)"""
+            def run_target_backbone():
                 with torch.no_grad():
                     x_gan = self.feature_extractor(target)
                     rpn_pred_cls_gan, rpn_pred_loc_gan = self.rpn(x_gan)
+                return x_gan, rpn_pred_cls_gan, rpn_pred_loc_gan
+
+            def run_target(dense=None):
+                """RPN + RCNN on the target image: top-512 proposals, no ground truth (:171-189)
+                (nothing downstream differentiates through this branch: its only product, the
+                cluster features, is detached by compute_cluster_targets — functions/mask.py:234)"""
+                x_gan, rpn_pred_cls_gan, rpn_pred_loc_gan = dense if dense is not None else run_target_backbone()
                 props_gan = rpn_proposals_device(None, rpn_pred_loc_gan.data, pcfg, image_info,
                                                  fg_scores=rpn_fg_scores(rpn_pred_cls_gan))
                 gan_rows = []
@@ -194,6 +198,12 @@ class FasterRCNN_AdEx(nn.Module):
             tstream = input.get('target_stream') if on_dev else None
             # (measured on B200: forking after the source backbone was issued schedules better than before it)
             early = os.environ.get("SCDA_EARLY_FORK", "0") == "1"
+            # default: BOTH dense backbones back to back on the current stream, then the two latency-bound
+            # proposal / RoI chains side by side.  (With the target's backbone beside the source's chain, the
+            # chain's kernels — 48-150 KB of shared memory each — could not share an SM with the persistent
+            # convolution CTAs and waited for the gaps between them: 2.02 -> 1.8x ms for the forward.)
+            dense_first = tstream is not None and not early and os.environ.get("SCDA_TARGET_DENSE_FIRST", "1") == "1"
+            target_dense = run_target_backbone() if dense_first else None
             if tstream is not None and early:
                 cur_stream = torch.cuda.current_stream()
                 tstream.wait_stream(cur_stream)
@@ -230,9 +240,12 @@ class FasterRCNN_AdEx(nn.Module):
                 if late == "0":
                     tstream.wait_event(after_rpn)
                     with torch.cuda.stream(tstream):
-                        tgt = run_target()
+                        tgt = run_target(target_dense)
+            from ... import timestamps as ts
+            ts.mark("src rpn head done")
             fg = rpn_fg_scores(rpn_pred_cls)
             props = rpn_proposals_device(None, rpn_pred_loc.data, pcfg, image_info, fg_scores=fg)
+            ts.mark("src proposals done")
             if tstream is not None and not early and late == "1":
                 tstream.wait_event(after_rpn)
                 with torch.cuda.stream(tstream):
@@ -240,6 +253,7 @@ class FasterRCNN_AdEx(nn.Module):
             rois, cls_targets, loc_targets, loc_weights = self._train_rois(
                 cfg, props, ground_truth_bboxes, image_info, rng.get('proposal'))
             assert rois.shape[1] == 5
+            ts.mark("src targets done")
             if os.environ.get("SCDA_DEBUG_TARGETS") == "1":
                 self._dbg = dict(orig=(rois, cls_targets, loc_targets, loc_weights),
                                  early=tuple(t.clone() for t in (rois, cls_targets, loc_targets, loc_weights)))
@@ -260,10 +274,12 @@ class FasterRCNN_AdEx(nn.Module):
                 x_cluster_fea, x_center_cluster = cluster_fn(
                     rois, x_fea, N_cluster=input['cluster_num'], threshold=input['threshold'])
 
+            ts.mark("src rcnn+kmeans done")
             if tstream is not None:
                 cur_stream.wait_stream(tstream)
             else:
                 tgt = run_target()
+            ts.mark("target joined")
             x_gan, proposals_gan, enough, x_fea_gan, clusters_gan = tgt
             assert x_gan.size() == x.size(), "gan_features does not match the backbone"
 

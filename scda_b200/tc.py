@@ -161,6 +161,18 @@ def conv3x3_dgrad_nhwc(dy, w_krsc, mask_src=None, out_dtype=torch.bfloat16):
 WGRAD_GEMM = os.environ.get("SCDA_WGRAD_GEMM", "1") != "0"
 
 
+def transpose_bf16(a):
+    """a bf16 [R, C] (row stride >= C) -> contiguous [C, R]"""
+    require_cuda(a)
+    assert a.dtype == torch.bfloat16 and a.dim() == 2 and a.stride(1) == 1
+    R, Cn = a.shape
+    out = torch.empty(Cn, R, dtype=torch.bfloat16, device=a.device)
+    with torch.cuda.device(a.device):
+        check(load().scda_transpose_bf16(R, Cn, a.data_ptr(), a.stride(0), out.data_ptr(), R, stream_ptr(a.device)),
+              "scda_transpose_bf16")
+    return out
+
+
 def linear_wgrad(dy, x, out=None, accumulate=False):
     """dW[Nout, Kin] fp32 (+)= dy[rows, Nout]^T @ x[rows, Kin]."""
     require_cuda(dy, x)
@@ -176,7 +188,7 @@ def linear_wgrad(dy, x, out=None, accumulate=False):
         # store with the next tile's MMAs) took 0.31 ms alone and 1.2 ms inside the iteration; the persistent
         # GEMM kernel (256-wide tiles, double-buffered TMEM accumulators) does it on dY transposed
         # (4 MB: one small copy) as out = dY^T[Nout, rows] . X[rows, Kin].
-        return gemm_nn(dy.t().contiguous(), x, out_dtype=torch.float32, out=out, accumulate=accumulate)
+        return gemm_nn(transpose_bf16(dy), x, out_dtype=torch.float32, out=out, accumulate=accumulate)
     if out is None:
         assert not accumulate
         out = torch.empty(nout, kin, dtype=torch.float32, device=x.device)

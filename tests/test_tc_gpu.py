@@ -185,3 +185,12 @@ def test_linear_wgrad_gemm_form_into_buffer(cuda_lib):
         _close(tc.linear_wgrad(dy, x), out / 2, rtol=1e-3)
     finally:
         tc.WGRAD_GEMM = True
+
+
+def test_transpose_bf16(cuda_lib):
+    import torch
+    from scda_b200 import tc
+    g = torch.Generator(device="cuda").manual_seed(3)
+    for R, C in ((512, 4096), (70, 33), (1, 5)):
+        a = torch.randn(R, C + 3, device="cuda", generator=g).bfloat16()[:, :C]       # row stride > C
+        assert torch.equal(tc.transpose_bf16(a), a.t().contiguous())
