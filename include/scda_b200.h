@@ -213,6 +213,21 @@ int scda_proposal_targets(int cap, int ldb, const float *boxes, const long long 
                           const double *keys_pad, float *rois, long long *labels, float *loc_targets,
                           float *loc_weights, cudaStream_t stream);
 
+/* --- RPN anchor targets ------------------------------------------------- */
+/* compute_anchor_targets for one image (functions/anchor_target.py:16-116): anchors32 float32 / anchors64
+ * float64 [fh*fw*A][4] (the same table, cell-major then anchor), gts float32 [G][5] (zero rows = padding).
+ * IoU (cython_bbox arithmetic), label 0 below neg_thresh, 1 above pos_thresh or where an anchor attains a
+ * ground truth's maximum (>= 0.1, ties kept, the largest ground-truth index wins the match), -1 otherwise; at
+ * most want_pos positives and batch_total labelled anchors survive, the rest go back to -1 — key-driven draws
+ * as scda_proposal_targets (keys_pos / keys_neg [>= fh*fw*A] float64: the members with the SMALLEST keys are
+ * removed).  Outputs: cls_targets int64 [A][fh][fw], loc_targets / loc_masks float32 [4A][fh][fw] (encode in
+ * float64 without +1 widths, utils/bbox_helper.py:60-85), normalizer[0] = max(1, labelled anchors).
+ * G <= 256, fh*fw*A <= 100 000.  One launch, no host synchronisation. */
+int scda_anchor_targets(int A, int fh, int fw, const float *anchors32, const double *anchors64, int G,
+                        const float *gts, float neg_thresh, float pos_thresh, int want_pos, int batch_total,
+                        const double *keys_pos, const double *keys_neg, long long *cls_targets, float *loc_targets,
+                        float *loc_masks, long long *normalizer, cudaStream_t stream);
+
 /* crops around the cluster centres (tools/faster_rcnn_train_val.py:411-438, 528-557): K windows of R x R pixels,
  * corner = clamp(int(centre) - R/2, 0, size - R) per axis, gathered from image [C, H, W] fp32 into
  * out [K, C, R, R]; centers [K][2] = (x, y) fp32 on the device.  R even, R <= H, W. */

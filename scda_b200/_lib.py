@@ -109,6 +109,7 @@ SIGNATURES = {
     "scda_transpose_bf16": (_i, [_i, _i, _p, C.c_longlong, _p, C.c_longlong, _p]),
     "scda_proposal_targets": (_i, [_i, _i, _p, _p, _i, _p, _i, _f, _f, _f, _f, _f, _i, _i, _i, _i, _p, _p, _f,
                                    _p, _p, _p, _p, _p, _p, _p, _p]),
+    "scda_anchor_targets": (_i, [_i, _i, _i, _p, _p, _i, _p, _f, _f, _i, _i, _p, _p, _p, _p, _p, _p, _p]),
     "scda_crop_regions": (_i, [_i, _i, _i, _i, _i, _p, _p, _p, _p]),
     "scda_conv3x3_set_plan": (_i, [_i, _i, _i]),
     "scda_conv3x3_wgrad_set_form": (_i, [_i]),

@@ -304,3 +304,241 @@ SCDA_API int scda_proposal_targets(int cap, int ldb, const float *boxes, const l
                                                      labels, loc_targets, loc_weights);
     return scda_launch_status();
 }
+
+// ---------------------------------------------------------------------------------------------------
+// RPN anchor targets as ONE kernel: compute_anchor_targets of the reference (functions/anchor_target.py:16-116)
+// for one image.  Reference: numpy on the host — cython IoU of the K*A anchors with the ground truth (:51),
+// per-anchor maximum / arg-maximum, per-ground-truth maximum with ties kept and maxima below 0.1 dropped
+// (:59-65), labels -1 / 0 / 1 (:69-79), np.random.choice sub-sampling to 128 positives and 256 in all (:82-94),
+// encode without +1 widths in float64 (utils/bbox_helper.py:60-85), three H2D copies.  The tensor-op form
+// (functions/anchor_target.py here, kept for batches of several images) is ~150 launches beside the backbone.
+//
+// One CTA of 1024 threads; thread t owns the anchors [t * per, (t + 1) * per) so that block scans give ordered
+// ranks.  The IoU row of an anchor (G <= 256 values) is recomputed in each of the two passes that need it
+// instead of being stored.  Draws follow functions/_sampling.py `drop`: candidate j (j-th member in ascending
+// index order) owns keys[j]; the (count - keep) members with the SMALLEST keys are removed (ties: lower rank
+// first) — an 8-pass radix selection of the cut-off key over keys[0 .. count), no sort.
+namespace {
+
+constexpr int kAT = 1024;
+
+struct AnchorParams {
+    int KA, A, fh, fw, G, want_pos, batch_total;
+    float neg_thresh, pos_thresh, gt_floor;
+};
+
+// exact cut of `drop`: the n_remove smallest (key, rank) pairs among keys[0 .. count).  Returns the cut-off key T
+// (sortable form), *n_lt = number of keys < T; the first (n_remove - *n_lt) ranks with key == T are removed too.
+__device__ unsigned long long select_smallest(const double *__restrict__ keys, int count, int n_remove, int *s_hist,
+                                              int *s_misc, int *n_lt)
+{
+    const int tid = threadIdx.x, lane = tid & 31;
+    unsigned long long prefix = 0ull, mask = 0ull;
+    int need = n_remove, below = 0;                  // need: rank (from the bottom, 1-based) inside the matching keys
+    for (int shift = 56; shift >= 0; shift -= 8) {
+        for (int d = tid; d < 256; d += kAT) s_hist[d] = 0;
+        __syncthreads();
+        for (int j = tid; j < count; j += kAT) {
+            const unsigned long long k = sortable64(keys[j]);
+            if ((k & mask) == prefix) atomicAdd(&s_hist[(int)((k >> shift) & 255ull)], 1);
+        }
+        __syncthreads();
+        if (tid < 32) {
+            int mine = 0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) mine += s_hist[8 * lane + q];
+            int incl = mine;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            const unsigned hit = __ballot_sync(0xffffffffu, incl >= need);
+            const int first = __ffs(hit) - 1;
+            if (lane == first) {
+                int under = incl - mine;
+                int d = 8 * lane;
+                for (int q = 0; q < 8; ++q, ++d) {
+                    const int h = s_hist[d];
+                    if (under + h >= need) break;
+                    under += h;
+                }
+                s_misc[0] = d;
+                s_misc[1] = under;
+            }
+        }
+        __syncthreads();
+        const int d = s_misc[0], under = s_misc[1];
+        prefix |= (unsigned long long)d << shift;
+        mask |= 255ull << shift;
+        need -= under;
+        below += under;
+        __syncthreads();
+    }
+    *n_lt = below;
+    return prefix;
+}
+
+__global__ void __launch_bounds__(kAT)
+anchor_targets_kernel(AnchorParams p, const float *__restrict__ anchors32, const double *__restrict__ anchors64,
+                      const float *__restrict__ gts, const double *__restrict__ keys_pos,
+                      const double *__restrict__ keys_neg, long long *__restrict__ cls_targets,
+                      float *__restrict__ loc_targets, float *__restrict__ loc_masks,
+                      long long *__restrict__ normalizer)
+{
+    extern __shared__ __align__(16) unsigned char a_smem[];
+    signed char *s_lab = reinterpret_cast<signed char *>(a_smem);                   // [KA]
+    unsigned char *s_arg = reinterpret_cast<unsigned char *>(s_lab + p.KA);         // [KA] matched ground truth
+    __shared__ float4 s_gt[kMaxG];
+    __shared__ int s_gtmax[kMaxG];                   // float bits of the per-ground-truth maximum (IoU >= 0)
+    __shared__ int s_hist[256];
+    __shared__ int s_w[33];
+    __shared__ int s_misc[2];
+    const int tid = threadIdx.x;
+    for (int g = tid; g < p.G; g += kAT) {
+        const float *q = gts + 5 * g;
+        s_gt[g] = make_float4(q[0], q[1], q[2], q[3]);
+        s_gtmax[g] = 0;
+    }
+    __syncthreads();
+    const int per = (p.KA + kAT - 1) / kAT;
+    const int i0 = min(p.KA, tid * per), i1 = min(p.KA, i0 + per);
+    // pass 1: per-ground-truth maxima
+    for (int i = i0; i < i1; ++i) {
+        const float4 a = __ldg(reinterpret_cast<const float4 *>(anchors32) + i);
+        for (int g = 0; g < p.G; ++g) {
+            const float v = iou_cython(a, s_gt[g]);
+            if (v > 0.f) atomicMax(&s_gtmax[g], __float_as_int(v));
+        }
+    }
+    __syncthreads();
+    // pass 2: labels
+    int cp = 0, cn = 0;
+    for (int i = i0; i < i1; ++i) {
+        const float4 a = __ldg(reinterpret_cast<const float4 *>(anchors32) + i);
+        float mx = -FLT_MAX;
+        int am = 0, last_hit = -1;
+        for (int g = 0; g < p.G; ++g) {
+            const float v = iou_cython(a, s_gt[g]);
+            if (v > mx) { mx = v; am = g; }
+            float gm = __int_as_float(s_gtmax[g]);
+            if (gm < p.gt_floor) gm = -1.f;
+            if (v == gm) last_hit = g;               // duplicates resolve to the largest g (:62-65)
+        }
+        int lab = -1;
+        if (mx < p.neg_thresh) lab = 0;
+        if (last_hit >= 0) lab = 1;
+        if (mx > p.pos_thresh) lab = 1;
+        s_lab[i] = (signed char)lab;
+        s_arg[i] = (unsigned char)(last_hit >= 0 ? last_hit : am);
+        cp += lab == 1;
+        cn += lab == 0;
+    }
+    int count_pos, count_neg;
+    int base_pos = block_scan_excl<kAT>(cp, s_w, &count_pos);
+    // positives: keep at most want_pos
+    int n_pos = count_pos;
+    if (count_pos > p.want_pos) {
+        int n_lt;
+        const int n_remove = count_pos - p.want_pos;
+        const unsigned long long T = select_smallest(keys_pos, count_pos, n_remove, s_hist, s_misc, &n_lt);
+        // ties on T: the first (n_remove - n_lt) of them in rank order go
+        int eq_mine = 0, r = base_pos;
+        for (int i = i0; i < i1; ++i)
+            if (s_lab[i] == 1) { eq_mine += sortable64(keys_pos[r]) == T; ++r; }
+        int eq_total;
+        int eq_before = block_scan_excl<kAT>(eq_mine, s_w, &eq_total);
+        const int quota = n_remove - n_lt;
+        r = base_pos;
+        for (int i = i0; i < i1; ++i)
+            if (s_lab[i] == 1) {
+                const unsigned long long k = sortable64(keys_pos[r]);
+                if (k < T || (k == T && eq_before++ < quota)) { s_lab[i] = -1; }
+                ++r;
+            }
+        n_pos = p.want_pos;
+    }
+    int base_neg = block_scan_excl<kAT>(cn, s_w, &count_neg);
+    const int want_neg = p.batch_total - n_pos;
+    int n_neg = count_neg;
+    if (count_neg > want_neg) {
+        int n_lt;
+        const int n_remove = count_neg - want_neg;
+        const unsigned long long T = select_smallest(keys_neg, count_neg, n_remove, s_hist, s_misc, &n_lt);
+        int eq_mine = 0, r = base_neg;
+        for (int i = i0; i < i1; ++i)
+            if (s_lab[i] == 0) { eq_mine += sortable64(keys_neg[r]) == T; ++r; }
+        int eq_total;
+        int eq_before = block_scan_excl<kAT>(eq_mine, s_w, &eq_total);
+        const int quota = n_remove - n_lt;
+        r = base_neg;
+        for (int i = i0; i < i1; ++i)
+            if (s_lab[i] == 0) {
+                const unsigned long long k = sortable64(keys_neg[r]);
+                if (k < T || (k == T && eq_before++ < quota)) { s_lab[i] = -1; }
+                ++r;
+            }
+        n_neg = want_neg;
+    }
+    __syncthreads();
+    if (tid == 0) normalizer[0] = max(1, n_pos + n_neg);
+    // outputs in their [A, fh, fw] / [4A, fh, fw] order: consecutive threads write consecutive addresses
+    const int plane = p.fh * p.fw;
+    for (int o = tid; o < p.A * plane; o += kAT) {
+        const int a = o / plane, cell = o - a * plane;
+        const int i = cell * p.A + a;
+        const int lab = s_lab[i];
+        cls_targets[o] = (long long)lab;
+        float t[4] = {0.f, 0.f, 0.f, 0.f};
+        if (lab == 1) {
+            // utils/bbox_helper.py:60-85: anchor in float64, ground-truth extents formed in float32 first
+            const double ax1 = anchors64[4 * i], ay1 = anchors64[4 * i + 1], ax2 = anchors64[4 * i + 2],
+                         ay2 = anchors64[4 * i + 3];
+            const float4 q = s_gt[s_arg[i]];
+            const double bw = __dsub_rn(ax2, ax1), bh = __dsub_rn(ay2, ay1);
+            const double bx = __dadd_rn(ax1, ax2) / 2.0, by = __dadd_rn(ay1, ay2) / 2.0;
+            const float gw = __fsub_rn(q.z, q.x), gh = __fsub_rn(q.w, q.y);
+            const float gx = __fmul_rn(__fadd_rn(q.x, q.z), 0.5f), gy = __fmul_rn(__fadd_rn(q.y, q.w), 0.5f);
+            t[0] = (float)__ddiv_rn(__dsub_rn((double)gx, bx), bw);
+            t[1] = (float)__ddiv_rn(__dsub_rn((double)gy, by), bh);
+            t[2] = (float)log(__ddiv_rn((double)gw, bw));
+            t[3] = (float)log(__ddiv_rn((double)gh, bh));
+        }
+        const float m = lab == 1 ? 1.f : 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            loc_targets[(long long)(a * 4 + k) * plane + cell] = t[k];
+            loc_masks[(long long)(a * 4 + k) * plane + cell] = m;
+        }
+    }
+}
+
+}  // namespace
+
+SCDA_API int scda_anchor_targets(int A, int fh, int fw, const float *anchors32, const double *anchors64, int G,
+                                 const float *gts, float neg_thresh, float pos_thresh, int want_pos,
+                                 int batch_total, const double *keys_pos, const double *keys_neg,
+                                 long long *cls_targets, float *loc_targets, float *loc_masks, long long *normalizer,
+                                 cudaStream_t stream)
+{
+    if (A <= 0 || fh <= 0 || fw <= 0 || G <= 0 || G > kMaxG || want_pos < 0 || batch_total < want_pos) return 0;
+    if (!anchors32 || !anchors64 || !gts || !keys_pos || !keys_neg || !cls_targets || !loc_targets || !loc_masks ||
+        !normalizer || (uintptr_t)anchors32 % 16)
+        return 0;
+    const long long KA = (long long)A * fh * fw;
+    if (KA > 100000) return 0;
+    const size_t smem = 2 * (size_t)KA + 16;
+    static size_t attr = 0;
+    if (smem > 32 * 1024 && smem > attr) {
+        cudaError_t e = cudaFuncSetAttribute(anchor_targets_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)smem);
+        if (e != cudaSuccess) return -(int)e;
+        attr = smem;
+    }
+    AnchorParams p;
+    p.KA = (int)KA; p.A = A; p.fh = fh; p.fw = fw; p.G = G; p.want_pos = want_pos; p.batch_total = batch_total;
+    p.neg_thresh = neg_thresh; p.pos_thresh = pos_thresh; p.gt_floor = 0.1f;
+    anchor_targets_kernel<<<1, kAT, smem, stream>>>(p, anchors32, anchors64, gts, keys_pos, keys_neg, cls_targets,
+                                                   loc_targets, loc_masks, normalizer);
+    return scda_launch_status();
+}

@@ -10,12 +10,29 @@ Same signature and outputs as the reference, except that `loc_normalizer` is ret
 0-dim device tensor instead of a Python int (it is only ever used as a divisor,
 models/faster_rcnn/faster_rcnn_adver_expansion_reweight_cluster.py:54-55).
 """
+import os
+
 import torch
 
+from .._lib import check, load, stream_ptr
 from ..extensions._cython_bbox.cython_bbox import bbox_overlaps_device
 from ..utils import anchor_helper
 from ..utils.bbox_helper import encode_t
 from . import _sampling
+
+
+_FORCE_TENSOR_OPS = os.environ.get('SCDA_AT_TENSOR_OPS', '0') == '1'      # debugging switch
+_A32 = {}
+
+
+def _anchors32(anchors64):
+    """float32 copy of the (cached) float64 anchor table, made once per table"""
+    key = (anchors64.data_ptr(), tuple(anchors64.shape))
+    ent = _A32.get(key)
+    if ent is None or ent[0] is not anchors64:
+        ent = (anchors64, anchors64.float().contiguous())
+        _A32[key] = ent
+    return ent[1]
 
 
 def compute_anchor_targets(feature_size, cfg, ground_truth_bboxes, image_info,
@@ -43,7 +60,24 @@ def compute_anchor_targets(feature_size, cfg, ground_truth_bboxes, image_info,
     gts = ground_truth_bboxes.float().contiguous()
     anchors64 = anchor_helper.anchors_device(fh, fw, cfg['anchor_ratios'], cfg['anchor_scales'],
                                              cfg['anchor_stride'], dev)
-    anchors32 = anchors64.float().contiguous()
+    anchors32 = _anchors32(anchors64)
+    G = gts.shape[1]
+    if B == 1 and 0 < G <= 256 and KA <= 100000 and gts.shape[2] >= 5 and not _FORCE_TENSOR_OPS:
+        # one kernel (csrc/target_ops.cu); the two key vectors are the draws of the reference, in its order
+        k_pos, k_neg = rng.uniform(KA, dev), rng.uniform(KA, dev)
+        g5 = gts[0] if gts.shape[2] == 5 else gts[0, :, :5].contiguous()
+        cls_targets = torch.empty(1, A, fh, fw, dtype=torch.int64, device=dev)
+        loc_targets = torch.empty(1, A * 4, fh, fw, dtype=torch.float32, device=dev)
+        loc_masks = torch.empty(1, A * 4, fh, fw, dtype=torch.float32, device=dev)
+        normalizer = torch.empty((), dtype=torch.int64, device=dev)
+        with torch.cuda.device(dev):
+            check(load().scda_anchor_targets(
+                A, fh, fw, anchors32.data_ptr(), anchors64.data_ptr(), G, g5.data_ptr(),
+                float(cfg['negative_iou_thresh']), float(cfg['positive_iou_thresh']),
+                int(cfg['positive_percent'] * cfg['rpn_batch_size']), int(cfg['rpn_batch_size']),
+                k_pos.data_ptr(), k_neg.data_ptr(), cls_targets.data_ptr(), loc_targets.data_ptr(),
+                loc_masks.data_ptr(), normalizer.data_ptr(), stream_ptr(dev)), "scda_anchor_targets")
+        return cls_targets, loc_targets, loc_masks, normalizer
 
     labels_all, argmax_all = [], []
     for b in range(B):
