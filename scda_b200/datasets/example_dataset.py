@@ -92,7 +92,7 @@ def _decode(path):
     img = Image.open(path)
     if img.mode != 'RGB':
         img = img.convert('RGB')
-    return np.asarray(img, dtype=np.uint8)
+    return np.array(img, dtype=np.uint8)            # a writable copy (torch.as_tensor warns on read-only views)
 
 
 def prepare_image(pixels_hwc_u8, new_h, new_w, flip=False, mode="nearest", device="cuda", out=None):
