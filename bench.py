@@ -415,7 +415,16 @@ def main():
     ap.add_argument("--no-parity-line", action="store_true", help="skip the bf16x3 sub-measurement")
     ap.add_argument("--no-graph-collectives", action="store_true",
                     help="world > 1: cut the graph at the all-reduces instead of capturing NCCL")
+    ap.add_argument("--config", type=int, choices=[2, 3, 5], default=None,
+                    help="BASELINE.json configs[1] / [2] / [4] instead of the headline configs[3]: forward-only "
+                         "per-stage us / detector-only train step / NMS + IoU sweep (one JSON line, 1 GPU)")
     args = ap.parse_args()
+    if args.config is not None:
+        sys.path.insert(0, os.path.join(ROOT, "scripts"))
+        import configbench
+        torch.cuda.set_device(0)
+        print(json.dumps(configbench.run(args.config)), flush=True)
+        return
     if args.impl == "reference":
         reference_arm(args)
         return
