@@ -182,10 +182,16 @@ def roofline_probe(dev, x3=False):
     hbm, tf, tf_sus, src = peaks()
     xs, ws, bs = [], [], []
     mult = 3 if x3 else 1
+    from scda_b200 import tc_detector
+    direct = tc_detector.FIRST_DIRECT and not x3       # conv1_1 reads the fp32 NCHW image (csrc/conv_first.cu)
     for cin, cout, h, w in VGG_CONVS:
-        cp = max(cin, 64) * mult
-        xs.append(torch.randn(1, h, w, cp, device=dev).bfloat16())
-        ws.append((torch.randn(cout, 3, 3, cp, device=dev) / (9 * cp) ** 0.5).bfloat16())
+        if cin < 64 and direct:
+            xs.append(torch.randn(1, cin, h, w, device=dev))
+            ws.append((torch.randn(cout, 3, 3, cin, device=dev) / (9 * cin) ** 0.5).bfloat16())
+        else:
+            cp = max(cin, 64) * mult
+            xs.append(torch.randn(1, h, w, cp, device=dev).bfloat16())
+            ws.append((torch.randn(cout, 3, 3, cp, device=dev) / (9 * cp) ** 0.5).bfloat16())
         bs.append(torch.zeros(cout, device=dev))
     flops = sum(2.0 * h * w * cin * cout * 9 for cin, cout, h, w in VGG_CONVS)
     flush = torch.zeros(64 * 1024 * 1024, device=dev)
@@ -195,7 +201,10 @@ def roofline_probe(dev, x3=False):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         for x, w, bias in zip(xs, ws, bs):
-            tc.conv3x3_nhwc(x, w, bias, relu=True, out_dtype=torch.float32 if x3 else torch.bfloat16)
+            if x.dtype == torch.float32:
+                tc.conv3x3_first_nchw(x, w, bias, relu=True)
+            else:
+                tc.conv3x3_nhwc(x, w, bias, relu=True, out_dtype=torch.float32 if x3 else torch.bfloat16)
         b.record()
         b.synchronize()
         if i >= 3:
@@ -207,6 +216,7 @@ def roofline_probe(dev, x3=False):
             "traffic_source": None if x3 else NCU_TRAFFIC_SOURCE,
             "kernel": "conv_halo_kernel (tcgen05 + TMA 3x3 convolution, input halo staged once for the nine taps, "
                       "+ bias + ReLU), 13 backbone launches"
+                      + (" (conv1_1 = conv_first_kernel: im2col in shared memory from the fp32 NCHW image)" if direct else "")
                       + (" on hi/lo split operands (3 bf16 MMAs per fp32 product), fp32 output" if x3 else ""),
             "peak_source": src + " (MEASURED_PEAKS.json bf16_tflops, burst: kernels timed alone)"
                            + (" / 3: three tensor-core products per algorithmic product" if x3 else ""),
@@ -278,7 +288,7 @@ def our_arm(args):
     cfg = load_cfg()
     tr = build_trainer(cfg, world_size=world, seed=0, use_graphs=not args.no_graphs,
                        overlap=not args.no_overlap,
-                       graph_collectives=False if args.no_graph_collectives else None,
+                       graph_collectives=False if args.no_graph_collectives else (True if args.graph_collectives else None),
                        force_cut=args.force_cut)
     if world > 1:
         from scda_b200.utils.distributed_utils import broadcast_params
@@ -395,7 +405,14 @@ def our_arm(args):
             line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
         print(json.dumps(line), flush=True)
     if world > 1:
+        # captured NCCL kernels pin their communicator: drop the graphs first; and never let a stuck
+        # teardown hold the launcher (the line is already printed)
+        if tr is not None:
+            tr.close()
+        threading.Timer(45.0, lambda: os._exit(0)).start()
+        dist.barrier()
         dist.destroy_process_group()
+        os._exit(0)
 
 
 def main():
@@ -415,6 +432,8 @@ def main():
     ap.add_argument("--no-parity-line", action="store_true", help="skip the bf16x3 sub-measurement")
     ap.add_argument("--no-graph-collectives", action="store_true",
                     help="world > 1: cut the graph at the all-reduces instead of capturing NCCL")
+    ap.add_argument("--graph-collectives", action="store_true",
+                    help="world > 1: capture the NCCL all-reduces inside the one iteration graph")
     ap.add_argument("--config", type=int, choices=[2, 3, 5], default=None,
                     help="BASELINE.json configs[1] / [2] / [4] instead of the headline configs[3]: forward-only "
                          "per-stage us / detector-only train step / NMS + IoU sweep (one JSON line, 1 GPU)")

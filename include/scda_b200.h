@@ -302,12 +302,26 @@ int scda_conv3x3_dgrad_bf16_nhwc(int NB, int H, int W, int Cin, int Cout, const 
                                  const void *w_krsc, void *dx, int flags, const void *mask_src,
                                  cudaStream_t stream);
 
+/* First convolution of the backbone straight from the fp32 NCHW image (models/faster_rcnn/
+ * vgg_adver_expansion_cluster.py:101-114, features[0] + ReLU): y[n,h,w,co] = relu?(bias[co] +
+ * sum x[n,ci,h+kh-1,w+kw-1] * w[co][kh][kw][ci]).  x fp32 [NB,Cin,H,W] (Cin <= 3; rounded to bf16 as it is
+ * staged), w bf16 [64][3][3][Cin], y bf16 NHWC [NB,H,W,64], fp32 accumulation.  The im2col exists only in
+ * shared memory (csrc/conv_first.cu); Cout must be 64. */
+int scda_conv3x3_first_nchw(int NB, int H, int W, int Cin, int Cout, const float *x, const void *w_krsc,
+                            const float *bias, void *y, int relu, cudaStream_t stream);
+
 /* Tuning / test hook for the two 3x3 entry points above: halo = 1 stages the input tile once for
  * all nine taps (csrc/conv_halo.cu, the default), 0 = one TMA box per tap (csrc/gemm_tc.cu);
  * block_n (0 auto | 64 | 128) and sub_tiles (0 auto | 1 | 2) force the halo kernel's tile plan.
  * A negative argument leaves that setting unchanged.  Results are identical up to fp32
  * summation order.  Process-wide, not synchronised with concurrent launches. */
 int scda_conv3x3_set_plan(int halo, int block_n, int sub_tiles);
+
+/* CTA-pair form of the halo kernel (tcgen05 cta_group::2: two SMs run one 256-pixel x block_n MMA per
+ * k-step and each stages half of every weight tile): -1 = the measured per-layer plan (default), 0 = never,
+ * 1 = wherever legal (stride 1; forward block_n 64 | 128 | 256, data gradient 128 | 256).  With pairs a
+ * block_n of 256 may be forced through scda_conv3x3_set_plan.  Same results up to fp32 summation order. */
+int scda_conv3x3_set_pair(int mode);
 
 /* C[M,N] = A[M,K] . B[K,N] + bias: B row-major with N contiguous (the data gradient of
  * nn.Linear, dX = dY . W, reads W[out,in] this way; no transposed weight copy is kept). */

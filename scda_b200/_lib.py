@@ -111,7 +111,9 @@ SIGNATURES = {
                                    _p, _p, _p, _p, _p, _p, _p, _p]),
     "scda_anchor_targets": (_i, [_i, _i, _i, _p, _p, _i, _p, _f, _f, _i, _i, _p, _p, _p, _p, _p, _p, _p]),
     "scda_crop_regions": (_i, [_i, _i, _i, _i, _i, _p, _p, _p, _p]),
+    "scda_conv3x3_first_nchw": (_i, [_i, _i, _i, _i, _i, _p, _p, _p, _p, _i, _p]),
     "scda_conv3x3_set_plan": (_i, [_i, _i, _i]),
+    "scda_conv3x3_set_pair": (_i, [_i]),
     "scda_conv3x3_wgrad_set_form": (_i, [_i]),
     "scda_adam_step": (_i, [_p, _p, _p, _p, _p, C.c_longlong, _i, _f, _f, _f, _f, _f, _f, _p, _p]),
 }

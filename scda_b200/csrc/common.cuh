@@ -16,7 +16,7 @@ static inline int scda_launch_status()
     return e == cudaSuccess ? 1 : -(int)e;
 }
 
-static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+__host__ __device__ static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 // Streaming 128-bit store: outputs that are written once and not re-read by
 // this kernel should not displace the L2-resident feature map.

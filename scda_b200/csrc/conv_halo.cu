@@ -68,13 +68,13 @@ struct HaloAStages {
     static constexpr int value = kBlockN == 64 ? 3 : 2;
 };
 
-template <int kBlockN, int kSub, int kBStages>
+template <int kBlockN, int kSub, int kBStages, int kCluster = 1>
 struct HaloSmem {
-    static constexpr int kAStages = HaloAStages<kBlockN>::value;
+    static constexpr int kAStages = kCluster == 2 ? 3 : HaloAStages<kBlockN>::value;
     static constexpr int kHaloW = kSubW * kSub + 2;
     static constexpr int kABox = kHaloW * kHaloH * 128;                 // bytes one halo box delivers
     static constexpr int kABytes = (kABox + 1023) / 1024 * 1024;
-    static constexpr int kBBytes = kBlockN * 128;
+    static constexpr int kBBytes = kBlockN / kCluster * 128;            // a CTA pair holds half of the weight tile each
     static constexpr int kBOffset = kAStages * kABytes;
     static constexpr int kBarOffset = kBOffset + kBStages * kBBytes;
     static constexpr int kNumBars = 2 * kAStages + 2 * kBStages + 4;
@@ -83,14 +83,18 @@ struct HaloSmem {
 
 struct HaloTile {
     int n0, img, h0, w0;
+    bool valid;                  // (pair) false for the phantom second tile of an odd tile count
 };
 
-template <int kBlockN, int kSub>
-__device__ __forceinline__ HaloTile halo_tile(const HaloParams &p, int tile)
+// tile = tile GROUP index: kCluster consecutive pixel tiles (one per CTA of the cluster) x one N tile
+template <int kBlockN, int kSub, int kCluster = 1>
+__device__ __forceinline__ HaloTile halo_tile(const HaloParams &p, int tile, int rank = 0)
 {
     HaloTile t;
-    const int m_tile = tile / p.n_tiles;
-    t.n0 = (tile - m_tile * p.n_tiles) * kBlockN;
+    const int m_group = tile / p.n_tiles;
+    const int m_tile = m_group * kCluster + rank;
+    t.valid = m_tile < p.m_tiles;
+    t.n0 = (tile - m_group * p.n_tiles) * kBlockN;
     const int per_img = p.tiles_h * p.tiles_w;
     t.img = m_tile / per_img;
     const int r = m_tile - t.img * per_img;
@@ -99,26 +103,31 @@ __device__ __forceinline__ HaloTile halo_tile(const HaloParams &p, int tile)
     return t;
 }
 
-template <int kBlockN, int kSub, int kSpec, bool kS2Dgrad = false>
+template <int kBlockN, int kSub, int kSpec, bool kS2Dgrad = false, int kCluster = 1>
 __device__ __forceinline__ void halo_epilogue(const HaloParams &p, const EpiParams &e, uint32_t tmem_base,
-                                              uint32_t bar_tfull, uint32_t bar_tempty, int ew, int lane)
+                                              uint32_t bar_tfull, uint32_t bar_tempty, int ew, int lane,
+                                              int rank = 0)
 {
     constexpr uint32_t kAccCols = kSub * kBlockN;
+    constexpr bool kPair = kCluster == 2;
     const int q = ew & 3;                 // TMEM lane quarter this warp may read
     const int sub = ew >> 2;
-    const int total_tiles = p.m_tiles * p.n_tiles;
+    const int total_tiles = ceil_div(p.m_tiles, kCluster) * p.n_tiles;
+    const int first_tile = blockIdx.x / kCluster, tile_step = gridDim.x / kCluster;
+    // (pair) the MMA lane that waits for the drained accumulators lives in the leader CTA
+    const uint32_t tempty_dst = kPair ? map_to_cta(bar_tempty, 0) : bar_tempty;
     const bool aligned = ((reinterpret_cast<uintptr_t>(e.out) | reinterpret_cast<uintptr_t>(e.bias) |
                            reinterpret_cast<uintptr_t>(e.mask_src)) & 15) == 0;
     const bool vec_ok = (e.ldc % 8 == 0) && aligned;
     uint32_t ti = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
-        const HaloTile t = halo_tile<kBlockN, kSub>(p, tile);
+    for (int tile = first_tile; tile < total_tiles; tile += tile_step, ++ti) {
+        const HaloTile t = halo_tile<kBlockN, kSub, kCluster>(p, tile, rank);
         const uint32_t acc = ti & 1;
         mbar_wait(bar_tfull + acc * 8, (ti >> 1) & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int row = q * 32 + lane;
         const int h = t.h0 + (row >> 3), w = t.w0 + (row & 7) + kSubW * sub;
-        const bool row_ok = h < p.H && w < p.W;
+        const bool row_ok = h < p.H && w < p.W && t.valid;
         long long out_row = ((long long)t.img * p.H + h) * p.W + w;
         int col_base = t.n0;
         if (kS2Dgrad) {
@@ -136,7 +145,10 @@ __device__ __forceinline__ void halo_epilogue(const HaloParams &p, const EpiPara
                 // this warp's share of the accumulator is in registers: hand the buffer back
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 __syncwarp();
-                if (lane == 0) mbar_arrive(bar_tempty + acc * 8);
+                if (lane == 0) {
+                    if (kPair) mbar_arrive_cluster(tempty_dst + acc * 8);
+                    else mbar_arrive(bar_tempty + acc * 8);
+                }
             }
             if (row_ok) epilogue_chunk<kSpec>(v, e, out_row, col_base + c0, vec_ok);
         }
@@ -149,12 +161,24 @@ __device__ __forceinline__ void halo_epilogue(const HaloParams &p, const EpiPara
 // the row dimension with element stride 2, so the halo box of virtual channel block (py, 64 of 2C) is the
 // phase image's tile, zero-filled outside; the weights are laid out [Cout][3x3 taps][4C] with the taps of the
 // two offsets {-1, 0} (tap_mask) — taps that are structurally zero are neither loaded nor multiplied.
-template <int kBlockN, int kSub, bool kBMn, int kBStages, bool kS2 = false>
+//
+// kCluster == 2 is the CTA-PAIR form (tcgen05 cta_group::2, the protocol of tc_gemm_kernel): the two CTAs of a
+// cluster own two consecutive pixel tiles of the same N tile and execute ONE 256 x kBlockN MMA per k-step.  Each
+// CTA stages its own halo and only HALF of every weight tile; the tensor core of each SM reads the other half out
+// of the peer's shared memory.  Bytes staged per SM per 128 px x 256 ch x 64 k x 9 taps of work: 334 KB as two
+// lone 128-wide tiles, 167 KB as one paired 256-wide tile — under the ~42 B/clk an SM can pull through the L2
+// fabric with every SM loading, which is what held the 256 / 512-channel layers at 65-75 % tensor pipe.
+// Both producers complete their bytes on the LEADER's full barriers; only the leader's MMA lane issues; its
+// commits arrive on the empty / accumulator-full barriers of BOTH CTAs; the epilogue warps of both CTAs arrive
+// on the leader's accumulator-empty barrier.
+template <int kBlockN, int kSub, bool kBMn, int kBStages, bool kS2 = false, int kCluster = 1>
 __global__ void __launch_bounds__(128 + 128 * kSub, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                  const HaloParams p)
 {
-    using L = HaloSmem<kBlockN, kSub, kBStages>;
+    static_assert(kCluster == 1 || (kCluster == 2 && !kS2), "one CTA or a CTA pair (stride-1 form)");
+    constexpr bool kPair = kCluster == 2;
+    using L = HaloSmem<kBlockN, kSub, kBStages, kCluster>;
     constexpr int kAStages = L::kAStages;
     constexpr bool kBRes = kBStages == 9;        // nine slots = the resident-weights form
     extern __shared__ uint8_t smem_raw[];
@@ -170,7 +194,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     constexpr uint32_t kAccCols = kSub * kBlockN;        // TMEM columns of one accumulator set
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int total_tiles = p.m_tiles * p.n_tiles;
+    const int rank = kPair ? (int)cluster_ctarank() : 0;
+    const bool leader = rank == 0;
+    const int total_tiles = ceil_div(p.m_tiles, kCluster) * p.n_tiles;         // tile groups
+    const int first_tile = blockIdx.x / kCluster, tile_step = gridDim.x / kCluster;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
@@ -187,31 +214,44 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(bar_tfull + a * 8, 1);
-            mbar_init(bar_tempty + a * 8, 4 * kSub);     // one arrival per epilogue warp
+            mbar_init(bar_tempty + a * 8, 4 * kSub * kCluster);     // one arrival per epilogue warp (of the pair)
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
-                         smem_u32((const void *)tmem_slot)), "r"(2u * kAccCols) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (kPair) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                             smem_u32((const void *)tmem_slot)), "r"(2u * kAccCols) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                             smem_u32((const void *)tmem_slot)), "r"(2u * kAccCols) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (kPair) cluster_sync_all();       // both CTAs' barriers exist before any remote traffic
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
+    // the barriers the loads complete on: this CTA's, or (pair) the leader's
+    const uint32_t afull_dst = kPair ? map_to_cta(bar_afull, 0) : bar_afull;
+    const uint32_t bfull_dst = kPair ? map_to_cta(bar_bfull, 0) : bar_bfull;
 
     if (warp == 3) {
         // ---- A producer: one halo box per (tile, channel block)
         if (elect_one()) {
             uint32_t it = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const HaloTile t = halo_tile<kBlockN, kSub>(p, tile);
+            for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
+                const HaloTile t = halo_tile<kBlockN, kSub, kCluster>(p, tile, rank);
                 for (int cb = 0; cb < p.cblocks; ++cb, ++it) {
                     const int s = it % kAStages;
                     mbar_wait(bar_aempty + s * 8, ((it / kAStages) & 1) ^ 1);
-                    mbar_expect_tx(bar_afull + s * 8, L::kABox);
-                    if (kS2 && !kBMn) {
+                    if (leader) mbar_expect_tx(bar_afull + s * 8, L::kABox * kCluster);
+                    if (kPair) {
+                        tma_load_4d_pair(base + s * L::kABytes, &map_a, afull_dst + s * 8, cb * 64, t.w0 - 1, t.h0 - 1,
+                                         t.img);
+                    } else if (kS2 && !kBMn) {
                         const int py = (cb * 64) / p.c2;
                         tma_load_4d(base + s * L::kABytes, &map_a, bar_afull + s * 8, cb * 64 - py * p.c2, t.w0 - 1,
                                     2 * (t.h0 - 1) + py, t.img);
@@ -228,27 +268,34 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             uint32_t it = 0;
             // kBRes: one channel block, one N tile -> the nine weight tiles are loaded ONCE and stay
             // in their nine slots for every pixel tile this CTA walks
-            for (int tile = blockIdx.x; tile < (kBRes ? min(total_tiles, (int)blockIdx.x + 1) : total_tiles);
-                 tile += gridDim.x) {
-                const HaloTile t = halo_tile<kBlockN, kSub>(p, tile);
+            constexpr int kHalfN = kBlockN / kCluster;           // weight rows / columns staged by this CTA
+            for (int tile = first_tile; tile < (kBRes ? min(total_tiles, first_tile + 1) : total_tiles);
+                 tile += tile_step) {
+                const HaloTile t = halo_tile<kBlockN, kSub, kCluster>(p, tile, rank);
+                const int nb = t.n0 + rank * kHalfN;
                 for (int cb = 0; cb < p.cblocks; ++cb) {
                     for (int tap = 0; tap < 9; ++tap) {
                         if (kS2 && !((p.tap_mask >> tap) & 1)) continue;
                         const int s = it % kBStages;
                         ++it;
                         if (!kBRes) mbar_wait(bar_bempty + s * 8, (((it - 1) / kBStages) & 1) ^ 1);
-                        mbar_expect_tx(bar_bfull + s * 8, L::kBBytes);
+                        if (leader) mbar_expect_tx(bar_bfull + s * 8, L::kBBytes * kCluster);
                         const uint32_t b_dst = base + L::kBOffset + s * L::kBBytes;
+                        const uint32_t fb = bfull_dst + s * 8;
                         if (kBMn) {
                             // data gradient: B straight from the forward weights W[co][tap][ci] seen
                             // as [co rows][9 * N cols]; reduction index = co (rows), output channel
                             // = ci (contiguous), tap mirrored
 #pragma unroll
-                            for (int c = 0; c < kBlockN / 64; ++c)
-                                tma_load_2d(b_dst + c * (64 * 128), &map_b, bar_bfull + s * 8,
-                                            (8 - tap) * p.N + t.n0 + c * 64, cb * 64);
+                            for (int c = 0; c < kHalfN / 64; ++c) {
+                                if (kPair) tma_load_2d_pair(b_dst + c * (64 * 128), &map_b, fb,
+                                                            (8 - tap) * p.N + nb + c * 64, cb * 64);
+                                else tma_load_2d(b_dst + c * (64 * 128), &map_b, fb,
+                                                 (8 - tap) * p.N + nb + c * 64, cb * 64);
+                            }
                         } else {
-                            tma_load_2d(b_dst, &map_b, bar_bfull + s * 8, tap * p.Cred + cb * 64, t.n0);
+                            if (kPair) tma_load_2d_pair(b_dst, &map_b, fb, tap * p.Cred + cb * 64, nb);
+                            else tma_load_2d(b_dst, &map_b, fb, tap * p.Cred + cb * 64, nb);
                         }
                     }
                 }
@@ -256,8 +303,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         }
     } else if (warp == 1) {
         // ---- MMA issuer
-        if (elect_one()) {
-            constexpr uint32_t idesc = make_idesc(128, kBlockN, 0, kBMn ? 1 : 0);
+        if (elect_one() && leader) {
+            constexpr uint32_t idesc = make_idesc(128 * kCluster, kBlockN, 0, kBMn ? 1 : 0);
             constexpr uint32_t kSbo = L::kHaloW * 128;
             // descriptors as (lo, hi) words: hi is constant, lo = start >> 4 (+ LBO field) and only
             // ever gets a compile-time offset added (tap / sub-tile row shift, K advance)
@@ -268,7 +315,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             const uint32_t b_lo0 = (uint32_t)b_proto + ((base + L::kBOffset) >> 4);
             constexpr uint32_t kBk = kBMn ? (16 * 128) >> 4 : 32 >> 4;      // K advance of B per MMA
             uint32_t ait = 0, bit = 0, ti = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
+            for (int tile = first_tile; tile < total_tiles; tile += tile_step, ++ti) {
                 const uint32_t acc = ti & 1;
                 mbar_wait(bar_tempty + acc * 8, ((ti >> 1) & 1) ^ 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -294,15 +341,23 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                             // rows (tap/3) * HW + tap%3 + 8*sub of 128 B each = 8 units of 16 B per row
                             const uint32_t a_off = (uint32_t)((tap / 3) * L::kHaloW + (tap % 3) + kSubW * sub) * 8u;
 #pragma unroll
-                            for (int k = 0; k < 4; ++k)
-                                umma_bf16_lohi(tmem_d + sub * kBlockN, a_lo + a_off + k * 2, a_hi, b_lo + k * kBk, b_hi,
-                                               idesc, first | (uint32_t)k);
+                            for (int k = 0; k < 4; ++k) {
+                                if (kPair) umma_bf16_pair_lohi(tmem_d + sub * kBlockN, a_lo + a_off + k * 2, a_hi,
+                                                               b_lo + k * kBk, b_hi, idesc, first | (uint32_t)k);
+                                else umma_bf16_lohi(tmem_d + sub * kBlockN, a_lo + a_off + k * 2, a_hi, b_lo + k * kBk,
+                                                    b_hi, idesc, first | (uint32_t)k);
+                            }
                         }
-                        if (!kBRes) umma_commit(bar_bempty + bs * 8);
+                        if (!kBRes) {
+                            if (kPair) umma_commit_pair(bar_bempty + bs * 8);
+                            else umma_commit(bar_bempty + bs * 8);
+                        }
                     }
-                    umma_commit(bar_aempty + as * 8);
+                    if (kPair) umma_commit_pair(bar_aempty + as * 8);
+                    else umma_commit(bar_aempty + as * 8);
                 }
-                umma_commit(bar_tfull + acc * 8);
+                if (kPair) umma_commit_pair(bar_tfull + acc * 8);
+                else umma_commit(bar_tfull + acc * 8);
             }
         }
     } else if (warp >= 4) {
@@ -313,7 +368,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         e.N = p.N;
         e.slope = p.slope;
 #define SCDA_HEPI(SPEC)                                                                                          \
-    halo_epilogue<kBlockN, kSub, SPEC, kS2 && kBMn>(p, e, tmem_base, bar_tfull, bar_tempty, warp - 4, lane)
+    halo_epilogue<kBlockN, kSub, SPEC, kS2 && kBMn, kCluster>(p, e, tmem_base, bar_tfull, bar_tempty, warp - 4, lane, \
+                                                              rank)
         if (kS2) {
             // discriminator layers: conv + bias + LeakyReLU; its data gradient through the LeakyReLU below
             if (kBMn) { e.N = p.c2; }
@@ -335,28 +391,52 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (kPair) cluster_sync_all();       // no CTA leaves while its peer may still signal or read it
     if (warp == 2) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2u * kAccCols)
-                     : "memory");
+        if (kPair)
+            asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2u * kAccCols)
+                         : "memory");
+        else
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2u * kAccCols)
+                         : "memory");
     }
 }
 
-template <int kBlockN, int kSub, bool kBMn, int kBStages, bool kS2 = false>
+template <int kBlockN, int kSub, bool kBMn, int kBStages, bool kS2 = false, int kCluster = 1>
 int launch_halo(const CUtensorMap &ma, const CUtensorMap &mb, const HaloParams &p, cudaStream_t stream)
 {
-    using L = HaloSmem<kBlockN, kSub, kBStages>;
+    using L = HaloSmem<kBlockN, kSub, kBStages, kCluster>;
     static_assert(L::kTotal <= 227 * 1024, "shared memory budget");
+    static_assert(2 * kSub * kBlockN <= 512, "TMEM columns");
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<kBlockN, kSub, kBMn, kBStages, kS2>,
+        cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<kBlockN, kSub, kBMn, kBStages, kS2, kCluster>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
         if (e != cudaSuccess) return -(int)e;
         attr_done = true;
     }
-    const long long tiles = (long long)p.m_tiles * p.n_tiles;
-    const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
-    conv_halo_kernel<kBlockN, kSub, kBMn, kBStages, kS2><<<grid, 128 + 128 * kSub, L::kTotal, stream>>>(ma, mb, p);
+    const long long groups = (long long)ceil_div(p.m_tiles, kCluster) * p.n_tiles;
+    const int max_clusters = num_sms() / kCluster;
+    const int clusters = (int)(groups < max_clusters ? groups : max_clusters);
+    if (kCluster == 1) {
+        conv_halo_kernel<kBlockN, kSub, kBMn, kBStages, kS2, 1><<<clusters, 128 + 128 * kSub, L::kTotal, stream>>>(ma, mb, p);
+        return scda_launch_status();
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(clusters * kCluster);
+    cfg.blockDim = dim3(128 + 128 * kSub);
+    cfg.dynamicSmemBytes = L::kTotal;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = kCluster;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, conv_halo_kernel<kBlockN, kSub, kBMn, kBStages, kS2, kCluster>, ma, mb, p);
+    if (e != cudaSuccess) return -(int)e;
     return scda_launch_status();
 }
 
@@ -371,7 +451,7 @@ int env_int(const char *name, int dflt)
 // Tile plan of the halo kernel for a layer: bn = N tile (64 | 128), sub = sub-tiles per CTA
 // (1 | 2); returns false where the per-tap kernel of gemm_tc.cu should be used instead.
 // scda_conv3x3_set_plan (or SCDA_CONV_HALO / SCDA_HALO_BN / SCDA_HALO_SUB at load) overrides it.
-static int g_enabled = -1, g_force_bn = 0, g_force_sub = 0, g_resident = 1, g_sub128 = 1;
+static int g_enabled = -1, g_force_bn = 0, g_force_sub = 0, g_resident = 1, g_sub128 = 1, g_pair = -1;
 
 static void plan_init()
 {
@@ -381,6 +461,16 @@ static void plan_init()
     g_force_sub = env_int("SCDA_HALO_SUB", 0);
     g_resident = env_int("SCDA_HALO_RESIDENT", 1);
     g_sub128 = env_int("SCDA_HALO_SUB128", 1) == 2 ? 2 : 1;
+    g_pair = env_int("SCDA_HALO_PAIR", -1);
+}
+
+// CTA-pair form of the halo kernel: -1 = the measured plan (scda_conv_halo_plan), 0 = never, 1 = wherever legal
+SCDA_API int scda_conv3x3_set_pair(int mode)
+{
+    plan_init();
+    if (mode < -1 || mode > 1) return 0;
+    g_pair = mode;
+    return 1;
 }
 
 SCDA_API int scda_conv3x3_set_plan(int halo, int block_n, int sub_tiles)
@@ -388,7 +478,7 @@ SCDA_API int scda_conv3x3_set_plan(int halo, int block_n, int sub_tiles)
     plan_init();
     if (halo >= 0) g_enabled = halo ? 1 : 0;
     if (block_n >= 0) {
-        if (block_n != 0 && block_n != 64 && block_n != 128) return 0;
+        if (block_n != 0 && block_n != 64 && block_n != 128 && block_n != 256) return 0;
         g_force_bn = block_n;
     }
     if (sub_tiles >= 0) {
@@ -398,9 +488,17 @@ SCDA_API int scda_conv3x3_set_plan(int halo, int block_n, int sub_tiles)
     return 1;
 }
 
-bool scda_conv_halo_plan(int NB, int H, int W, int Cred, int Nout, bool dgrad, int *bn, int *sub)
+// where the pair form measured faster than the lone-CTA plan on B200 (scripts/halobench.py)
+static bool pair_pays(int Cred, int Nout, int pb, long long m_pairs)
+{
+    (void)Cred; (void)Nout; (void)pb; (void)m_pairs;
+    return false;
+}
+
+bool scda_conv_halo_plan(int NB, int H, int W, int Cred, int Nout, bool dgrad, int *bn, int *sub, int *cluster)
 {
     plan_init();
+    *cluster = 1;
     // forward: the reduction walks whole 64-channel blocks of a K-major weight row (tap, ci), so Cred
     // must be a multiple of 64; 32 output channels ride in a 64-wide N tile whose upper weight rows are
     // TMA out-of-bounds zeros.  Data gradient: 32 reduction channels (Cout_fwd = 32) are a 64-channel
@@ -421,6 +519,31 @@ bool scda_conv_halo_plan(int NB, int H, int W, int Cred, int Nout, bool dgrad, i
     }
     if (g_force_bn == 64 || (g_force_bn == 128 && Nout % 128 == 0)) b = g_force_bn;
     if (g_force_sub == 1 || g_force_sub == 2) s = g_force_sub;
+    // CTA pairs (one 256-pixel x b MMA per k-step, half a weight tile staged per SM).  The data gradient's
+    // MN-major weight operand is staged in 64-column chunks, so a pair needs b >= 128 there.
+    if (g_pair != 0) {
+        const long long m_pairs = ((long long)NB * th * ceil_div(W, kSubW) + 1) / 2;
+        const int min_b = dgrad ? 128 : 64;
+        int pb = 0;
+        if (g_force_bn == 256 && Nout % 256 == 0) pb = 256;
+        else if (g_force_bn && g_force_bn >= min_b && Nout % g_force_bn == 0) pb = g_force_bn;
+        else if (!g_force_bn) {
+            // widest N tile that still gives ~every SM pair a tile group
+            for (int cand = 256; cand >= min_b; cand >>= 1)
+                if (Nout % cand == 0 && (m_pairs * (Nout / cand) >= (long long)(num_sms() / 2) * 3 / 4 || cand == min_b)) {
+                    pb = cand;
+                    break;
+                }
+        }
+        const bool want = g_pair == 1 || pair_pays(Cred, Nout, pb, m_pairs);
+        if (pb && want && Nout % pb == 0) {
+            *bn = pb;
+            *sub = 1;
+            *cluster = 2;
+            return true;
+        }
+    }
+    if (b == 256) b = 128;          // (a forced 256 only exists as a pair)
     *bn = b;
     *sub = s;
     return true;
@@ -428,7 +551,7 @@ bool scda_conv_halo_plan(int NB, int H, int W, int Cred, int Nout, bool dgrad, i
 
 int scda_conv_halo_launch(int NB, int H, int W, int Cred, int Nout, const void *a, const void *w_krsc,
                           const float *bias, void *out, int flags, const void *mask_src, bool dgrad, int bn,
-                          int sub, cudaStream_t stream)
+                          int sub, int cluster, cudaStream_t stream)
 {
     const int region_w = kSubW * sub;
     HaloParams p = {};
@@ -454,6 +577,12 @@ int scda_conv_halo_launch(int NB, int H, int W, int Cred, int Nout, const void *
         cuuint64_t db[2] = {(cuuint64_t)9 * Nout, (cuuint64_t)Cred}, sb[1] = {(cuuint64_t)9 * Nout * 2};
         cuuint32_t bb[2] = {64, 64};
         if (!make_map(&mb, w_krsc, 2, db, sb, bb)) return 0;
+        if (cluster == 2) {
+            if (sub != 1) return 0;
+            if (bn == 256) return launch_halo<256, 1, true, 8, false, 2>(ma, mb, p, stream);
+            if (bn == 128) return launch_halo<128, 1, true, 8, false, 2>(ma, mb, p, stream);
+            return 0;
+        }
         if (bn == 64 && resident) return sub == 1 ? launch_halo<64, 1, true, 9>(ma, mb, p, stream)
                                                   : launch_halo<64, 2, true, 9>(ma, mb, p, stream);
         if (bn == 64) return sub == 1 ? launch_halo<64, 1, true, 8>(ma, mb, p, stream)
@@ -462,8 +591,16 @@ int scda_conv_halo_launch(int NB, int H, int W, int Cred, int Nout, const void *
                         : launch_halo<128, 2, true, 8>(ma, mb, p, stream);
     }
     cuuint64_t db[2] = {(cuuint64_t)9 * Cred, (cuuint64_t)Nout}, sb[1] = {(cuuint64_t)9 * Cred * 2};
-    cuuint32_t bb[2] = {64, (cuuint32_t)bn};
+    cuuint32_t bb[2] = {64, (cuuint32_t)(bn / cluster)};
     if (!make_map(&mb, w_krsc, 2, db, sb, bb)) return 0;
+    if (cluster == 2) {
+        if (sub != 1) return 0;
+        if (bn == 256) return launch_halo<256, 1, false, 8, false, 2>(ma, mb, p, stream);
+        if (bn == 128) return launch_halo<128, 1, false, 8, false, 2>(ma, mb, p, stream);
+        if (bn == 64 && resident) return launch_halo<64, 1, false, 9, false, 2>(ma, mb, p, stream);
+        if (bn == 64) return launch_halo<64, 1, false, 8, false, 2>(ma, mb, p, stream);
+        return 0;
+    }
     if (bn == 64 && resident) return sub == 1 ? launch_halo<64, 1, false, 9>(ma, mb, p, stream)
                                               : launch_halo<64, 2, false, 9>(ma, mb, p, stream);
     if (bn == 64) return sub == 1 ? launch_halo<64, 1, false, 8>(ma, mb, p, stream)

@@ -836,10 +836,10 @@ SCDA_API int scda_conv3x3_bf16_nhwc(int NB, int H, int W, int Cin, int Cout, con
     if ((flags & kFlagMaskPos) && !mask_src) return 0;
     if ((flags & kFlagAccumulate) && !(flags & kFlagOutF32)) return 0;
     {
-        int hbn, hsub;       // halo form (conv_halo.cu): the input tile is staged once for all 9 taps
-        if (!(flags & kFlagMulSrc) && scda_conv_halo_plan(NB, H, W, Cin, Cout, false, &hbn, &hsub))
+        int hbn, hsub, hcl;  // halo form (conv_halo.cu): the input tile is staged once for all 9 taps
+        if (!(flags & kFlagMulSrc) && scda_conv_halo_plan(NB, H, W, Cin, Cout, false, &hbn, &hsub, &hcl))
             return scda_conv_halo_launch(NB, H, W, Cin, Cout, x, w_krsc, bias, y, flags, mask_src, false, hbn,
-                                         hsub, stream);
+                                         hsub, hcl, stream);
     }
     int TW = 16, TH = 8;
     if (W % 16) {                                 // narrow maps: 8 x 16 tile turned around
@@ -877,10 +877,10 @@ SCDA_API int scda_conv3x3_dgrad_bf16_nhwc(int NB, int H, int W, int Cin, int Cou
     if ((flags & kFlagMaskPos) && !mask_src) return 0;
     if (flags & (kFlagAccumulate | kFlagMulSrc | kFlagRelu)) return 0;
     {
-        int hbn, hsub;
-        if (scda_conv_halo_plan(NB, H, W, Cout, Cin, true, &hbn, &hsub))
+        int hbn, hsub, hcl;
+        if (scda_conv_halo_plan(NB, H, W, Cout, Cin, true, &hbn, &hsub, &hcl))
             return scda_conv_halo_launch(NB, H, W, Cout, Cin, dy, w_krsc, nullptr, dx, flags, mask_src, true, hbn,
-                                         hsub, stream);
+                                         hsub, hcl, stream);
     }
     if (Cout % kBlockK) return 0;              // (the per-tap form needs whole 64-channel blocks)
     int TW = 16, TH = 8;

@@ -108,10 +108,10 @@ class FlatAdam(object):
     def zero_grad(self):
         self.bucket.zero()
 
-    def all_reduce(self, lo=0, hi=None):
+    def all_reduce(self, lo=0, hi=None, group=None):
         self.bucket.rebind()
         self.bucket.settle(lo, hi)
-        self.bucket.all_reduce(lo=lo, hi=hi)
+        self.bucket.all_reduce(lo=lo, hi=hi, group=group)
 
     def offset_of(self, param):
         """start of `param`'s segment in the flat buffers (bucket boundaries)"""
@@ -247,6 +247,8 @@ class SCDATrainer(object):
         self.split_detector = os.environ.get("SCDA_SPLIT_DETECTOR", "1") != "0"
         self.wgrad_side = os.environ.get("SCDA_WGRAD_SIDE", "0") != "0"     # measured: 7.69 ms with, 7.59 without
         self._det_head_lo, self._oside = None, None
+        self._comm_per_stream = os.environ.get("SCDA_ONE_COMM", "0") == "0"
+        self._groups = None
         self._side = None
         self._tside = None
         self._aside = None
@@ -266,6 +268,27 @@ class SCDATrainer(object):
 
     def nets(self):
         return (self.model, self.dec_model, self.dis_model, self.dis_model_patch)
+
+    def release_graphs(self):
+        """Drop the captured iteration graphs (the next iteration re-captures).  With world > 1 and the
+        all-reduces captured, call this before dist.destroy_process_group(): NCCL will not destroy a
+        communicator while a live CUDA graph still holds kernels captured on it — the teardown waits forever."""
+        import gc
+        torch.cuda.synchronize()
+        for ent in self._by_shape.values():
+            ent['graphs'] = None
+        self._graphs = None
+        gc.collect()
+        torch.cuda.synchronize()
+
+    def close(self):
+        """release the graphs and the per-stream communicators (world > 1)"""
+        self.release_graphs()
+        if self._groups is not None:
+            import torch.distributed as dist
+            for g in self._groups.values():
+                dist.destroy_process_group(g)
+            self._groups = None
 
     def train_mode(self):
         for n in self.nets():
@@ -571,8 +594,29 @@ class SCDATrainer(object):
 
     def _reduce_fn(self):
         if self.world_size > 1:
-            return lambda opt, lo=0, hi=None: opt.all_reduce(lo, hi)
+            return lambda opt, lo=0, hi=None: opt.all_reduce(lo, hi, group=self._group_of(opt, lo))
         return lambda opt, lo=0, hi=None: None
+
+    def _group_of(self, opt, lo=0):
+        """One NCCL communicator per stream that issues collectives (`main`: backbone + RPN bucket of the
+        detector, `opt`: its head bucket, `side`: image discriminator and decoder, `patch`: patch
+        discriminator).  Collectives of ONE communicator must run in the same order on every rank; two
+        forked branches of a captured graph carry no such order between them, which is what hung the
+        captured form with a single communicator (profiles/r1_ddp2_check.txt, item 1).  With a
+        communicator per branch every communicator sees one stream's program order, on every rank."""
+        if not self._comm_per_stream or not self.overlap:
+            return None
+        import torch.distributed as dist
+        if self._groups is None:
+            if not (dist.is_available() and dist.is_initialized()):
+                return None
+            # created in the same order on every rank (the eager warm-up iteration gets here first)
+            self._groups = {k: dist.new_group(backend=dist.get_backend()) for k in ("main", "opt", "side", "patch")}
+        if opt is self.opt:
+            return self._groups["opt" if (lo > 0 and self.split_detector) else "main"]
+        if opt is self.opt_dis_patch:
+            return self._groups["patch"]
+        return self._groups["side"]
 
     def _segments(self):
         """world > 1 with the collectives NOT captured: the iteration cut at its four gradient
@@ -626,7 +670,10 @@ class SCDATrainer(object):
         if self._whole_graph():
             reduce = self._reduce_fn()
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, pool=torch.cuda.graph_pool_handle()):
+            # world > 1: NCCL's watchdog thread polls events while we capture; only THIS thread's calls
+            # belong to the capture
+            mode = "thread_local" if self.world_size > 1 else "global"
+            with torch.cuda.graph(g, pool=torch.cuda.graph_pool_handle(), capture_error_mode=mode):
                 self._body(reduce)
             return [g]
         pools = {k: torch.cuda.graph_pool_handle() for k in ('main', 'side', 'patch', 'opt')}
@@ -652,9 +699,9 @@ class SCDATrainer(object):
                 g, opt = by_name[n]
                 g.replay()
                 if isinstance(opt, tuple):
-                    opt[0].all_reduce(opt[1], opt[2])
+                    opt[0].all_reduce(opt[1], opt[2], group=self._group_of(opt[0], opt[1]))
                 elif opt is not None:
-                    opt.all_reduce()
+                    opt.all_reduce(group=self._group_of(opt))
         run(['fwd'])
         if not self.overlap:
             run(['dis', 'dis_patch', 'dec', 'fake', 'det_bwd', 'step', 'out'])
@@ -677,7 +724,7 @@ class SCDATrainer(object):
             run(['det_bwd_head'])
             osd.wait_stream(main)
             with torch.cuda.stream(osd):
-                self.opt.all_reduce(self._head_lo(), None)
+                self.opt.all_reduce(self._head_lo(), None, group=self._group_of(self.opt, self._head_lo()))
                 run(['step_head'])
             run(['det_bwd_body', 'step_body'])
             main.wait_stream(osd)

@@ -131,10 +131,33 @@ def conv3x3_nhwc(x, w_krsc, bias=None, relu=False, out_dtype=torch.bfloat16, mas
     return y
 
 
+def conv3x3_first_nchw(image, w_krsc, bias, relu=True):
+    """first backbone convolution straight from the fp32 NCHW image (scda_conv3x3_first_nchw): image
+    [NB,Cin<=3,H,W] fp32, w_krsc [64,3,3,Cin] bf16, bias [64] fp32 -> [NB,H,W,64] bf16 (+ReLU)"""
+    require_cuda(image, w_krsc, bias)
+    assert image.dtype == torch.float32 and image.is_contiguous() and image.dim() == 4
+    NB, Cin, H, W = image.shape
+    Cout = w_krsc.shape[0]
+    assert w_krsc.dtype == torch.bfloat16 and w_krsc.is_contiguous() and tuple(w_krsc.shape) == (Cout, 3, 3, Cin)
+    assert bias.dtype == torch.float32 and bias.is_contiguous()
+    y = torch.empty(NB, H, W, Cout, dtype=torch.bfloat16, device=image.device)
+    with torch.cuda.device(image.device):
+        check(load().scda_conv3x3_first_nchw(NB, H, W, Cin, Cout, image.data_ptr(), w_krsc.data_ptr(),
+                                             bias.data_ptr(), y.data_ptr(), int(bool(relu)),
+                                             stream_ptr(image.device)), "scda_conv3x3_first_nchw")
+    return y
+
+
 def set_conv_plan(halo=-1, block_n=-1, sub_tiles=-1):
-    """tuning / test hook (scda_conv3x3_set_plan): halo 1|0, block_n 0|64|128, sub_tiles 0|1|2"""
+    """tuning / test hook (scda_conv3x3_set_plan): halo 1|0, block_n 0|64|128|256 (256: pairs only), sub_tiles 0|1|2"""
     if load().scda_conv3x3_set_plan(int(halo), int(block_n), int(sub_tiles)) != 1:
         raise ValueError("scda_conv3x3_set_plan: bad arguments")
+
+
+def set_conv_pair(mode=-1):
+    """tuning / test hook (scda_conv3x3_set_pair): CTA-pair form of the halo kernel, -1 plan | 0 never | 1 always"""
+    if load().scda_conv3x3_set_pair(int(mode)) != 1:
+        raise ValueError("scda_conv3x3_set_pair: bad argument")
 
 
 def conv3x3_dgrad_nhwc(dy, w_krsc, mask_src=None, out_dtype=torch.bfloat16):

@@ -19,6 +19,8 @@ bf16 weight shadows: `shadow(p)` returns a bf16 copy in the layout the kernels w
 re-derives it whenever `p._version` moved; engine.FlatAdam refreshes the big ones inside
 its fused optimiser kernel and stamps `p._scda_shadow_version`.
 """
+import os
+
 import torch
 
 from . import tc
@@ -286,20 +288,57 @@ def _sink_bias(p, g2d):
 
 
 # ---------------------------------------------------------------------- backbone
+# conv1_1 straight from the fp32 NCHW image (csrc/conv_first.cu); SCDA_FIRST_DIRECT=0 restores the padded form
+FIRST_DIRECT = os.environ.get("SCDA_FIRST_DIRECT", "1") != "0"
+_PAD_STREAMS = {}
+
+
+def _pad_stream(device):
+    key = torch.device(device).index
+    if key not in _PAD_STREAMS:
+        _PAD_STREAMS[key] = torch.cuda.Stream(device=device)
+    return _PAD_STREAMS[key]
+
+
 class _BackboneFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, image, rt, *params):
         assert image.is_cuda and image.dtype == torch.float32 and image.dim() == 4
-        x = tc.nchw_f32_to_nhwc_bf16(image.contiguous(), 64)
+        image = image.contiguous()
+        m0 = rt.convs[0][0]
+        direct = FIRST_DIRECT and m0.weight.shape[0] == 64 and m0.weight.shape[1] <= 3
+        need_grad = any(ctx.needs_input_grad[2:])
+        pad_done = None
+        if not direct:
+            x = tc.nchw_f32_to_nhwc_bf16(image, 64)
+        elif need_grad:
+            # conv1_1 reads the fp32 image itself (csrc/conv_first.cu); the zero-padded NHWC copy is only an
+            # operand of conv1_1's weight gradient: made on a side stream beside the backbone, joined at its end
+            cur = torch.cuda.current_stream()
+            side = _pad_stream(image.device)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                x = tc.nchw_f32_to_nhwc_bf16(image, 64)
+                pad_done = torch.cuda.Event()
+                pad_done.record(side)
+            x.record_stream(cur)
+            image.record_stream(side)
+        else:
+            x = image.new_empty(0)        # (no backward: nothing needs the padded copy)
         saved = [x]
         n = len(rt.convs)
         for i, (m, pool) in enumerate(rt.convs):
-            w = rt.conv1_weight() if i == 0 else rt.shadow(m.weight)
-            y = tc.conv3x3_nhwc(x, w, m.bias.detach(), relu=True)
+            if i == 0 and direct:
+                y = tc.conv3x3_first_nchw(image, rt.shadow(m.weight), m.bias.detach(), relu=True)
+            else:
+                w = rt.conv1_weight() if i == 0 else rt.shadow(m.weight)
+                y = tc.conv3x3_nhwc(x, w, m.bias.detach(), relu=True)
             saved.append(y)
             x = tc.maxpool2x2_nhwc(y) if pool else y
             if pool:
                 saved.append(x)
+        if pad_done is not None:
+            torch.cuda.current_stream().wait_event(pad_done)
         ctx.rt = rt
         ctx.cin = image.shape[1]
         ctx.save_for_backward(*saved)

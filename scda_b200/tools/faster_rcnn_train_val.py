@@ -256,6 +256,8 @@ def main(argv=None):
             best_recall = max(best_recall, validate(args, cfg, tr.model, val_loader, rank, world))
         if rank == 0:
             logger.info('saved %s', save_checkpoint(args, tr, epoch, best_recall))
+    if world > 1:
+        tr.close()          # captured NCCL kernels pin their communicators: graphs first, then the groups
     return history
 
 

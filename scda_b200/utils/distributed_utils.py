@@ -140,11 +140,12 @@ class FlatGradBucket(object):
                     view.copy_(p.grad)
                 p.grad = view
 
-    def all_reduce(self, async_op=False, lo=0, hi=None):
-        """SUM all-reduce of the flat buffer, or of its slice [lo, hi) (a gradient bucket)"""
+    def all_reduce(self, async_op=False, lo=0, hi=None, group=None):
+        """SUM all-reduce of the flat buffer, or of its slice [lo, hi) (a gradient bucket), on
+        `group` (None = the default process group)"""
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
             buf = self.flat if (lo == 0 and hi is None) else self.flat[lo:hi]
-            return dist.all_reduce(buf, async_op=async_op)
+            return dist.all_reduce(buf, async_op=async_op, group=group)
         return None
 
 

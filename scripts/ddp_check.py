@@ -25,7 +25,8 @@ def main():
     cfg = bench.load_cfg()
     tr = build_trainer(cfg, lr=1e-4, world_size=world, seed=rank,      # different init per rank ...
                        overlap="--no-overlap" not in sys.argv,
-                       graph_collectives=False if "--no-graph-collectives" in sys.argv else None)
+                       graph_collectives=False if "--no-graph-collectives" in sys.argv else
+                       (True if "--graph-collectives" in sys.argv else None))
     for net in tr.nets():
         broadcast_params(net)                                          # ... made equal here
     for o in (tr.opt, tr.opt_dec, tr.opt_dis, tr.opt_dis_patch):       # shadows follow the masters
@@ -52,7 +53,12 @@ def main():
         ok = ok and bool(flags.item()) and moved > 0
     if rank == 0:
         print("whole graph:", tr._whole_graph(), " loss", float(out["loss"]), " DDP_CHECK", "OK" if ok else "FAILED")
+    sys.stdout.flush()
+    tr.close()
+    import threading
+    threading.Timer(45.0, lambda: os._exit(0 if ok else 1)).start()
     dist.destroy_process_group()
+    os._exit(0 if ok else 1)
 
 
 if __name__ == "__main__":

@@ -16,7 +16,8 @@ from scripts.convbench import LAYERS, peak, timeit  # noqa: E402
 
 EXTRA = [("rpn3x3", 32, 64, 512, 512), ("dec_res", 64, 64, 128, 128), ("dec_up1", 128, 128, 128, 64)]
 PLANS = [("per_tap", 0, 0, 0), ("halo_64x1", 1, 64, 1), ("halo_64x2", 1, 64, 2), ("halo_128x1", 1, 128, 1),
-         ("halo_128x2", 1, 128, 2), ("halo_auto", 1, 0, 0)]
+         ("halo_128x2", 1, 128, 2), ("pair_64", 1, 64, 0), ("pair_128", 1, 128, 0), ("pair_256", 1, 256, 0),
+         ("halo_auto", 1, 0, 0)]
 
 
 def main():
@@ -36,8 +37,12 @@ def main():
         for what in passes:
             row = {}
             for plan, halo, bn, sub in PLANS:
-                if bn == 128 and (Cout if what == "fwd" else Cin) % 128:
+                nout = Cout if what == "fwd" else Cin
+                if bn >= 128 and nout % bn:
                     continue
+                if plan == "pair_64" and what == "dgrad":
+                    continue                   # (MN-major weight chunks are 64 columns: a pair needs N >= 128)
+                tc.set_conv_pair(1 if plan.startswith("pair") else (-1 if plan == "halo_auto" else 0))
                 tc.set_conv_plan(halo, bn, sub)
                 t = timeit(fns[what], flush, iters=7, warm=2)
                 row[plan] = round(t * 1e6, 1)
@@ -46,6 +51,7 @@ def main():
                               "best_tflops": round(fl / row[best] / 1e6, 1),
                               "best_frac_bf16_peak": round(fl / row[best] / 1e6 / pk, 3)}), flush=True)
     tc.set_conv_plan(1, 0, 0)
+    tc.set_conv_pair(-1)
 
 
 if __name__ == "__main__":
