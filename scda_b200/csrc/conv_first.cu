@@ -5,7 +5,7 @@
 // the two-pass form this build used before: nchw_to_nhwc (fp32 NCHW -> bf16 NHWC zero-padded 3 -> 64 channels:
 // a 67 MB write per 512 x 1024 image) followed by the 64-channel halo convolution, which spent 21 of every 22
 // MMAs on the zero padding (47 us for 1.8 GFLOP of real work).  Here a CTA builds the [128 pixels x 32] bf16
-// patch matrix of a pixel tile in shared memory (27 real columns k = (kh * 3 + kw) * Cin + ci, 5 zero columns;
+// patch matrix of a pixel tile in shared memory (27 columns k = (kh * 3 + kw) * 3 + ci, 5 zero columns;
 // the 128B-swizzled K-major layout the UMMA descriptors of tc_ptx.cuh describe, written with ordinary stores and
 // published to the async proxy with fence.proxy.async), multiplies it with the resident [64 x 32] weight tile by
 // TWO tcgen05 MMAs (M128 N64 K16) and writes bias + ReLU + bf16 NHWC from TMEM.  HBM traffic = the image once
@@ -86,9 +86,11 @@ __global__ void __launch_bounds__(kThreads, 2) conv_first_kernel(const FirstPara
         uint32_t pk[4];
 #pragma unroll
         for (int h = 0; h < 4; ++h) {
-            const int k0 = c * 8 + h * 2;
-            const float lo = k0 < p.K ? __bfloat162float(p.w[co * p.K + k0]) : 0.f;
-            const float hi = k0 + 1 < p.K ? __bfloat162float(p.w[co * p.K + k0 + 1]) : 0.f;
+            // patch column k = tap * 3 + ci whatever Cin is (the producers unroll three channels per tap)
+            const int k0 = c * 8 + h * 2, k1 = k0 + 1;
+            const int t0 = k0 / 3, c0 = k0 - t0 * 3, t1 = k1 / 3, c1 = k1 - t1 * 3;
+            const float lo = (t0 < 9 && c0 < p.Cin) ? __bfloat162float(p.w[co * p.K + t0 * p.Cin + c0]) : 0.f;
+            const float hi = (t1 < 9 && c1 < p.Cin) ? __bfloat162float(p.w[co * p.K + t1 * p.Cin + c1]) : 0.f;
             const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
             pk[h] = *reinterpret_cast<const uint32_t *>(&v);
         }
