@@ -42,12 +42,35 @@ smooth_l1_fwd_kernel(const float *__restrict__ pred, const float *__restrict__ m
     __shared__ float sh[32];
     const float thr = 1.f / sigma2, half = 0.5f / sigma2;
     float acc = 0.f;
-    for (long long i = threadIdx.x; i < n; i += kLT) {
-        const float p = mask ? pred[i] * mask[i] : pred[i];
-        const float d = p - target[i];
+    auto term = [&](float p, float m, float t) {
+        const float d = p * m - t;
         const float a = fabsf(d);
-        acc += a < thr ? d * d * sigma2 * 0.5f : a - half;
+        return a < thr ? d * d * sigma2 * 0.5f : a - half;
+    };
+    long long done = 0;
+    if (((reinterpret_cast<uintptr_t>(pred) | reinterpret_cast<uintptr_t>(target) |
+          reinterpret_cast<uintptr_t>(mask)) & 15) == 0) {
+        // 16-byte loads, two in flight per operand: the single block is bound by load latency, not bandwidth
+        const long long n4 = n / 4;
+        const float4 *p4 = reinterpret_cast<const float4 *>(pred), *t4 = reinterpret_cast<const float4 *>(target);
+        const float4 *m4 = reinterpret_cast<const float4 *>(mask);
+        const float4 one = make_float4(1.f, 1.f, 1.f, 1.f);
+        long long i = threadIdx.x;
+        for (; i + kLT < n4; i += 2 * kLT) {
+            const float4 pa = p4[i], pb = p4[i + kLT], ta = t4[i], tb = t4[i + kLT];
+            const float4 ma = mask ? m4[i] : one, mb = mask ? m4[i + kLT] : one;
+            acc += term(pa.x, ma.x, ta.x) + term(pa.y, ma.y, ta.y) + term(pa.z, ma.z, ta.z) + term(pa.w, ma.w, ta.w);
+            acc += term(pb.x, mb.x, tb.x) + term(pb.y, mb.y, tb.y) + term(pb.z, mb.z, tb.z) + term(pb.w, mb.w, tb.w);
+        }
+        for (; i < n4; i += kLT) {
+            const float4 pa = p4[i], ta = t4[i];
+            const float4 ma = mask ? m4[i] : one;
+            acc += term(pa.x, ma.x, ta.x) + term(pa.y, ma.y, ta.y) + term(pa.z, ma.z, ta.z) + term(pa.w, ma.w, ta.w);
+        }
+        done = n4 * 4;
     }
+    for (long long i = done + threadIdx.x; i < n; i += kLT)
+        acc += term(pred[i], mask ? mask[i] : 1.f, target[i]);
     const float s = block_sum(acc, sh);
     if (threadIdx.x == 0) out[0] = s;
 }

@@ -253,6 +253,7 @@ class SCDATrainer(object):
         self._tside = None
         self._aside = None
         self._pside = None
+        self._ksides, self._gan_go = None, None
         if overlap and hasattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch"):
             # gradients are produced on whichever stream ran the forward of their branch and are
             # accumulated into the flat buffers there; the mismatch torch warns about is intended
@@ -412,18 +413,33 @@ class SCDATrainer(object):
         if self.overlap:
             x['target_stream'] = self._target_stream()
             x['aux_stream'] = self._aux_stream()
+            x['side_streams'] = self._kmeans_streams()
+            x['on_clusters'] = self._on_clusters
         if self.rng is not None:
             x['rng'] = self.rng
         if self.taps is not None:
             x['taps'] = self.taps
+        self._gan_go = None
         outputs = self.model(x, b['target'])
         st['det_losses'] = outputs['losses']
         st['feat'] = outputs['feature_map']
         st['acc'] = outputs['accuracy']
-        centers_source, centers_target = outputs['cluster_centers']
+        if self._gan_go is None:
+            self._on_clusters(outputs['cluster_centers'], outputs['cluster_features'], mark=False)
+
+    def _on_clusters(self, centers, features, mark=True):
+        """crops around the cluster centres (tools/faster_rcnn_train_val.py:411-438,528-557).  Called by the
+        detector's forward as soon as the clusters are known — before its loss kernels — and marks that point
+        of the stream: everything phases 1-3 read (crops, cluster features) exists there, so the
+        reconstruction chain is forked from the mark instead of from the end of the forward."""
+        b = self._static
+        centers_source, centers_target = centers
         b['cs'] = crops_device(b['image'], centers_source, self.recon_size, self.new_w, self.new_h)
         b['ct'] = crops_device(b['target'], centers_target, self.recon_size, self.new_w, self.new_h)
-        b['xs'], b['xt'] = outputs['cluster_features']
+        b['xs'], b['xt'] = features
+        if mark:
+            self._gan_go = torch.cuda.Event()
+            self._gan_go.record(torch.cuda.current_stream())
 
     def _seg_det_backward(self):
         """(4) detector backward (:736-745).  The two "fake" terms of the reference's loss carry
@@ -555,6 +571,11 @@ class SCDATrainer(object):
             self._side = torch.cuda.Stream(device=self.opt.flat.device, priority=-1)
         return self._side
 
+    def _kmeans_streams(self):
+        if self._ksides is None:
+            self._ksides = tuple(torch.cuda.Stream(device=self.opt.flat.device) for _ in range(2))
+        return self._ksides
+
     def _aux_stream(self):
         if self._aside is None:
             self._aside = torch.cuda.Stream(device=self.opt.flat.device)
@@ -573,13 +594,18 @@ class SCDATrainer(object):
         bound), and they join before the losses are assembled."""
         from . import timestamps as ts
         gan_ops.PAIR_STREAMS = bool(self.overlap and self.pair_streams)
+        from . import tc_detector
+        tc_detector.MASK_SIDE_STREAMS = bool(self.overlap)
         ts.mark("start")
         self._seg_forward()
         ts.mark("forward done")
         if self.overlap:
             main = torch.cuda.current_stream()
             side = self._side_stream()
-            side.wait_stream(main)
+            if self._gan_go is not None:
+                side.wait_event(self._gan_go)       # (recorded on `main` behind the crops, _on_clusters)
+            else:
+                side.wait_stream(main)
             with torch.cuda.stream(side):
                 self._gan_chain(reduce)
                 ts.mark("gan chain done")
@@ -667,6 +693,8 @@ class SCDATrainer(object):
         therefore allocate from different pools."""
         torch.cuda.synchronize()
         gan_ops.PAIR_STREAMS = bool(self.overlap and self.pair_streams)
+        from . import tc_detector
+        tc_detector.MASK_SIDE_STREAMS = bool(self.overlap)
         if self._whole_graph():
             reduce = self._reduce_fn()
             g = torch.cuda.CUDAGraph()

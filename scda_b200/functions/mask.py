@@ -78,11 +78,34 @@ def kmeans_regions_device(proposals, N_cluster, threshold, max_iter=300, tol=1e-
     return labels, centers, counts, index
 
 
-def cluster_targets_device(proposals, features, N_cluster=4, threshold=128, taps=None):
+def kmeans_regions_forked(proposals, N_cluster, threshold, stream):
+    """The k-means of `cluster_targets_device` issued on `stream`, forked from the current stream: the
+    clustering reads the RoI table only (functions/mask.py:196-209 of the reference clusters the box
+    CENTRES), so it can run beside RoIPool -> fc6 -> fc7 instead of behind them (0.13-0.19 ms of a single
+    CTA, profiles/r2_timeline_b_forward.txt).  -> a handle for `cluster_targets_device(..., pre=handle)`,
+    which joins the stream."""
+    cur = torch.cuda.current_stream()
+    rois = proposals.detach().float()
+    stream.wait_stream(cur)
+    with torch.cuda.stream(stream):
+        res = kmeans_regions_device(rois, N_cluster, threshold)
+    rois.record_stream(stream)
+    return res, stream
+
+
+def cluster_targets_device(proposals, features, N_cluster=4, threshold=128, taps=None, pre=None):
     """-> batch_rois [N_cluster, threshold, F] (detached) and centres as a DEVICE fp32 [K, 2];
-    `taps` (a dict, tests only) receives the row index and the labels the gather used"""
+    `taps` (a dict, tests only) receives the row index and the labels the gather used;
+    `pre`: the clustering already issued by `kmeans_regions_forked` on the same proposals"""
     assert features.is_cuda
-    labels, centers, _, index = kmeans_regions_device(proposals.detach().float(), N_cluster, threshold)
+    if pre is not None:
+        (labels, centers, _, index), stream = pre
+        cur = torch.cuda.current_stream()
+        cur.wait_stream(stream)
+        for t in (labels, centers, index):
+            t.record_stream(cur)
+    else:
+        labels, centers, _, index = kmeans_regions_device(proposals.detach().float(), N_cluster, threshold)
     rows = features.detach().float().index_select(0, index)
     if taps is not None:
         taps.update(index=index, labels=labels, centers=centers)

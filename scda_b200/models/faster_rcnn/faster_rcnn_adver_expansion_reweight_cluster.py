@@ -18,7 +18,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from ...functions.anchor_target import compute_anchor_targets
-from ...functions.mask import cluster_targets_device, compute_cluster_targets
+from ...functions.mask import cluster_targets_device, compute_cluster_targets, kmeans_regions_forked
 from ...functions.predict_bbox import compute_predicted_bboxes
 from ...functions.proposal_target import compute_proposal_targets, proposal_targets_device
 from ...functions.rpn_proposal import compute_rpn_proposals, rpn_proposals_device
@@ -152,6 +152,13 @@ class FasterRCNN_AdEx(nn.Module):
             # type, centres as a host numpy array
             on_dev = bool(input.get('device_clusters', False))
             cluster_fn = cluster_targets_device if on_dev else compute_cluster_targets
+            # input['side_streams'] = (s0, s1): the k-means of the source / target RoIs runs on s0 / s1 beside
+            # the RCNN head (it reads the RoI table only), joined where the rows are gathered
+            kstreams = input.get('side_streams') if (on_dev and taps is None) else None
+            # input['on_clusters'](centres, features): called as soon as both are known, BEFORE the four
+            # detection losses are joined — the engine crops the regions there, so the reconstruction chain
+            # does not wait for the loss kernels
+            on_clusters = input.get('on_clusters') if on_dev else None
 
             def run_target_backbone():
                 with torch.no_grad():
@@ -178,13 +185,16 @@ class FasterRCNN_AdEx(nn.Module):
                     ks = [int(n.item()) for _, n in gan_rows]
                     proposals_gan = torch.cat([r[:k] for (r, _), k in zip(gan_rows, ks)], 0)[:n_t].contiguous()
                     enough = torch.tensor(proposals_gan.shape[0] == n_t, device=x_gan.device)
+                pre = None
+                if kstreams is not None and proposals_gan.shape[0] == n_t:
+                    pre = kmeans_regions_forked(proposals_gan, input['cluster_num'], input['threshold'], kstreams[1])
                 with torch.no_grad():
                     x_fea_gan, _, _ = self.rcnn(x_gan, proposals_gan)
                 clusters = None
                 if on_dev and proposals_gan.shape[0] == n_t:
                     ktap = {} if taps is not None else None
                     clusters = cluster_targets_device(proposals_gan, x_fea_gan, N_cluster=input['cluster_num'],
-                                                      threshold=input['threshold'], taps=ktap)
+                                                      threshold=input['threshold'], taps=ktap, pre=pre)
                     if taps is not None:
                         taps.update(cluster_tgt=ktap)
                 if taps is not None:
@@ -257,6 +267,9 @@ class FasterRCNN_AdEx(nn.Module):
             if os.environ.get("SCDA_DEBUG_TARGETS") == "1":
                 self._dbg = dict(orig=(rois, cls_targets, loc_targets, loc_weights),
                                  early=tuple(t.clone() for t in (rois, cls_targets, loc_targets, loc_weights)))
+            pre_src = None
+            if kstreams is not None:
+                pre_src = kmeans_regions_forked(rois, input['cluster_num'], input['threshold'], kstreams[0])
             x_fea, rcnn_pred_cls, rcnn_pred_loc = self.rcnn(x, rois)
             if tstream is not None and not early and late == "2":
                 tstream.wait_event(after_rpn)
@@ -270,6 +283,9 @@ class FasterRCNN_AdEx(nn.Module):
                             rois_targets=(rois, cls_targets, loc_targets, loc_weights), feat=x,
                             rpn_cls=rpn_pred_cls, rpn_loc=rpn_pred_loc, fc7=x_fea, rcnn_cls=rcnn_pred_cls,
                             rcnn_loc=rcnn_pred_loc, proposals=props, fg_scores=fg)
+            elif pre_src is not None:
+                x_cluster_fea, x_center_cluster = cluster_targets_device(
+                    rois, x_fea, N_cluster=input['cluster_num'], threshold=input['threshold'], pre=pre_src)
             else:
                 x_cluster_fea, x_center_cluster = cluster_fn(
                     rois, x_fea, N_cluster=input['cluster_num'], threshold=input['threshold'])
@@ -283,26 +299,6 @@ class FasterRCNN_AdEx(nn.Module):
             x_gan, proposals_gan, enough, x_fea_gan, clusters_gan = tgt
             assert x_gan.size() == x.size(), "gan_features does not match the backbone"
 
-            # the RPN losses are only needed by the backward: computed here, at the end of the forward,
-            # so that the proposal / RoI stages above never wait for the anchor targets
-            if anchor_pre is not None:
-                torch.cuda.current_stream().wait_stream(astream)
-                for t_ in anchor_pre:
-                    if torch.is_tensor(t_):
-                        t_.record_stream(torch.cuda.current_stream())
-            if taps is not None:
-                taps.update(anchor_targets=partial_fn['anchor_target_fn'](rpn_pred_loc.size()))
-            rpn_loss_cls, rpn_loss_loc, rpn_acc = self._add_rpn_loss(
-                partial_fn['anchor_target_fn'], rpn_pred_cls, rpn_pred_loc)
-            rcnn_loss_cls, rcnn_loss_loc, rcnn_acc = self._add_rcnn_loss(
-                rcnn_pred_cls, rcnn_pred_loc, cls_targets, loc_targets, loc_weights)
-            if os.environ.get("SCDA_DEBUG_TARGETS") == "1":
-                self._dbg['late'] = tuple(t.clone() for t in (rois, cls_targets, loc_targets, loc_weights))
-                self._dbg['pred'] = (rcnn_pred_cls.detach().clone(), rcnn_pred_loc.detach().clone())
-            outputs['losses'] = [rpn_loss_cls, rpn_loss_loc, rcnn_loss_cls, rcnn_loss_loc]
-            outputs['accuracy'] = [rpn_acc, rcnn_acc]
-            outputs['predict'] = [props]
-            outputs['feature_map'] = x          # (engine: the detector's backward is cut here, see SCDATrainer)
             # fewer than 512 surviving target proposals: reuse the source clusters (:207-215)
             if proposals_gan.shape[0] != n_t:
                 logger.info("Different channels {} at target image".format(x_fea_gan.size(0)))
@@ -324,6 +320,30 @@ class FasterRCNN_AdEx(nn.Module):
                     threshold=input['threshold'])
                 outputs['cluster_features'] = [x_cluster_fea, x_cluster_fea_gan]
                 outputs['cluster_centers'] = [x_center_cluster, x_center_cluster_gan]
+            if on_clusters is not None:
+                on_clusters(outputs['cluster_centers'], outputs['cluster_features'])
+
+            # the four losses are only needed by the backward: computed here, at the end of the forward,
+            # so that the proposal / RoI stages above never wait for the anchor targets and the consumer of
+            # the clusters (on_clusters) never waits for the loss kernels
+            if anchor_pre is not None:
+                torch.cuda.current_stream().wait_stream(astream)
+                for t_ in anchor_pre:
+                    if torch.is_tensor(t_):
+                        t_.record_stream(torch.cuda.current_stream())
+            if taps is not None:
+                taps.update(anchor_targets=partial_fn['anchor_target_fn'](rpn_pred_loc.size()))
+            rpn_loss_cls, rpn_loss_loc, rpn_acc = self._add_rpn_loss(
+                partial_fn['anchor_target_fn'], rpn_pred_cls, rpn_pred_loc)
+            rcnn_loss_cls, rcnn_loss_loc, rcnn_acc = self._add_rcnn_loss(
+                rcnn_pred_cls, rcnn_pred_loc, cls_targets, loc_targets, loc_weights)
+            if os.environ.get("SCDA_DEBUG_TARGETS") == "1":
+                self._dbg['late'] = tuple(t.clone() for t in (rois, cls_targets, loc_targets, loc_weights))
+                self._dbg['pred'] = (rcnn_pred_cls.detach().clone(), rcnn_pred_loc.detach().clone())
+            outputs['losses'] = [rpn_loss_cls, rpn_loss_loc, rcnn_loss_cls, rcnn_loss_loc]
+            outputs['accuracy'] = [rpn_acc, rcnn_acc]
+            outputs['predict'] = [props]
+            outputs['feature_map'] = x          # (engine: the detector's backward is cut here, see SCDATrainer)
         else:
             proposals = partial_fn['rpn_proposal_fn'](self._rpn_scores(rpn_pred_cls).data,
                                                       rpn_pred_loc.data)

@@ -434,8 +434,36 @@ def _dropout_scale(shape, p, device):
     """keep/scale tensor of nn.Dropout(p) in training: 0 with probability p, else 1/(1-p)."""
     if p <= 0.0:
         return None
-    keep = torch.rand(shape, device=device) >= p
-    return keep.to(torch.bfloat16) * (1.0 / (1.0 - p))
+    return torch.empty(shape, dtype=torch.bfloat16, device=device).bernoulli_(1.0 - p).mul_(1.0 / (1.0 - p))
+
+
+# The two keep/scale tensors of the RCNN head do not depend on the RoI features: with MASK_SIDE_STREAMS (set by
+# the engine with its stream overlap) they are drawn on a helper stream beside RoIPool instead of between
+# RoIPool and fc6 (one helper per issuing stream: the source and the target branch run side by side).
+MASK_SIDE_STREAMS = False
+_MASK_STREAMS = {}
+
+
+def _dropout_scales(shapes, ps, device):
+    if not MASK_SIDE_STREAMS or not torch.cuda.is_available() or all(p <= 0.0 for p in ps):
+        return [_dropout_scale(sh, p, device) for sh, p in zip(shapes, ps)], None
+    cur = torch.cuda.current_stream()
+    side = _MASK_STREAMS.get(cur.cuda_stream)
+    if side is None:
+        side = _MASK_STREAMS[cur.cuda_stream] = torch.cuda.Stream(device=device)
+    side.wait_stream(cur)
+    with torch.cuda.stream(side):
+        out = [_dropout_scale(sh, p, device) for sh, p in zip(shapes, ps)]
+    return out, side
+
+
+def _join_masks(masks, side):
+    if side is not None:
+        cur = torch.cuda.current_stream()
+        cur.wait_stream(side)
+        for m in masks:
+            if m is not None:
+                m.record_stream(cur)
 
 
 # Side stream for the big fc6 / fc7 weight gradients of the RCNN head's backward (set by the engine; None =
@@ -453,9 +481,9 @@ class _RcnnHeadFn(torch.autograd.Function):
         NB, H, W, C = feat.shape
         R = rois.shape[0]
         rois = rois.contiguous().float()
+        (dm6, dm7), mside = _dropout_scales(((R, w6.shape[0]), (R, w7.shape[0])), p_drop, feat.device)
         x, argmax = tc.roi_pool_nhwc(feat, rois, ph, pw, scale)      # [R, C*ph*pw] bf16, fc6's order
-        dm6 = _dropout_scale((R, w6.shape[0]), p_drop[0], feat.device)
-        dm7 = _dropout_scale((R, w7.shape[0]), p_drop[1], feat.device)
+        _join_masks((dm6, dm7), mside)
         h6 = tc.gemm_tn(x, rt.shadow(w6), b6.detach(), relu=True, mul_src=dm6)
         h7 = tc.gemm_tn(h6, rt.shadow(w7), b7.detach(), relu=True, mul_src=dm7)
         wcat, bcat, nc, nl = rt.rcnn_cat()
