@@ -235,13 +235,15 @@ class SCDATrainer(object):
         # beside the detector's backward and optimiser step (nothing flows between them: the
         # cluster features are detached, functions/mask.py:234 of the reference).
         # graph_collectives (world > 1): capture the NCCL all-reduces inside the one graph;
-        # None = the SCDA_GRAPH_COLLECTIVES environment variable, default OFF: on 2 x B200 the
-        # captured form hung (NCCL 2.28.9 / torch 2.11, profiles/r1_ddp2_check.txt), the cut form is
-        # what the multi-GPU numbers are measured with.
+        # None = the SCDA_GRAPH_COLLECTIVES environment variable, default ON.  (With ONE communicator the
+        # captured form hung on 2 x B200, profiles/r1_ddp2_check.txt: two forked branches of the capture
+        # issued collectives with no order between them.  With a communicator per issuing stream
+        # (`_group_of`) it replays on 2 and on 8 GPUs: 8 x B200 987 images/s vs 958 for the cut plan,
+        # profiles/r2_scale8.txt.)  SCDA_GRAPH_COLLECTIVES=0 / graph_collectives=False select the cut plan.
         self.overlap = overlap
         self.pair_streams = os.environ.get("SCDA_PAIR_STREAMS", "1") != "0"
         if graph_collectives is None:
-            graph_collectives = os.environ.get("SCDA_GRAPH_COLLECTIVES", "0") != "0"
+            graph_collectives = os.environ.get("SCDA_GRAPH_COLLECTIVES", "1") != "0"
         self.graph_collectives = graph_collectives
         self.force_cut = force_cut          # tests: the cut (world > 1) replay plan on one GPU
         self.split_detector = os.environ.get("SCDA_SPLIT_DETECTOR", "1") != "0"
