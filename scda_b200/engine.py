@@ -248,6 +248,8 @@ class SCDATrainer(object):
         self.force_cut = force_cut          # tests: the cut (world > 1) replay plan on one GPU
         self.split_detector = os.environ.get("SCDA_SPLIT_DETECTOR", "1") != "0"
         self.wgrad_side = os.environ.get("SCDA_WGRAD_SIDE", "0") != "0"     # measured: 7.69 ms with, 7.59 without
+        # the backbone's weight / bias gradients on their own stream beside its data-gradient chain
+        self.body_wgrad_side = os.environ.get("SCDA_BODY_WGRAD_SIDE", "1") != "0"
         self._det_head_lo, self._oside = None, None
         self._comm_per_stream = os.environ.get("SCDA_ONE_COMM", "0") == "0"
         self._groups = None
@@ -255,7 +257,7 @@ class SCDATrainer(object):
         self._tside = None
         self._aside = None
         self._pside = None
-        self._ksides, self._gan_go = None, None
+        self._ksides, self._gan_go, self._bwside = None, None, None
         if overlap and hasattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch"):
             # gradients are produced on whichever stream ran the forward of their branch and are
             # accumulated into the flat buffers there; the mismatch torch warns about is intended
@@ -480,8 +482,13 @@ class SCDATrainer(object):
         rpn_cls_loss, rpn_loc_loss = st['det_losses'][:2]
         lo = self._head_lo()
         front = [p for p, off in zip(self.opt.params, self.opt.offsets) if off < lo]
-        torch.autograd.backward([(rpn_cls_loss + rpn_loc_loss) / ws, st['feat']], [None, st.pop('g_feat')],
-                                inputs=front)
+        from . import tc_detector
+        tc_detector.BODY_WGRAD_STREAM = self._body_wgrad_stream() if (self.overlap and self.body_wgrad_side) else None
+        try:
+            torch.autograd.backward([(rpn_cls_loss + rpn_loc_loss) / ws, st['feat']], [None, st.pop('g_feat')],
+                                    inputs=front)
+        finally:
+            tc_detector.BODY_WGRAD_STREAM = None
         st.pop('feat')
 
     def _seg_step_head(self):
@@ -572,6 +579,11 @@ class SCDATrainer(object):
         if self._side is None:
             self._side = torch.cuda.Stream(device=self.opt.flat.device, priority=-1)
         return self._side
+
+    def _body_wgrad_stream(self):
+        if self._bwside is None:
+            self._bwside = torch.cuda.Stream(device=self.opt.flat.device)
+        return self._bwside
 
     def _kmeans_streams(self):
         if self._ksides is None:

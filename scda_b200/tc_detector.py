@@ -367,20 +367,36 @@ class _BackboneFn(torch.autograd.Function):
             g = g.to(torch.bfloat16)
         g = torch.where(outs[last] > 0, g, torch.zeros_like(g))       # ReLU of the last conv
         grads = [None] * (2 * len(rt.convs))
+        # BODY_WGRAD_STREAM: nothing in the backward reads a layer's weight / bias gradient, and they need only
+        # that layer's dY — they go to the side stream, the data-gradient chain (dgrad -> pool -> dgrad ...)
+        # stays on the current one; joined at the end
+        side = BODY_WGRAD_STREAM if g.is_cuda else None
+        cur = torch.cuda.current_stream() if side is not None else None
         for i in range(last, -1, -1):
             m, _ = rt.convs[i]
             cout = m.weight.shape[0]
-            grads[2 * i + 1] = _sink_bias(m.bias, g.view(-1, cout))
-            if i == 0:
-                grads[0] = _sink_conv_wgrad(m.weight, ins[0], g, cin_real=ctx.cin)
-                break
-            grads[2 * i] = _sink_conv_wgrad(m.weight, ins[i], g)
+            if side is not None:
+                side.wait_stream(cur)
+                with torch.cuda.stream(side):
+                    grads[2 * i + 1] = _sink_bias(m.bias, g.view(-1, cout))
+                    grads[2 * i] = _sink_conv_wgrad(m.weight, ins[i], g, cin_real=ctx.cin if i == 0 else None)
+                g.record_stream(side)
+                if i == 0:
+                    break
+            else:
+                grads[2 * i + 1] = _sink_bias(m.bias, g.view(-1, cout))
+                if i == 0:
+                    grads[0] = _sink_conv_wgrad(m.weight, ins[0], g, cin_real=ctx.cin)
+                    break
+                grads[2 * i] = _sink_conv_wgrad(m.weight, ins[i], g)
             w = rt.shadow(m.weight)
             if rt.convs[i - 1][1]:          # the input of conv i is a pooled map
                 d_pooled = tc.conv3x3_dgrad_nhwc(g, w)
                 g = tc.maxpool2x2_bwd_nhwc(outs[i - 1], d_pooled, relu_mask=True)
             else:
                 g = tc.conv3x3_dgrad_nhwc(g, w, mask_src=ins[i])
+        if side is not None:
+            cur.wait_stream(side)
         return (None, None) + tuple(grads)
 
 
@@ -472,6 +488,8 @@ def _join_masks(masks, side):
 # (fc7 -> fc6 -> RoIPool backward -> backbone) instead of in front of it.  The engine joins the stream before
 # the head bucket's all-reduce / Adam.
 WGRAD_STREAM = None
+# The same for the backbone's 13 weight / bias gradients (set by the engine with its stream overlap).
+BODY_WGRAD_STREAM = None
 
 
 class _RcnnHeadFn(torch.autograd.Function):

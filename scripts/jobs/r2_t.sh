@@ -1,0 +1,7 @@
+# backbone weight gradients on a side stream: A/B step time, tests
+set -x
+T=r2_t
+SCDA_BODY_WGRAD_SIDE=0 timeout 300 python bench.py --steps 50 --no-cpu-baseline --no-parity-line > gpurun_out/${T}_bench_off.json 2> gpurun_out/${T}_bench_off.err; echo rc=$?; cut -c1-200 gpurun_out/${T}_bench_off.json
+SCDA_BODY_WGRAD_SIDE=1 timeout 300 python bench.py --steps 50 --no-cpu-baseline --no-parity-line > gpurun_out/${T}_bench_on.json 2> gpurun_out/${T}_bench_on.err; echo rc=$?; cut -c1-200 gpurun_out/${T}_bench_on.json
+SCDA_TIMESTAMPS=1 timeout 300 python scripts/phase_times.py > gpurun_out/${T}_phases.txt 2>&1; tail -16 gpurun_out/${T}_phases.txt
+timeout 900 python -m pytest tests/test_engine_gpu.py tests/test_iteration_parity_gpu.py tests/test_tc_detector_gpu.py -x -q > gpurun_out/${T}_test.log 2>&1; echo rc=$?; tail -3 gpurun_out/${T}_test.log
