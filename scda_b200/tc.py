@@ -224,7 +224,10 @@ def linear_wgrad(dy, x, out=None, accumulate=False):
     return out
 
 
-WGRAD3 = os.environ.get("SCDA_WGRAD3", "0") == "1"      # three taps per CTA (csrc/gemm_tc.cu: tc_wgrad3_kernel)
+# three taps (one kernel column) per CTA (csrc/gemm_tc.cu: tc_wgrad3_kernel): the default.  Per layer 5-30 % faster than
+# the one-tap form (conv1_2 116 -> 81 us, conv3_2 / conv4_2 58 -> 50 us) and 7.00 -> 6.84 ms per iteration
+# (gpurun r2_u); SCDA_WGRAD3=0 selects the one-tap form.
+WGRAD3 = os.environ.get("SCDA_WGRAD3", "1") == "1"
 
 
 def _wgrad_splits(NB, H, W, Cin, Cout, target_ctas):

@@ -141,7 +141,7 @@ def test_conv3x3_wgrad(cuda_lib, NB, H, W, Cin, Cout):
             _close(tc.conv3x3_wgrad_nhwc(x, dy), ref, rtol=3e-3)
             _close(tc.conv3x3_wgrad_nhwc(x, dy, target_ctas=9), ref, rtol=3e-3)       # no split
     finally:
-        tc.set_wgrad_form(False)
+        tc.set_wgrad_form(True)             # the default form
 
 
 def test_conv3x3_dgrad_via_flipped_weights(cuda_lib):
