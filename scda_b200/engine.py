@@ -258,6 +258,7 @@ class SCDATrainer(object):
         self._aside = None
         self._pside = None
         self._ksides, self._gan_go, self._bwside = None, None, None
+        self._copy_stream, self._stage, self._prefetched = None, {}, None
         if overlap and hasattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch"):
             # gradients are produced on whichever stream ran the forward of their branch and are
             # accumulated into the flat buffers there; the mismatch torch warns about is intended
@@ -775,6 +776,39 @@ class SCDATrainer(object):
         main.wait_stream(side)
         run(['out'])
 
+    @staticmethod
+    def _src_key(image, gts, target):
+        return tuple((id(t), t.data_ptr(), tuple(t.shape), t.dtype) for t in (image, gts, target))
+
+    def prefetch(self, image, gts, target):
+        """Start the host -> device copy of the NEXT iteration's inputs (pinned host tensors) on a copy
+        stream, so that it runs beside the iteration in flight (the role of the reference's DataLoader
+        workers + `.cuda()` at the top of its loop, tools/faster_rcnn_train_val.py:528-533, made
+        asynchronous).  `iteration()` called with the same tensors then takes the device copies instead of
+        copying from the host.  Optional: without it `iteration()` copies its inputs itself."""
+        dev = self.opt.flat.device
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=dev)
+        shape_key = (tuple(image.shape), tuple(target.shape), tuple(gts.shape), gts.dtype)
+        st = self._stage.get(shape_key)
+        if st is None:
+            st = {'buf': {'image': torch.empty(image.shape, dtype=torch.float32, device=dev),
+                          'target': torch.empty(target.shape, dtype=torch.float32, device=dev),
+                          'gts': torch.empty(gts.shape, dtype=gts.dtype, device=dev)},
+                  'free': torch.cuda.Event()}
+            st['free'].record(torch.cuda.current_stream())
+            self._stage[shape_key] = st
+        cs = self._copy_stream
+        cs.wait_event(st['free'])                # the previous iteration has taken its inputs out of `buf`
+        with torch.cuda.stream(cs):
+            st['buf']['image'].copy_(image, non_blocking=True)
+            st['buf']['target'].copy_(target, non_blocking=True)
+            st['buf']['gts'].copy_(gts, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(cs)
+        self._prefetched = {'src': self._src_key(image, gts, target), 'buf': st['buf'], 'done': done,
+                            'free': st['free']}
+
     def iteration(self, cfg, image, image_info, gts, target, lr=None):
         """One iteration; returns a dict of 0-dim loss tensors (no host sync here).
 
@@ -793,9 +827,19 @@ class SCDATrainer(object):
             self._by_shape[key] = ent
         self._static, self._st = ent['static'], ent['st']
         b = self._static
-        b['image'].copy_(image, non_blocking=True)
-        b['target'].copy_(target, non_blocking=True)
-        b['gts'].copy_(gts, non_blocking=True)
+        pf, self._prefetched = self._prefetched, None
+        if pf is not None and pf['src'] == self._src_key(image, gts, target):
+            # the inputs are already on the device (prefetch): wait for that copy, move them into the
+            # graph's fixed buffers (12.6 MB device to device) and hand the staging buffers back
+            main = torch.cuda.current_stream()
+            main.wait_event(pf['done'])
+            for k in ('image', 'target', 'gts'):
+                b[k].copy_(pf['buf'][k], non_blocking=True)
+            pf['free'].record(main)
+        else:
+            b['image'].copy_(image, non_blocking=True)
+            b['target'].copy_(target, non_blocking=True)
+            b['gts'].copy_(gts, non_blocking=True)
         for o in (self.opt_dis, self.opt_dis_patch, self.opt_dec, self.opt):
             o.begin_step(lr)
         if not self.use_graphs or ent['calls'] == 0 or self.taps is not None or self.rng is not None:

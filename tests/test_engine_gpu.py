@@ -192,3 +192,28 @@ def test_stale_direct_gradient_is_zeroed_before_autograd_accumulates(cuda_lib):
     model._fp32_graph = False
     assert float(grads[0].abs().max()) > 0
     assert torch.allclose(grads[0], grads[1], rtol=1e-5, atol=1e-7), "second step accumulated onto stale gradients"
+
+
+def test_prefetched_inputs_reach_the_graph_buffers(cuda_lib):
+    """SCDATrainer.prefetch: the next iteration's pinned host inputs go up on the copy stream; iteration()
+    called with the same tensors takes the device copies (no second H2D), with other tensors it copies
+    itself.  Either way the graph's fixed input buffers hold exactly the inputs of THAT iteration."""
+    import torch
+    tr, cfg = _trainer(True)
+    batches = []
+    for seed in range(3):
+        img, tgt, gts, info = _batch(seed)
+        batches.append((img.cpu().pin_memory(), tgt.cpu().pin_memory(), gts.cpu().pin_memory(), info))
+    tr.prefetch(batches[0][0], batches[0][2], batches[0][1])
+    for it in range(5):                      # eager, capture + replay, replays
+        img, tgt, gts, info = batches[it % 3]
+        out = tr.iteration(cfg, img, info, gts, tgt)
+        assert tr._prefetched is None
+        if it in (0, 1, 3):                  # prefetch the next batch on some steps only
+            nxt = batches[(it + 1) % 3]
+            tr.prefetch(nxt[0], nxt[2], nxt[1])
+        torch.cuda.synchronize()
+        b = tr._static
+        assert torch.equal(b['image'].cpu(), img) and torch.equal(b['target'].cpu(), tgt)
+        assert torch.equal(b['gts'].cpu(), gts)
+        assert bool(torch.isfinite(out['loss']))
