@@ -250,6 +250,8 @@ class SCDATrainer(object):
         self.wgrad_side = os.environ.get("SCDA_WGRAD_SIDE", "0") != "0"     # measured: 7.69 ms with, 7.59 without
         # the backbone's weight / bias gradients on their own stream beside its data-gradient chain
         self.body_wgrad_side = os.environ.get("SCDA_BODY_WGRAD_SIDE", "1") != "0"
+        # the same for the decoder's convolution nodes in phase 3 (gan_ops.WGRAD_SIDE)
+        self.gan_wgrad_side = os.environ.get("SCDA_GAN_WGRAD_SIDE", "1") != "0"
         self._det_head_lo, self._oside = None, None
         self._comm_per_stream = os.environ.get("SCDA_ONE_COMM", "0") == "0"
         self._groups = None
@@ -392,6 +394,7 @@ class SCDATrainer(object):
         from . import disc_ops
         with disc_ops.frozen_params():          # through the discriminators to the decoder only
             recon_loss.backward(inputs=self.opt_dec.params)
+        gan_ops.join_wgrad_streams()
         st['dec_loss'] = recon_loss.detach()
         st.pop('recon'), st.pop('t_patch_pro'), st.pop('s_patch_pro'), st.pop('t_patch_mean', None)
 
@@ -609,6 +612,7 @@ class SCDATrainer(object):
         bound), and they join before the losses are assembled."""
         from . import timestamps as ts
         gan_ops.PAIR_STREAMS = bool(self.overlap and self.pair_streams)
+        gan_ops.WGRAD_SIDE = bool(self.overlap and self.gan_wgrad_side)
         from . import tc_detector
         tc_detector.MASK_SIDE_STREAMS = bool(self.overlap)
         ts.mark("start")
@@ -631,6 +635,7 @@ class SCDATrainer(object):
             self._gan_chain(reduce)
             self._det_chain(reduce)
         self._seg_outputs()
+        gan_ops.WGRAD_SIDE = False             # (module-level switches: only inside an iteration of this engine)
         ts.mark("end")
 
     def _reduce_fn(self):
@@ -708,6 +713,7 @@ class SCDATrainer(object):
         therefore allocate from different pools."""
         torch.cuda.synchronize()
         gan_ops.PAIR_STREAMS = bool(self.overlap and self.pair_streams)
+        gan_ops.WGRAD_SIDE = bool(self.overlap and self.gan_wgrad_side)
         from . import tc_detector
         tc_detector.MASK_SIDE_STREAMS = bool(self.overlap)
         if self._whole_graph():
@@ -726,6 +732,7 @@ class SCDATrainer(object):
             with torch.cuda.graph(g, pool=pools[where]):
                 fn()
             graphs.append(g)
+        gan_ops.WGRAD_SIDE = False
         return graphs
 
     def _replay_cut(self, graphs):

@@ -192,6 +192,37 @@ def _helper_stream(cur):
     return st
 
 
+# Weight / bias gradients of the decoder's convolution nodes on a helper stream: nothing in the backward reads
+# them (they are reduced straight into the flat gradient buffer), so the data-gradient chain of phase 3 —
+# InstanceNorm backward -> dgrad -> next node, the tail of the iteration's critical path — does not queue behind
+# colsum + weight gradient + slab reduction of every node.  Set by the engine; joined by `join_wgrad_streams()`
+# before the gradients are used (all-reduce / Adam).
+WGRAD_SIDE = False
+_WG_PENDING = []
+
+
+def _wgrad_stream(cur):
+    key = ("wg", cur.device.index, cur.cuda_stream)
+    st = _HELPERS.get(key)
+    if st is None:
+        st = torch.cuda.Stream(device=cur.device, priority=cur.priority)
+        _HELPERS[key] = st
+    return st
+
+
+def join_wgrad_streams():
+    """the current stream waits for every helper stream that still carries weight-gradient work"""
+    if not _WG_PENDING:
+        return
+    cur = torch.cuda.current_stream()
+    seen = set()
+    while _WG_PENDING:
+        st = _WG_PENDING.pop()
+        if st.cuda_stream not in seen:
+            seen.add(st.cuda_stream)
+            cur.wait_stream(st)
+
+
 def _tensors(obj):
     if torch.is_tensor(obj):
         yield obj
@@ -302,8 +333,22 @@ class _ConvINActTC(torch.autograd.Function):
             if ctx.needs_input_grad[0]:
                 dx = tc.conv3x3_dgrad_nhwc(ds, shadow3_of(weight)[1], out_dtype=torch.float32).permute(0, 3, 1, 2)
             return dx, gw, gb, None, None, None, None
-        gb = _sink_bias(bias, dc.view(-1, O)) if bias is not None and ctx.needs_input_grad[2] else None
-        gw = _sink_conv_wgrad(weight, xn, dc) if ctx.needs_input_grad[1] else None
+        if WGRAD_SIDE and dc.is_cuda:
+            cur = torch.cuda.current_stream()
+            side = _wgrad_stream(cur)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                gb = _sink_bias(bias, dc.view(-1, O)) if bias is not None and ctx.needs_input_grad[2] else None
+                gw = _sink_conv_wgrad(weight, xn, dc) if ctx.needs_input_grad[1] else None
+            dc.record_stream(side)                # both operands are released when this node returns,
+            xb.record_stream(side)                # while the helper stream may still be reading them
+            if gw is None and gb is None:
+                _WG_PENDING.append(side)          # written in place: joined by join_wgrad_streams()
+            else:
+                cur.wait_stream(side)             # handed to autograd on this stream
+        else:
+            gb = _sink_bias(bias, dc.view(-1, O)) if bias is not None and ctx.needs_input_grad[2] else None
+            gw = _sink_conv_wgrad(weight, xn, dc) if ctx.needs_input_grad[1] else None
         if ctx.needs_input_grad[0]:
             dx = tc.conv3x3_dgrad_nhwc(dc, shadow_of(weight), out_dtype=x_dtype).permute(0, 3, 1, 2)
         return dx, gw, gb, None, None, None, None

@@ -18,22 +18,40 @@ SHAPES = {"conv1_1p": (512, 1024, 64, 64), "conv1_2": (512, 1024, 64, 64), "conv
 
 
 def main():
-    names = sys.argv[1:] or list(SHAPES)
+    """usage: prof_conv.py [--pass=fwd|dgrad|wgrad] [layer ...]"""
+    what = "fwd"
+    names = []
+    for a in sys.argv[1:]:
+        if a.startswith("--pass="):
+            what = a.split("=", 1)[1]
+        else:
+            names.append(a)
+    names = names or list(SHAPES)
     dev = torch.device("cuda")
     data = {}
+
+    def run(x, w, b, dy, out):
+        if what == "fwd":
+            tc.conv3x3_nhwc(x, w, b, relu=True)
+        elif what == "dgrad":
+            tc.conv3x3_dgrad_nhwc(dy, w, mask_src=x)
+        else:
+            tc.conv3x3_wgrad_nhwc(x, dy, out=out)        # the weight-gradient kernel + reduce_slabs
+
     for n in names:
         H, W, Cin, Cout = SHAPES[n]
         x = torch.randn(1, H, W, Cin, device=dev).bfloat16()
         w = (torch.randn(Cout, 3, 3, Cin, device=dev) / (9 * Cin) ** 0.5).bfloat16()
         b = torch.zeros(Cout, device=dev)
-        data[n] = (x, w, b)
+        dy = torch.randn(1, H, W, Cout, device=dev).bfloat16()
+        out = torch.empty(Cout, 3, 3, Cin, device=dev)
+        data[n] = (x, w, b, dy, out)
         for _ in range(2):
-            tc.conv3x3_nhwc(x, w, b, relu=True)
+            run(*data[n])
     torch.cuda.synchronize()
     torch.cuda.profiler.start()
     for n in names:
-        x, w, b = data[n]
-        tc.conv3x3_nhwc(x, w, b, relu=True)
+        run(*data[n])
     torch.cuda.synchronize()
     torch.cuda.profiler.stop()
 
