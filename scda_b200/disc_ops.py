@@ -25,6 +25,23 @@ LEAKY, OUT_F32, MASK_POS, MASK_LEAKY = 128, 2, 4, 256
 FREEZE_PARAMS = False
 
 
+# The mirror case: phase 1 differentiates the image discriminator's loss w.r.t. the discriminator's parameters
+# only (`backward(inputs=dis.params)`), but the reconstructions it was applied to require grad (they come out of
+# the decoder), so needs_input_grad[0] is True and the first layer's INPUT gradient (0.08-0.1 ms per decoder,
+# l1_bwd_x_kernel) would be computed and dropped.  The engine sets this around that backward.
+FREEZE_INPUT = False
+
+
+class frozen_inputs(object):
+    def __enter__(self):
+        global FREEZE_INPUT
+        self.prev, FREEZE_INPUT = FREEZE_INPUT, True
+
+    def __exit__(self, *exc):
+        global FREEZE_INPUT
+        FREEZE_INPUT = self.prev
+
+
 class frozen_params(object):
     def __enter__(self):
         global FREEZE_PARAMS
@@ -165,6 +182,8 @@ class _ImageDisFn(torch.autograd.Function):
         need = ctx.needs_input_grad                     # x, w1, b1, w2, b2, w3, b3, w4, b4, slope
         if FREEZE_PARAMS:
             need = (need[0],) + (False,) * 9
+        if FREEZE_INPUT:
+            need = (False,) + tuple(need[1:])
         slope, dev, lib = ctx.slope, x.device, load()
         N, _, H, W = x.shape
         P, C = y3.numel() // y3.shape[3], y3.shape[3]
@@ -190,13 +209,14 @@ class _ImageDisFn(torch.autograd.Function):
                                         _ptr(dw4), _ptr(db4), stream_ptr(dev)), "scda_head_dot_bwd")
         if need[7] and not (_direct(w4) and _direct(b4) and w4.grad.is_contiguous()):
             grads[7], grads[8] = dw4.view_as(w4), db4.view_as(b4)
+        from .gan_ops import run_wgrad_side          # (weight / bias gradients beside the data-gradient chain)
         if need[5]:
-            grads[5] = _sink_s2_wgrad(w3, y2, d3)
-            grads[6] = _sink_bias_bf16(b3, d3.view(-1, C))
+            grads[5], grads[6] = run_wgrad_side(
+                lambda: (_sink_s2_wgrad(w3, y2, d3), _sink_bias_bf16(b3, d3.view(-1, C))), d3, y2)
         d2 = conv_s2_dgrad(d3, s2_weights(w3), y2.shape[3], mask_src=y2, slope=slope)
         if need[3]:
-            grads[3] = _sink_s2_wgrad(w2, y1, d2)
-            grads[4] = _sink_bias_bf16(b2, d2.view(-1, d2.shape[3]))
+            grads[3], grads[4] = run_wgrad_side(
+                lambda: (_sink_s2_wgrad(w2, y1, d2), _sink_bias_bf16(b2, d2.view(-1, d2.shape[3]))), d2, y1)
         if not (need[0] or need[1]):
             return tuple(grads)
         d1 = conv_s2_dgrad(d2, s2_weights(w2), y1.shape[3], mask_src=y1, slope=slope)

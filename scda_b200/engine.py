@@ -349,7 +349,10 @@ class SCDATrainer(object):
             t_patch_mean.record_stream(cur)
         adloss_target = (t_patch_mean * _bce_rows(t_dis, score_0) + _bce_rows(t_real, score_1)).sum()
         adloss = (adloss_source + adloss_target) / ws
-        adloss.backward(retain_graph=True, inputs=self.opt_dis.params)
+        from . import disc_ops
+        with disc_ops.frozen_inputs():          # parameters of the discriminator only: no gradient to the decoder here
+            adloss.backward(retain_graph=True, inputs=self.opt_dis.params)
+        gan_ops.join_wgrad_streams()
         st['dis_loss'] = adloss.detach()
 
     def _soft(self, name, flag, like):

@@ -210,6 +210,26 @@ def _wgrad_stream(cur):
     return st
 
 
+def run_wgrad_side(fn, *operands):
+    """fn() -> tuple of gradients (None = written in place).  With WGRAD_SIDE it runs on the helper stream of
+    the current stream; `operands`: the tensors it reads that the caller may release before it is done."""
+    if not (WGRAD_SIDE and torch.cuda.is_available()):
+        return fn()
+    cur = torch.cuda.current_stream()
+    side = _wgrad_stream(cur)
+    side.wait_stream(cur)
+    with torch.cuda.stream(side):
+        out = fn()
+    for t in operands:
+        if t is not None and t.is_cuda:
+            t.record_stream(side)
+    if all(o is None for o in out):
+        _WG_PENDING.append(side)              # joined by join_wgrad_streams()
+    else:
+        cur.wait_stream(side)                 # handed to autograd on this stream
+    return out
+
+
 def join_wgrad_streams():
     """the current stream waits for every helper stream that still carries weight-gradient work"""
     if not _WG_PENDING:
@@ -333,22 +353,10 @@ class _ConvINActTC(torch.autograd.Function):
             if ctx.needs_input_grad[0]:
                 dx = tc.conv3x3_dgrad_nhwc(ds, shadow3_of(weight)[1], out_dtype=torch.float32).permute(0, 3, 1, 2)
             return dx, gw, gb, None, None, None, None
-        if WGRAD_SIDE and dc.is_cuda:
-            cur = torch.cuda.current_stream()
-            side = _wgrad_stream(cur)
-            side.wait_stream(cur)
-            with torch.cuda.stream(side):
-                gb = _sink_bias(bias, dc.view(-1, O)) if bias is not None and ctx.needs_input_grad[2] else None
-                gw = _sink_conv_wgrad(weight, xn, dc) if ctx.needs_input_grad[1] else None
-            dc.record_stream(side)                # both operands are released when this node returns,
-            xb.record_stream(side)                # while the helper stream may still be reading them
-            if gw is None and gb is None:
-                _WG_PENDING.append(side)          # written in place: joined by join_wgrad_streams()
-            else:
-                cur.wait_stream(side)             # handed to autograd on this stream
-        else:
-            gb = _sink_bias(bias, dc.view(-1, O)) if bias is not None and ctx.needs_input_grad[2] else None
-            gw = _sink_conv_wgrad(weight, xn, dc) if ctx.needs_input_grad[1] else None
+        need = ctx.needs_input_grad
+        # (both operands are released when this node returns, while the helper stream may still be reading them)
+        gb, gw = run_wgrad_side(lambda: (_sink_bias(bias, dc.view(-1, O)) if bias is not None and need[2] else None,
+                                         _sink_conv_wgrad(weight, xn, dc) if need[1] else None), dc, xb)
         if ctx.needs_input_grad[0]:
             dx = tc.conv3x3_dgrad_nhwc(dc, shadow_of(weight), out_dtype=x_dtype).permute(0, 3, 1, 2)
         return dx, gw, gb, None, None, None, None
