@@ -21,7 +21,8 @@ def _run(extra, port):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("extra,port", [(["--no-graph-collectives"], 29541), (["--no-graph-collectives", "--no-overlap"], 29542)])
+@pytest.mark.parametrize("extra,port", [(["--graph-collectives"], 29543),         # the default: NCCL captured in the one graph
+                                        (["--no-graph-collectives"], 29541), (["--no-graph-collectives", "--no-overlap"], 29542)])
 def test_two_ranks_hold_identical_parameters(cuda_lib, extra, port):
     import torch
     if torch.cuda.device_count() < 2:
