@@ -354,6 +354,7 @@ def our_arm(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, ms2 = float(t[0]), float(t[1])
     parity = None
+    fallbacks_main = dict(gan_ops.LIBRARY_CALLS)        # library (cuDNN / torch) layers met by the headline run
     if rank == 0 and world == 1 and args.precision == "bf16" and not args.no_parity_line:
         # the same iteration in the fp32-parity precision mode (tc.set_precision('bf16x3')), timed in
         # this process right after the headline run: a second trainer, 3 warm-up + 10 timed steps
@@ -376,7 +377,10 @@ def our_arm(args):
                            "~2^-16 per product; the reference's arithmetic is fp32)",
                   "value": 1e3 / pms, "unit": UNIT, "ms_per_step": pms, "steps": 10, "warmup": 4,
                   "roofline": {k: roof3[k] for k in ("bound", "achieved", "peak", "unit", "frac", "peak_source")},
-                  "parity": "tests/test_iteration_parity_gpu.py, profiles/r2_iteration_parity.txt"}
+                  "parity": "tests/test_iteration_parity_gpu.py, profiles/r2_iteration_parity.txt",
+                  # (this mode keeps the two discriminators on cuDNN fp32: they have no split-operand form)
+                  "library_fallbacks": {k: v - fallbacks_main.get(k, 0) for k, v in gan_ops.LIBRARY_CALLS.items()
+                                        if v - fallbacks_main.get(k, 0) > 0}}
         del tr3
         tc.set_precision("bf16")
         tr = None
@@ -405,7 +409,7 @@ def our_arm(args):
                                       "started before the previous step's loss is read back; every copy is "
                                       "inside the timed region"},
                 "gpu_launches": launches, "roofline": roof,
-                "library_fallbacks": dict(gan_ops.LIBRARY_CALLS)}
+                "library_fallbacks": fallbacks_main}
         if parity is not None:
             line["parity_mode"] = parity
         if world == 1:

@@ -157,6 +157,53 @@ reduce_slabs_kernel(const float *__restrict__ slabs, long long slab_stride, int 
     }
 }
 
+// Small outputs, many slabs (conv1_2: 36 864 elements x 49 slabs): with one thread per four elements only 36 blocks
+// run and each thread walks 49 dependent-latency loads (15 us).  Here kLanes threads share an element group:
+// lane l adds slabs l, l + kLanes, ... (independent loads), the lane sums are added in lane order — a fixed order,
+// so the result is still deterministic.  Block = (256 / kLanes) element groups x kLanes slab lanes.
+template <int kLanes>
+__global__ void __launch_bounds__(256)
+reduce_slabs_lanes_kernel(const float *__restrict__ slabs, long long slab_stride, int n_slabs,
+                          float *__restrict__ dst, long long n, int accumulate)
+{
+    constexpr int kElems = 256 / kLanes;
+    __shared__ float4 part[kLanes][kElems];
+    const int e = threadIdx.x % kElems, l = threadIdx.x / kElems;
+    for (long long i0 = (long long)blockIdx.x * kElems * 4; i0 < n; i0 += (long long)gridDim.x * kElems * 4) {
+        const long long i = i0 + e * 4;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < n) {
+            int sidx = l;
+            for (; sidx + 3 * kLanes < n_slabs; sidx += 4 * kLanes) {
+                const float4 v0 = ld_stream_f4(slabs + (long long)sidx * slab_stride + i);
+                const float4 v1 = ld_stream_f4(slabs + (long long)(sidx + kLanes) * slab_stride + i);
+                const float4 v2 = ld_stream_f4(slabs + (long long)(sidx + 2 * kLanes) * slab_stride + i);
+                const float4 v3 = ld_stream_f4(slabs + (long long)(sidx + 3 * kLanes) * slab_stride + i);
+                acc.x += v0.x; acc.y += v0.y; acc.z += v0.z; acc.w += v0.w;
+                acc.x += v1.x; acc.y += v1.y; acc.z += v1.z; acc.w += v1.w;
+                acc.x += v2.x; acc.y += v2.y; acc.z += v2.z; acc.w += v2.w;
+                acc.x += v3.x; acc.y += v3.y; acc.z += v3.z; acc.w += v3.w;
+            }
+            for (; sidx < n_slabs; sidx += kLanes) {
+                const float4 v = ld_stream_f4(slabs + (long long)sidx * slab_stride + i);
+                acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+            }
+        }
+        part[l][e] = acc;
+        __syncthreads();
+        if (l == 0 && i < n) {
+            float4 r = accumulate ? *reinterpret_cast<const float4 *>(dst + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int k = 0; k < kLanes; ++k) {
+                const float4 v = part[k][e];
+                r.x += v.x; r.y += v.y; r.z += v.z; r.w += v.w;
+            }
+            *reinterpret_cast<float4 *>(dst + i) = r;
+        }
+        __syncthreads();
+    }
+}
+
 // ------------------------------------------------------------------ column sums (bias gradient)
 // x bf16 [M, ld] -> out fp32 [N] (+=).  Block = 256 threads = 8 row lanes x 32 column
 // pairs; grid.x covers column pairs, grid.y cuts the rows; partial sums meet in out[]
@@ -188,6 +235,55 @@ colsum_kernel(const __nv_bfloat16 *__restrict__ x, long long ld, long long M, in
         }
         red_add_f32(out + c, acc.x);
         if (c + 1 < N) red_add_f32(out + c + 1, acc.y);
+    }
+}
+
+// The same with 16-byte loads (N, ld multiples of 8, x 16-byte aligned): thread t of a block owns the 8-column
+// group t % groups (groups = columns of this block / 8 <= 256) and every lanes_r-th row of the block's row range,
+// four loads in flight.  The 4-byte form above keeps ~1 KB per block in flight and streamed conv1_2's 67 MB
+// gradient at ~2 TB/s (35 us inside the iteration); this one is bound by HBM.
+__global__ void __launch_bounds__(256)
+colsum8_kernel(const __nv_bfloat16 *__restrict__ x, long long ld, long long M, int N, float *__restrict__ out)
+{
+    __shared__ float part[256][9];                   // (+1: the final column walk is conflict free)
+    const int c_base = blockIdx.y * 2048;
+    const int groups = min(256, (N - c_base) >> 3);
+    const int lanes_r = 256 / groups;
+    const int g = threadIdx.x % groups, lr = threadIdx.x / groups;
+    const long long rows_per = (M + gridDim.x - 1) / gridDim.x;
+    const long long r0 = (long long)blockIdx.x * rows_per, r1 = min(M, r0 + rows_per);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    auto add = [&](const uint4 &q) {
+        const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&q);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            acc[2 * j] += __low2float(h[j]);
+            acc[2 * j + 1] += __high2float(h[j]);
+        }
+    };
+    if (lr < lanes_r) {
+        const __nv_bfloat16 *col = x + c_base + g * 8;
+        long long r = r0 + lr;
+        for (; r + 3ll * lanes_r < r1; r += 4ll * lanes_r) {
+            const uint4 q0 = __ldg(reinterpret_cast<const uint4 *>(col + r * ld));
+            const uint4 q1 = __ldg(reinterpret_cast<const uint4 *>(col + (r + lanes_r) * ld));
+            const uint4 q2 = __ldg(reinterpret_cast<const uint4 *>(col + (r + 2ll * lanes_r) * ld));
+            const uint4 q3 = __ldg(reinterpret_cast<const uint4 *>(col + (r + 3ll * lanes_r) * ld));
+            add(q0); add(q1); add(q2); add(q3);
+        }
+        for (; r < r1; r += lanes_r) add(__ldg(reinterpret_cast<const uint4 *>(col + r * ld)));
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) part[threadIdx.x][j] = acc[j];
+    __syncthreads();
+    // thread t < groups * 8: column t of the block, the row lanes added in order
+    for (int t = threadIdx.x; t < groups * 8; t += 256) {
+        const int gg = t >> 3, j = t & 7;
+        float s = 0.f;
+        for (int k = 0; k < lanes_r; ++k) s += part[k * groups + gg][j];
+        red_add_f32(out + c_base + t, s);
     }
 }
 
@@ -319,7 +415,18 @@ SCDA_API int scda_reduce_slabs_f32(const float *slabs, long long slab_stride, in
 {
     if (!slabs || !dst || n <= 0 || n_slabs < 1) return 0;
     if (n % 4 || slab_stride % 4 || ((uintptr_t)slabs | (uintptr_t)dst) % 16) return 0;
-    reduce_slabs_kernel<<<grid_for(n / 4, 256), 256, 0, stream>>>(slabs, slab_stride, n_slabs, dst, n, accumulate);
+    // enough threads for ~2 blocks per SM: split the slab walk over 2 / 4 / 8 lanes when the output alone is too small
+    const long long want = (long long)kNumSMs * 2 * 256;
+    int lanes = 1;
+    while (lanes < 8 && (n / 4) * lanes < want && lanes * 2 <= n_slabs) lanes *= 2;
+    if (lanes == 8)
+        reduce_slabs_lanes_kernel<8><<<grid_for(n / 4, 32), 256, 0, stream>>>(slabs, slab_stride, n_slabs, dst, n, accumulate);
+    else if (lanes == 4)
+        reduce_slabs_lanes_kernel<4><<<grid_for(n / 4, 64), 256, 0, stream>>>(slabs, slab_stride, n_slabs, dst, n, accumulate);
+    else if (lanes == 2)
+        reduce_slabs_lanes_kernel<2><<<grid_for(n / 4, 128), 256, 0, stream>>>(slabs, slab_stride, n_slabs, dst, n, accumulate);
+    else
+        reduce_slabs_kernel<<<grid_for(n / 4, 256), 256, 0, stream>>>(slabs, slab_stride, n_slabs, dst, n, accumulate);
     return scda_launch_status();
 }
 
@@ -327,6 +434,16 @@ SCDA_API int scda_colsum_bf16(long long M, int N, const void *x, long long ld, f
 {
     // out[N] += column sums of x[M, ld] (bf16); N and ld even
     if (M <= 0 || N <= 0 || !x || !out || (N & 1) || (ld & 1) || ((uintptr_t)x % 4)) return 0;
+    if (N % 8 == 0 && ld % 8 == 0 && ((uintptr_t)x % 16) == 0 && (N <= 2048 || N % 2048 == 0)) {
+        const int cols = N < 2048 ? N : 2048, groups = cols / 8, lanes_r = 256 / groups;
+        long long blocks = (M + 8ll * lanes_r - 1) / (8ll * lanes_r);          // >= 8 rows per thread
+        const long long cap = (long long)kNumSMs * 4 / ceil_div(N, 2048);
+        if (blocks > cap) blocks = cap;
+        if (blocks < 1) blocks = 1;
+        colsum8_kernel<<<dim3((unsigned)blocks, ceil_div(N, 2048)), 256, 0, stream>>>((const __nv_bfloat16 *)x, ld, M, N,
+                                                                                    out);
+        return scda_launch_status();
+    }
     const int gx = ceil_div(N, 64);
     long long gy = (M + 255) / 256;
     const long long cap = (long long)kNumSMs * 8 / gx;

@@ -67,7 +67,8 @@ def test_layout_kernels(cuda_lib, NB, C, H, W, Cpad):
         assert torch.equal(back, x.bfloat16().float())
 
 
-@pytest.mark.parametrize("M,N", [(2048, 512), (524288, 64), (512, 4096), (300, 46), (7, 2)])
+@pytest.mark.parametrize("M,N", [(2048, 512), (524288, 64), (512, 4096), (300, 46), (7, 2), (1001, 24), (33, 256), (100000, 128),
+                                 (5, 2048), (3, 8)])
 def test_colsum_and_reduce_slabs(cuda_lib, M, N):
     import torch
     from scda_b200 import tc
@@ -83,6 +84,14 @@ def test_colsum_and_reduce_slabs(cuda_lib, M, N):
     assert torch.allclose(dst, part.sum(0) + 2, rtol=1e-6, atol=1e-6)
     tc.reduce_slabs(part, dst, accumulate=False)
     assert torch.allclose(dst, part.sum(0), rtol=1e-6, atol=1e-6)
+    for slabs, rows in ((49, 64), (2, 64), (12, 512), (3, 4096)):       # 8 / 2 / 4 / 1 slab lanes per element group
+        part = torch.randn(slabs, rows, 576, device="cuda", generator=g)
+        dst = torch.full((rows, 576), -1.0, device="cuda")
+        tc.reduce_slabs(part, dst, accumulate=True)
+        assert torch.allclose(dst, part.double().sum(0).float() - 1, rtol=1e-5, atol=1e-5)
+        again = torch.full((rows, 576), -1.0, device="cuda")
+        tc.reduce_slabs(part, again, accumulate=True)
+        assert torch.equal(dst, again), "the slab reduction must be deterministic"
 
 
 @pytest.mark.parametrize("NB,H,W,Cin,Cout", [(1, 8, 16, 64, 64), (1, 32, 64, 512, 512), (2, 16, 32, 128, 256),
