@@ -252,6 +252,9 @@ class SCDATrainer(object):
         self.body_wgrad_side = os.environ.get("SCDA_BODY_WGRAD_SIDE", "1") != "0"
         # the same for the decoder's convolution nodes in phase 3 (gan_ops.WGRAD_SIDE)
         self.gan_wgrad_side = os.environ.get("SCDA_GAN_WGRAD_SIDE", "1") != "0"
+        # third gradient bucket of the detector (conv4_1 .. RPN head), see _det_chain
+        self.mid_bucket = os.environ.get("SCDA_MID_BUCKET", "1") != "0"
+        self._mid_off, self._mid_conv = None, None
         self._det_head_lo, self._oside = None, None
         self._comm_per_stream = os.environ.get("SCDA_ONE_COMM", "0") == "0"
         self._groups = None
@@ -474,6 +477,17 @@ class SCDATrainer(object):
             self._det_head_lo = self.opt.offset_of(self.model.classifier[0].weight)
         return self._det_head_lo
 
+    def _mid_lo(self):
+        """start of the third bucket = conv4_1's weight (the 8th convolution of the VGG16 stack); None when the
+        backbone is not that stack"""
+        if self._mid_off is None:
+            convs = [m for m in self.model.features if isinstance(m, torch.nn.Conv2d)]
+            if len(convs) != 13:
+                self._mid_off = -1
+            else:
+                self._mid_off, self._mid_conv = self.opt.offset_of(convs[7].weight), 7
+        return self._mid_off if self._mid_off > 0 else None
+
     def _seg_det_backward_head(self):
         st, ws = self._st, float(self.world_size)
         rpn_cls_loss, rpn_loc_loss, rcnn_cls_loss, rcnn_loc_loss = st['det_losses']
@@ -574,10 +588,32 @@ class SCDATrainer(object):
             reduce(self.opt, lo, None)
             self._seg_step_head()
             ts.mark("head adam done")
-        self._seg_det_backward_body()
+        # a third bucket: conv4_1 .. conv5_3 + the RPN head (62 of the 69 MB in front of the head bucket) are
+        # complete when the backward reaches conv3_3; they are reduced and stepped on the opt stream (behind the
+        # head bucket, same communicator) while conv3_3 .. conv1_1 run.  What is left for the tail of the
+        # iteration is the all-reduce and Adam of 7 MB.
+        mid = self._mid_lo() if self.mid_bucket else None
+
+        fired = []
+
+        def mid_ready(main_stream, wgrad_stream):
+            fired.append(True)
+            osd.wait_stream(main_stream)
+            if wgrad_stream is not None:
+                osd.wait_stream(wgrad_stream)
+            with torch.cuda.stream(osd):
+                reduce(self.opt, mid, lo)
+                self.opt.step_dev(lo=mid, hi=lo)
+
+        tc_detector.BODY_BUCKET_HOOK = (self._mid_conv, mid_ready) if mid is not None else None
+        try:
+            self._seg_det_backward_body()
+        finally:
+            tc_detector.BODY_BUCKET_HOOK = None
         ts.mark("det body backward done")
-        reduce(self.opt, 0, lo)
-        self._seg_step_body()
+        tail_hi = mid if fired else lo        # (a backbone form without the hook, e.g. the fp32-parity mode: two buckets)
+        reduce(self.opt, 0, tail_hi)
+        self.opt.step_dev(lo=0, hi=tail_hi)
         cur.wait_stream(osd)
 
     def _side_stream(self):
@@ -659,8 +695,18 @@ class SCDATrainer(object):
         if self._groups is None:
             if not (dist.is_available() and dist.is_initialized()):
                 return None
-            # created in the same order on every rank (the eager warm-up iteration gets here first)
-            self._groups = {k: dist.new_group(backend=dist.get_backend()) for k in ("main", "opt", "side", "patch")}
+            # created in the same order on every rank (the eager warm-up iteration gets here first).
+            # SCDA_NCCL_OPT_CTAS=n caps the CTAs of the `opt` communicator: its one collective, the 478 MB head
+            # bucket, runs beside the backbone's backward with ~3 ms of slack, so it can give SMs back to it.
+            def make(name):
+                cap = int(os.environ.get("SCDA_NCCL_OPT_CTAS", "0")) if name == "opt" else 0
+                if cap > 0 and dist.get_backend() == "nccl":
+                    opts = dist.ProcessGroupNCCL.Options()
+                    opts.config.max_ctas = cap
+                    opts.config.min_ctas = min(cap, 1)
+                    return dist.new_group(backend="nccl", pg_options=opts)
+                return dist.new_group(backend=dist.get_backend())
+            self._groups = {k: make(k) for k in ("main", "opt", "side", "patch")}
         if opt is self.opt:
             return self._groups["opt" if (lo > 0 and self.split_detector) else "main"]
         if opt is self.opt_dis_patch:

@@ -372,9 +372,12 @@ class _BackboneFn(torch.autograd.Function):
         # stays on the current one; joined at the end
         side = BODY_WGRAD_STREAM if g.is_cuda else None
         cur = torch.cuda.current_stream() if side is not None else None
+        hook = BODY_BUCKET_HOOK if g.is_cuda else None
         for i in range(last, -1, -1):
             m, _ = rt.convs[i]
             cout = m.weight.shape[0]
+            if hook is not None and i == hook[0] - 1:
+                hook[1](torch.cuda.current_stream(), side)
             if side is not None:
                 side.wait_stream(cur)
                 with torch.cuda.stream(side):
@@ -490,6 +493,10 @@ def _join_masks(masks, side):
 WGRAD_STREAM = None
 # The same for the backbone's 13 weight / bias gradients (set by the engine with its stream overlap).
 BODY_WGRAD_STREAM = None
+# (k, fn): fn(main_stream, wgrad_stream_or_None) is called from the backbone's backward once everything of the
+# convolutions k .. 12 has been ISSUED (weight / bias gradients and the data gradient that reads conv k's
+# weights): the engine reduces and steps that bucket of parameters while the rest of the backward runs.
+BODY_BUCKET_HOOK = None
 
 
 class _RcnnHeadFn(torch.autograd.Function):
