@@ -140,6 +140,21 @@ int scda_nms_groups(int groups, int n_cap, const int *n_dev, const float *boxes,
 int scda_nms_mask(int n, const float *boxes, unsigned long long *mask, float thresh,
                   cudaStream_t stream);
 
+/* --- final detections of one image (functions/predict_bbox.py:13-66) ------------------- */
+/* Front half: per foreground class c = 1 .. num_classes-1 the score threshold (:39-42; <= 0: none), the
+ * descending-score order (:44-45) and the float64 decode + clip of the class's deltas (:26-31,38) ->
+ * dets [num_classes-1][n][5] (x1, y1, x2, y2, score; rows behind n_live[c-1] carry score -1), the input
+ * layout of scda_nms_groups.  rois [n][roi_stride] (batch, x1, y1, x2, y2, ...), cls [n][num_classes]
+ * probabilities, loc [n][4*num_classes]; stds / means: 4 host doubles each (normalize != 0). n <= 1024. */
+int scda_predict_prepare(int n, int num_classes, const float *rois, int roi_stride, const float *cls,
+                         const float *loc, int normalize, const double *stds, const double *means,
+                         double img_h, double img_w, float score_thresh, float *dets, int *n_live,
+                         cudaStream_t stream);
+/* Back half (:53-63): the survivors of all classes (keep / n_keep as written by scda_nms_groups) ranked by
+ * descending score -> rows [top_n][7] (batch, x1, y1, x2, y2, score, class) and count[0] = rows written. */
+int scda_predict_topn(int groups, int n, const float *dets, const int64_t *keep, const int64_t *n_keep,
+                      float batch_ix, int top_n, float *rows, int *count, cudaStream_t stream);
+
 /* --- IoU, cython_bbox convention -------------------------------------- */
 /* replaces cython_bbox.bbox_overlaps (extensions/_cython_bbox/cython_bbox.pyx:32-73,
  * reached through utils/bbox_helper.py:8-9): boxes [n,4], query [k,4] -> out [n,k];

@@ -35,6 +35,8 @@ SIGNATURES = {
     "scda_nms_dyn": (_i, [_i, _p, _p, _f, _i, _p, _p, _p, _z, _p]),
     "scda_nms_mask": (_i, [_i, _p, _p, _f, _p]),
     "scda_nms_groups": (_i, [_i, _i, _p, _p, _f, _p, _p, _p]),
+    "scda_predict_prepare": (_i, [_i, _i, _p, _i, _p, _p, _i, _p, _p, C.c_double, C.c_double, _f, _p, _p, _p]),
+    "scda_predict_topn": (_i, [_i, _i, _p, _p, _p, _f, _i, _p, _p, _p]),
     "scda_bbox_overlaps": (_i, [_i, _p, _i, _p, _p, _p]),
     "scda_sigmoid_focal_loss_sum": (_i, [_i, _p, _p, _f, _f, _f, _i, _p, _p, _p]),
     "scda_softmax_focal_loss_sum": (_i, [_i, _p, _p, _f, _f, _f, _i, _p, _p, _p, _p]),

@@ -1,5 +1,10 @@
 """Final detections at test time (mirrors functions/predict_bbox.py:13-66 of the reference).
 
+One image per call with a top-n (the evaluation loop's case): three launches — csrc/predict_ops.cu
+(threshold + sort + float64 decode per class; ranking of the survivors) around ONE scda_nms_groups — and one
+synchronisation for the number of rows (`_predict_one_image`).  Batches of several images / no top-n: the
+tensor-op form below.
+
 Reference: D2H of rois / class probabilities / deltas, then per class and per image: numpy decode,
 clip, argsort, H2D, GPU NMS mask, D2H, host scan — eight NMS round trips per image — and a numpy
 top-n.  Here all classes of an image are decoded at once, sorted with ONE batched sort and suppressed by
@@ -13,6 +18,10 @@ import torch
 
 from .._lib import check, load, stream_ptr
 from ..utils.bbox_helper import clip_t
+
+
+# tests: True sends single-image calls through the tensor-op form too (the two forms are compared)
+FORCE_TENSOR_PATH = False
 
 
 def _decode_all_classes(rb, pred_loc, num_classes, cfg, dev):
@@ -45,6 +54,36 @@ def nms_groups(dets, n_live, thresh):
     return keep, num
 
 
+def _predict_one_image(rois, pred_cls, pred_loc, info_row, cfg):
+    """One image, cfg['top_n'] > 0: three launches (csrc/predict_ops.cu around scda_nms_groups) and one
+    synchronisation for the number of rows.  -> CUDA float [M, 7]"""
+    import ctypes as C
+    dev = pred_cls.device
+    n, num_classes = pred_cls.shape[0:2]
+    Cc, top_n = num_classes - 1, int(cfg['top_n'])
+    rois = rois.contiguous()
+    cls = pred_cls.reshape(n, num_classes).float().contiguous()
+    loc = pred_loc.reshape(n, num_classes * 4).float().contiguous()
+    dets = torch.empty(Cc, n, 5, dtype=torch.float32, device=dev)
+    n_live = torch.empty(Cc, dtype=torch.int32, device=dev)
+    norm = bool(cfg['bbox_normalize_stats_precomputed'])
+    stds = (C.c_double * 4)(*[float(v) for v in cfg['bbox_normalize_stds']]) if norm else None
+    means = (C.c_double * 4)(*[float(v) for v in cfg['bbox_normalize_means']]) if norm else None
+    lib, st = load(), stream_ptr(dev)
+    with torch.cuda.device(dev):
+        check(lib.scda_predict_prepare(n, num_classes, rois.data_ptr(), rois.stride(0), cls.data_ptr(), loc.data_ptr(),
+                                       1 if norm else 0, stds, means, float(info_row[0]), float(info_row[1]),
+                                       float(cfg['score_thresh']), dets.data_ptr(), n_live.data_ptr(), st),
+              "scda_predict_prepare")
+    keep, n_keep = nms_groups(dets, n_live, cfg['nms_iou_thresh'])
+    rows = torch.empty(top_n, 7, dtype=torch.float32, device=dev)
+    count = torch.empty(1, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.scda_predict_topn(Cc, n, dets.data_ptr(), keep.data_ptr(), n_keep.data_ptr(), 0.0, top_n,
+                                    rows.data_ptr(), count.data_ptr(), st), "scda_predict_topn")
+    return rows[:int(count.item())]
+
+
 def compute_predicted_bboxes(rois, pred_cls, pred_loc, image_info, cfg):
     '''
     :param rois: [N, k] k>=5, batch_ix, x1, y1, x2, y2
@@ -60,6 +99,10 @@ def compute_predicted_bboxes(rois, pred_cls, pred_loc, image_info, cfg):
         image_info = image_info.cpu().numpy()
     N, num_classes = pred_cls.shape[0:2]
     Cc = num_classes - 1
+    if (len(image_info) == 1 and 0 < N <= 1024 and cfg['top_n'] > 0 and 2 <= num_classes <= 65
+            and rois.shape[1] >= 5 and pred_cls.dim() <= 4 and not FORCE_TENSOR_PATH):
+        # one image per call (the reference's evaluation loop runs batch size 1 per GPU): every RoI is image 0's
+        return _predict_one_image(rois, pred_cls, pred_loc, image_info[0], cfg)
     B = len(image_info) if N == 0 else int(rois[:, 0].max().item()) + 1
     per_image = []          # (rows [Cc, nb, 7], valid [Cc, nb])
     for b in range(B):

@@ -57,6 +57,36 @@ def test_predicted_bboxes_vs_oracle(cuda_lib, top_n):
     np.testing.assert_allclose(out[:, 1:5], ref[:, 1:5], rtol=1e-5, atol=1e-3)
 
 
+@pytest.mark.parametrize("n,thresh,seed", [(300, 0.0, 0), (300, 0.05, 1), (1024, 0.0, 2), (37, 0.3, 3), (1, 0.0, 4)])
+def test_predicted_bboxes_single_image_kernels(cuda_lib, n, thresh, seed):
+    """One image: the three-launch form (csrc/predict_ops.cu around scda_nms_groups) against the oracle's numpy
+    restatement of functions/predict_bbox.py:13-66 and, row for row, against the tensor-op form."""
+    import torch
+    from oracle import host
+    from scda_b200.functions import predict_bbox as pb
+    cfg = dict(_inputs.load_cfg()["test_predict_bbox_cfg"], top_n=100, score_thresh=thresh)
+    r = np.random.RandomState(seed)
+    rois = _inputs.rois_uniform(n, 20 + seed, img_w=1024, img_h=512, wh=(16, 300))
+    rois[:, 0] = 0
+    cls = r.dirichlet(np.ones(9) * 0.3, n).astype(np.float32)
+    loc = (r.standard_normal((n, 36)) * 0.5).astype(np.float32)
+    info = np.array([[512, 1024, 1.0]], np.float32)
+    args = (torch.from_numpy(rois).cuda(), torch.from_numpy(cls).cuda(), torch.from_numpy(loc).cuda(), info, cfg)
+    out = pb.compute_predicted_bboxes(*args)
+    try:
+        pb.FORCE_TENSOR_PATH = True
+        slow = pb.compute_predicted_bboxes(*args)
+    finally:
+        pb.FORCE_TENSOR_PATH = False
+    assert out.shape == slow.shape and torch.equal(out, slow)
+    ref = host.compute_predicted_bboxes(rois, cls, loc, info, cfg)
+    out = out.cpu().numpy()
+    assert out.shape == ref.shape
+    assert np.array_equal(out[:, 0], ref[:, 0]) and np.array_equal(out[:, 6], ref[:, 6])
+    np.testing.assert_allclose(out[:, 5], ref[:, 5], rtol=0, atol=0)
+    np.testing.assert_allclose(out[:, 1:5], ref[:, 1:5], rtol=1e-5, atol=1e-3)
+
+
 @pytest.mark.parametrize("mode,flip,shape,new", [("nearest", False, (1024, 2048), (512, 1024)),
                                                  ("nearest", True, (375, 500), (600, 800)),
                                                  ("bilinear", False, (1024, 2048), (512, 1024)),
