@@ -161,8 +161,9 @@ def reference_arm(args):
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch, averaged over the 13 backbone launches, from the
 # committed `ncu --set full` capture of the same kernels (scripts/prof_conv.py)
-NCU_DRAM_BYTES_PER_LAUNCH = 24.32e6
-NCU_TRAFFIC_SOURCE = "profiles/r1_ncu_conv_k_halo_final.txt (sum over the 9 shapes x multiplicity / 13)"
+NCU_DRAM_BYTES_PER_LAUNCH = 24.15e6
+NCU_TRAFFIC_SOURCE = ("profiles/r2_final_ncu_conv_fwd.txt: dram read + write of the 9 backbone shapes x multiplicity = 314.0 MB / 13 "
+                      "launches (conv1_1 counted in its 64-channel halo form; round 1: 24.32 MB)")
 
 VGG_CONVS = [(3, 64, 512, 1024), (64, 64, 512, 1024), (64, 128, 256, 512), (128, 128, 256, 512),
              (128, 256, 128, 256), (256, 256, 128, 256), (256, 256, 128, 256), (256, 512, 64, 128),
