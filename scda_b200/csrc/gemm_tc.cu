@@ -1012,7 +1012,11 @@ SCDA_API int scda_conv3x3_wgrad_bf16_nhwc_ld(int NB, int H, int W, int Cin, int 
     p.k_per_split = ceil_div(p.total_k_blocks, splits);
     if (ceil_div(p.total_k_blocks, p.k_per_split) != splits) return 0;   // every slab must be written
     p.out = dw_partials; p.ldo = 9ll * Cin; p.split_stride = (long long)Cout * 9 * Cin;
-    if (wgrad_three_taps()) {
+    // one unsplit pass over a short reduction with enough (tap, tile) CTAs to fill the GPU: the one-tap form
+    // (the host planner asks for splits == 1 only there, scda_b200/tc.py: _wgrad_splits)
+    const bool short_k = splits == 1 && p.total_k_blocks <= 16 &&
+                         9 * ceil_div(Cout, kBlockM) * ceil_div(Cin, bn) >= 96;
+    if (wgrad_three_taps() && !short_k) {
         // the X box is two image rows taller: one box per 64-channel chunk serves taps r = 0, 1, 2
         cuuint32_t box3[4] = {64, (cuuint32_t)TW, (cuuint32_t)(TH + 2), 1};
         CUtensorMap mb3;

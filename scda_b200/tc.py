@@ -230,11 +230,20 @@ def linear_wgrad(dy, x, out=None, accumulate=False):
 WGRAD3 = os.environ.get("SCDA_WGRAD3", "1") == "1"
 
 
+SHORT_K_ONE_TAP = os.environ.get("SCDA_WGRAD_SHORT_K", "1") == "1"
+
+
 def _wgrad_splits(NB, H, W, Cin, Cout, target_ctas):
     """how many ranges the pixel reduction is cut into: enough CTAs for `target_ctas`, every
     range non-empty.  CTAs per range = (taps or kernel columns) x Cout tiles x Cin tiles."""
     tiles = NB * H * W // 128
-    base = (3 if WGRAD3 else 9) * ((Cout + 127) // 128) * ((Cin + (63 if Cin <= 64 else 127)) // (64 if Cin <= 64 else 128))
+    co_t, ci_t = (Cout + 127) // 128, (Cin + (63 if Cin <= 64 else 127)) // (64 if Cin <= 64 else 128)
+    if WGRAD3 and SHORT_K_ONE_TAP and tiles <= 16 and 9 * co_t * ci_t >= 96:
+        # short reduction, big output (conv5_x / RPN: 16 pixel tiles, 512 x 4608 outputs): one tap per CTA fills
+        # the GPU without any split, so no slab is written and re-read (the C side picks that form when
+        # splits == 1 on such a shape; cuDNN's weight gradient was 2.2x faster here, profiles/r2_final_convbench.jsonl)
+        return 1
+    base = (3 if WGRAD3 else 9) * co_t * ci_t
     splits = max(1, min(tiles, target_ctas // max(base, 1)))
     per = -(-tiles // splits)
     return -(-tiles // per)
@@ -260,15 +269,24 @@ def conv3x3_wgrad_nhwc(x, dy, target_ctas=None, out=None, accumulate=False):
     if target_ctas is None:
         target_ctas = 148 if WGRAD3 else 296          # one wave of one-CTA-per-SM blocks / two waves
     splits = _wgrad_splits(NB, H, W, Cin, Cout, target_ctas)
-    part = torch.empty(splits, Cout, 3, 3, Cin, dtype=torch.float32, device=x.device)
+    if out is not None:
+        assert out.dtype == torch.float32 and out.numel() == Cout * 9 * Cin
+    # one slab that overwrites: the gradient buffer itself is the slab (its storage is [Cout][3][3][Cin]: a
+    # contiguous [Cout,3,3,Cin] tensor or a channels_last [Cout,Cin,3,3] view of the flat gradient)
+    dense = out is not None and ((tuple(out.shape) == (Cout, 3, 3, Cin) and out.is_contiguous())
+                                 or (tuple(out.shape) == (Cout, Cin, 3, 3)
+                                     and out.is_contiguous(memory_format=torch.channels_last)))
+    direct = splits == 1 and dense and not accumulate
+    part = None if direct else torch.empty(splits, Cout, 3, 3, Cin, dtype=torch.float32, device=x.device)
     with torch.cuda.device(x.device):
         check(load().scda_conv3x3_wgrad_bf16_nhwc(NB, H, W, Cin, Cout, x.data_ptr(), dy.data_ptr(),
-                                                  part.data_ptr(), splits, stream_ptr(x.device)),
+                                                  out.data_ptr() if direct else part.data_ptr(), splits,
+                                                  stream_ptr(x.device)),
               "scda_conv3x3_wgrad_bf16_nhwc")
     if out is None:
         return part[0] if splits == 1 else part.sum(0)
-    assert out.dtype == torch.float32 and out.numel() == part[0].numel()
-    reduce_slabs(part, out, accumulate)
+    if not direct:
+        reduce_slabs(part, out, accumulate)
     return out
 
 

@@ -46,8 +46,14 @@ def timeit(fn, flush, iters=6, warm=2):
 
 
 def main():
+    """`lib_us`: the same product through the library the reference would use today — cuDNN (bf16, channels_last,
+    benchmark mode: its best algorithm) for the convolutions, cuBLAS (torch.matmul, bf16) for the fc layers —
+    timed the same way.  The library calls compute the bare product (no bias / ReLU / mask epilogue, no split-K
+    slab reduction beyond their own)."""
+    import torch.nn.functional as F
     dev = torch.device("cuda")
     pk = peak()
+    torch.backends.cudnn.benchmark = True
     flush = torch.zeros(64 * 1024 * 1024, device=dev)
     out = []
     for name, H, W, Cin, Cout in LAYERS:
@@ -56,12 +62,24 @@ def main():
         dy = torch.randn(1, H, W, Cout, device=dev).bfloat16()
         bias = torch.zeros(Cout, device=dev)
         fl = 2.0 * H * W * Cin * Cout * 9
+        out_w = torch.empty(Cout, 3, 3, Cin, device=dev)
+        xc, wc, dyc = x.permute(0, 3, 1, 2), w.permute(0, 3, 1, 2), dy.permute(0, 3, 1, 2)   # channels_last views
+        lib = {"fwd": lambda: F.conv2d(xc, wc, None, padding=1),
+               "dgrad": lambda: torch.nn.grad.conv2d_input(xc.shape, wc, dyc, padding=1),
+               "wgrad": lambda: torch.nn.grad.conv2d_weight(xc, wc.shape, dyc, padding=1)}
         for what, fn in (("fwd", lambda: tc.conv3x3_nhwc(x, w, bias, relu=True)),
                          ("dgrad", lambda: tc.conv3x3_dgrad_nhwc(dy, w, mask_src=x)),
-                         ("wgrad", lambda: tc.conv3x3_wgrad_nhwc(x, dy))):
+                         ("wgrad", lambda: tc.conv3x3_wgrad_nhwc(x, dy, out=out_w))):
             t = timeit(fn, flush)
+            try:
+                tl = timeit(lib[what], flush, warm=4)
+            except Exception as e:                      # (a shape the library rejects)
+                print("# %s %s: library call failed: %s" % (name, what, e), file=sys.stderr)
+                tl = float("nan")
             out.append({"layer": name, "pass": what, "us": round(t * 1e6, 1),
-                        "tflops": round(fl / t / 1e12, 1), "frac_bf16_peak": round(fl / t / 1e12 / pk, 3)})
+                        "tflops": round(fl / t / 1e12, 1), "frac_bf16_peak": round(fl / t / 1e12 / pk, 3),
+                        "lib_us": round(tl * 1e6, 1), "lib": "cuDNN bf16 channels_last",
+                        "speedup_vs_lib": round(tl / t, 2)})
             print(json.dumps(out[-1]), flush=True)
     for name, M, N, K in GEMMS:
         a = torch.randn(M, K, device=dev).bfloat16()
@@ -70,12 +88,17 @@ def main():
         fl = 2.0 * M * N * K
         bpad = torch.zeros((N + 7) // 8 * 8, K, device=dev, dtype=torch.bfloat16)
         bpad[:N] = b
+        lib = {"fwd": lambda: torch.matmul(a, b.t()), "dgrad": lambda: torch.matmul(dyy, bpad),
+               "wgrad": lambda: torch.matmul(dyy.t(), a)}
         for what, fn in (("fwd", lambda: tc.gemm_tn(a, b)),
                          ("dgrad", lambda: tc.gemm_nn(dyy, bpad)),
                          ("wgrad", lambda: tc.linear_wgrad(dyy, a))):
             t = timeit(fn, flush)
+            tl = timeit(lib[what], flush, warm=4)
             out.append({"layer": name, "pass": what, "us": round(t * 1e6, 1),
-                        "tflops": round(fl / t / 1e12, 1), "frac_bf16_peak": round(fl / t / 1e12 / pk, 3)})
+                        "tflops": round(fl / t / 1e12, 1), "frac_bf16_peak": round(fl / t / 1e12 / pk, 3),
+                        "lib_us": round(tl * 1e6, 1), "lib": "cuBLAS bf16 (bf16 output; ours writes fp32 weight gradients)",
+                        "speedup_vs_lib": round(tl / t, 2)})
             print(json.dumps(out[-1]), flush=True)
 
 

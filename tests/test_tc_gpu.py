@@ -140,6 +140,16 @@ def test_conv3x3_wgrad(cuda_lib, NB, H, W, Cin, Cout):
             tc.set_wgrad_form(three)
             _close(tc.conv3x3_wgrad_nhwc(x, dy), ref, rtol=3e-3)
             _close(tc.conv3x3_wgrad_nhwc(x, dy, target_ctas=9), ref, rtol=3e-3)       # no split
+            # into a gradient buffer: overwrite (the buffer is the slab when nothing is split), then accumulate;
+            # both storage forms the sinks pass ([Cout,3,3,Cin] contiguous, channels_last [Cout,Cin,3,3] view)
+            o = torch.full((Cout, 3, 3, Cin), 7.0, device="cuda")
+            tc.conv3x3_wgrad_nhwc(x, dy, out=o)
+            _close(o, ref, rtol=3e-3)
+            tc.conv3x3_wgrad_nhwc(x, dy, out=o, accumulate=True)
+            _close(o, 2 * ref, rtol=3e-3)
+            ocl = torch.full((Cout, 3, 3, Cin), -3.0, device="cuda").permute(0, 3, 1, 2)
+            tc.conv3x3_wgrad_nhwc(x, dy, out=ocl)
+            _close(ocl.permute(0, 2, 3, 1), ref, rtol=3e-3)
     finally:
         tc.set_wgrad_form(True)             # the default form
 
