@@ -14,7 +14,7 @@ import torch
 
 from . import tc
 from ._lib import check, load, require_cuda, stream_ptr
-from .tc_detector import _direct, _is_krsc, _take_fresh, shadow_of
+from .tc_detector import _clear_fresh, _direct, _is_krsc, _take_fresh, shadow_of
 
 LEAKY, OUT_F32, MASK_POS, MASK_LEAKY = 128, 2, 4, 256
 
@@ -137,7 +137,7 @@ def _sink_s2_wgrad(p, x, dy):
 def _sink_bias_bf16(p, g2d):
     if _direct(p) and p.grad.is_contiguous():
         if _take_fresh(p):
-            p.grad.zero_()
+            _clear_fresh(p)
         tc.colsum_into(g2d, p.grad)
         return None
     out = torch.zeros(p.shape, dtype=torch.float32, device=p.device)
@@ -197,9 +197,9 @@ class _ImageDisFn(torch.autograd.Function):
             direct = _direct(w4) and _direct(b4) and w4.grad.is_contiguous()
             if direct:
                 if _take_fresh(w4):
-                    w4.grad.zero_()
+                    _clear_fresh(w4)
                 if _take_fresh(b4):
-                    b4.grad.zero_()
+                    _clear_fresh(b4)
                 dw4, db4 = w4.grad, b4.grad
             else:
                 dw4 = torch.zeros(C, dtype=torch.float32, device=dev)

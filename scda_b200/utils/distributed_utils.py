@@ -81,6 +81,11 @@ def flat_view(flat, off, p):
     return seg.view(p.shape)
 
 
+# FlatGradBucket.zero() does not zero a direct-written gradient of at least this many elements (its writer
+# overwrites it); smaller ones ARE zeroed there, so a sink that finds such a gradient marked fresh has nothing to clear
+DIRECT_SKIP_NUMEL = 1 << 20
+
+
 class FlatGradBucket(object):
     """All gradients of one network as views into one contiguous fp32 buffer, so the
     data-parallel exchange is a single all-reduce and the optimiser can sweep one array."""
@@ -108,7 +113,7 @@ class FlatGradBucket(object):
         for p, off in zip(self.params, self.offsets):
             if getattr(p, "_scda_direct_grad", False):
                 p._scda_grad_fresh = True
-                if p.numel() >= (1 << 20):
+                if p.numel() >= DIRECT_SKIP_NUMEL:
                     skip.append((off, off + p.numel()))
         if not skip:
             self.flat.zero_()
@@ -128,7 +133,7 @@ class FlatGradBucket(object):
             if off < lo or (hi is not None and off >= hi):
                 continue
             if getattr(p, "_scda_grad_fresh", False):
-                if p.numel() >= (1 << 20):
+                if p.numel() >= DIRECT_SKIP_NUMEL:
                     v.zero_()
                 p._scda_grad_fresh = False
 
