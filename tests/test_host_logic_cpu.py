@@ -108,3 +108,45 @@ def test_smooth_l1_reference_formula_matches_oracle():
     got = float(_smooth_l1_masked(torch.from_numpy(p), torch.from_numpy(m), torch.from_numpy(t)))
     assert abs(got - float(want)) <= 1e-5 * max(1.0, abs(float(want)))
     assert abs(float(smooth_l1_loss_with_sigma(torch.from_numpy(p * m), torch.from_numpy(t))) - got) <= 1e-6
+
+
+def test_short_reduction_layers_are_not_split(monkeypatch):
+    """conv5_x / RPN (16 pixel tiles, 4 x 4 x 9 = 144 (tap, tile) CTAs): one unsplit pass, so the kernel writes the
+    gradient buffer itself; layers with too few tiles to fill the GPU, or with a long reduction, keep their split."""
+    from scda_b200 import tc
+    monkeypatch.setattr(tc, "WGRAD3", True)
+    monkeypatch.setattr(tc, "SHORT_K_ONE_TAP", True)
+    assert tc._wgrad_splits(1, 32, 64, 512, 512, 148) == 1
+    assert tc._wgrad_splits(1, 32, 64, 64, 64, 148) > 1          # 9 CTAs per pass: split to fill the SMs
+    assert tc._wgrad_splits(1, 64, 128, 512, 512, 148) > 1        # 64 pixel tiles: the three-tap split form
+    monkeypatch.setattr(tc, "SHORT_K_ONE_TAP", False)
+    assert tc._wgrad_splits(1, 32, 64, 512, 512, 148) > 1
+
+
+def test_fresh_small_gradients_are_already_zero():
+    """FlatGradBucket.zero() zeroes every gradient except the large direct-written ones and marks all direct ones
+    fresh; a sink that finds a SMALL gradient fresh therefore clears nothing (tc_detector._clear_fresh), a large
+    one is cleared by the sink itself."""
+    from scda_b200.tc_detector import _clear_fresh, _take_fresh
+    from scda_b200.utils.distributed_utils import DIRECT_SKIP_NUMEL, FlatGradBucket
+    small = torch.nn.Parameter(torch.zeros(64))
+    large = torch.nn.Parameter(torch.zeros(DIRECT_SKIP_NUMEL))
+    plain = torch.nn.Parameter(torch.zeros(32))
+    bucket = FlatGradBucket([small, large, plain])
+    for p in (small, large):
+        p._scda_direct_grad = True
+    bucket.flat.fill_(3.0)
+    bucket.zero()
+    assert float(small.grad.abs().sum()) == 0 and float(plain.grad.abs().sum()) == 0
+    assert float(large.grad.min()) == 3.0, "the large direct gradient is left for its writer"
+    assert small._scda_grad_fresh and large._scda_grad_fresh and not getattr(plain, "_scda_grad_fresh", False)
+    assert _take_fresh(small) and not _take_fresh(small)
+    _clear_fresh(small)
+    assert _take_fresh(large)
+    _clear_fresh(large)
+    assert float(large.grad.abs().sum()) == 0
+    # a large gradient nobody wrote this step is zeroed by settle()
+    bucket.flat.fill_(5.0)
+    bucket.zero()
+    bucket.settle()
+    assert float(bucket.flat.abs().sum()) == 0
